@@ -1,0 +1,99 @@
+"""ctypes binding of libflypclip.so (C ABI in include/flyp_clip.h).
+
+The product path has no CPU or PyTorch fallback: if the shared library is missing, or a call is made without a CUDA
+device, this module raises.  Build the library with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C flyp_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflypclip.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+FLYP_BF16 = 0
+FLYP_F32 = 1
+
+# name -> (restype, argtypes); must list every symbol declared in include/flyp_clip.h
+SIGNATURES = {
+    "flyp_last_error": (c_char_p, []),
+    "flyp_version": (c_int, []),
+    "flyp_clip_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "flyp_clip_fwd_local": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "flyp_clip_fwd_finish": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    "flyp_clip_bwd_local": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "flyp_ce_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "flyp_ce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                            c_void_p, c_void_p, c_size_t, c_void_p]),
+    "flyp_ce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                            c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "flyp_l2norm_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "flyp_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "flyp_debug_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]),
+}
+
+_lib = None
+
+
+class FlypError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libflypclip.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC_DIR], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise FlypError("building libflypclip.so failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (never falls back to anything else)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FlypError(f"{LIB_PATH} not found: the CUDA extension is not built (run __graft_entry__.build()); "
+                        "flyp_b200 has no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().flyp_last_error()
+        raise FlypError(f"libflypclip error {rc}: {msg.decode() if msg else '?'}")
+
+
+def dtype_code(t) -> int:
+    import torch
+    if t.dtype == torch.bfloat16:
+        return FLYP_BF16
+    if t.dtype == torch.float32:
+        return FLYP_F32
+    raise FlypError(f"unsupported feature dtype {t.dtype} (bf16 and fp32 only)")
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,482 @@
+// api.cu — the C ABI of libflypclip.so (include/flyp_clip.h): argument checking, workspace carving, TMA descriptor
+// construction and kernel orchestration.  No allocation, no device synchronisation, no state kept between calls.
+#include "../../include/flyp_clip.h"
+#include "aux_kernels.cuh"
+#include "clip_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_OK(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) return fail(FLYP_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__));   \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 row-major [rows][cols] (leading dimension ld elements) -> tiles of [128 rows][64 cols], 128-byte swizzle,
+// out-of-bounds elements read as zero.
+int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, bool f16 = false) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return fail(FLYP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(FLYP_ERR_ARG, "feature pointer not 16-byte aligned");
+    if ((ld % 8) != 0) return fail(FLYP_ERR_ARG, "leading dimension %d not a multiple of 8", ld);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)flyp::KCHUNK, (cuuint32_t)flyp::TILE};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FLYP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = v > 0 ? v : 148;
+    }
+    return cached[dev];
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Number of M splits per N block for the forward sweep: minimise the makespan in tile units (a work item costs its
+// tiles plus ~2 tile-times to refill the stationary operand).
+int pick_m_split(int m_tiles, int n_tiles, int sms) {
+    int best = 1;
+    double best_cost = 1e30;
+    const int max_split = m_tiles < 64 ? m_tiles : 64;
+    for (int sp = 1; sp <= max_split; ++sp) {
+        const int items = n_tiles * sp;
+        const int rounds = ceil_div(items, sms);
+        const double cost = (double)rounds * (ceil_div(m_tiles, sp) + 2.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+    }
+    return best;
+}
+
+float shift_slack(int n_m, int n_n) {
+    int n = n_m > n_n ? n_m : n_n;
+    int lg = 0;
+    while ((1 << lg) < n) ++lg;
+    return 126.f - 2.f - (float)lg;
+}
+
+struct Carver {
+    uint8_t* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 256);
+        T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return r;
+    }
+};
+
+// ---- workspace of one forward statistics pass over S = A . B^T ([n_m] x [n_n]) ------------------------------------
+struct StatsWs {
+    int m_tiles, n_tiles, m_split, ld_rows, ld_cols;
+    float *rowpart, *rowmax, *colpart;   // fast pass + robust row pass
+    float *rowpart2, *rowmax2;           // robust column pass (roles swapped): [m_tiles*2][ld_cols]
+    float* t2;                           // [ld_rows] positive logit of each row, log2 units
+    int* pos;                            // [ld_rows] positive column of each row, -1 = none
+    int* pos_t;                          // [ld_cols] robust column pass: positive row of each column
+    float* t2_t;                         // [ld_cols] scratch (unused values) for the column pass
+    int* flag;
+};
+void carve_stats(Carver& c, int n_m, int n_n, bool want_cols, StatsWs& w) {
+    w.m_tiles = ceil_div(n_m, flyp::TILE);
+    w.n_tiles = ceil_div(n_n, flyp::TILE);
+    w.m_split = pick_m_split(w.m_tiles, w.n_tiles, 148);
+    w.ld_rows = w.m_tiles * flyp::TILE;
+    w.ld_cols = w.n_tiles * flyp::TILE;
+    w.rowpart = c.take<float>((size_t)w.n_tiles * 2 * w.ld_rows);
+    w.rowmax = c.take<float>((size_t)w.n_tiles * 2 * w.ld_rows);
+    w.colpart = c.take<float>((size_t)w.m_split * w.ld_cols);
+    if (want_cols) {
+        w.rowpart2 = c.take<float>((size_t)w.m_tiles * 2 * w.ld_cols);
+        w.rowmax2 = c.take<float>((size_t)w.m_tiles * 2 * w.ld_cols);
+    } else {
+        w.rowpart2 = w.rowmax2 = nullptr;
+    }
+    w.t2 = c.take<float>(w.ld_rows);
+    w.pos = c.take<int>(w.ld_rows);
+    w.pos_t = want_cols ? c.take<int>(w.ld_cols) : nullptr;
+    w.t2_t = want_cols ? c.take<float>(w.ld_cols) : nullptr;
+    w.flag = c.take<int>(1);
+}
+
+// Statistics of S = scale * A . B^T with one positive per row (labels, or column pos_offset + i):
+//   row_lse[n_m] natural-log logsumexp, row_nll[n_m] = row_lse - positive logit, and (col_stat != null) the column
+//   triples (m_j, sum_j, t_j), see k_fwd_finalize.  The positives are excluded from the tensor-core sums and added back
+//   exactly, so a loss much smaller than the logits keeps full relative accuracy.
+int run_stats(const void* A, const void* B, const float* scale, int n_m, int n_n, int dim, int dtype,
+              const int64_t* labels, int pos_offset, const StatsWs& w, float* row_lse, float* row_nll,
+              float* col_stat, int* status, float* dbg_logits, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    int rc;
+    if ((rc = make_tmap(&tmA, A, n_m, dim, dim)) != 0) return rc;
+    if ((rc = make_tmap(&tmB, B, n_n, dim, dim)) != 0) return rc;
+    const int sms = num_sms();
+    const float slack = shift_slack(n_m, n_n);
+    CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(int), st));
+
+    flyp::FwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_m = n_m; p.n_n = n_n; p.kc = ceil_div(dim, flyp::KCHUNK);
+    p.m_tiles = w.m_tiles; p.n_tiles = w.n_tiles; p.m_split = w.m_split;
+    p.ld_rows = w.ld_rows; p.ld_cols = w.ld_cols;
+    p.scale = scale; p.shift_slack = slack;
+    p.rowpart = w.rowpart; p.colpart = w.colpart; p.rowmax = w.rowmax; p.colmax = nullptr;
+    p.dbg_logits = dbg_logits;
+    if (dbg_logits == nullptr) {
+        flyp::launch_pair_dot(A, B, dtype, scale, n_m, w.ld_rows, n_n, dim, labels, pos_offset, w.t2, w.pos, st);
+        CUDA_OK(cudaGetLastError());
+        p.pos = w.pos;
+    }
+    flyp::launch_fwd(tmA, tmB, p, /*robust=*/false, nullptr, sms, st);
+    CUDA_OK(cudaGetLastError());
+    if (dbg_logits != nullptr) return 0;
+    flyp::launch_fwd_finalize(w.rowpart, w.n_tiles * 2, w.ld_rows, n_m, w.colpart, w.m_split, w.ld_cols, n_n, scale,
+                              slack, w.t2, w.pos, pos_offset, row_lse, row_nll, col_stat, w.flag, st);
+    CUDA_OK(cudaGetLastError());
+
+    // Robust recomputation, gated on the device flag (the kernels return immediately when the fast path was adequate).
+    flyp::launch_fwd(tmA, tmB, p, /*robust=*/true, w.flag, sms, st);
+    CUDA_OK(cudaGetLastError());
+    if (col_stat != nullptr) {
+        // roles swapped: rows of S^T are the columns of S; the positive of column j is local row j - pos_offset
+        flyp::launch_pair_dot(B, A, dtype, scale, n_n, w.ld_cols, n_m, dim, nullptr, -pos_offset, w.t2_t, w.pos_t, st);
+        CUDA_OK(cudaGetLastError());
+        flyp::FwdParams pt = p;
+        pt.n_m = n_n; pt.n_n = n_m; pt.m_tiles = w.n_tiles; pt.n_tiles = w.m_tiles;
+        pt.m_split = 1; pt.ld_rows = w.ld_cols; pt.ld_cols = w.ld_rows;
+        pt.rowpart = w.rowpart2; pt.rowmax = w.rowmax2; pt.colpart = nullptr; pt.pos = w.pos_t;
+        flyp::launch_fwd(tmB, tmA, pt, /*robust=*/true, w.flag, sms, st);
+        CUDA_OK(cudaGetLastError());
+    }
+    flyp::launch_fwd_finalize_robust(w.rowpart, w.rowmax, w.n_tiles * 2, w.ld_rows, n_m, w.rowpart2, w.rowmax2,
+                                     w.m_tiles * 2, w.ld_cols, n_n, w.t2, row_lse, row_nll, col_stat, w.flag, st);
+    CUDA_OK(cudaGetLastError());
+    if (status != nullptr) CUDA_OK(cudaMemcpyAsync(status, w.flag, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---- workspace of the backward sweeps -----------------------------------------------------------------------------
+struct VecSet { float *w, *l2, *d; int* lab; };
+void carve_vecs(Carver& c, int n_pad, VecSet& v) {
+    v.w = c.take<float>(n_pad); v.l2 = c.take<float>(n_pad); v.d = c.take<float>(n_pad); v.lab = c.take<int>(n_pad);
+}
+
+int check_common(int n_m, int n_n, int dim, int dtype) {
+    if (n_m <= 0 || n_n <= 0) return fail(FLYP_ERR_ARG, "empty operand (%d x %d)", n_m, n_n);
+    if (dim <= 0 || dim % 8 != 0) return fail(FLYP_ERR_ARG, "dim=%d must be a positive multiple of 8", dim);
+    if (dtype != FLYP_BF16) return fail(FLYP_ERR_ARG, "dtype %d not supported by this build (bf16 only)", dtype);
+    return 0;
+}
+
+int run_sweep(const void* A, const void* B, const void* B_f16, const float* scale, int n_m, int n_n, int dim, const float* wr,
+              const float* lr, const float* wc, const float* lc, const int* labr, const float* dr, const int* labc,
+              const float* dc, const void* a_rows_for_dscale, void* out, int out_fp32, float out_mul, float* dscale_part,
+              const uint32_t* gmax_bits, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    int rc;
+    if ((rc = make_tmap(&tmA, A, n_m, dim, dim)) != 0) return rc;
+    if ((rc = make_tmap(&tmB, B, n_n, dim, dim)) != 0) return rc;
+    CUtensorMap tmBd;
+    if ((rc = make_tmap(&tmBd, B_f16, n_n, dim, dim, true)) != 0) return rc;
+    flyp::BwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_m = n_m; p.n_n = n_n; p.kc = ceil_div(dim, flyp::KCHUNK);
+    p.m_tiles = ceil_div(n_m, flyp::TILE); p.n_tiles = ceil_div(n_n, flyp::TILE);
+    p.d_out = dim; p.d_parts = ceil_div(dim, 256);
+    p.scale = scale; p.wr = wr; p.lr = lr; p.wc = wc; p.lc = lc;
+    p.labr = labr; p.dr = dr; p.labc = labc; p.dc = dc;
+    p.a_rows = a_rows_for_dscale; p.lda = dim;
+    p.out = out; p.ld_out = dim; p.out_fp32 = out_fp32; p.out_mul = out_mul; p.gmax_bits = gmax_bits;
+    p.dscale_part = dscale_part;
+    flyp::launch_bwd(tmA, tmB, tmBd, p, num_sms(), st);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* flyp_last_error(void) { return g_err; }
+int flyp_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------ clip
+struct ClipWs {
+    StatsWs stats;
+    VecSet rows, cols;       // bwd vectors: by local image row / by text column
+    float* dscale_part;
+    uint32_t* gmax_bits;
+    uint16_t *img16, *txt16;  // fp16 staging copies of the features (backward only)
+    size_t bytes;
+};
+static void carve_clip(void* base, int n_rows, int n_cols, int dim, ClipWs& w) {
+    Carver c(base);
+    carve_stats(c, n_rows, n_cols, true, w.stats);
+    const int rp = ceil_div(n_rows, flyp::TILE) * flyp::TILE, cp = ceil_div(n_cols, flyp::TILE) * flyp::TILE;
+    carve_vecs(c, rp, w.rows);
+    carve_vecs(c, cp, w.cols);
+    w.dscale_part = c.take<float>((size_t)ceil_div(n_rows, flyp::TILE) * ceil_div(dim, 256));
+    w.gmax_bits = c.take<uint32_t>(1);
+    w.img16 = c.take<uint16_t>((size_t)n_rows * dim);
+    w.txt16 = c.take<uint16_t>((size_t)n_cols * dim);
+    w.bytes = align_up(c.off, 256);
+}
+
+int flyp_clip_workspace_bytes(int n_rows, int n_cols, int dim, int dtype, size_t* bytes) {
+    int rc = check_common(n_rows, n_cols, dim, dtype);
+    if (rc) return rc;
+    if (!bytes) return fail(FLYP_ERR_ARG, "bytes is null");
+    ClipWs w;
+    carve_clip(nullptr, n_rows, n_cols, dim, w);
+    *bytes = w.bytes;
+    return 0;
+}
+
+int flyp_clip_fwd_local(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
+                        int dtype, int row_offset, float* row_lse, float* row_nll, float* col_stat, int* status,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(n_rows, n_cols, dim, dtype);
+    if (rc) return rc;
+    if (!img || !txt || !scale || !row_lse || !row_nll || !col_stat || !workspace)
+        return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (row_offset < 0 || row_offset + n_rows > n_cols)
+        return fail(FLYP_ERR_ARG, "row_offset %d + n_rows %d exceeds n_cols %d", row_offset, n_rows, n_cols);
+    ClipWs w;
+    carve_clip(workspace, n_rows, n_cols, dim, w);
+    if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return run_stats(img, txt, scale, n_rows, n_cols, dim, dtype, nullptr, row_offset, w.stats, row_lse, row_nll,
+                     col_stat, status, nullptr, st);
+}
+
+int flyp_clip_fwd_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
+                         int row_offset, float* col_lse, float* col_nll, float* loss, void* stream) {
+    if (!col_stat_all || !row_nll || !col_lse || !col_nll || !loss) return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (world < 1 || n_rows <= 0 || n_cols <= 0) return fail(FLYP_ERR_ARG, "bad sizes");
+    flyp::launch_clip_finish(col_stat_all, world, row_nll, n_rows, n_cols, row_offset, col_lse, col_nll, loss,
+                             static_cast<cudaStream_t>(stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
+                        int dtype, int row_offset, const float* row_lse, const float* row_nll, const float* col_lse,
+                        const float* col_nll, const float* g_row, const float* g_col, float grad_mul, int grad_dtype,
+                        void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    int rc = check_common(n_rows, n_cols, dim, dtype);
+    if (rc) return rc;
+    if (!img || !txt || !scale || !row_lse || !row_nll || !col_lse || !col_nll || !g_row || !g_col || !workspace)
+        return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (grad_dtype != FLYP_BF16 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad grad_dtype %d", grad_dtype);
+    if (row_offset < 0 || row_offset + n_rows > n_cols)
+        return fail(FLYP_ERR_ARG, "row_offset %d + n_rows %d exceeds n_cols %d", row_offset, n_rows, n_cols);
+    ClipWs w;
+    carve_clip(workspace, n_rows, n_cols, dim, w);
+    if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rp = ceil_div(n_rows, flyp::TILE) * flyp::TILE, cp = ceil_div(n_cols, flyp::TILE) * flyp::TILE;
+    CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, sizeof(uint32_t), st));
+    // rows: w = g_row/2, positive column row_offset + i, exact dS there from the saved cross-entropies
+    flyp::launch_bwd_prep(n_rows, rp, g_row, 0.5f, row_lse, row_nll, nullptr, row_offset, n_cols, g_col, col_nll, 0.5f,
+                          w.rows.w, w.rows.l2, w.rows.lab, w.rows.d, w.gmax_bits, st);
+    // columns: w = g_col/2, positive local row j - row_offset
+    flyp::launch_bwd_prep(n_cols, cp, g_col, 0.5f, col_lse, col_nll, nullptr, -row_offset, n_rows, g_row, row_nll, 0.5f,
+                          w.cols.w, w.cols.l2, w.cols.lab, w.cols.d, w.gmax_bits, st);
+    CUDA_OK(cudaGetLastError());
+    if (d_img) {
+        flyp::launch_to_f16(txt, dtype, (size_t)n_cols * dim, w.txt16, st);
+        CUDA_OK(cudaGetLastError());
+        rc = run_sweep(img, txt, w.txt16, scale, n_rows, n_cols, dim, w.rows.w, w.rows.l2, w.cols.w, w.cols.l2, w.rows.lab,
+                       w.rows.d, nullptr, nullptr, d_scale ? img : nullptr, d_img, grad_dtype, grad_mul,
+                       d_scale ? w.dscale_part : nullptr, w.gmax_bits, st);
+        if (rc) return rc;
+        if (d_scale) {
+            flyp::launch_sum_parts(w.dscale_part, ceil_div(n_rows, flyp::TILE) * ceil_div(dim, 256), d_scale, st);
+            CUDA_OK(cudaGetLastError());
+        }
+    } else if (d_scale) {
+        return fail(FLYP_ERR_ARG, "d_scale requires d_img");
+    }
+    if (d_txt) {
+        flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
+        CUDA_OK(cudaGetLastError());
+        rc = run_sweep(txt, img, w.img16, scale, n_cols, n_rows, dim, w.cols.w, w.cols.l2, w.rows.w, w.rows.l2, w.cols.lab,
+                       w.cols.d, nullptr, nullptr, nullptr, d_txt, grad_dtype, grad_mul, nullptr, w.gmax_bits, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ ce head
+struct CeWs {
+    StatsWs stats;
+    VecSet v;
+    float* dscale_part;
+    uint32_t* gmax_bits;
+    uint16_t *a16, *b16;
+    size_t bytes;
+};
+static void carve_ce(void* base, int n, int n_classes, int dim, CeWs& w) {
+    Carver c(base);
+    carve_stats(c, n, n_classes, false, w.stats);
+    const int np = ceil_div(n, flyp::TILE) * flyp::TILE;
+    carve_vecs(c, np, w.v);
+    w.dscale_part = c.take<float>((size_t)ceil_div(n, flyp::TILE) * ceil_div(dim, 256));
+    w.gmax_bits = c.take<uint32_t>(1);
+    w.a16 = c.take<uint16_t>((size_t)n * dim);
+    w.b16 = c.take<uint16_t>((size_t)n_classes * dim);
+    w.bytes = align_up(c.off, 256);
+}
+
+int flyp_ce_workspace_bytes(int n, int n_classes, int dim, int dtype, size_t* bytes) {
+    int rc = check_common(n, n_classes, dim, dtype);
+    if (rc) return rc;
+    if (!bytes) return fail(FLYP_ERR_ARG, "bytes is null");
+    CeWs w;
+    carve_ce(nullptr, n, n_classes, dim, w);
+    *bytes = w.bytes;
+    return 0;
+}
+
+int flyp_ce_fwd(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
+                const int64_t* labels, int label_offset, float* loss, float* lse, void* workspace,
+                size_t workspace_bytes, void* stream) {
+    int rc = check_common(n, n_classes, dim, dtype);
+    if (rc) return rc;
+    if (!a || !b || !scale || !loss || !lse || !workspace) return fail(FLYP_ERR_ARG, "null pointer argument");
+    CeWs w;
+    carve_ce(workspace, n, n_classes, dim, w);
+    if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
+    return run_stats(a, b, scale, n, n_classes, dim, dtype, labels, label_offset, w.stats, lse, loss, nullptr,
+                     nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
+                const int64_t* labels, int label_offset, const float* lse, const float* loss, const float* g,
+                int grad_dtype, void* d_a, void* d_b, float* d_scale, void* workspace, size_t workspace_bytes,
+                void* stream) {
+    int rc = check_common(n, n_classes, dim, dtype);
+    if (rc) return rc;
+    if (!a || !b || !scale || !lse || !loss || !g || !workspace) return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (grad_dtype != FLYP_BF16 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad grad_dtype %d", grad_dtype);
+    CeWs w;
+    carve_ce(workspace, n, n_classes, dim, w);
+    if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int np = ceil_div(n, flyp::TILE) * flyp::TILE;
+    CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, sizeof(uint32_t), st));
+    // w = g, positive = label, dS there = g * expm1(-loss)
+    flyp::launch_bwd_prep(n, np, g, 1.0f, lse, loss, labels, label_offset, n_classes, nullptr, nullptr, 1.0f, w.v.w,
+                          w.v.l2, w.v.lab, w.v.d, w.gmax_bits, st);
+    CUDA_OK(cudaGetLastError());
+    if (d_a) {
+        flyp::launch_to_f16(b, dtype, (size_t)n_classes * dim, w.b16, st);
+        CUDA_OK(cudaGetLastError());
+        rc = run_sweep(a, b, w.b16, scale, n, n_classes, dim, w.v.w, w.v.l2, nullptr, nullptr, w.v.lab, w.v.d, nullptr,
+                       nullptr, d_scale ? a : nullptr, d_a, grad_dtype, 1.0f, d_scale ? w.dscale_part : nullptr,
+                       w.gmax_bits, st);
+        if (rc) return rc;
+        if (d_scale) {
+            flyp::launch_sum_parts(w.dscale_part, ceil_div(n, flyp::TILE) * ceil_div(dim, 256), d_scale, st);
+            CUDA_OK(cudaGetLastError());
+        }
+    } else if (d_scale) {
+        return fail(FLYP_ERR_ARG, "d_scale requires d_a");
+    }
+    if (d_b) {
+        // rows = classes, columns = samples: only the column (sample) softmax term exists
+        flyp::launch_to_f16(a, dtype, (size_t)n * dim, w.a16, st);
+        CUDA_OK(cudaGetLastError());
+        rc = run_sweep(b, a, w.a16, scale, n_classes, n, dim, nullptr, nullptr, w.v.w, w.v.l2, nullptr, nullptr, w.v.lab,
+                       w.v.d, nullptr, d_b, grad_dtype, 1.0f, nullptr, w.gmax_bits, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ l2 normalise
+int flyp_l2norm_fwd(const void* x, int n, int dim, int dtype, void* y, float* inv_norm, void* stream) {
+    if (!x || !y) return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (n <= 0 || dim <= 0 || dim % 8 != 0) return fail(FLYP_ERR_ARG, "bad shape [%d, %d] (dim %% 8 must be 0)", n, dim);
+    if (dtype != FLYP_BF16 && dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad dtype %d", dtype);
+    flyp::launch_l2norm_fwd(x, n, dim, dtype, y, inv_norm, static_cast<cudaStream_t>(stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int flyp_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n, int dim, int dtype, void* dx,
+                    void* stream) {
+    if (!y || !dy || !inv_norm || !dx) return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (n <= 0 || dim <= 0 || dim % 8 != 0) return fail(FLYP_ERR_ARG, "bad shape [%d, %d] (dim %% 8 must be 0)", n, dim);
+    if (dtype != FLYP_BF16 && dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad dtype %d", dtype);
+    flyp::launch_l2norm_bwd(y, dy, inv_norm, n, dim, dtype, dx, static_cast<cudaStream_t>(stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ debug logits
+int flyp_debug_logits(const void* a, const void* b, int n_m, int n_n, int dim, int dtype, float* out,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(n_m, n_n, dim, dtype);
+    if (rc) return rc;
+    if (!a || !b || !out || !workspace) return fail(FLYP_ERR_ARG, "null pointer argument");
+    ClipWs w;
+    carve_clip(workspace, n_m, n_n, dim, w);
+    if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
+    // scale is irrelevant for raw dot products but the kernel reads it: park a 1.0f in the (unused) d(scale) scratch
+    float* one = w.dscale_part;
+    static const float h_one = 1.0f;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_OK(cudaMemcpyAsync(one, &h_one, sizeof(float), cudaMemcpyHostToDevice, st));
+    return run_stats(a, b, one, n_m, n_n, dim, dtype, nullptr, 0, w.stats, nullptr, nullptr, nullptr, nullptr, out, st);
+}
+
+}  // extern "C"

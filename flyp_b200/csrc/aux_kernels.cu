@@ -1,0 +1,389 @@
+// aux_kernels.cu — the HBM-bound helper kernels of the ClipLoss path (see aux_kernels.cuh).
+#include "aux_kernels.cuh"
+#include "clip_kernels.cuh"
+#include <cuda_bf16.h>
+
+namespace flyp {
+
+constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr float LN2_F = 0.6931471805599453f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// 8 consecutive elements -> fp32
+template <bool F32>
+__device__ __forceinline__ void load8(const void* base, size_t elem, float (&v)[8]) {
+    if (F32) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
+        float4 a = __ldg(p), b = __ldg(p + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[2 * e] = __uint_as_float(w[e] << 16);
+            v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+        }
+    }
+}
+template <bool F32>
+__device__ __forceinline__ void store8(void* base, size_t elem, const float (&v)[8]) {
+    if (F32) {
+        float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem);
+        p[0] = make_float4(v[0], v[1], v[2], v[3]);
+        p[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        uint4 u;
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(v[0], v[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[2], v[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[4], v[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[6], v[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem) = u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pair logits
+// t2[i] = scale * log2(e) * <A[i,:], B[idx(i),:]> (-inf when row i has no valid positive), pos[i] = idx(i) or -1.
+// Rows [n, n_pad) are padding: pos = -1, t2 = -inf.
+template <bool F32>
+__global__ void k_pair_dot(const void* __restrict__ A, const void* __restrict__ B, const float* __restrict__ scale,
+                           int n, int n_pad, int n_b, int dim, const int64_t* __restrict__ labels, int offset,
+                           float* __restrict__ t2, int* __restrict__ pos) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    long long idx = -1;
+    if (row < n) idx = labels ? labels[row] : (long long)offset + row;
+    const bool ok = idx >= 0 && idx < n_b;
+    float acc = 0.f;
+    if (ok) {
+        for (int d = lane * 8; d < dim; d += 256) {
+            float a[8], b[8];
+            load8<F32>(A, (size_t)row * dim + d, a);
+            load8<F32>(B, (size_t)idx * dim + d, b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc = fmaf(a[e], b[e], acc);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        t2[row] = ok ? acc * scale[0] * LOG2E_F : -INFINITY;
+        pos[row] = ok ? (int)idx : -1;
+    }
+}
+
+void launch_pair_dot(const void* A, const void* B, int dtype, const float* scale, int n, int n_pad, int n_b, int dim,
+                     const int64_t* labels, int offset, float* t2, int* pos, cudaStream_t st) {
+    if (n_pad <= 0) return;
+    const int wpb = 8;
+    dim3 grid((n_pad + wpb - 1) / wpb), block(wpb * 32);
+    if (dtype == 1) k_pair_dot<true><<<grid, block, 0, st>>>(A, B, scale, n, n_pad, n_b, dim, labels, offset, t2, pos);
+    else k_pair_dot<false><<<grid, block, 0, st>>>(A, B, scale, n, n_pad, n_b, dim, labels, offset, t2, pos);
+}
+
+// log2-domain logaddexp of a (off-positive mass) and t (positive logit): returns lse2 and nll = ln2 * (lse2 - t)
+__device__ __forceinline__ void lse_with_positive(float a, float t, float& lse2, float& nll) {
+    if (t == -INFINITY) { lse2 = a; nll = a * LN2_F; return; }      // no positive: nll degenerates to lse
+    if (a == -INFINITY) { lse2 = t; nll = 0.f; return; }
+    if (t >= a) {
+        const float r = exp2f(a - t);
+        lse2 = t + log2f(1.f + r);
+        nll = log1pf(r);
+    } else {
+        const float r = exp2f(t - a);
+        lse2 = a + log2f(1.f + r);
+        nll = (a - t) * LN2_F + log1pf(r);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ finalize (fast)
+// col_stat layout: [3][n_n] = (m_j log2 reference, sum_j of exp2(x - m_j) over the local rows EXCLUDING positives,
+//                              t_j log2 positive logit of column j if its row is local else -inf)
+__global__ void k_fwd_finalize(const float* __restrict__ rowpart, int n_rowparts, int ld_rows, int n_m,
+                               const float* __restrict__ colpart, int n_colparts, int ld_cols, int n_n,
+                               const float* __restrict__ scale, float slack, const float* __restrict__ t2,
+                               const int* __restrict__ pos, int col_pos_offset, float* __restrict__ row_lse,
+                               float* __restrict__ row_nll, float* __restrict__ col_stat, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float c1 = scale[0] * LOG2E_F;
+    const float c0 = fixed_shift(c1, slack);
+    // A sum is trustworthy when the mass lost to flush-to-zero (< n * 2^-126 in shifted units) is below fp32
+    // resolution of either the sum itself or of the (exactly known) positive term it is added to.
+    const float lg_r = log2f((float)n_n), lg_c = log2f((float)n_m);
+    bool bad = false;
+    if (i < n_m) {
+        float sum = 0.f;
+        for (int p = 0; p < n_rowparts; ++p) sum += rowpart[(size_t)p * ld_rows + i];
+        const float t = t2 ? t2[i] : -INFINITY;
+        const float a = sum > 0.f ? log2f(sum) + c0 : -INFINITY;
+        float lse2, nll;
+        lse_with_positive(a, t, lse2, nll);
+        row_lse[i] = lse2 * LN2_F;
+        if (row_nll) row_nll[i] = nll;
+        const bool ok = !isinf(sum) && (sum >= exp2f(lg_r - 101.f) || t >= c0 - 101.f + lg_r);
+        bad |= !ok;
+    }
+    if (i < n_n && col_stat != nullptr) {
+        float sum = 0.f;
+        for (int p = 0; p < n_colparts; ++p) sum += colpart[(size_t)p * ld_cols + i];
+        const int r = i - col_pos_offset;                    // local row whose positive is column i
+        const float t = (r >= 0 && r < n_m && t2 && pos[r] == i) ? t2[r] : -INFINITY;
+        col_stat[i] = c0;
+        col_stat[n_n + i] = sum;
+        col_stat[2 * n_n + i] = t;
+        const bool ok = !isinf(sum) && (sum >= exp2f(lg_c - 101.f) || t >= c0 - 101.f + lg_c);
+        bad |= !ok;
+    }
+    if (bad) atomicOr(flag, 1);
+}
+
+void launch_fwd_finalize(const float* rowpart, int n_rowparts, int ld_rows, int n_m, const float* colpart,
+                         int n_colparts, int ld_cols, int n_n, const float* scale, float slack, const float* t2,
+                         const int* pos, int col_pos_offset, float* row_lse, float* row_nll, float* col_stat,
+                         int* flag, cudaStream_t st) {
+    const int n = n_m > n_n ? n_m : n_n;
+    k_fwd_finalize<<<(n + 255) / 256, 256, 0, st>>>(rowpart, n_rowparts, ld_rows, n_m, colpart, n_colparts, ld_cols,
+                                                    n_n, scale, slack, t2, pos, col_pos_offset, row_lse, row_nll,
+                                                    col_stat, flag);
+}
+
+// ------------------------------------------------------------------------------------------------ finalize (robust)
+__device__ __forceinline__ void merge_pairs(const float* __restrict__ part, const float* __restrict__ pmax, int np,
+                                            int ld, int i, float& m_out, float& s_out) {
+    float m = -INFINITY;
+    for (int p = 0; p < np; ++p) m = fmaxf(m, pmax[(size_t)p * ld + i]);
+    float s = 0.f;
+    if (m > -INFINITY) {
+        for (int p = 0; p < np; ++p) {
+            const float pm = pmax[(size_t)p * ld + i];
+            if (pm > -INFINITY) s += part[(size_t)p * ld + i] * exp2f(pm - m);
+        }
+    }
+    m_out = m;
+    s_out = s;
+}
+
+__global__ void k_fwd_finalize_robust(const float* __restrict__ rowpart, const float* __restrict__ rowmax,
+                                      int n_rowparts, int ld_rows, int n_m, const float* __restrict__ colpart,
+                                      const float* __restrict__ colmax, int n_colparts, int ld_cols, int n_n,
+                                      const float* __restrict__ t2, float* __restrict__ row_lse,
+                                      float* __restrict__ row_nll, float* __restrict__ col_stat,
+                                      const int* __restrict__ flag) {
+    if (*flag == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_m) {
+        float m, s;
+        merge_pairs(rowpart, rowmax, n_rowparts, ld_rows, i, m, s);
+        const float a = s > 0.f ? log2f(s) + m : -INFINITY;
+        float lse2, nll;
+        lse_with_positive(a, t2 ? t2[i] : -INFINITY, lse2, nll);
+        row_lse[i] = lse2 * LN2_F;
+        if (row_nll) row_nll[i] = nll;
+    }
+    if (i < n_n && col_stat != nullptr) {
+        float m, s;
+        merge_pairs(colpart, colmax, n_colparts, ld_cols, i, m, s);
+        col_stat[i] = m;          // the positive-logit row (col_stat[2 n_n + i]) was already written by the fast finalize
+        col_stat[n_n + i] = s;
+    }
+}
+
+void launch_fwd_finalize_robust(const float* rowpart, const float* rowmax, int n_rowparts, int ld_rows, int n_m,
+                                const float* colpart, const float* colmax, int n_colparts, int ld_cols, int n_n,
+                                const float* t2, float* row_lse, float* row_nll, float* col_stat, const int* flag,
+                                cudaStream_t st) {
+    const int n = n_m > n_n ? n_m : n_n;
+    k_fwd_finalize_robust<<<(n + 255) / 256, 256, 0, st>>>(rowpart, rowmax, n_rowparts, ld_rows, n_m, colpart, colmax,
+                                                           n_colparts, ld_cols, n_n, t2, row_lse, row_nll, col_stat,
+                                                           flag);
+}
+
+// ------------------------------------------------------------------------------------------------ clip finish
+// col_stat_all[world][3 * n_cols] -> col_lse[n_cols]; loss[i] = 0.5 * (row_nll[i] + col_nll[row_offset + i])
+__global__ void k_clip_finish(const float* __restrict__ col_stat_all, int world, const float* __restrict__ row_nll,
+                              int n_rows, int n_cols, int row_offset, float* __restrict__ col_lse,
+                              float* __restrict__ col_nll, float* __restrict__ loss) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cols) return;
+    const size_t ldw = (size_t)3 * n_cols;
+    float m = -INFINITY, t = -INFINITY;
+    for (int w = 0; w < world; ++w) {
+        if (col_stat_all[w * ldw + n_cols + j] > 0.f) m = fmaxf(m, col_stat_all[w * ldw + j]);
+        t = fmaxf(t, col_stat_all[w * ldw + 2 * n_cols + j]);
+    }
+    float s = 0.f;
+    for (int w = 0; w < world; ++w) {
+        const float sw = col_stat_all[w * ldw + n_cols + j];
+        if (sw > 0.f) s += sw * exp2f(col_stat_all[w * ldw + j] - m);
+    }
+    const float a = s > 0.f ? log2f(s) + m : -INFINITY;
+    float lse2, nll;
+    lse_with_positive(a, t, lse2, nll);
+    col_lse[j] = lse2 * LN2_F;
+    col_nll[j] = nll;
+    const int i = j - row_offset;
+    if (i >= 0 && i < n_rows) loss[i] = 0.5f * (row_nll[i] + nll);
+}
+
+void launch_clip_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
+                        int row_offset, float* col_lse, float* col_nll, float* loss, cudaStream_t st) {
+    k_clip_finish<<<(n_cols + 255) / 256, 256, 0, st>>>(col_stat_all, world, row_nll, n_rows, n_cols, row_offset,
+                                                        col_lse, col_nll, loss);
+}
+
+// ------------------------------------------------------------------------------------------------ bwd vectors
+__global__ void k_bwd_prep(int n, int n_pad, const float* __restrict__ g, float wmul, const float* __restrict__ lse,
+                           const float* __restrict__ nll, const int64_t* __restrict__ labels, int lab_offset,
+                           int lab_range, const float* __restrict__ g2, const float* __restrict__ nll2, float dmul, float* __restrict__ w, float* __restrict__ l2,
+                           int* __restrict__ lab, float* __restrict__ d, uint32_t* __restrict__ gmax_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float wi = 0.f, li = 0.f, di = 0.f;
+    int lb = -1;
+    uint32_t gb = 0u;
+    if (i < n) gb = __float_as_uint(fabsf(g[i]));
+    gb = __reduce_max_sync(0xffffffffu, gb);
+    if ((threadIdx.x & 31) == 0 && gb != 0u && gmax_bits) atomicMax(gmax_bits, gb);
+    if (i >= n_pad) return;
+    if (i < n) {
+        const float gi = g[i];
+        wi = wmul * gi;
+        li = lse[i] * LOG2E_F;
+        long long t = labels ? labels[i] : (long long)i + lab_offset;
+        if (t >= 0 && t < lab_range) {
+            lb = (int)t;
+            // softmax - 1 at the positive = expm1(-nll), free of cancellation
+            di = dmul * (gi * expm1f(-nll[i]) + (g2 ? g2[lb] * expm1f(-nll2[lb]) : 0.f));
+        }
+    }
+    if (w) w[i] = wi;
+    if (l2) l2[i] = li;
+    if (lab) lab[i] = lb;
+    if (d) d[i] = di;
+}
+
+void launch_bwd_prep(int n, int n_pad, const float* g, float wmul, const float* lse, const float* nll,
+                     const int64_t* labels, int lab_offset, int lab_range, const float* g2, const float* nll2,
+                     float dmul, float* w, float* l2, int* lab, float* d, uint32_t* gmax_bits, cudaStream_t st) {
+    k_bwd_prep<<<(n_pad + 255) / 256, 256, 0, st>>>(n, n_pad, g, wmul, lse, nll, labels, lab_offset, lab_range, g2,
+                                                    nll2, dmul, w, l2, lab, d, gmax_bits);
+}
+
+__global__ void k_sum_parts(const float* __restrict__ parts, int n, float* __restrict__ out) {
+    __shared__ float sm[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += parts[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) out[0] = v;
+    }
+}
+void launch_sum_parts(const float* parts, int n, float* out, cudaStream_t st) {
+    k_sum_parts<<<1, 256, 0, st>>>(parts, n, out);
+}
+
+// ------------------------------------------------------------------------------------------------ fp16 staging copy
+// The dA MMA multiplies the fp16-staged dS tile with the features, and tcgen05 kind::f16 needs both operands in the
+// same 16-bit format, so the backward keeps an fp16 copy of the features (exact for bf16 inputs within fp16 range).
+template <bool F32>
+__global__ void k_to_f16(const void* __restrict__ src, size_t n8, void* __restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    float v[8];
+    load8<F32>(src, i * 8, v);
+    uint4 u;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v[2 * e + 1]), "f"(v[2 * e]));
+        w[e] = r;
+    }
+    reinterpret_cast<uint4*>(dst)[i] = u;
+}
+void launch_to_f16(const void* src, int dtype, size_t n_elems, void* dst, cudaStream_t st) {
+    const size_t n8 = n_elems / 8;
+    if (n8 == 0) return;
+    const unsigned grid = (unsigned)((n8 + 255) / 256);
+    if (dtype == 1) k_to_f16<true><<<grid, 256, 0, st>>>(src, n8, dst);
+    else k_to_f16<false><<<grid, 256, 0, st>>>(src, n8, dst);
+}
+
+// ------------------------------------------------------------------------------------------------ L2 normalise
+// One warp per row, 128-bit accesses.  The row is read twice (second read is an L1/L2 hit), written once.
+template <bool F32>
+__global__ void k_l2norm_fwd(const void* __restrict__ x, int n, int dim, void* __restrict__ y,
+                             float* __restrict__ inv_norm) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    float ss = 0.f;
+    for (int d = lane * 8; d < dim; d += 256) {
+        float v[8];
+        load8<F32>(x, (size_t)row * dim + d, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(v[e], v[e], ss);
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / sqrtf(ss);   // no epsilon: matches x / x.norm(dim=-1, keepdim=True)
+    if (lane == 0 && inv_norm) inv_norm[row] = inv;
+    for (int d = lane * 8; d < dim; d += 256) {
+        float v[8];
+        load8<F32>(x, (size_t)row * dim + d, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= inv;
+        store8<F32>(y, (size_t)row * dim + d, v);
+    }
+}
+void launch_l2norm_fwd(const void* x, int n, int dim, int dtype, void* y, float* inv_norm, cudaStream_t st) {
+    if (n <= 0) return;
+    const int wpb = 8;
+    dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
+    if (dtype == 1) k_l2norm_fwd<true><<<grid, block, 0, st>>>(x, n, dim, y, inv_norm);
+    else k_l2norm_fwd<false><<<grid, block, 0, st>>>(x, n, dim, y, inv_norm);
+}
+
+template <bool F32>
+__global__ void k_l2norm_bwd(const void* __restrict__ y, const void* __restrict__ dy,
+                             const float* __restrict__ inv_norm, int n, int dim, void* __restrict__ dx) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    float dot = 0.f;
+    for (int d = lane * 8; d < dim; d += 256) {
+        float a[8], b[8];
+        load8<F32>(y, (size_t)row * dim + d, a);
+        load8<F32>(dy, (size_t)row * dim + d, b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dot = fmaf(a[e], b[e], dot);
+    }
+    dot = warp_sum(dot);
+    const float inv = inv_norm[row];
+    for (int d = lane * 8; d < dim; d += 256) {
+        float a[8], b[8], o[8];
+        load8<F32>(y, (size_t)row * dim + d, a);
+        load8<F32>(dy, (size_t)row * dim + d, b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (b[e] - a[e] * dot) * inv;
+        store8<F32>(dx, (size_t)row * dim + d, o);
+    }
+}
+void launch_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n, int dim, int dtype, void* dx,
+                       cudaStream_t st) {
+    if (n <= 0) return;
+    const int wpb = 8;
+    dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
+    if (dtype == 1) k_l2norm_bwd<true><<<grid, block, 0, st>>>(y, dy, inv_norm, n, dim, dx);
+    else k_l2norm_bwd<false><<<grid, block, 0, st>>>(y, dy, inv_norm, n, dim, dx);
+}
+
+}  // namespace flyp

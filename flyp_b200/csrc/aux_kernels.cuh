@@ -1,0 +1,46 @@
+// aux_kernels.cuh — small HBM-bound kernels around the tcgen05 sweeps: pair logits, statistic finalisation, vector
+// preparation for the backward sweeps, partial reductions, L2 normalisation.  All are warp-reduced / vectorised.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace flyp {
+
+// t2[i] = scale * log2(e) * <A[i,:], B[idx(i),:]>, pos[i] = idx(i) (int32), idx(i) = labels ? labels[i] : offset + i;
+// rows without a valid positive (and padding rows [n, n_pad)) get t2 = -inf, pos = -1.
+void launch_pair_dot(const void* A, const void* B, int dtype, const float* scale, int n, int n_pad, int n_b, int dim,
+                     const int64_t* labels, int offset, float* t2, int* pos, cudaStream_t st);
+
+// Fast-path finalize: rowpart[P][ld_rows] -> row_lse (natural log) and row_nll (= lse - positive logit, computed
+// without cancellation); colpart[MS][ld_cols] -> col_stat[3][n_n].  Sets *flag = 1 when the fixed shift was inadequate.
+void launch_fwd_finalize(const float* rowpart, int n_rowparts, int ld_rows, int n_m, const float* colpart,
+                         int n_colparts, int ld_cols, int n_n, const float* scale, float slack, const float* t2,
+                         const int* pos, int col_pos_offset, float* row_lse, float* row_nll, float* col_stat,
+                         int* flag, cudaStream_t st);
+// Robust finalize (no-op when *flag == 0): merges exact (max, sum) pairs.  col_* may be null (rows only).
+void launch_fwd_finalize_robust(const float* rowpart, const float* rowmax, int n_rowparts, int ld_rows, int n_m,
+                                const float* colpart, const float* colmax, int n_colparts, int ld_cols, int n_n,
+                                const float* t2, float* row_lse, float* row_nll, float* col_stat, const int* flag,
+                                cudaStream_t st);
+// col_stat_all[world][3*n_cols] -> col_lse; loss[i] = 0.5 (row_nll[i] + col_nll[off+i])
+void launch_clip_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
+                        int row_offset, float* col_lse, float* col_nll, float* loss, cudaStream_t st);
+
+// Vectors consumed by bwd_kernel, padded with zeros / -1 to a multiple of 128 entries.
+//   w[i] = wmul * g[i]; l2[i] = lse[i] * log2(e); lab[i] = labels ? labels[i] : (i + lab_offset if in [0, lab_range) else -1)
+//   d[i] = dmul * (g[i] expm1(-nll[i]) + (g2 ? g2[lab[i]] expm1(-nll2[lab[i]]) : 0))  (0 when lab[i] < 0): the exact
+//          value of dS at the positive;  *gmax_bits = max(*gmax_bits, bits(max|g|))
+void launch_bwd_prep(int n, int n_pad, const float* g, float wmul, const float* lse, const float* nll,
+                     const int64_t* labels, int lab_offset, int lab_range, const float* g2, const float* nll2,
+                     float dmul, float* w, float* l2, int* lab, float* d, uint32_t* gmax_bits, cudaStream_t st);
+// out[0] = sum(parts[0..n))   (single block, fixed order -> deterministic)
+void launch_sum_parts(const float* parts, int n, float* out, cudaStream_t st);
+
+// dst (fp16, n_elems) = saturating round-to-nearest of src (bf16 or fp32); n_elems % 8 == 0
+void launch_to_f16(const void* src, int dtype, size_t n_elems, void* dst, cudaStream_t st);
+
+void launch_l2norm_fwd(const void* x, int n, int dim, int dtype, void* y, float* inv_norm, cudaStream_t st);
+void launch_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n, int dim, int dtype, void* dx,
+                       cudaStream_t st);
+
+}  // namespace flyp

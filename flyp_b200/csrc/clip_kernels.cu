@@ -1,0 +1,605 @@
+// clip_kernels.cu — the tcgen05 / TMEM / TMA kernels of the ClipLoss hot path (sm_100a only).
+//
+// Reference semantics being replaced (joliang17/FLYP):
+//   clip/loss.py:117-118   logits = logit_scale * image_features @ text_features.T      -> S tiles in TMEM
+//   clip/loss.py:208-209   F.cross_entropy(logits, arange, reduction='none') both ways  -> fused exp2/sum epilogue
+//   autograd of the above  (softmax - onehot) @ features                                 -> bwd_kernel
+// The B x B logit matrix only ever exists as 128 x 128 fp32 tiles in tensor memory.
+//
+// Warp roles in both kernels (384 threads, one CTA per SM, persistent over a static work list):
+//   warp 0   TMA producer (one elected lane)        warp 1   tcgen05.mma issuer (one elected lane)
+//   warp 2   TMEM allocator                         warps 4..11  epilogue (TMEM -> registers -> statistics / dS)
+#include "clip_kernels.cuh"
+#include "sm100.cuh"
+
+namespace flyp {
+using namespace sm100;
+
+constexpr int NTHREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr float LOG2E = 1.4426950408889634f;
+
+DEVI uint8_t* align1024(uint8_t* p) {
+    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+DEVI void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ===================================================================================================================
+// Forward statistics kernel
+// ===================================================================================================================
+template <bool STAT>
+struct FwdCfg {
+    static constexpr int STAGE_BYTES = STAT ? CHUNK_BYTES : 2 * CHUNK_BYTES;
+    static constexpr int STAGES = STAT ? 5 : 6;
+    static constexpr int KC_MAX = 8;
+    static constexpr int STAT_BYTES = STAT ? KC_MAX * CHUNK_BYTES : 0;
+    static constexpr int RED_BYTES = 4 * TILE * 4;
+    static constexpr int ACC_STAGES = 4;
+    static constexpr int SMEM_BYTES = STAT_BYTES + STAGES * STAGE_BYTES + RED_BYTES + 256 + 1024;
+};
+
+size_t fwd_smem_bytes(bool stationary) {
+    return stationary ? FwdCfg<true>::SMEM_BYTES : FwdCfg<false>::SMEM_BYTES;
+}
+
+template <bool STAT, bool ROBUST>
+__global__ void __launch_bounds__(NTHREADS, 1)
+fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p,
+           const int* __restrict__ gate) {
+    using Cfg = FwdCfg<STAT>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int ACC_STAGES = Cfg::ACC_STAGES;
+    if (ROBUST && gate != nullptr && *gate == 0) return;  // fast path was adequate: nothing to do (grid-uniform)
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* stat_b = smem;
+    uint8_t* ring = smem + Cfg::STAT_BYTES;
+    float* red = reinterpret_cast<float*>(ring + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red) + Cfg::RED_BYTES);
+    // barrier map: [0,S) full  [S,2S) empty  2S bfull  2S+1 bfree  [2S+2, +ACC) tfull  [.., +ACC) tempty
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    const uint32_t BFULL = bar0 + 8u * (2 * STAGES), BFREE = bar0 + 8u * (2 * STAGES + 1);
+    auto TFULL = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+    auto TEMPTY = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + ACC_STAGES + s); };
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 + 2 * ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = p.n_tiles * p.m_split;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(BFULL, 1); mbar_init(BFREE, 1);
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), EPI_THREADS); }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    }
+    if (warp == 2) { tmem_alloc(smem_u32(tmem_holder), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int nb = item / p.m_split, ms = item % p.m_split;
+                const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
+                const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
+                if (STAT) {
+                    mbar_wait(BFREE, (it & 1) ^ 1);
+                    mbar_expect_tx(BFULL, p.kc * CHUNK_BYTES);
+                    for (int c = 0; c < p.kc; ++c)
+                        tma_load_2d(smem_u32(stat_b + c * CHUNK_BYTES), &tmB, BFULL, c * KCHUNK, nb * TILE);
+                }
+                for (int mt = mt0; mt < mt1; ++mt) {
+                    for (int c = 0; c < p.kc; ++c) {
+                        mbar_wait(EMPTY(stage), phase ^ 1);
+                        mbar_expect_tx(FULL(stage), Cfg::STAGE_BYTES);
+                        uint8_t* dst = ring + stage * Cfg::STAGE_BYTES;
+                        tma_load_2d(smem_u32(dst), &tmA, FULL(stage), c * KCHUNK, mt * TILE);
+                        if (!STAT) tma_load_2d(smem_u32(dst + CHUNK_BYTES), &tmB, FULL(stage), c * KCHUNK, nb * TILE);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t IDESC = umma_idesc_bf16(TILE, TILE, 0, 0);
+            int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0; uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int ms = item % p.m_split;
+                const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
+                const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
+                if (STAT) { mbar_wait(BFULL, it & 1); tc_fence_after(); }
+                for (int mt = mt0; mt < mt1; ++mt) {
+                    mbar_wait(TEMPTY(as), aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * TILE;
+                    for (int c = 0; c < p.kc; ++c) {
+                        mbar_wait(FULL(stage), phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(ring + stage * Cfg::STAGE_BYTES);
+                        const uint32_t b_addr = STAT ? smem_u32(stat_b + c * CHUNK_BYTES) : a_addr + CHUNK_BYTES;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                                      umma_desc_sw128(b_addr + k * 32, 16, 1024), IDESC, (c | k) != 0);
+                        }
+                        umma_commit(EMPTY(stage));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(TFULL(as));
+                    if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+                }
+                if (STAT) umma_commit(BFREE);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3;          // TMEM lane quarter this warp may access
+        const int h = (warp - 4) >> 2;   // column half handled by this warp
+        const float s = *p.scale;
+        const float c1 = s * LOG2E;
+        const float c0 = fixed_shift(c1, p.shift_slack);
+        int as = 0; uint32_t aphase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int nb = item / p.m_split, ms = item % p.m_split;
+            const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
+            const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
+            const int col0 = nb * TILE + h * 64;
+            const bool n_edge = (nb == p.n_tiles - 1) && (p.n_n % TILE != 0);
+            float ca[64];
+#pragma unroll
+            for (int k = 0; k < 64; ++k) ca[k] = 0.f;
+
+            for (int mt = mt0; mt < mt1; ++mt) {
+                mbar_wait(TFULL(as), aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * TILE + h * 64;
+                const int row = mt * TILE + q * 32 + lane;
+                const bool rowvalid = row < p.n_m;
+                const bool edge = n_edge || ((mt == p.m_tiles - 1) && (p.n_m % TILE != 0));
+                float rs = 0.f, rmax = -INFINITY;
+                // rel: index (within this thread's 64 columns) of the row's positive, excluded from the sums
+                int rel = -1;
+                if (p.pos != nullptr) rel = p.pos[row] - col0;
+                const bool has_pos = __any_sync(0xffffffffu, rel >= 0 && rel < 64);
+                if (!ROBUST) {
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(taddr + cc * 32, r);
+                        tmem_ld_wait();
+                        if (p.dbg_logits != nullptr && rowvalid) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                int col = col0 + cc * 32 + k;
+                                if (col < p.n_n) p.dbg_logits[(size_t)row * p.n_n + col] = __uint_as_float(r[k]);
+                            }
+                        }
+                        if (!edge && !has_pos) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                float e = ex2f(fmaf(__uint_as_float(r[k]), c1, -c0));
+                                rs += e;
+                                ca[cc * 32 + k] += e;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                float e = ex2f(fmaf(__uint_as_float(r[k]), c1, -c0));
+                                const bool keep = rowvalid && (col0 + cc * 32 + k) < p.n_n && (cc * 32 + k) != rel;
+                                e = keep ? e : 0.f;
+                                rs += e;
+                                ca[cc * 32 + k] += e;
+                            }
+                        }
+                    }
+                } else {
+                    // robust: exact per-tile (max, sum) pair for this row over this thread's 64 columns
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(taddr, r0);
+                    tmem_ld_32x32b_x32(taddr + 32, r1);
+                    tmem_ld_wait();
+                    float x[64];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        x[k] = __uint_as_float(r0[k]) * c1;
+                        x[32 + k] = __uint_as_float(r1[k]) * c1;
+                    }
+                    if (edge || has_pos) {
+#pragma unroll
+                        for (int k = 0; k < 64; ++k)
+                            if (!rowvalid || (col0 + k) >= p.n_n || k == rel) x[k] = -INFINITY;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) rmax = fmaxf(rmax, x[k]);
+                    const float mref = (rmax == -INFINITY) ? 0.f : rmax;
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) rs += ex2f(x[k] - mref);
+                }
+                tc_fence_before();
+                mbar_arrive(TEMPTY(as));
+                if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+                p.rowpart[(size_t)(nb * 2 + h) * p.ld_rows + row] = rs;
+                if (ROBUST) p.rowmax[(size_t)(nb * 2 + h) * p.ld_rows + row] = rmax;
+            }
+
+            if (!ROBUST) {
+                // column sums: butterfly transpose-reduce over the 32 lanes -> lane l owns columns 2l, 2l+1
+#pragma unroll
+                for (int off = 16, n = 64; off >= 1; off >>= 1, n >>= 1) {
+                    const int half = n >> 1;
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int k = 0; k < half; ++k) {
+                        float send = up ? ca[k] : ca[k + half];
+                        float keep = up ? ca[k + half] : ca[k];
+                        ca[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                red[q * TILE + h * 64 + 2 * lane] = ca[0];
+                red[q * TILE + h * 64 + 2 * lane + 1] = ca[1];
+                epi_bar_sync();
+                const int et = threadIdx.x - 128;
+                if (et < TILE) {
+                    float v = (red[et] + red[TILE + et]) + (red[2 * TILE + et] + red[3 * TILE + et]);
+                    p.colpart[(size_t)ms * p.ld_cols + nb * TILE + et] = v;
+                }
+                epi_bar_sync();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+void launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, bool robust, const int* gate,
+                int num_sms, cudaStream_t st) {
+    const bool stat = p.kc <= FwdCfg<true>::KC_MAX;
+    const int n_items = p.n_tiles * p.m_split;
+    const int grid = n_items < num_sms ? n_items : num_sms;
+    const size_t smem = fwd_smem_bytes(stat);
+#define FLYP_LAUNCH_FWD(S, R)                                                                                  \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(fwd_kernel<S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        fwd_kernel<S, R><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p, gate);                                     \
+    } while (0)
+    if (stat) { if (robust) FLYP_LAUNCH_FWD(true, true); else FLYP_LAUNCH_FWD(true, false); }
+    else      { if (robust) FLYP_LAUNCH_FWD(false, true); else FLYP_LAUNCH_FWD(false, false); }
+#undef FLYP_LAUNCH_FWD
+}
+
+// ===================================================================================================================
+// Backward sweep kernel: gradient w.r.t. the M-side operand, 256 output columns per work item.
+// ===================================================================================================================
+struct BwdCfg {
+    static constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;   // A chunk + B chunk of the S contraction
+    static constexpr int STAGES = 4;
+    static constexpr int TB_BYTES = 4 * CHUNK_BYTES;      // B operand of the dA MMA: [128 n][256 d] as 4 MN-major boxes
+    static constexpr int DS_BYTES = 2 * CHUNK_BYTES;      // dS tile [128 m][128 n] bf16, K-major SW128
+    static constexpr int RED_BYTES = 64;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TB_BYTES + DS_BYTES + RED_BYTES + 256 + 1024;
+    static constexpr int DPART = 256;
+};
+size_t bwd_smem_bytes() { return BwdCfg::SMEM_BYTES; }
+
+template <bool ROW_TERM, bool COL_TERM>
+__global__ void __launch_bounds__(NTHREADS, 1)
+bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+           const __grid_constant__ CUtensorMap tmBd, const BwdParams p) {
+    using Cfg = BwdCfg;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024(smem_raw);
+    uint8_t* ring = smem;
+    uint8_t* tb = ring + STAGES * Cfg::STAGE_BYTES;
+    uint8_t* ds = tb + Cfg::TB_BYTES;
+    float* red = reinterpret_cast<float*>(ds + Cfg::DS_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red) + Cfg::RED_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto SFULL = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+    auto SEMPTY = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+    const uint32_t TBFULL = bar0 + 8u * (2 * STAGES + 4), TBEMPTY = bar0 + 8u * (2 * STAGES + 5);
+    const uint32_t DSFULL = bar0 + 8u * (2 * STAGES + 6), DSEMPTY = bar0 + 8u * (2 * STAGES + 7);
+    const uint32_t ACCFULL = bar0 + 8u * (2 * STAGES + 8), ACCEMPTY = bar0 + 8u * (2 * STAGES + 9);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = p.m_tiles * p.d_parts;
+    const int NT = p.n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(SFULL(s), 1); mbar_init(SEMPTY(s), EPI_THREADS); }
+        mbar_init(TBFULL, 1); mbar_init(TBEMPTY, 1);
+        mbar_init(DSFULL, EPI_THREADS); mbar_init(DSEMPTY, 1);
+        mbar_init(ACCFULL, 1); mbar_init(ACCEMPTY, EPI_THREADS);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBd);
+    }
+    if (warp == 2) { tmem_alloc(smem_u32(tmem_holder), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t TM_ACC = tmem_base, TM_S = tmem_base + Cfg::DPART;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0; uint32_t g = 0;  // g: running tile counter (TB buffer phase)
+            auto load_s = [&](int mb, int n) {
+                for (int c = 0; c < p.kc; ++c) {
+                    mbar_wait(EMPTY(stage), phase ^ 1);
+                    mbar_expect_tx(FULL(stage), Cfg::STAGE_BYTES);
+                    uint8_t* dst = ring + stage * Cfg::STAGE_BYTES;
+                    tma_load_2d(smem_u32(dst), &tmA, FULL(stage), c * KCHUNK, mb * TILE);
+                    tma_load_2d(smem_u32(dst + CHUNK_BYTES), &tmB, FULL(stage), c * KCHUNK, n * TILE);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            };
+            auto load_tb = [&](int dp, int n) {
+                mbar_wait(TBEMPTY, (g & 1) ^ 1);
+                mbar_expect_tx(TBFULL, Cfg::TB_BYTES);
+                for (int j = 0; j < 4; ++j)
+                    tma_load_2d(smem_u32(tb + j * CHUNK_BYTES), &tmBd, TBFULL, dp * Cfg::DPART + j * KCHUNK, n * TILE);
+                ++g;
+            };
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int mb = item / p.d_parts, dp = item % p.d_parts;
+                // same order as the MMA issuer consumes: S(0), S(1), dA(0), S(2), dA(1), ...
+                load_s(mb, 0);
+                for (int t = 1; t < NT; ++t) { load_s(mb, t); load_tb(dp, t - 1); }
+                load_tb(dp, NT - 1);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t IDESC_S = umma_idesc_bf16(TILE, TILE, 0, 0);
+            // A = dS staged as scaled fp16, B = fp16 copy of the features (MN-major): a_format = b_format = 0 (F16)
+            constexpr uint32_t IDESC_D = umma_idesc_bf16(TILE, Cfg::DPART, 0, 1) & ~((7u << 7) | (7u << 10));
+            int stage = 0; uint32_t phase = 0; uint32_t gs = 0, gd = 0, it = 0;
+            auto mma_s = [&]() {
+                const int sb = gs & 1;
+                mbar_wait(SEMPTY(sb), ((gs >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = TM_S + sb * TILE;
+                for (int c = 0; c < p.kc; ++c) {
+                    mbar_wait(FULL(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ring + stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + CHUNK_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                                  umma_desc_sw128(b_addr + k * 32, 16, 1024), IDESC_S, (c | k) != 0);
+                    umma_commit(EMPTY(stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(SFULL(sb));
+                ++gs;
+            };
+            auto mma_d = [&](bool first) {
+                if (first) { mbar_wait(ACCEMPTY, (it & 1) ^ 1); }
+                mbar_wait(DSFULL, gd & 1);
+                mbar_wait(TBFULL, gd & 1);
+                tc_fence_after();
+                const uint32_t ds_addr = smem_u32(ds), tb_addr = smem_u32(tb);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    // A: dS rows m, K = n (K-major, two 64-wide chunks). B: [K = n rows][N = d], MN-major boxes.
+                    const uint64_t ad = umma_desc_sw128(ds_addr + (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32, 16, 1024);
+                    const uint64_t bd = umma_desc_sw128(tb_addr + kk * 16 * 128, CHUNK_BYTES, 1024);
+                    umma_bf16(TM_ACC, ad, bd, IDESC_D, (!first) || (kk != 0));
+                }
+                umma_commit(DSEMPTY);
+                umma_commit(TBEMPTY);
+                ++gd;
+            };
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                mma_s();
+                for (int t = 1; t < NT; ++t) { mma_s(); mma_d(t == 1); }
+                mma_d(NT == 1);
+                umma_commit(ACCFULL);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int et = threadIdx.x - 128;
+        const float s = *p.scale;
+        const float c1 = s * LOG2E;
+        // dS is staged in fp16 scaled by G = 2^k with |dS| * G < 2^14 (|dS| <= max|g|); 1/G is folded into the output.
+        float G = 1.f, invG = 1.f;
+        {
+            const uint32_t gb = *p.gmax_bits;
+            if ((gb & 0x7fffffffu) != 0u) {
+                int ge = 13 - ((int)((gb >> 23) & 0xffu) - 127);
+                ge = ge < -100 ? -100 : (ge > 100 ? 100 : ge);
+                G = __uint_as_float((uint32_t)(ge + 127) << 23);
+                invG = __uint_as_float((uint32_t)(127 - ge) << 23);
+            }
+        }
+        uint32_t gs = 0, it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int mb = item / p.d_parts, dp = item % p.d_parts;
+            const int rloc = q * 32 + lane;
+            const int m = mb * TILE + rloc;
+            const bool rowvalid = m < p.n_m;
+            float wr_m = 0.f, lr_m = 0.f, dr_m = 0.f;
+            int labr_m = -1;
+            if (rowvalid) {
+                if (ROW_TERM) { wr_m = p.wr[m] * G; lr_m = p.lr[m]; }
+                if (p.labr != nullptr) { labr_m = p.labr[m]; dr_m = p.dr[m] * G; }
+            }
+            for (int t = 0; t < NT; ++t, ++gs) {
+                const int sb = gs & 1;
+                mbar_wait(SFULL(sb), (gs >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = TM_S + ((uint32_t)(q * 32) << 16) + sb * TILE + h * 64;
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32b_x32(taddr, r0);
+                tmem_ld_32x32b_x32(taddr + 32, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(SEMPTY(sb));
+                const int n0 = t * TILE + h * 64;
+                float v[64];
+#pragma unroll
+                for (int k4 = 0; k4 < 16; ++k4) {
+                    float lcs[4] = {0.f, 0.f, 0.f, 0.f}, wcs[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (COL_TERM) {
+                        const float4 lc4 = __ldg(reinterpret_cast<const float4*>(p.lc + n0) + k4);
+                        const float4 wc4 = __ldg(reinterpret_cast<const float4*>(p.wc + n0) + k4);
+                        lcs[0] = lc4.x; lcs[1] = lc4.y; lcs[2] = lc4.z; lcs[3] = lc4.w;
+                        wcs[0] = wc4.x * G; wcs[1] = wc4.y * G; wcs[2] = wc4.z * G; wcs[3] = wc4.w * G;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = k4 * 4 + j;
+                        const float x = __uint_as_float(k < 32 ? r0[k & 31] : r1[k & 31]) * c1;
+                        float acc = 0.f;
+                        if (ROW_TERM) acc = wr_m * ex2f(x - lr_m);
+                        if (COL_TERM) acc = fmaf(wcs[j], ex2f(x - lcs[j]), acc);
+                        v[k] = acc;
+                    }
+                }
+                if (p.labr != nullptr) {
+                    const int rel = labr_m - n0;
+                    if (__any_sync(0xffffffffu, rel >= 0 && rel < 64)) {
+#pragma unroll
+                        for (int k = 0; k < 64; ++k) v[k] = (k == rel) ? dr_m : v[k];
+                    }
+                }
+                if (p.labc != nullptr) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 16; ++k4) {
+                        const int4 lb4 = __ldg(reinterpret_cast<const int4*>(p.labc + n0) + k4);
+                        const float4 dc4 = __ldg(reinterpret_cast<const float4*>(p.dc + n0) + k4);
+                        v[k4 * 4 + 0] = (lb4.x == m) ? dc4.x * G : v[k4 * 4 + 0];
+                        v[k4 * 4 + 1] = (lb4.y == m) ? dc4.y * G : v[k4 * 4 + 1];
+                        v[k4 * 4 + 2] = (lb4.z == m) ? dc4.z * G : v[k4 * 4 + 2];
+                        v[k4 * 4 + 3] = (lb4.w == m) ? dc4.w * G : v[k4 * 4 + 3];
+                    }
+                }
+                uint32_t pk[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) pk[k] = pack_f16x2(v[2 * k], v[2 * k + 1]);
+                // dS buffer is free once the dA MMA of the previous tile has completed
+                mbar_wait(DSEMPTY, (gs & 1) ^ 1);
+                uint8_t* rowp = ds + h * CHUNK_BYTES + rloc * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    *reinterpret_cast<uint4*>(rowp + ((j ^ (rloc & 7)) << 4)) = val;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(DSFULL);
+            }
+            // -------- item done: drain the accumulator (this thread: row m, 128 of the 256 columns)
+            mbar_wait(ACCFULL, it & 1);
+            tc_fence_after();
+            const float omul = s * p.out_mul * invG;
+            float dsum = 0.f;
+            const int dbase = dp * Cfg::DPART + h * 128;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(TM_ACC + ((uint32_t)(q * 32) << 16) + h * 128 + cc * 32, r);
+                tmem_ld_wait();
+                const int d0 = dbase + cc * 32;
+                if (rowvalid) {
+                    if (p.a_rows != nullptr) {
+                        const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(p.a_rows) + (size_t)m * p.lda;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (d0 + j * 8 < p.d_out) {
+                                const uint4 av = __ldg(reinterpret_cast<const uint4*>(arow + d0 + j * 8));
+                                const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float lo = __uint_as_float(aw[e] << 16);
+                                    const float hi = __uint_as_float(aw[e] & 0xffff0000u);
+                                    dsum = fmaf(__uint_as_float(r[j * 8 + 2 * e]), lo, dsum);
+                                    dsum = fmaf(__uint_as_float(r[j * 8 + 2 * e + 1]), hi, dsum);
+                                }
+                            }
+                        }
+                    }
+                    if (p.out_fp32) {
+                        float* orow = reinterpret_cast<float*>(p.out) + (size_t)m * p.ld_out;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (d0 + j * 4 < p.d_out) {
+                                float4 o = make_float4(__uint_as_float(r[4 * j]) * omul, __uint_as_float(r[4 * j + 1]) * omul,
+                                                       __uint_as_float(r[4 * j + 2]) * omul, __uint_as_float(r[4 * j + 3]) * omul);
+                                *reinterpret_cast<float4*>(orow + d0 + j * 4) = o;
+                            }
+                        }
+                    } else {
+                        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.ld_out;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (d0 + j * 8 < p.d_out) {
+                                uint4 o;
+                                o.x = pack_bf16x2(__uint_as_float(r[8 * j]) * omul, __uint_as_float(r[8 * j + 1]) * omul);
+                                o.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * omul, __uint_as_float(r[8 * j + 3]) * omul);
+                                o.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * omul, __uint_as_float(r[8 * j + 5]) * omul);
+                                o.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * omul, __uint_as_float(r[8 * j + 7]) * omul);
+                                *reinterpret_cast<uint4*>(orow + d0 + j * 8) = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(ACCEMPTY);
+            if (p.dscale_part != nullptr) {
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
+                if (lane == 0) red[warp - 4] = dsum;
+                epi_bar_sync();
+                if (et == 0) {
+                    float tot = 0.f;
+                    for (int w = 0; w < 8; ++w) tot += red[w];
+                    p.dscale_part[item] = tot * invG;
+                }
+                epi_bar_sync();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
+                int num_sms, cudaStream_t st) {
+    const int n_items = p.m_tiles * p.d_parts;
+    const int grid = n_items < num_sms ? n_items : num_sms;
+    const size_t smem = bwd_smem_bytes();
+    const bool row_term = p.wr != nullptr, col_term = p.wc != nullptr;
+#define FLYP_LAUNCH_BWD(R, C)                                                                                  \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(bwd_kernel<R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        bwd_kernel<R, C><<<grid, NTHREADS, smem, st>>>(tmA, tmB, tmBd, p);                                     \
+    } while (0)
+    if (row_term && col_term) FLYP_LAUNCH_BWD(true, true);
+    else if (row_term) FLYP_LAUNCH_BWD(true, false);
+    else FLYP_LAUNCH_BWD(false, true);
+#undef FLYP_LAUNCH_BWD
+}
+
+}  // namespace flyp

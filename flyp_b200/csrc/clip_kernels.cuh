@@ -1,0 +1,82 @@
+// clip_kernels.cuh — parameter blocks shared by the kernels (clip_kernels.cu) and the C-ABI host code (api.cu).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace flyp {
+
+constexpr int TILE = 128;       // S tile is TILE x TILE (M rows on TMEM lanes, N columns on TMEM columns)
+constexpr int KCHUNK = 64;      // bf16 elements per 128-byte swizzle row
+constexpr int CHUNK_BYTES = TILE * KCHUNK * 2;  // one [128 x 64] bf16 SW128 operand chunk = 16 KiB
+
+// Fixed exponent shift (log2 units) shared by the forward kernel and its finalize step.  |x| <= |c1| for unit-norm
+// rows; c0 = |c1| keeps the dominant terms near exp2(0).  When the range [-2|c1|, 0] would underflow fp32 the window
+// is slid up as far as the overflow bound (slack) allows.  Whether the window was adequate is checked a posteriori
+// (k_fwd_finalize); if not, the robust (per-tile max) kernels recompute the statistics exactly.
+__host__ __device__ inline float fixed_shift(float c1, float slack) {
+    float ac = c1 < 0.f ? -c1 : c1;
+    float c0 = ac;
+    if (2.f * ac > 100.f) { float a = 100.f - ac, b = ac - slack; c0 = a > b ? a : b; }
+    return c0;
+}
+
+// ---- forward: per-row / per-column sum of exp2(c1 * <a_m, b_n> - c0) -------------------------------------------
+struct FwdParams {
+    int n_m, n_n;            // valid rows of the M-side / N-side operand
+    int kc;                  // number of 64-wide K chunks (ceil(K / 64))
+    int m_tiles, n_tiles;    // ceil(n / 128)
+    int m_split;             // each N block is swept by m_split work items
+    int ld_rows;             // leading dimension (floats) of rowpart / rowmax  (>= m_tiles * 128)
+    int ld_cols;             // leading dimension (floats) of colpart / colmax  (>= n_tiles * 128)
+    const float* scale;      // device scalar: logit_scale (already exp-ed)
+    const int* pos;          // [ld_rows] positive column of each M row (-1: none); that element is EXCLUDED from all
+                             // sums (it is added back exactly by the finalize step); nullptr: no exclusion
+    float shift_slack;       // c0 = c1 - shift_slack (log2 units), see DESIGN.md "fixed shift"
+    float* rowpart;          // [n_tiles * 2][ld_rows]  partial row sums, one per (N block, column half)
+    float* colpart;          // [m_split][ld_cols]      partial column sums, one per M split
+    float* rowmax;           // robust mode only: running log2-domain max paired with rowpart
+    float* colmax;           // robust mode only
+    float* dbg_logits;       // optional [n_m][n_n] fp32 raw dot products (debug / argmax path), may be null
+};
+
+// ---- backward sweep: dA[m, :] = s * sum_n dS[m, n] * B[n, :]  with dS recomputed from the S tile ------------------
+//  dS[m,n] = wr[m] * exp2(x - lr[m]) + wc[n] * exp2(x - lc[n]), except at the positives, where the value is REPLACED
+//  by the exactly precomputed dr[m] (n == labr[m]) / dc[n] (m == labc[n])  (softmax - 1 without cancellation)
+//  x = c1 * <a_m, b_n>
+struct BwdParams {
+    int n_m, n_n;
+    int kc;                  // K chunks of the S contraction
+    int m_tiles, n_tiles;
+    int d_out;               // number of output columns (= feature dim D)
+    int d_parts;             // ceil(d_out / 256)
+    const float* scale;
+    const float* wr;         // [m] weights of the row-softmax term (nullptr -> term absent)
+    const float* lr;         // [m] row logsumexp, log2 domain
+    const float* wc;         // [n]
+    const float* lc;         // [n] column logsumexp, log2 domain
+    const int* labr;         // [m] positive column of row m (or -1), nullptr -> none
+    const float* dr;         // [m] value of dS at (m, labr[m])
+    const int* labc;         // [n] positive row of column n (or -1), nullptr -> none
+    const float* dc;         // [n]
+    const void* a_rows;      // M-side operand rows (bf16, ld = lda elements) for the d(scale) reduction; may be null
+    int lda;
+    void* out;               // [n_m][ld_out] gradient w.r.t. the M-side operand
+    int ld_out;
+    int out_fp32;            // 1: out is fp32, 0: bf16
+    float out_mul;           // extra factor folded into the output (e.g. W for gather_with_grad)
+    const uint32_t* gmax_bits;  // device word: bit pattern of max |upstream grad| (dS is staged as scaled fp16)
+    float* dscale_part;      // [m_tiles * d_parts] partial sums of <acc, a> (unscaled), may be null
+};
+
+// robust = exact per-tile (max, sum) row statistics only; gate (device int, may be null): the robust kernel returns
+// immediately when *gate == 0.
+void launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, bool robust, const int* gate,
+                int num_sms, cudaStream_t st);
+// tmBd: tensor map used for the N-side operand rows as the B operand of the dA MMA (box [64 d][128 n]).
+void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
+                int num_sms, cudaStream_t st);
+size_t fwd_smem_bytes(bool stationary);
+size_t bwd_smem_bytes();
+
+}  // namespace flyp

@@ -1,0 +1,112 @@
+/* flyp_clip.h — C ABI of libflypclip.so: the B200 (sm_100a) implementation of FLYP's contrastive-loss hot path.
+ *
+ * Every entry point replaces a piece of the reference's Python (joliang17/FLYP); citations are file:line in that repo.
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated; the caller owns every buffer,
+ *     including the workspace (size from the matching *_workspace_bytes call).  The library allocates nothing.
+ *   - all work is enqueued on the cudaStream_t passed in (as void*); no entry point synchronises the device.
+ *   - return 0 on success, a negative code on error; flyp_last_error() returns the message (thread-local).
+ *   - `scale` is a device pointer to the already-exponentiated logit_scale (clip/model.py:378), so no host sync.
+ *   - dtype: FLYP_BF16 features are bf16; FLYP_F32 features are fp32 (evaluated as 3-way bf16 split products, fp32
+ *     accumulation).  All statistics, losses and d(scale) are fp32.  Gradients have the feature dtype.
+ *   - feature matrices are row-major, contiguous ([n, dim], leading dimension = dim), 16-byte aligned, dim % 8 == 0.
+ */
+#ifndef FLYP_CLIP_H
+#define FLYP_CLIP_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { FLYP_BF16 = 0, FLYP_F32 = 1 };
+enum {
+    FLYP_OK = 0,
+    FLYP_ERR_ARG = -1,      /* bad argument (shape, alignment, dtype) */
+    FLYP_ERR_CUDA = -2,     /* CUDA runtime / driver error */
+    FLYP_ERR_WORKSPACE = -3 /* workspace too small */
+};
+
+const char* flyp_last_error(void);
+int flyp_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Symmetric contrastive loss, row-sharded.  Replaces clip/loss.py:103-118 (logits) + :194-211 (labels, two
+ * cross-entropies, per-item average).  A rank holds n_rows local image rows and all n_cols text rows; local row i is
+ * global row row_offset + i and its positive text is column row_offset + i (clip/loss.py:66-67 ordering).
+ * world_size == 1: n_rows == n_cols, row_offset == 0.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int flyp_clip_workspace_bytes(int n_rows, int n_cols, int dim, int dtype, size_t* bytes);
+
+/* Forward, local part.  The positive logit of every row is kept out of the tensor-core sums and added back exactly,
+ * so losses much smaller than the logits keep full relative accuracy.  Out:
+ *   row_lse[n_rows]      natural-log logsumexp_j S[i, j]                  (image->text direction, exact per rank)
+ *   row_nll[n_rows]      row_lse[i] - S[i, row_offset + i]                (image->text cross-entropy of item i)
+ *   col_stat[3 * n_cols] partial column statistics over the LOCAL rows, log2 units:
+ *                        [0, n) m_j reference, [n, 2n) sum_i exp2(S[i,j] log2e - m_j) over local rows excluding the
+ *                        positive, [2n, 3n) positive logit of column j if its row is local, else -inf.
+ *                        Triples from different ranks merge exactly in flyp_clip_fwd_finish (the only cross-rank
+ *                        exchange of the loss).
+ *   status[1]            device int (may be NULL): 0 = fixed-shift fast path used, 1 = robust recomputation used */
+int flyp_clip_fwd_local(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
+                        int dtype, int row_offset, float* row_lse, float* row_nll, float* col_stat, int* status,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Forward, finish.  col_stat_all = world x [3 * n_cols] (the gathered col_stat of every rank, rank-major).  Out:
+ *   col_lse[n_cols] natural-log logsumexp_i S[i, j] over ALL rows;
+ *   col_nll[n_cols] col_lse[j] - S[j, j]                                        (text->image cross-entropy of item j)
+ *   loss[n_rows]    0.5 * (row_nll[i] + col_nll[row_offset + i])                (clip/loss.py:208-209) */
+int flyp_clip_fwd_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
+                         int row_offset, float* col_lse, float* col_nll, float* loss, void* stream);
+
+/* Backward, local part (autograd of clip/loss.py:117-118,208-209).  row_lse/row_nll/col_lse/col_nll are the saved
+ * forward outputs; g_row[n_rows] / g_col[n_cols] are the upstream gradients on the loss entries of the local rows / of
+ * all columns' items.  Out (each may be NULL to skip):
+ *   d_img[n_rows, dim]  complete gradient of the local image rows (grad_dtype: FLYP_BF16 or FLYP_F32)
+ *   d_txt[n_cols, dim]  this rank's PARTIAL gradient of every text row (sum over ranks = full gradient)
+ *   d_scale[1]          this rank's partial d loss / d logit_scale (fp32; requires d_img)
+ * grad_mul is folded into d_img / d_txt (1 for gather_with_grad=False, world for True). */
+int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
+                        int dtype, int row_offset, const float* row_lse, const float* row_nll, const float* col_lse,
+                        const float* col_nll, const float* g_row, const float* g_col, float grad_mul, int grad_dtype,
+                        void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * One-directional softmax cross-entropy over logits = scale * A . B^T with integer targets.  Replaces
+ * src/models/ce_ablation.py:122-123 (A = image features [n, dim], B = class text features [n_classes, dim]) and
+ * serves clip/loss.py:109-111 (local_loss blocks).  labels: int64 device vector or NULL (then target = label_offset + i).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int flyp_ce_workspace_bytes(int n, int n_classes, int dim, int dtype, size_t* bytes);
+/* Out: loss[n] = lse[i] - logit[i, target_i] (reduction='none'), lse[n] natural-log logsumexp (saved for backward). */
+int flyp_ce_fwd(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
+                const int64_t* labels, int label_offset, float* loss, float* lse, void* workspace,
+                size_t workspace_bytes, void* stream);
+/* lse / loss: the saved forward outputs; g[n] upstream gradient on loss.  Out (each may be NULL): d_a[n, dim],
+ * d_b[n_classes, dim] (grad_dtype), d_scale[1] fp32 (requires d_a). */
+int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
+                const int64_t* labels, int label_offset, const float* lse, const float* loss, const float* g,
+                int grad_dtype, void* d_a, void* d_b, float* d_scale, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Row-wise L2 normalisation x / ||x||_2 (no epsilon), clip/model.py:375-376, src/models/ce_ablation.py:115-118.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* y[n, dim] = x / ||x||; inv_norm[n] = 1 / ||x|| (fp32, saved for backward). */
+int flyp_l2norm_fwd(const void* x, int n, int dim, int dtype, void* y, float* inv_norm, void* stream);
+/* dx = (dy - y <y, dy>) * inv_norm */
+int flyp_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n, int dim, int dtype, void* dx,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Debug / evaluation: raw dot products <a_i, b_j> as fp32 [n_m, n_n] through the same tensor-core path (used by the
+ * argmax-parity tests and the zero-shot argmax, src/models/eval.py:158).  Not used by the loss.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int flyp_debug_logits(const void* a, const void* b, int n_m, int n_n, int dim, int dtype, float* out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLYP_CLIP_H */
