@@ -1,0 +1,57 @@
+"""Host-side behaviour of the drop-in module that needs no GPU: constructor/attribute compatibility with
+clip/loss.py:73-92, empty state_dict, loud failure without CUDA, unsupported variants."""
+import inspect
+
+import pytest
+import torch
+
+import flyp_b200
+from flyp_b200 import ClipLoss, gather_features
+from flyp_b200._lib import FlypError
+
+
+def test_constructor_signature_and_attributes():
+    sig = inspect.signature(ClipLoss.__init__)
+    names = list(sig.parameters)[1:7]
+    assert names == ["local_loss", "gather_with_grad", "cache_labels", "rank", "world_size", "use_horovod"]
+    for k in names[:3] + ["use_horovod"]:
+        assert sig.parameters[k].default is False
+    assert sig.parameters["rank"].default == 0 and sig.parameters["world_size"].default == 1
+    m = ClipLoss(local_loss=False, gather_with_grad=False, cache_labels=True, rank=0, world_size=1)  # flyp_loss.py:365
+    for attr in ("local_loss", "gather_with_grad", "cache_labels", "rank", "world_size", "use_horovod",
+                 "prev_num_logits", "labels"):
+        assert hasattr(m, attr)
+    assert m.prev_num_logits == 0 and m.labels == {}
+    assert len(m.state_dict()) == 0 and len(list(m.parameters())) == 0
+    fsig = inspect.signature(ClipLoss.forward)
+    assert list(fsig.parameters)[1:] == ["image_features", "text_features", "logit_scale", "ground_labels", "ignore",
+                                         "google_sup_loss"]
+
+
+def test_no_cpu_fallback():
+    m = ClipLoss()
+    x = torch.randn(8, 16)
+    with pytest.raises(FlypError):
+        m(x, x, torch.tensor(10.0))
+    with pytest.raises(FlypError):
+        flyp_b200.contrastive_cross_entropy(x, x, torch.tensor(10.0))
+    with pytest.raises(FlypError):
+        flyp_b200.l2_normalize(x)
+
+
+def test_unsupported_variants_raise():
+    m = ClipLoss()
+    x = torch.randn(8, 16)
+    with pytest.raises(NotImplementedError):
+        m(x, x, torch.tensor(10.0), ground_labels=torch.arange(8))
+    with pytest.raises(AssertionError):
+        m(x, x, torch.tensor(10.0), ignore=True, google_sup_loss=True)
+    with pytest.raises(NotImplementedError):
+        gather_features(x, x, use_horovod=True, world_size=2)
+    with pytest.raises(NotImplementedError):
+        ClipLoss(world_size=2, use_horovod=True)(x.cuda() if torch.cuda.is_available() else x, x, torch.tensor(1.0))
+
+
+def test_clip_namespace_mirrors_reference_import_path():
+    from flyp_b200.clip.loss import ClipLoss as C2, gather_features as g2
+    assert C2 is ClipLoss and g2 is gather_features
