@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -46,14 +47,14 @@ EncodeTiledFn get_encode() {
 
 // bf16 row-major [rows][cols] (leading dimension ld elements) -> tiles of [128 rows][64 cols], 128-byte swizzle,
 // out-of-bounds elements read as zero.
-int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, bool f16 = false) {
+int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, bool f16 = false, int box_rows = flyp::TILE) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(FLYP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(FLYP_ERR_ARG, "feature pointer not 16-byte aligned");
     if ((ld % 8) != 0) return fail(FLYP_ERR_ARG, "leading dimension %d not a multiple of 8", ld);
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)flyp::KCHUNK, (cuuint32_t)flyp::TILE};
+    cuuint32_t box[2] = {(cuuint32_t)flyp::KCHUNK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -76,6 +77,19 @@ int num_sms() {
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// The CTA-pair backward sweep handles feature dims that are multiples of 128 up to 512; FLYP_BWD_IMPL=1 forces the
+// single-CTA kernel (kept for other dims and for A/B measurements).
+bool use_pair_kernel(int dim) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("FLYP_BWD_IMPL");
+        forced = (e && e[0] == '1') ? 1 : 0;
+    }
+    return forced == 0 && dim % 128 == 0 && dim <= 512;
+}
+int dscale_parts_per_tile(int dim) { return use_pair_kernel(dim) ? 2 : ceil_div(dim, 256); }
+constexpr int VEC_PAD = 256;   // per-row / per-column vectors are padded to this many entries
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Number of M splits per N block for the forward sweep: minimise the makespan in tile units (a work item costs its
@@ -235,7 +249,13 @@ int run_sweep(const void* A, const void* B, const void* B_f16, const float* scal
     p.a_rows = a_rows_for_dscale; p.lda = dim;
     p.out = out; p.ld_out = dim; p.out_fp32 = out_fp32; p.out_mul = out_mul; p.gmax_bits = gmax_bits;
     p.dscale_part = dscale_part;
-    flyp::launch_bwd(tmA, tmB, tmBd, p, num_sms(), st);
+    if (use_pair_kernel(dim)) {
+        CUtensorMap tmA64;
+        if ((rc = make_tmap(&tmA64, A, n_m, dim, dim, false, 64)) != 0) return rc;
+        flyp::launch_bwd_pair(tmA64, tmB, tmBd, p, num_sms(), st);
+    } else {
+        flyp::launch_bwd(tmA, tmB, tmBd, p, num_sms(), st);
+    }
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -259,10 +279,10 @@ struct ClipWs {
 static void carve_clip(void* base, int n_rows, int n_cols, int dim, ClipWs& w) {
     Carver c(base);
     carve_stats(c, n_rows, n_cols, true, w.stats);
-    const int rp = ceil_div(n_rows, flyp::TILE) * flyp::TILE, cp = ceil_div(n_cols, flyp::TILE) * flyp::TILE;
+    const int rp = ceil_div(n_rows, VEC_PAD) * VEC_PAD, cp = ceil_div(n_cols, VEC_PAD) * VEC_PAD;
     carve_vecs(c, rp, w.rows);
     carve_vecs(c, cp, w.cols);
-    w.dscale_part = c.take<float>((size_t)ceil_div(n_rows, flyp::TILE) * ceil_div(dim, 256));
+    w.dscale_part = c.take<float>((size_t)ceil_div(n_rows, flyp::TILE) * dscale_parts_per_tile(dim));
     w.gmax_bits = c.take<uint32_t>(1);
     w.img16 = c.take<uint16_t>((size_t)n_rows * dim);
     w.txt16 = c.take<uint16_t>((size_t)n_cols * dim);
@@ -322,7 +342,7 @@ int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, in
     carve_clip(workspace, n_rows, n_cols, dim, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int rp = ceil_div(n_rows, flyp::TILE) * flyp::TILE, cp = ceil_div(n_cols, flyp::TILE) * flyp::TILE;
+    const int rp = ceil_div(n_rows, VEC_PAD) * VEC_PAD, cp = ceil_div(n_cols, VEC_PAD) * VEC_PAD;
     CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, sizeof(uint32_t), st));
     // rows: w = g_row/2, positive column row_offset + i, exact dS there from the saved cross-entropies
     flyp::launch_bwd_prep(n_rows, rp, g_row, 0.5f, row_lse, row_nll, nullptr, row_offset, n_cols, g_col, col_nll, 0.5f,
@@ -339,7 +359,7 @@ int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, in
                        d_scale ? w.dscale_part : nullptr, w.gmax_bits, st);
         if (rc) return rc;
         if (d_scale) {
-            flyp::launch_sum_parts(w.dscale_part, ceil_div(n_rows, flyp::TILE) * ceil_div(dim, 256), d_scale, st);
+            flyp::launch_sum_parts(w.dscale_part, ceil_div(n_rows, flyp::TILE) * dscale_parts_per_tile(dim), d_scale, st);
             CUDA_OK(cudaGetLastError());
         }
     } else if (d_scale) {
@@ -367,9 +387,9 @@ struct CeWs {
 static void carve_ce(void* base, int n, int n_classes, int dim, CeWs& w) {
     Carver c(base);
     carve_stats(c, n, n_classes, false, w.stats);
-    const int np = ceil_div(n, flyp::TILE) * flyp::TILE;
+    const int np = ceil_div(n, VEC_PAD) * VEC_PAD;
     carve_vecs(c, np, w.v);
-    w.dscale_part = c.take<float>((size_t)ceil_div(n, flyp::TILE) * ceil_div(dim, 256));
+    w.dscale_part = c.take<float>((size_t)ceil_div(n, flyp::TILE) * dscale_parts_per_tile(dim));
     w.gmax_bits = c.take<uint32_t>(1);
     w.a16 = c.take<uint16_t>((size_t)n * dim);
     w.b16 = c.take<uint16_t>((size_t)n_classes * dim);
@@ -411,7 +431,7 @@ int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_c
     carve_ce(workspace, n, n_classes, dim, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int np = ceil_div(n, flyp::TILE) * flyp::TILE;
+    const int np = ceil_div(n, VEC_PAD) * VEC_PAD;
     CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, sizeof(uint32_t), st));
     // w = g, positive = label, dS there = g * expm1(-loss)
     flyp::launch_bwd_prep(n, np, g, 1.0f, lse, loss, labels, label_offset, n_classes, nullptr, nullptr, 1.0f, w.v.w,
@@ -425,7 +445,7 @@ int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_c
                        w.gmax_bits, st);
         if (rc) return rc;
         if (d_scale) {
-            flyp::launch_sum_parts(w.dscale_part, ceil_div(n, flyp::TILE) * ceil_div(dim, 256), d_scale, st);
+            flyp::launch_sum_parts(w.dscale_part, ceil_div(n, flyp::TILE) * dscale_parts_per_tile(dim), d_scale, st);
             CUDA_OK(cudaGetLastError());
         }
     } else if (d_scale) {

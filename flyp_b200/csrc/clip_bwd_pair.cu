@@ -1,0 +1,357 @@
+// clip_bwd_pair.cu — backward sweep on CTA pairs (tcgen05 cta_group::2), feature dim <= 512 and a multiple of 128.
+//
+// One cluster of two CTAs (an SM pair) owns a block of 128 M-rows and walks over the N side in steps of 256 columns.
+// Per step
+//   (1) S = A_blk . B_step^T as ONE pair MMA (M = 128: each CTA supplies 64 rows of A; N = 256: each CTA supplies
+//       128 rows of B).  Each CTA receives the logits of ITS 64 rows for all 256 columns
+//       (TMEM lanes 0..63 = columns 0..127, lanes 64..127 = columns 128..255).
+//   (2) the epilogue warps of each CTA turn their S slice into dS (softmax weights, exact value at the positive),
+//       stage it as scaled fp16 in shared memory as [64 rows][256 cols] K-major.
+//   (3) dA^T[d, m] += sum_n B16[n, d] * dS[m, n] as pair MMAs with M = 256 feature columns (128 per CTA), N = 128 rows
+//       (the B operand of a pair MMA is split across the two CTAs by halves of N, i.e. exactly the 64-row dS slices
+//       the two CTAs produced - the tensor core shares them, no software exchange), K = 256.
+// Every logit tile is therefore recomputed once per sweep (not once per 256 output columns as in bwd_kernel) and both
+// CTAs run at full pair-MMA rate.  The accumulators (2 x 128 columns) live in TMEM for the whole row block together
+// with two S stages (2 x 128 columns).
+//
+// Shared memory per CTA: stationary A half-block (64 rows x D, <= 64 KiB), one ring of eight 16 KiB slots that carries,
+// in consumption order, the B chunks of the S product and the fp16 feature boxes of the dA^T product, and the dS tile.
+#include "clip_kernels.cuh"
+#include "sm100.cuh"
+
+namespace flyp {
+using namespace sm100;
+
+namespace {
+constexpr int NTHREADS2 = 384;
+constexpr int EPI_ALL = 512;          // epilogue threads of both CTAs
+constexpr float LOG2E2 = 1.4426950408889634f;
+
+struct PairCfg {
+    static constexpr int SLOT = 16384;
+    static constexpr int NSLOT = 8;
+    static constexpr int IST_BYTES = 65536;            // 8 chunks [64 rows][64] bf16
+    static constexpr int DS_BYTES = 32768;             // 4 chunks [64 rows][64] fp16
+    static constexpr int RED_BYTES = 64;
+    static constexpr int SMEM_BYTES = IST_BYTES + NSLOT * SLOT + DS_BYTES + RED_BYTES + 256 + 1024;
+    static constexpr int NSTEP = 256;                  // N columns per step
+};
+
+DEVI uint8_t* align1024p(uint8_t* p) {
+    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+DEVI void epi_bar_sync2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+}  // namespace
+
+size_t bwd_pair_smem_bytes() { return PairCfg::SMEM_BYTES; }
+
+template <bool ROW_TERM, bool COL_TERM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS2, 1)
+bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmBd, const BwdParams p) {
+    using Cfg = PairCfg;
+    constexpr int NSLOT = Cfg::NSLOT;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = align1024p(smem_raw);
+    uint8_t* ist = smem;
+    uint8_t* ring = ist + Cfg::IST_BYTES;
+    uint8_t* ds = ring + NSLOT * Cfg::SLOT;
+    float* red = reinterpret_cast<float*>(ds + Cfg::DS_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red) + Cfg::RED_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (NSLOT + s); };
+    auto SFULL = [&](int s) { return bar0 + 8u * (2 * NSLOT + s); };
+    auto SEMPTY = [&](int s) { return bar0 + 8u * (2 * NSLOT + 2 + s); };
+    const uint32_t DSFULL = bar0 + 8u * (2 * NSLOT + 4), DSEMPTY = bar0 + 8u * (2 * NSLOT + 5);
+    const uint32_t ACCFULL = bar0 + 8u * (2 * NSLOT + 6), ACCEMPTY = bar0 + 8u * (2 * NSLOT + 7);
+    const uint32_t IFULL = bar0 + 8u * (2 * NSLOT + 8), IFREE = bar0 + 8u * (2 * NSLOT + 9);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int n_items = p.m_tiles;
+    const int NJ = (p.n_n + Cfg::NSTEP - 1) / Cfg::NSTEP;
+    const int KC = p.kc;                         // 64-wide K chunks of the S contraction (even)
+    const int ND = (p.d_out + 255) / 256;        // pair MMAs of the dA^T product (256 feature columns each)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(SFULL(s), 1); mbar_init(SEMPTY(s), EPI_ALL); }
+        mbar_init(DSFULL, EPI_ALL); mbar_init(DSEMPTY, 1);
+        mbar_init(ACCFULL, 1); mbar_init(ACCEMPTY, EPI_ALL);
+        mbar_init(IFULL, 1); mbar_init(IFREE, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmA64); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBd);
+    }
+    if (warp == 2) { tmem_alloc_cg2(smem_u32(tmem_holder), 512); tmem_relinquish_cg2(); }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t TM_ACC = tmem_base, TM_S = tmem_base + 256;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
+        if (elect_one()) {
+            int slot = 0; uint32_t ph = 0; uint32_t it = 0;
+            auto put = [&](const CUtensorMap* tm, int c0, int c1) {
+                mbar_wait(EMPTY(slot), ph ^ 1);
+                if (cta == 0) mbar_expect_tx(FULL(slot), 2 * Cfg::SLOT);
+                tma_load_2d_cg2(smem_u32(ring + slot * Cfg::SLOT), tm, mapa(FULL(slot), 0), c0, c1);
+                if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+            };
+            auto load_s = [&](int t) {
+                for (int c = 0; c < KC; ++c) put(&tmB, c * KCHUNK, t * Cfg::NSTEP + (int)cta * 128);
+            };
+            auto load_t = [&](int t) {
+                for (int dblk = 0; dblk < ND; ++dblk)
+                    for (int jh = 0; jh < 2; ++jh)
+                        for (int dsub = 0; dsub < 2; ++dsub)
+                            put(&tmBd, (dblk * 2 + (int)cta) * 128 + dsub * 64, t * Cfg::NSTEP + jh * 128);
+            };
+            for (int item = pair; item < n_items; item += npairs, ++it) {
+                mbar_wait(IFREE, (it & 1) ^ 1);
+                if (cta == 0) mbar_expect_tx(IFULL, 2 * KC * 8192);
+                for (int c = 0; c < KC; ++c)
+                    tma_load_2d_cg2(smem_u32(ist + c * 8192), &tmA64, mapa(IFULL, 0), c * KCHUNK,
+                                    item * TILE + (int)cta * 64);
+                load_s(0);
+                for (int t = 1; t < NJ; ++t) { load_s(t); load_t(t - 1); }
+                load_t(NJ - 1);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (cta == 0 && elect_one()) {
+            constexpr uint32_t IDESC_S = umma_idesc(128, 256, 1, 1, 0, 0);     // bf16 x bf16, both K-major
+            constexpr uint32_t IDESC_D = umma_idesc(256, 128, 0, 0, 1, 0);     // fp16 x fp16, A MN-major, B K-major
+            int slot = 0; uint32_t ph = 0; uint32_t gs = 0, gd = 0, it = 0;
+            auto adv = [&]() { if (++slot == NSLOT) { slot = 0; ph ^= 1; } };
+            auto mma_s = [&]() {
+                const int sb = gs & 1;
+                mbar_wait(SEMPTY(sb), ((gs >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = TM_S + sb * 128;
+                for (int c = 0; c < KC; ++c) {
+                    mbar_wait(FULL(slot), ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(ist + c * 8192);
+                    const uint32_t b_addr = smem_u32(ring + slot * Cfg::SLOT);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16_cg2(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
+                                     umma_desc_sw128(b_addr + k * 32, 16, 1024), IDESC_S, (c | k) != 0);
+                    umma_commit_cg2(EMPTY(slot));
+                    adv();
+                }
+                umma_commit_cg2(SFULL(sb));
+                ++gs;
+            };
+            auto mma_d = [&](bool first) {
+                if (first) mbar_wait(ACCEMPTY, (it & 1) ^ 1);
+                mbar_wait(DSFULL, gd & 1);
+                tc_fence_after();
+                const uint32_t ds_addr = smem_u32(ds);
+                for (int dblk = 0; dblk < ND; ++dblk) {
+                    for (int jh = 0; jh < 2; ++jh) {
+                        mbar_wait(FULL(slot), ph);          // the two feature boxes (64 + 64 columns) of this K half
+                        mbar_wait(FULL(slot + 1), ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(ring + slot * Cfg::SLOT);
+#pragma unroll
+                        for (int k8 = 0; k8 < 8; ++k8) {
+                            const int kk = jh * 8 + k8;
+                            // A: [K = 16 n-rows][M = 128 feature columns as two 64-wide boxes], MN-major
+                            const uint64_t ad = umma_desc_sw128(a_addr + k8 * 2048, Cfg::SLOT, 1024);
+                            // B: dS [N = 64 rows per CTA][K], K-major, four 64-wide chunks of 8 KiB
+                            const uint64_t bd = umma_desc_sw128(ds_addr + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
+                            umma_f16_cg2(TM_ACC + dblk * 128, ad, bd, IDESC_D, !(first && kk == 0));
+                        }
+                        umma_commit_cg2(EMPTY(slot));
+                        umma_commit_cg2(EMPTY(slot + 1));
+                        adv(); adv();
+                    }
+                }
+                umma_commit_cg2(DSEMPTY);
+                ++gd;
+            };
+            for (int item = pair; item < n_items; item += npairs, ++it) {
+                mbar_wait(IFULL, it & 1);
+                tc_fence_after();
+                mma_s();
+                for (int t = 1; t < NJ; ++t) { mma_s(); mma_d(t == 1); }
+                mma_d(NJ == 1);
+                umma_commit_cg2(ACCFULL);
+                umma_commit_cg2(IFREE);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (both CTAs)
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int et = threadIdx.x - 128;
+        const float s = *p.scale;
+        const float c1 = s * LOG2E2;
+        float G = 1.f, invG = 1.f;
+        {
+            const uint32_t gb = *p.gmax_bits;
+            if ((gb & 0x7fffffffu) != 0u) {
+                int ge = 13 - ((int)((gb >> 23) & 0xffu) - 127);
+                ge = ge < -100 ? -100 : (ge > 100 ? 100 : ge);
+                G = __uint_as_float((uint32_t)(ge + 127) << 23);
+                invG = __uint_as_float((uint32_t)(127 - ge) << 23);
+            }
+        }
+        const uint32_t R_SEMPTY0 = mapa(SEMPTY(0), 0), R_SEMPTY1 = mapa(SEMPTY(1), 0);
+        const uint32_t R_DSFULL = mapa(DSFULL, 0), R_ACCEMPTY = mapa(ACCEMPTY, 0);
+        const int rloc = (q & 1) * 32 + lane;       // row within this CTA's 64-row slice
+        const int jq = q >> 1;                      // which 128-column half of the step this lane quarter holds
+        uint32_t gs = 0, it = 0;
+        for (int item = pair; item < n_items; item += npairs, ++it) {
+            const int m = item * TILE + (int)cta * 64 + rloc;
+            const bool rowvalid = m < p.n_m;
+            float wr_m = 0.f, lr_m = 0.f, dr_m = 0.f;
+            int labr_m = -1;
+            if (rowvalid) {
+                if (ROW_TERM) { wr_m = p.wr[m] * G; lr_m = p.lr[m]; }
+                if (p.labr != nullptr) { labr_m = p.labr[m]; dr_m = p.dr[m] * G; }
+            }
+            for (int t = 0; t < NJ; ++t, ++gs) {
+                const int sb = gs & 1;
+                mbar_wait(SFULL(sb), (gs >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = TM_S + ((uint32_t)(q * 32) << 16) + sb * 128 + h * 64;
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32b_x32(taddr, r0);
+                tmem_ld_32x32b_x32(taddr + 32, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive_cluster(sb ? R_SEMPTY1 : R_SEMPTY0);
+                const int n0 = t * Cfg::NSTEP + jq * 128 + h * 64;
+                float v[64];
+#pragma unroll
+                for (int k4 = 0; k4 < 16; ++k4) {
+                    float lcs[4] = {0.f, 0.f, 0.f, 0.f}, wcs[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (COL_TERM) {
+                        const float4 lc4 = __ldg(reinterpret_cast<const float4*>(p.lc + n0) + k4);
+                        const float4 wc4 = __ldg(reinterpret_cast<const float4*>(p.wc + n0) + k4);
+                        lcs[0] = lc4.x; lcs[1] = lc4.y; lcs[2] = lc4.z; lcs[3] = lc4.w;
+                        wcs[0] = wc4.x * G; wcs[1] = wc4.y * G; wcs[2] = wc4.z * G; wcs[3] = wc4.w * G;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = k4 * 4 + j;
+                        const float x = __uint_as_float(k < 32 ? r0[k & 31] : r1[k & 31]) * c1;
+                        float acc = 0.f;
+                        if (ROW_TERM) acc = wr_m * ex2f(x - lr_m);
+                        if (COL_TERM) acc = fmaf(wcs[j], ex2f(x - lcs[j]), acc);
+                        v[k] = acc;
+                    }
+                }
+                if (p.labr != nullptr) {
+                    const int rel = labr_m - n0;
+                    if (__any_sync(0xffffffffu, rel >= 0 && rel < 64)) {
+#pragma unroll
+                        for (int k = 0; k < 64; ++k) v[k] = (k == rel) ? dr_m : v[k];
+                    }
+                }
+                if (p.labc != nullptr) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 16; ++k4) {
+                        const int4 lb4 = __ldg(reinterpret_cast<const int4*>(p.labc + n0) + k4);
+                        const float4 dc4 = __ldg(reinterpret_cast<const float4*>(p.dc + n0) + k4);
+                        v[k4 * 4 + 0] = (lb4.x == m) ? dc4.x * G : v[k4 * 4 + 0];
+                        v[k4 * 4 + 1] = (lb4.y == m) ? dc4.y * G : v[k4 * 4 + 1];
+                        v[k4 * 4 + 2] = (lb4.z == m) ? dc4.z * G : v[k4 * 4 + 2];
+                        v[k4 * 4 + 3] = (lb4.w == m) ? dc4.w * G : v[k4 * 4 + 3];
+                    }
+                }
+                uint32_t pk[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) pk[k] = pack_f16x2(v[2 * k], v[2 * k + 1]);
+                mbar_wait(DSEMPTY, (gs & 1) ^ 1);
+                uint8_t* rowp = ds + (jq * 2 + h) * 8192 + rloc * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    *reinterpret_cast<uint4*>(rowp + ((j ^ (rloc & 7)) << 4)) = val;
+                }
+                fence_proxy_async_smem();
+                mbar_arrive_cluster(R_DSFULL);
+            }
+            // -------- row block done: drain dA^T (lanes = feature columns, TMEM columns = the 128 rows of the block)
+            mbar_wait(ACCFULL, it & 1);
+            tc_fence_after();
+            const float omul = s * p.out_mul * invG;
+            float dsum = 0.f;
+            for (int dblk = 0; dblk < ND; ++dblk) {
+                const int d = (dblk * 2 + (int)cta) * 128 + q * 32 + lane;
+                const bool dvalid = d < p.d_out;
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(TM_ACC + ((uint32_t)(q * 32) << 16) + dblk * 128 + h * 64 + cc * 32, r);
+                    tmem_ld_wait();
+                    if (dvalid) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            const int mi = item * TILE + h * 64 + cc * 32 + k;
+                            if (mi < p.n_m) {
+                                const float a = __uint_as_float(r[k]);
+                                if (p.a_rows != nullptr) {
+                                    const __nv_bfloat16 av =
+                                        reinterpret_cast<const __nv_bfloat16*>(p.a_rows)[(size_t)mi * p.lda + d];
+                                    dsum = fmaf(a, __bfloat162float(av), dsum);
+                                }
+                                if (p.out_fp32)
+                                    reinterpret_cast<float*>(p.out)[(size_t)mi * p.ld_out + d] = a * omul;
+                                else
+                                    reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)mi * p.ld_out + d] =
+                                        __float2bfloat16_rn(a * omul);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(R_ACCEMPTY);
+            if (p.dscale_part != nullptr) {
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
+                if (lane == 0) red[warp - 4] = dsum;
+                epi_bar_sync2();
+                if (et == 0) {
+                    float tot = 0.f;
+                    for (int w = 0; w < 8; ++w) tot += red[w];
+                    p.dscale_part[item * 2 + (int)cta] = tot * invG;
+                }
+                epi_bar_sync2();
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_cg2(tmem_base, 512);
+}
+
+void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
+                     int num_sms, cudaStream_t st) {
+    const int n_items = p.m_tiles;
+    int npairs = num_sms / 2;
+    if (n_items < npairs) npairs = n_items;
+    const int grid = npairs * 2;
+    const size_t smem = bwd_pair_smem_bytes();
+    const bool row_term = p.wr != nullptr, col_term = p.wc != nullptr;
+#define FLYP_LAUNCH_BWD2(R, C)                                                                                 \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(bwd_pair_kernel<R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        bwd_pair_kernel<R, C><<<grid, NTHREADS2, smem, st>>>(tmA64, tmB, tmBd, p);                             \
+    } while (0)
+    if (row_term && col_term) FLYP_LAUNCH_BWD2(true, true);
+    else if (row_term) FLYP_LAUNCH_BWD2(true, false);
+    else FLYP_LAUNCH_BWD2(false, true);
+#undef FLYP_LAUNCH_BWD2
+}
+
+}  // namespace flyp

@@ -66,7 +66,7 @@ struct BwdParams {
     int out_fp32;            // 1: out is fp32, 0: bf16
     float out_mul;           // extra factor folded into the output (e.g. W for gather_with_grad)
     const uint32_t* gmax_bits;  // device word: bit pattern of max |upstream grad| (dS is staged as scaled fp16)
-    float* dscale_part;      // [m_tiles * d_parts] partial sums of <acc, a> (unscaled), may be null
+    float* dscale_part;      // [m_tiles * max(d_parts, 2)] partial sums of <acc, a> (unscaled), may be null
 };
 
 // robust = exact per-tile (max, sum) row statistics only; gate (device int, may be null): the robust kernel returns
@@ -76,6 +76,11 @@ void launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams&
 // tmBd: tensor map used for the N-side operand rows as the B operand of the dA MMA (box [64 d][128 n]).
 void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
                 int num_sms, cudaStream_t st);
+// CTA-pair variant (clip_bwd_pair.cu): requires d_out % 128 == 0, d_out <= 512; tmA64 has box [64 rows][64 cols];
+// column vectors padded to a multiple of 256; dscale_part has 2 entries per M tile.
+void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
+                     int num_sms, cudaStream_t st);
+size_t bwd_pair_smem_bytes();
 size_t fwd_smem_bytes(bool stationary);
 size_t bwd_smem_bytes();
 
