@@ -176,7 +176,9 @@ DEVI void cluster_sync_all() {
 }
 // arrive on an mbarrier that may live in the peer CTA (address from mapa)
 DEVI void mbar_arrive_cluster(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+    // default semantics (.release.cta), as CUTLASS' ClusterBarrier::arrive: a cluster-scope release would cost a
+    // MEMBAR.ALL.GPU + ERRBAR per arrival (measured: a third of the epilogue's issue slots)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load issued by either CTA of a pair into its OWN smem; the bytes are credited to `cluster_bar`
 // (normally the leader CTA's barrier, address from mapa)
