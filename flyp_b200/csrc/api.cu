@@ -63,6 +63,8 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, bool
     return 0;
 }
 
+unsigned long long* g_prof_buf = nullptr;   // debug only (flyp_debug_profile)
+
 int num_sms() {
     static int cached[64] = {0};
     int dev = 0;
@@ -88,7 +90,23 @@ bool use_pair_kernel(int dim) {
     }
     return forced == 0 && dim % 128 == 0 && dim <= 512;
 }
-int dscale_parts_per_tile(int dim) { return use_pair_kernel(dim) ? 2 : ceil_div(dim, 256); }
+// number of d(scale) partial slots / fp32 tail-partial blocks a sweep over m_tiles row blocks may use
+int num_sms();
+// d(scale) partial slots and fp32 tail-partial floats a backward sweep over n_m rows x n_n columns may use
+size_t sweep_dscale_slots(int n_m, int n_n, int dim) {
+    const int m_tiles = ceil_div(n_m, flyp::TILE);
+    if (!use_pair_kernel(dim)) return (size_t)m_tiles * ceil_div(dim, 256);
+    int full = m_tiles;
+    const int k = flyp::bwd_pair_tail_split(m_tiles, n_n, num_sms(), &full);
+    return (size_t)(full + (m_tiles - full) * k) * 2;
+}
+size_t sweep_part_floats(int n_m, int n_n, int dim) {
+    if (!use_pair_kernel(dim)) return 0;
+    const int m_tiles = ceil_div(n_m, flyp::TILE);
+    int full = m_tiles;
+    const int k = flyp::bwd_pair_tail_split(m_tiles, n_n, num_sms(), &full);
+    return k > 1 ? (size_t)(m_tiles - full) * k * flyp::TILE * dim : 0;
+}
 constexpr int VEC_PAD = 256;   // per-row / per-column vectors are padded to this many entries
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -217,9 +235,10 @@ int run_stats(const void* A, const void* B, const float* scale, int n_m, int n_n
 }
 
 // ---- workspace of the backward sweeps -----------------------------------------------------------------------------
-struct VecSet { float *w, *l2, *d; int* lab; };
+struct VecSet { float *w, *l2, *d, *f; int* lab; };
 void carve_vecs(Carver& c, int n_pad, VecSet& v) {
-    v.w = c.take<float>(n_pad); v.l2 = c.take<float>(n_pad); v.d = c.take<float>(n_pad); v.lab = c.take<int>(n_pad);
+    v.w = c.take<float>(n_pad); v.l2 = c.take<float>(n_pad); v.d = c.take<float>(n_pad); v.f = c.take<float>(n_pad);
+    v.lab = c.take<int>(n_pad);
 }
 
 int check_common(int n_m, int n_n, int dim, int dtype) {
@@ -231,8 +250,9 @@ int check_common(int n_m, int n_n, int dim, int dtype) {
 
 int run_sweep(const void* A, const void* B, const void* B_f16, const float* scale, int n_m, int n_n, int dim, const float* wr,
               const float* lr, const float* wc, const float* lc, const int* labr, const float* dr, const int* labc,
-              const float* dc, const void* a_rows_for_dscale, void* out, int out_fp32, float out_mul, float* dscale_part,
-              const uint32_t* gmax_bits, cudaStream_t st) {
+              const float* dc, const float* fa, const float* fb, const float* fast_info, const void* a_rows_for_dscale,
+              void* out, int out_fp32, float out_mul, float* dscale_part, float* part_scratch, const uint32_t* gmax_bits,
+              cudaStream_t st) {
     CUtensorMap tmA, tmB;
     int rc;
     if ((rc = make_tmap(&tmA, A, n_m, dim, dim)) != 0) return rc;
@@ -246,13 +266,25 @@ int run_sweep(const void* A, const void* B, const void* B_f16, const float* scal
     p.d_out = dim; p.d_parts = ceil_div(dim, 256);
     p.scale = scale; p.wr = wr; p.lr = lr; p.wc = wc; p.lc = lc;
     p.labr = labr; p.dr = dr; p.labc = labc; p.dc = dc;
+    p.fa = fa; p.fb = fb; p.fast_info = fast_info;
     p.a_rows = a_rows_for_dscale; p.lda = dim;
     p.out = out; p.ld_out = dim; p.out_fp32 = out_fp32; p.out_mul = out_mul; p.gmax_bits = gmax_bits;
     p.dscale_part = dscale_part;
+    p.prof = g_prof_buf;
+    p.full_items = p.m_tiles; p.split_k = 1; p.part_out = nullptr;
     if (use_pair_kernel(dim)) {
         CUtensorMap tmA64;
         if ((rc = make_tmap(&tmA64, A, n_m, dim, dim, false, 64)) != 0) return rc;
+        const char* ns = getenv("FLYP_NO_SPLIT");          // A/B switch for measurements
+        if (part_scratch != nullptr && !(ns && ns[0] == '1')) {
+            p.split_k = flyp::bwd_pair_tail_split(p.m_tiles, n_n, num_sms(), &p.full_items);
+            p.part_out = part_scratch;
+        }
         flyp::launch_bwd_pair(tmA64, tmB, tmBd, p, num_sms(), st);
+        CUDA_OK(cudaGetLastError());
+        if (p.split_k > 1)
+            flyp::launch_reduce_parts(part_scratch, p.m_tiles - p.full_items, p.split_k, p.full_items, n_m, dim, out,
+                                      dim, out_fp32, st);
     } else {
         flyp::launch_bwd(tmA, tmB, tmBd, p, num_sms(), st);
     }
@@ -272,7 +304,10 @@ struct ClipWs {
     StatsWs stats;
     VecSet rows, cols;       // bwd vectors: by local image row / by text column
     float* dscale_part;
-    uint32_t* gmax_bits;
+    size_t n_dscale;
+    float* part_scratch;      // fp32 partial outputs of split tail blocks (pair kernel)
+    uint32_t* gmax_bits;      // {bits(max|g|), key(max lse2), key(min lse2)}
+    float* fast_info;         // {c0, valid}
     uint16_t *img16, *txt16;  // fp16 staging copies of the features (backward only)
     size_t bytes;
 };
@@ -282,8 +317,15 @@ static void carve_clip(void* base, int n_rows, int n_cols, int dim, ClipWs& w) {
     const int rp = ceil_div(n_rows, VEC_PAD) * VEC_PAD, cp = ceil_div(n_cols, VEC_PAD) * VEC_PAD;
     carve_vecs(c, rp, w.rows);
     carve_vecs(c, cp, w.cols);
-    w.dscale_part = c.take<float>((size_t)ceil_div(n_rows, flyp::TILE) * dscale_parts_per_tile(dim));
-    w.gmax_bits = c.take<uint32_t>(1);
+    w.n_dscale = sweep_dscale_slots(n_rows, n_cols, dim);
+    w.dscale_part = c.take<float>(w.n_dscale);
+    {
+        const size_t a = sweep_part_floats(n_rows, n_cols, dim), b = sweep_part_floats(n_cols, n_rows, dim);
+        const size_t n = a > b ? a : b;
+        w.part_scratch = n ? c.take<float>(n) : nullptr;
+    }
+    w.gmax_bits = c.take<uint32_t>(4);
+    w.fast_info = c.take<float>(2);
     w.img16 = c.take<uint16_t>((size_t)n_rows * dim);
     w.txt16 = c.take<uint16_t>((size_t)n_cols * dim);
     w.bytes = align_up(c.off, 256);
@@ -343,23 +385,27 @@ int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, in
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int rp = ceil_div(n_rows, VEC_PAD) * VEC_PAD, cp = ceil_div(n_cols, VEC_PAD) * VEC_PAD;
-    CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, sizeof(uint32_t), st));
+    CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, 2 * sizeof(uint32_t), st));
+    CUDA_OK(cudaMemsetAsync(w.gmax_bits + 2, 0xff, sizeof(uint32_t), st));
     // rows: w = g_row/2, positive column row_offset + i, exact dS there from the saved cross-entropies
     flyp::launch_bwd_prep(n_rows, rp, g_row, 0.5f, row_lse, row_nll, nullptr, row_offset, n_cols, g_col, col_nll, 0.5f,
                           w.rows.w, w.rows.l2, w.rows.lab, w.rows.d, w.gmax_bits, st);
     // columns: w = g_col/2, positive local row j - row_offset
     flyp::launch_bwd_prep(n_cols, cp, g_col, 0.5f, col_lse, col_nll, nullptr, -row_offset, n_rows, g_row, row_nll, 0.5f,
                           w.cols.w, w.cols.l2, w.cols.lab, w.cols.d, w.gmax_bits, st);
+    flyp::launch_bwd_fast_vectors(w.gmax_bits, rp, w.rows.w, w.rows.l2, w.rows.f, cp, w.cols.w, w.cols.l2, w.cols.f,
+                                  w.fast_info, st);
     CUDA_OK(cudaGetLastError());
     if (d_img) {
         flyp::launch_to_f16(txt, dtype, (size_t)n_cols * dim, w.txt16, st);
         CUDA_OK(cudaGetLastError());
         rc = run_sweep(img, txt, w.txt16, scale, n_rows, n_cols, dim, w.rows.w, w.rows.l2, w.cols.w, w.cols.l2, w.rows.lab,
-                       w.rows.d, nullptr, nullptr, d_scale ? img : nullptr, d_img, grad_dtype, grad_mul,
-                       d_scale ? w.dscale_part : nullptr, w.gmax_bits, st);
+                       w.rows.d, nullptr, nullptr, w.rows.f, w.cols.f, w.fast_info, d_scale ? img : nullptr, d_img,
+                       grad_dtype, grad_mul,
+                       d_scale ? w.dscale_part : nullptr, w.part_scratch, w.gmax_bits, st);
         if (rc) return rc;
         if (d_scale) {
-            flyp::launch_sum_parts(w.dscale_part, ceil_div(n_rows, flyp::TILE) * dscale_parts_per_tile(dim), d_scale, st);
+            flyp::launch_sum_parts(w.dscale_part, (int)w.n_dscale, d_scale, st);
             CUDA_OK(cudaGetLastError());
         }
     } else if (d_scale) {
@@ -369,7 +415,8 @@ int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, in
         flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
         CUDA_OK(cudaGetLastError());
         rc = run_sweep(txt, img, w.img16, scale, n_cols, n_rows, dim, w.cols.w, w.cols.l2, w.rows.w, w.rows.l2, w.cols.lab,
-                       w.cols.d, nullptr, nullptr, nullptr, d_txt, grad_dtype, grad_mul, nullptr, w.gmax_bits, st);
+                       w.cols.d, nullptr, nullptr, w.cols.f, w.rows.f, w.fast_info, nullptr, d_txt, grad_dtype, grad_mul,
+                       nullptr, w.part_scratch, w.gmax_bits, st);
         if (rc) return rc;
     }
     return 0;
@@ -380,7 +427,10 @@ struct CeWs {
     StatsWs stats;
     VecSet v;
     float* dscale_part;
+    size_t n_dscale;
+    float* part_scratch;
     uint32_t* gmax_bits;
+    float* fast_info;
     uint16_t *a16, *b16;
     size_t bytes;
 };
@@ -389,8 +439,15 @@ static void carve_ce(void* base, int n, int n_classes, int dim, CeWs& w) {
     carve_stats(c, n, n_classes, false, w.stats);
     const int np = ceil_div(n, VEC_PAD) * VEC_PAD;
     carve_vecs(c, np, w.v);
-    w.dscale_part = c.take<float>((size_t)ceil_div(n, flyp::TILE) * dscale_parts_per_tile(dim));
-    w.gmax_bits = c.take<uint32_t>(1);
+    w.n_dscale = sweep_dscale_slots(n, n_classes, dim);
+    w.dscale_part = c.take<float>(w.n_dscale);
+    {
+        const size_t a = sweep_part_floats(n, n_classes, dim), b = sweep_part_floats(n_classes, n, dim);
+        const size_t nn = a > b ? a : b;
+        w.part_scratch = nn ? c.take<float>(nn) : nullptr;
+    }
+    w.gmax_bits = c.take<uint32_t>(4);
+    w.fast_info = c.take<float>(2);
     w.a16 = c.take<uint16_t>((size_t)n * dim);
     w.b16 = c.take<uint16_t>((size_t)n_classes * dim);
     w.bytes = align_up(c.off, 256);
@@ -432,20 +489,22 @@ int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_c
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int np = ceil_div(n, VEC_PAD) * VEC_PAD;
-    CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, sizeof(uint32_t), st));
+    CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, 2 * sizeof(uint32_t), st));
+    CUDA_OK(cudaMemsetAsync(w.gmax_bits + 2, 0xff, sizeof(uint32_t), st));
     // w = g, positive = label, dS there = g * expm1(-loss)
     flyp::launch_bwd_prep(n, np, g, 1.0f, lse, loss, labels, label_offset, n_classes, nullptr, nullptr, 1.0f, w.v.w,
                           w.v.l2, w.v.lab, w.v.d, w.gmax_bits, st);
+    flyp::launch_bwd_fast_vectors(w.gmax_bits, np, w.v.w, w.v.l2, w.v.f, 0, nullptr, nullptr, nullptr, w.fast_info, st);
     CUDA_OK(cudaGetLastError());
     if (d_a) {
         flyp::launch_to_f16(b, dtype, (size_t)n_classes * dim, w.b16, st);
         CUDA_OK(cudaGetLastError());
         rc = run_sweep(a, b, w.b16, scale, n, n_classes, dim, w.v.w, w.v.l2, nullptr, nullptr, w.v.lab, w.v.d, nullptr,
-                       nullptr, d_scale ? a : nullptr, d_a, grad_dtype, 1.0f, d_scale ? w.dscale_part : nullptr,
-                       w.gmax_bits, st);
+                       nullptr, w.v.f, nullptr, w.fast_info, d_scale ? a : nullptr, d_a, grad_dtype, 1.0f,
+                       d_scale ? w.dscale_part : nullptr, w.part_scratch, w.gmax_bits, st);
         if (rc) return rc;
         if (d_scale) {
-            flyp::launch_sum_parts(w.dscale_part, ceil_div(n, flyp::TILE) * dscale_parts_per_tile(dim), d_scale, st);
+            flyp::launch_sum_parts(w.dscale_part, (int)w.n_dscale, d_scale, st);
             CUDA_OK(cudaGetLastError());
         }
     } else if (d_scale) {
@@ -456,7 +515,8 @@ int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_c
         flyp::launch_to_f16(a, dtype, (size_t)n * dim, w.a16, st);
         CUDA_OK(cudaGetLastError());
         rc = run_sweep(b, a, w.a16, scale, n_classes, n, dim, nullptr, nullptr, w.v.w, w.v.l2, nullptr, nullptr, w.v.lab,
-                       w.v.d, nullptr, d_b, grad_dtype, 1.0f, nullptr, w.gmax_bits, st);
+                       w.v.d, nullptr, w.v.f, w.fast_info, nullptr, d_b, grad_dtype, 1.0f, nullptr, w.part_scratch, w.gmax_bits,
+                       st);
         if (rc) return rc;
     }
     return 0;
@@ -479,6 +539,11 @@ int flyp_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n,
     if (dtype != FLYP_BF16 && dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad dtype %d", dtype);
     flyp::launch_l2norm_bwd(y, dy, inv_norm, n, dim, dtype, dx, static_cast<cudaStream_t>(stream));
     CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int flyp_debug_profile(void* device_buffer_16_u64) {
+    g_prof_buf = static_cast<unsigned long long*>(device_buffer_16_u64);
     return 0;
 }
 

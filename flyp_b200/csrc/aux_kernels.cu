@@ -245,10 +245,23 @@ __global__ void k_bwd_prep(int n, int n_pad, const float* __restrict__ g, float 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float wi = 0.f, li = 0.f, di = 0.f;
     int lb = -1;
-    uint32_t gb = 0u;
-    if (i < n) gb = __float_as_uint(fabsf(g[i]));
+    // words: [0] bits of max|g|, [1] / [2] order-preserving keys of max / min of lse (log2 units) over live entries
+    uint32_t gb = 0u, khi = 0u, klo = 0xffffffffu;
+    if (i < n) {
+        gb = __float_as_uint(fabsf(g[i]));
+        if (g[i] != 0.f) {
+            const uint32_t u = __float_as_uint(lse[i] * LOG2E_F);
+            khi = klo = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        }
+    }
     gb = __reduce_max_sync(0xffffffffu, gb);
-    if ((threadIdx.x & 31) == 0 && gb != 0u && gmax_bits) atomicMax(gmax_bits, gb);
+    khi = __reduce_max_sync(0xffffffffu, khi);
+    klo = __reduce_min_sync(0xffffffffu, klo);
+    if ((threadIdx.x & 31) == 0 && gmax_bits) {
+        if (gb != 0u) atomicMax(gmax_bits, gb);
+        if (khi != 0u) atomicMax(gmax_bits + 1, khi);
+        if (klo != 0xffffffffu) atomicMin(gmax_bits + 2, klo);
+    }
     if (i >= n_pad) return;
     if (i < n) {
         const float gi = g[i];
@@ -274,6 +287,33 @@ void launch_bwd_prep(int n, int n_pad, const float* g, float wmul, const float* 
                                                     nll2, dmul, w, l2, lab, d, gmax_bits);
 }
 
+// Fast (single-exponential) form of the backward epilogue: c0 = centre of the lse range, valid when the range is at
+// most 200 log2 units wide; f[i] = w[i] * 2^(c0 - l2[i]).
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__global__ void k_bwd_fast_vectors(const uint32_t* __restrict__ words, int n_a, const float* __restrict__ w_a,
+                                   const float* __restrict__ l_a, float* __restrict__ f_a, int n_b,
+                                   const float* __restrict__ w_b, const float* __restrict__ l_b,
+                                   float* __restrict__ f_b, float* __restrict__ info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t khi = words[1], klo = words[2];
+    float c0 = 0.f, valid = 1.f;
+    if (khi != 0u && klo != 0xffffffffu) {
+        const float hi = key_to_float(khi), lo = key_to_float(klo);
+        c0 = 0.5f * (hi + lo);
+        valid = (hi - lo <= 200.f && isfinite(hi) && isfinite(lo)) ? 1.f : 0.f;
+    }
+    if (i == 0) { info[0] = c0; info[1] = valid; }
+    if (i < n_a) { const float w = w_a[i]; f_a[i] = (w == 0.f) ? 0.f : w * exp2f(c0 - l_a[i]); }
+    if (f_b != nullptr && i < n_b) { const float w = w_b[i]; f_b[i] = (w == 0.f) ? 0.f : w * exp2f(c0 - l_b[i]); }
+}
+void launch_bwd_fast_vectors(const uint32_t* words, int n_a, const float* w_a, const float* l_a, float* f_a, int n_b,
+                             const float* w_b, const float* l_b, float* f_b, float* info, cudaStream_t st) {
+    const int n = n_a > n_b ? n_a : n_b;
+    k_bwd_fast_vectors<<<(n + 255) / 256, 256, 0, st>>>(words, n_a, w_a, l_a, f_a, n_b, w_b, l_b, f_b, info);
+}
+
 __global__ void k_sum_parts(const float* __restrict__ parts, int n, float* __restrict__ out) {
     __shared__ float sm[32];
     float acc = 0.f;
@@ -289,6 +329,33 @@ __global__ void k_sum_parts(const float* __restrict__ parts, int n, float* __res
 }
 void launch_sum_parts(const float* parts, int n, float* out, cudaStream_t st) {
     k_sum_parts<<<1, 256, 0, st>>>(parts, n, out);
+}
+
+// ------------------------------------------------------------------------------------------------ tail partial sums
+// out[(first_blk + blk) * 128 + r][d] = sum_k part[(blk * split_k + k)][r][d]   (bwd pair kernel, split tail blocks)
+template <bool F32OUT>
+__global__ void k_reduce_parts(const float* __restrict__ part, int n_blocks, int split_k, int first_blk, int n_m,
+                               int d_out, void* __restrict__ out, int ld_out) {
+    const size_t per_blk = (size_t)128 * d_out;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n_blocks * per_blk) return;
+    const int blk = (int)(i / per_blk);
+    const size_t rem = i - (size_t)blk * per_blk;
+    const int r = (int)(rem / d_out), d = (int)(rem - (size_t)r * d_out);
+    const int m = (first_blk + blk) * 128 + r;
+    if (m >= n_m) return;
+    float acc = 0.f;
+    for (int k = 0; k < split_k; ++k) acc += part[((size_t)(blk * split_k + k) * 128 + r) * d_out + d];
+    if (F32OUT) reinterpret_cast<float*>(out)[(size_t)m * ld_out + d] = acc;
+    else reinterpret_cast<__nv_bfloat16*>(out)[(size_t)m * ld_out + d] = __float2bfloat16_rn(acc);
+}
+void launch_reduce_parts(const float* part, int n_blocks, int split_k, int first_blk, int n_m, int d_out, void* out,
+                         int ld_out, int out_fp32, cudaStream_t st) {
+    const size_t n = (size_t)n_blocks * 128 * d_out;
+    if (n == 0) return;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (out_fp32) k_reduce_parts<true><<<grid, 256, 0, st>>>(part, n_blocks, split_k, first_blk, n_m, d_out, out, ld_out);
+    else k_reduce_parts<false><<<grid, 256, 0, st>>>(part, n_blocks, split_k, first_blk, n_m, d_out, out, ld_out);
 }
 
 // ------------------------------------------------------------------------------------------------ fp16 staging copy

@@ -29,13 +29,20 @@ void launch_clip_finish(const float* col_stat_all, int world, const float* row_n
 // Vectors consumed by bwd_kernel, padded with zeros / -1 to a multiple of 128 entries.
 //   w[i] = wmul * g[i]; l2[i] = lse[i] * log2(e); lab[i] = labels ? labels[i] : (i + lab_offset if in [0, lab_range) else -1)
 //   d[i] = dmul * (g[i] expm1(-nll[i]) + (g2 ? g2[lab[i]] expm1(-nll2[lab[i]]) : 0))  (0 when lab[i] < 0): the exact
-//          value of dS at the positive;  *gmax_bits = max(*gmax_bits, bits(max|g|))
+//          value of dS at the positive;  gmax_bits[0..2] accumulate {bits(max|g|), key(max lse2), key(min lse2)}
 void launch_bwd_prep(int n, int n_pad, const float* g, float wmul, const float* lse, const float* nll,
                      const int64_t* labels, int lab_offset, int lab_range, const float* g2, const float* nll2,
                      float dmul, float* w, float* l2, int* lab, float* d, uint32_t* gmax_bits, cudaStream_t st);
+// words = {bits(max|g|), key(max lse2), key(min lse2)} as accumulated by launch_bwd_prep; computes the centre c0 of the
+// lse range, info = {c0, valid}, and f_x[i] = w_x[i] * 2^(c0 - l_x[i]) for both vector sets (f_b may be null).
+void launch_bwd_fast_vectors(const uint32_t* words, int n_a, const float* w_a, const float* l_a, float* f_a, int n_b,
+                             const float* w_b, const float* l_b, float* f_b, float* info, cudaStream_t st);
 // out[0] = sum(parts[0..n))   (single block, fixed order -> deterministic)
 void launch_sum_parts(const float* parts, int n, float* out, cudaStream_t st);
 
+// sums the fp32 partial outputs of the split tail blocks of the pair backward sweep into `out`
+void launch_reduce_parts(const float* part, int n_blocks, int split_k, int first_blk, int n_m, int d_out, void* out,
+                         int ld_out, int out_fp32, cudaStream_t st);
 // dst (fp16, n_elems) = saturating round-to-nearest of src (bf16 or fp32); n_elems % 8 == 0
 void launch_to_f16(const void* src, int dtype, size_t n_elems, void* dst, cudaStream_t st);
 

@@ -18,6 +18,7 @@
 // in consumption order, the B chunks of the S product and the fp16 feature boxes of the dA^T product, and the dS tile.
 #include "clip_kernels.cuh"
 #include "sm100.cuh"
+#include "bwd_common.cuh"
 
 namespace flyp {
 using namespace sm100;
@@ -41,7 +42,35 @@ DEVI uint8_t* align1024p(uint8_t* p) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
 DEVI void epi_bar_sync2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+struct ItemInfo { int mb, t0, t1, part; };
+DEVI ItemInfo item_info(int item, const BwdParams& p, int NJ) {
+    ItemInfo r;
+    if (item < p.full_items) { r.mb = item; r.t0 = 0; r.t1 = NJ; r.part = -1; return r; }
+    const int idx = item - p.full_items;
+    const int blk = idx / p.split_k, prt = idx - blk * p.split_k;
+    r.mb = p.full_items + blk;
+    r.t0 = (int)((long long)prt * NJ / p.split_k);
+    r.t1 = (int)((long long)(prt + 1) * NJ / p.split_k);
+    r.part = idx;
+    return r;
+}
 }  // namespace
+
+int bwd_pair_tail_split(int m_tiles, int n_cols, int num_sms, int* full_items) {
+    const int npairs = num_sms / 2;
+    const int NJ = (n_cols + PairCfg::NSTEP - 1) / PairCfg::NSTEP;
+    const int rem = npairs > 0 ? m_tiles % npairs : 0;
+    int k = 1;
+    if (m_tiles > npairs && rem > 0 && rem <= npairs / 2) {
+        k = npairs / rem;
+        if (k > 8) k = 8;
+        if (k > NJ) k = NJ;
+        if (k < 1) k = 1;
+    }
+    *full_items = (k > 1) ? m_tiles - rem : m_tiles;
+    return k;
+}
 
 size_t bwd_pair_smem_bytes() { return PairCfg::SMEM_BYTES; }
 
@@ -71,7 +100,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int n_items = p.m_tiles;
+    const int n_items = p.full_items + (p.m_tiles - p.full_items) * p.split_k;
     const int NJ = (p.n_n + Cfg::NSTEP - 1) / Cfg::NSTEP;
     const int KC = p.kc;                         // 64-wide K chunks of the S contraction (even)
     const int ND = (p.d_out + 255) / 256;        // pair MMAs of the dA^T product (256 feature columns each)
@@ -96,8 +125,12 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
         // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
         if (elect_one()) {
             int slot = 0; uint32_t ph = 0; uint32_t it = 0;
+            const bool prof = p.prof != nullptr && pair == 0;
+            long long w_empty = 0;
+            const long long t_begin = clock64();
             auto put = [&](const CUtensorMap* tm, int c0, int c1) {
-                mbar_wait(EMPTY(slot), ph ^ 1);
+                if (prof) { const long long t0 = clock64(); mbar_wait(EMPTY(slot), ph ^ 1); w_empty += clock64() - t0; }
+                else mbar_wait(EMPTY(slot), ph ^ 1);
                 if (cta == 0) mbar_expect_tx(FULL(slot), 2 * Cfg::SLOT);
                 tma_load_2d_cg2(smem_u32(ring + slot * Cfg::SLOT), tm, mapa(FULL(slot), 0), c0, c1);
                 if (++slot == NSLOT) { slot = 0; ph ^= 1; }
@@ -112,15 +145,17 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                             put(&tmBd, (dblk * 2 + (int)cta) * 128 + dsub * 64, t * Cfg::NSTEP + jh * 128);
             };
             for (int item = pair; item < n_items; item += npairs, ++it) {
+                const ItemInfo ii = item_info(item, p, NJ);
                 mbar_wait(IFREE, (it & 1) ^ 1);
                 if (cta == 0) mbar_expect_tx(IFULL, 2 * KC * 8192);
                 for (int c = 0; c < KC; ++c)
                     tma_load_2d_cg2(smem_u32(ist + c * 8192), &tmA64, mapa(IFULL, 0), c * KCHUNK,
-                                    item * TILE + (int)cta * 64);
-                load_s(0);
-                for (int t = 1; t < NJ; ++t) { load_s(t); load_t(t - 1); }
-                load_t(NJ - 1);
+                                    ii.mb * TILE + (int)cta * 64);
+                load_s(ii.t0);
+                for (int t = ii.t0 + 1; t < ii.t1; ++t) { load_s(t); load_t(t - 1); }
+                load_t(ii.t1 - 1);
             }
+            if (prof) { p.prof[8 + cta * 2] = (unsigned long long)(clock64() - t_begin); p.prof[9 + cta * 2] = w_empty; }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -128,14 +163,21 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             constexpr uint32_t IDESC_S = umma_idesc(128, 256, 1, 1, 0, 0);     // bf16 x bf16, both K-major
             constexpr uint32_t IDESC_D = umma_idesc(256, 128, 0, 0, 1, 0);     // fp16 x fp16, A MN-major, B K-major
             int slot = 0; uint32_t ph = 0; uint32_t gs = 0, gd = 0, it = 0;
+            const bool prof = p.prof != nullptr && pair == 0;
+            long long w_sempty = 0, w_full_s = 0, w_dsfull = 0, w_full_t = 0, w_acc = 0, w_ifull = 0;
+            const long long t_begin = clock64();
+            auto twait = [&](uint32_t bar, uint32_t parity, long long& acc) {
+                if (prof) { const long long t0 = clock64(); mbar_wait(bar, parity); acc += clock64() - t0; }
+                else mbar_wait(bar, parity);
+            };
             auto adv = [&]() { if (++slot == NSLOT) { slot = 0; ph ^= 1; } };
             auto mma_s = [&]() {
                 const int sb = gs & 1;
-                mbar_wait(SEMPTY(sb), ((gs >> 1) & 1) ^ 1);
+                twait(SEMPTY(sb), ((gs >> 1) & 1) ^ 1, w_sempty);
                 tc_fence_after();
                 const uint32_t d_tmem = TM_S + sb * 128;
                 for (int c = 0; c < KC; ++c) {
-                    mbar_wait(FULL(slot), ph);
+                    twait(FULL(slot), ph, w_full_s);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(ist + c * 8192);
                     const uint32_t b_addr = smem_u32(ring + slot * Cfg::SLOT);
@@ -150,14 +192,14 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 ++gs;
             };
             auto mma_d = [&](bool first) {
-                if (first) mbar_wait(ACCEMPTY, (it & 1) ^ 1);
-                mbar_wait(DSFULL, gd & 1);
+                if (first) twait(ACCEMPTY, (it & 1) ^ 1, w_acc);
+                twait(DSFULL, gd & 1, w_dsfull);
                 tc_fence_after();
                 const uint32_t ds_addr = smem_u32(ds);
                 for (int dblk = 0; dblk < ND; ++dblk) {
                     for (int jh = 0; jh < 2; ++jh) {
-                        mbar_wait(FULL(slot), ph);          // the two feature boxes (64 + 64 columns) of this K half
-                        mbar_wait(FULL(slot + 1), ph);
+                        twait(FULL(slot), ph, w_full_t);    // the two feature boxes (64 + 64 columns) of this K half
+                        twait(FULL(slot + 1), ph, w_full_t);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(ring + slot * Cfg::SLOT);
 #pragma unroll
@@ -178,13 +220,20 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 ++gd;
             };
             for (int item = pair; item < n_items; item += npairs, ++it) {
-                mbar_wait(IFULL, it & 1);
+                const ItemInfo ii = item_info(item, p, NJ);
+                const int nj = ii.t1 - ii.t0;
+                twait(IFULL, it & 1, w_ifull);
                 tc_fence_after();
                 mma_s();
-                for (int t = 1; t < NJ; ++t) { mma_s(); mma_d(t == 1); }
-                mma_d(NJ == 1);
+                for (int t = 1; t < nj; ++t) { mma_s(); mma_d(t == 1); }
+                mma_d(nj == 1);
                 umma_commit_cg2(ACCFULL);
                 umma_commit_cg2(IFREE);
+            }
+            if (prof) {
+                p.prof[0] = (unsigned long long)(clock64() - t_begin);
+                p.prof[1] = w_sempty; p.prof[2] = w_full_s; p.prof[3] = w_dsfull; p.prof[4] = w_full_t;
+                p.prof[5] = w_acc; p.prof[6] = w_ifull; p.prof[7] = gs;
             }
         }
     } else if (warp >= 4) {
@@ -193,33 +242,27 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
         const int et = threadIdx.x - 128;
         const float s = *p.scale;
         const float c1 = s * LOG2E2;
-        float G = 1.f, invG = 1.f;
-        {
-            const uint32_t gb = *p.gmax_bits;
-            if ((gb & 0x7fffffffu) != 0u) {
-                int ge = 13 - ((int)((gb >> 23) & 0xffu) - 127);
-                ge = ge < -100 ? -100 : (ge > 100 ? 100 : ge);
-                G = __uint_as_float((uint32_t)(ge + 127) << 23);
-                invG = __uint_as_float((uint32_t)(127 - ge) << 23);
-            }
-        }
+        float G, invG;
+        staging_scale(p.gmax_bits, G, invG);
+        const bool fast = p.fast_info != nullptr && p.fast_info[1] != 0.f;
+        const float c0 = fast ? p.fast_info[0] : 0.f;
         const uint32_t R_SEMPTY0 = mapa(SEMPTY(0), 0), R_SEMPTY1 = mapa(SEMPTY(1), 0);
         const uint32_t R_DSFULL = mapa(DSFULL, 0), R_ACCEMPTY = mapa(ACCEMPTY, 0);
         const int rloc = (q & 1) * 32 + lane;       // row within this CTA's 64-row slice
         const int jq = q >> 1;                      // which 128-column half of the step this lane quarter holds
         uint32_t gs = 0, it = 0;
+        const bool prof = p.prof != nullptr && pair == 0 && cta == 0 && threadIdx.x == 128;
+        long long w_sfull = 0, w_dsempty = 0, w_accfull = 0;
+        const long long t_begin = clock64();
         for (int item = pair; item < n_items; item += npairs, ++it) {
-            const int m = item * TILE + (int)cta * 64 + rloc;
-            const bool rowvalid = m < p.n_m;
-            float wr_m = 0.f, lr_m = 0.f, dr_m = 0.f;
-            int labr_m = -1;
-            if (rowvalid) {
-                if (ROW_TERM) { wr_m = p.wr[m] * G; lr_m = p.lr[m]; }
-                if (p.labr != nullptr) { labr_m = p.labr[m]; dr_m = p.dr[m] * G; }
-            }
-            for (int t = 0; t < NJ; ++t, ++gs) {
+            const ItemInfo ii = item_info(item, p, NJ);
+            const int m = ii.mb * TILE + (int)cta * 64 + rloc;
+            const RowCtx rc = load_row_ctx<ROW_TERM>(p, m, fast, G);
+            const bool want_ds = p.dscale_part != nullptr;
+            float dsum = 0.f;
+            for (int t = ii.t0; t < ii.t1; ++t, ++gs) {
                 const int sb = gs & 1;
-                mbar_wait(SFULL(sb), (gs >> 1) & 1);
+                { const long long t0 = clock64(); mbar_wait(SFULL(sb), (gs >> 1) & 1); w_sfull += clock64() - t0; }
                 tc_fence_after();
                 const uint32_t taddr = TM_S + ((uint32_t)(q * 32) << 16) + sb * 128 + h * 64;
                 uint32_t r0[32], r1[32];
@@ -230,61 +273,18 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 mbar_arrive_cluster(sb ? R_SEMPTY1 : R_SEMPTY0);
                 const int n0 = t * Cfg::NSTEP + jq * 128 + h * 64;
                 float v[64];
-#pragma unroll
-                for (int k4 = 0; k4 < 16; ++k4) {
-                    float lcs[4] = {0.f, 0.f, 0.f, 0.f}, wcs[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (COL_TERM) {
-                        const float4 lc4 = __ldg(reinterpret_cast<const float4*>(p.lc + n0) + k4);
-                        const float4 wc4 = __ldg(reinterpret_cast<const float4*>(p.wc + n0) + k4);
-                        lcs[0] = lc4.x; lcs[1] = lc4.y; lcs[2] = lc4.z; lcs[3] = lc4.w;
-                        wcs[0] = wc4.x * G; wcs[1] = wc4.y * G; wcs[2] = wc4.z * G; wcs[3] = wc4.w * G;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int k = k4 * 4 + j;
-                        const float x = __uint_as_float(k < 32 ? r0[k & 31] : r1[k & 31]) * c1;
-                        float acc = 0.f;
-                        if (ROW_TERM) acc = wr_m * ex2f(x - lr_m);
-                        if (COL_TERM) acc = fmaf(wcs[j], ex2f(x - lcs[j]), acc);
-                        v[k] = acc;
-                    }
-                }
-                if (p.labr != nullptr) {
-                    const int rel = labr_m - n0;
-                    if (__any_sync(0xffffffffu, rel >= 0 && rel < 64)) {
-#pragma unroll
-                        for (int k = 0; k < 64; ++k) v[k] = (k == rel) ? dr_m : v[k];
-                    }
-                }
-                if (p.labc != nullptr) {
-#pragma unroll
-                    for (int k4 = 0; k4 < 16; ++k4) {
-                        const int4 lb4 = __ldg(reinterpret_cast<const int4*>(p.labc + n0) + k4);
-                        const float4 dc4 = __ldg(reinterpret_cast<const float4*>(p.dc + n0) + k4);
-                        v[k4 * 4 + 0] = (lb4.x == m) ? dc4.x * G : v[k4 * 4 + 0];
-                        v[k4 * 4 + 1] = (lb4.y == m) ? dc4.y * G : v[k4 * 4 + 1];
-                        v[k4 * 4 + 2] = (lb4.z == m) ? dc4.z * G : v[k4 * 4 + 2];
-                        v[k4 * 4 + 3] = (lb4.w == m) ? dc4.w * G : v[k4 * 4 + 3];
-                    }
-                }
+                ds_tile<ROW_TERM, COL_TERM>(r0, r1, p, rc, n0, c1, fast, c0, G, v, want_ds, dsum);
                 uint32_t pk[32];
-#pragma unroll
-                for (int k = 0; k < 32; ++k) pk[k] = pack_f16x2(v[2 * k], v[2 * k + 1]);
-                mbar_wait(DSEMPTY, (gs & 1) ^ 1);
-                uint8_t* rowp = ds + (jq * 2 + h) * 8192 + rloc * 128;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                    *reinterpret_cast<uint4*>(rowp + ((j ^ (rloc & 7)) << 4)) = val;
-                }
+                pack_ds(v, pk);
+                { const long long t0 = clock64(); mbar_wait(DSEMPTY, (gs & 1) ^ 1); w_dsempty += clock64() - t0; }
+                store_ds_row(ds + (jq * 2 + h) * 8192 + rloc * 128, rloc, pk);
                 fence_proxy_async_smem();
                 mbar_arrive_cluster(R_DSFULL);
             }
             // -------- row block done: drain dA^T (lanes = feature columns, TMEM columns = the 128 rows of the block)
-            mbar_wait(ACCFULL, it & 1);
+            { const long long t0 = clock64(); mbar_wait(ACCFULL, it & 1); w_accfull += clock64() - t0; }
             tc_fence_after();
             const float omul = s * p.out_mul * invG;
-            float dsum = 0.f;
             for (int dblk = 0; dblk < ND; ++dblk) {
                 const int d = (dblk * 2 + (int)cta) * 128 + q * 32 + lane;
                 const bool dvalid = d < p.d_out;
@@ -296,15 +296,13 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                     if (dvalid) {
 #pragma unroll
                         for (int k = 0; k < 32; ++k) {
-                            const int mi = item * TILE + h * 64 + cc * 32 + k;
+                            const int ri = h * 64 + cc * 32 + k;
+                            const int mi = ii.mb * TILE + ri;
                             if (mi < p.n_m) {
                                 const float a = __uint_as_float(r[k]);
-                                if (p.a_rows != nullptr) {
-                                    const __nv_bfloat16 av =
-                                        reinterpret_cast<const __nv_bfloat16*>(p.a_rows)[(size_t)mi * p.lda + d];
-                                    dsum = fmaf(a, __bfloat162float(av), dsum);
-                                }
-                                if (p.out_fp32)
+                                if (ii.part >= 0)
+                                    p.part_out[((size_t)ii.part * TILE + ri) * p.d_out + d] = a * omul;
+                                else if (p.out_fp32)
                                     reinterpret_cast<float*>(p.out)[(size_t)mi * p.ld_out + d] = a * omul;
                                 else
                                     reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)mi * p.ld_out + d] =
@@ -329,6 +327,10 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 epi_bar_sync2();
             }
         }
+        if (prof) {
+            p.prof[12] = (unsigned long long)(clock64() - t_begin);
+            p.prof[13] = w_sfull; p.prof[14] = w_dsempty; p.prof[15] = w_accfull;
+        }
     }
     tc_fence_before();
     cluster_sync_all();
@@ -337,7 +339,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
 
 void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
                      int num_sms, cudaStream_t st) {
-    const int n_items = p.m_tiles;
+    const int n_items = p.full_items + (p.m_tiles - p.full_items) * p.split_k;
     int npairs = num_sms / 2;
     if (n_items < npairs) npairs = n_items;
     const int grid = npairs * 2;

@@ -11,6 +11,7 @@
 //   warp 2   TMEM allocator                         warps 4..11  epilogue (TMEM -> registers -> statistics / dS)
 #include "clip_kernels.cuh"
 #include "sm100.cuh"
+#include "bwd_common.cuh"
 
 namespace flyp {
 using namespace sm100;
@@ -421,29 +422,20 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const int et = threadIdx.x - 128;
         const float s = *p.scale;
         const float c1 = s * LOG2E;
-        // dS is staged in fp16 scaled by G = 2^k with |dS| * G < 2^14 (|dS| <= max|g|); 1/G is folded into the output.
-        float G = 1.f, invG = 1.f;
-        {
-            const uint32_t gb = *p.gmax_bits;
-            if ((gb & 0x7fffffffu) != 0u) {
-                int ge = 13 - ((int)((gb >> 23) & 0xffu) - 127);
-                ge = ge < -100 ? -100 : (ge > 100 ? 100 : ge);
-                G = __uint_as_float((uint32_t)(ge + 127) << 23);
-                invG = __uint_as_float((uint32_t)(127 - ge) << 23);
-            }
-        }
+        float G, invG;
+        staging_scale(p.gmax_bits, G, invG);
+        const bool fast = p.fast_info != nullptr && p.fast_info[1] != 0.f;
+        const float c0 = fast ? p.fast_info[0] : 0.f;
         uint32_t gs = 0, it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int mb = item / p.d_parts, dp = item % p.d_parts;
             const int rloc = q * 32 + lane;
             const int m = mb * TILE + rloc;
             const bool rowvalid = m < p.n_m;
-            float wr_m = 0.f, lr_m = 0.f, dr_m = 0.f;
-            int labr_m = -1;
-            if (rowvalid) {
-                if (ROW_TERM) { wr_m = p.wr[m] * G; lr_m = p.lr[m]; }
-                if (p.labr != nullptr) { labr_m = p.labr[m]; dr_m = p.dr[m] * G; }
-            }
+            const RowCtx rc = load_row_ctx<ROW_TERM>(p, m, fast, G);
+            // the S tile is recomputed once per 256-column output part: only part 0 contributes to d(scale)
+            const bool want_ds = p.dscale_part != nullptr && dp == 0;
+            float dsum = 0.f;
             for (int t = 0; t < NT; ++t, ++gs) {
                 const int sb = gs & 1;
                 mbar_wait(SFULL(sb), (gs >> 1) & 1);
@@ -457,54 +449,12 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 mbar_arrive(SEMPTY(sb));
                 const int n0 = t * TILE + h * 64;
                 float v[64];
-#pragma unroll
-                for (int k4 = 0; k4 < 16; ++k4) {
-                    float lcs[4] = {0.f, 0.f, 0.f, 0.f}, wcs[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (COL_TERM) {
-                        const float4 lc4 = __ldg(reinterpret_cast<const float4*>(p.lc + n0) + k4);
-                        const float4 wc4 = __ldg(reinterpret_cast<const float4*>(p.wc + n0) + k4);
-                        lcs[0] = lc4.x; lcs[1] = lc4.y; lcs[2] = lc4.z; lcs[3] = lc4.w;
-                        wcs[0] = wc4.x * G; wcs[1] = wc4.y * G; wcs[2] = wc4.z * G; wcs[3] = wc4.w * G;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int k = k4 * 4 + j;
-                        const float x = __uint_as_float(k < 32 ? r0[k & 31] : r1[k & 31]) * c1;
-                        float acc = 0.f;
-                        if (ROW_TERM) acc = wr_m * ex2f(x - lr_m);
-                        if (COL_TERM) acc = fmaf(wcs[j], ex2f(x - lcs[j]), acc);
-                        v[k] = acc;
-                    }
-                }
-                if (p.labr != nullptr) {
-                    const int rel = labr_m - n0;
-                    if (__any_sync(0xffffffffu, rel >= 0 && rel < 64)) {
-#pragma unroll
-                        for (int k = 0; k < 64; ++k) v[k] = (k == rel) ? dr_m : v[k];
-                    }
-                }
-                if (p.labc != nullptr) {
-#pragma unroll
-                    for (int k4 = 0; k4 < 16; ++k4) {
-                        const int4 lb4 = __ldg(reinterpret_cast<const int4*>(p.labc + n0) + k4);
-                        const float4 dc4 = __ldg(reinterpret_cast<const float4*>(p.dc + n0) + k4);
-                        v[k4 * 4 + 0] = (lb4.x == m) ? dc4.x * G : v[k4 * 4 + 0];
-                        v[k4 * 4 + 1] = (lb4.y == m) ? dc4.y * G : v[k4 * 4 + 1];
-                        v[k4 * 4 + 2] = (lb4.z == m) ? dc4.z * G : v[k4 * 4 + 2];
-                        v[k4 * 4 + 3] = (lb4.w == m) ? dc4.w * G : v[k4 * 4 + 3];
-                    }
-                }
+                ds_tile<ROW_TERM, COL_TERM>(r0, r1, p, rc, n0, c1, fast, c0, G, v, want_ds, dsum);
                 uint32_t pk[32];
-#pragma unroll
-                for (int k = 0; k < 32; ++k) pk[k] = pack_f16x2(v[2 * k], v[2 * k + 1]);
+                pack_ds(v, pk);
                 // dS buffer is free once the dA MMA of the previous tile has completed
                 mbar_wait(DSEMPTY, (gs & 1) ^ 1);
-                uint8_t* rowp = ds + h * CHUNK_BYTES + rloc * 128;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint4 val = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                    *reinterpret_cast<uint4*>(rowp + ((j ^ (rloc & 7)) << 4)) = val;
-                }
+                store_ds_row(ds + h * CHUNK_BYTES + rloc * 128, rloc, pk);
                 fence_proxy_async_smem();
                 mbar_arrive(DSFULL);
             }
@@ -512,7 +462,6 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             mbar_wait(ACCFULL, it & 1);
             tc_fence_after();
             const float omul = s * p.out_mul * invG;
-            float dsum = 0.f;
             const int dbase = dp * Cfg::DPART + h * 128;
 #pragma unroll 1
             for (int cc = 0; cc < 4; ++cc) {
@@ -521,23 +470,6 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 tmem_ld_wait();
                 const int d0 = dbase + cc * 32;
                 if (rowvalid) {
-                    if (p.a_rows != nullptr) {
-                        const __nv_bfloat16* arow = reinterpret_cast<const __nv_bfloat16*>(p.a_rows) + (size_t)m * p.lda;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (d0 + j * 8 < p.d_out) {
-                                const uint4 av = __ldg(reinterpret_cast<const uint4*>(arow + d0 + j * 8));
-                                const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float lo = __uint_as_float(aw[e] << 16);
-                                    const float hi = __uint_as_float(aw[e] & 0xffff0000u);
-                                    dsum = fmaf(__uint_as_float(r[j * 8 + 2 * e]), lo, dsum);
-                                    dsum = fmaf(__uint_as_float(r[j * 8 + 2 * e + 1]), hi, dsum);
-                                }
-                            }
-                        }
-                    }
                     if (p.out_fp32) {
                         float* orow = reinterpret_cast<float*>(p.out) + (size_t)m * p.ld_out;
 #pragma unroll

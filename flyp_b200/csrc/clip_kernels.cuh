@@ -66,6 +66,14 @@ struct BwdParams {
     int out_fp32;            // 1: out is fp32, 0: bf16
     float out_mul;           // extra factor folded into the output (e.g. W for gather_with_grad)
     const uint32_t* gmax_bits;  // device word: bit pattern of max |upstream grad| (dS is staged as scaled fp16)
+    const float* fa;         // [m] fast form: wr 2^(c0 - lr)      (see bwd_common.cuh)
+    const float* fb;         // [n] fast form: wc 2^(c0 - lc)
+    const float* fast_info;  // device {c0, valid}: valid != 0 -> single-exponential epilogue
+    // tail splitting (pair kernel): M blocks [0, full_items) are swept whole; each of the remaining blocks is swept by
+    // split_k work items over disjoint column ranges that write fp32 partials to part_out[idx][128][d_out]
+    int full_items, split_k;
+    float* part_out;
+    unsigned long long* prof; // optional debug: per-role wait-cycle counters of cluster 0 (see tools/pair_prof.py)
     float* dscale_part;      // [m_tiles * max(d_parts, 2)] partial sums of <acc, a> (unscaled), may be null
 };
 
@@ -81,6 +89,8 @@ void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
                      int num_sms, cudaStream_t st);
 size_t bwd_pair_smem_bytes();
+// how launch_bwd_pair splits the tail: returns split_k (1 = no split) and sets full_items
+int bwd_pair_tail_split(int m_tiles, int n_cols, int num_sms, int* full_items);
 size_t fwd_smem_bytes(bool stationary);
 size_t bwd_smem_bytes();
 

@@ -106,6 +106,10 @@ int flyp_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n,
 int flyp_debug_logits(const void* a, const void* b, int n_m, int n_n, int dim, int dtype, float* out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Debug: while set (non-NULL, 16 x uint64 device words), the backward sweep of cluster 0 records per-role wait-cycle
+ * counters there (tools/pair_prof.py).  Pass NULL to switch it off.  Not thread-safe; never used by the product path. */
+int flyp_debug_profile(void* device_buffer_16_u64);
+
 #ifdef __cplusplus
 }
 #endif
