@@ -82,26 +82,26 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // The CTA-pair backward sweep handles feature dims that are multiples of 128 up to 512; FLYP_BWD_IMPL=1 forces the
 // single-CTA kernel (kept for other dims and for A/B measurements).
-bool use_pair_kernel(int dim) {
+bool use_pair_kernel(int dim, int dtype = FLYP_BF16) {
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("FLYP_BWD_IMPL");
         forced = (e && e[0] == '1') ? 1 : 0;
     }
-    return forced == 0 && dim % 128 == 0 && dim <= 512;
+    return forced == 0 && dtype == FLYP_BF16 && dim % 128 == 0 && dim <= 512;
 }
 // number of d(scale) partial slots / fp32 tail-partial blocks a sweep over m_tiles row blocks may use
 int num_sms();
 // d(scale) partial slots and fp32 tail-partial floats a backward sweep over n_m rows x n_n columns may use
-size_t sweep_dscale_slots(int n_m, int n_n, int dim) {
+size_t sweep_dscale_slots(int n_m, int n_n, int dim, int dtype) {
     const int m_tiles = ceil_div(n_m, flyp::TILE);
-    if (!use_pair_kernel(dim)) return (size_t)m_tiles * ceil_div(dim, 256);
+    if (!use_pair_kernel(dim, dtype)) return (size_t)m_tiles * ceil_div(dim, 256);
     int full = m_tiles;
     const int k = flyp::bwd_pair_tail_split(m_tiles, n_n, num_sms(), &full);
     return (size_t)(full + (m_tiles - full) * k) * 2;
 }
-size_t sweep_part_floats(int n_m, int n_n, int dim) {
-    if (!use_pair_kernel(dim)) return 0;
+size_t sweep_part_floats(int n_m, int n_n, int dim, int dtype) {
+    if (!use_pair_kernel(dim, dtype)) return 0;
     const int m_tiles = ceil_div(n_m, flyp::TILE);
     int full = m_tiles;
     const int k = flyp::bwd_pair_tail_split(m_tiles, n_n, num_sms(), &full);
@@ -109,6 +109,7 @@ size_t sweep_part_floats(int n_m, int n_n, int dim) {
 }
 constexpr int VEC_PAD = 256;   // per-row / per-column vectors are padded to this many entries
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int plane_cols(int dim) { return ceil_div(dim, 64) * 64; }
 
 // Number of M splits per N block for the forward sweep: minimise the makespan in tile units (a work item costs its
 // tiles plus ~2 tile-times to refill the stationary operand).
@@ -155,8 +156,9 @@ struct StatsWs {
     int* pos_t;                          // [ld_cols] robust column pass: positive row of each column
     float* t2_t;                         // [ld_cols] scratch (unused values) for the column pass
     int* flag;
+    uint16_t *planes_a, *planes_b;       // fp32 features: three bf16 planes each ([n][3 * plane_cols])
 };
-void carve_stats(Carver& c, int n_m, int n_n, bool want_cols, StatsWs& w) {
+void carve_stats(Carver& c, int n_m, int n_n, int dim, int dtype, bool want_cols, StatsWs& w) {
     w.m_tiles = ceil_div(n_m, flyp::TILE);
     w.n_tiles = ceil_div(n_n, flyp::TILE);
     w.m_split = pick_m_split(w.m_tiles, w.n_tiles, 148);
@@ -176,6 +178,12 @@ void carve_stats(Carver& c, int n_m, int n_n, bool want_cols, StatsWs& w) {
     w.pos_t = want_cols ? c.take<int>(w.ld_cols) : nullptr;
     w.t2_t = want_cols ? c.take<float>(w.ld_cols) : nullptr;
     w.flag = c.take<int>(1);
+    if (dtype == FLYP_F32) {
+        w.planes_a = c.take<uint16_t>((size_t)n_m * 3 * plane_cols(dim));
+        w.planes_b = c.take<uint16_t>((size_t)n_n * 3 * plane_cols(dim));
+    } else {
+        w.planes_a = w.planes_b = nullptr;
+    }
 }
 
 // Statistics of S = scale * A . B^T with one positive per row (labels, or column pos_offset + i):
@@ -187,15 +195,26 @@ int run_stats(const void* A, const void* B, const float* scale, int n_m, int n_n
               float* col_stat, int* status, float* dbg_logits, cudaStream_t st) {
     CUtensorMap tmA, tmB;
     int rc;
-    if ((rc = make_tmap(&tmA, A, n_m, dim, dim)) != 0) return rc;
-    if ((rc = make_tmap(&tmB, B, n_n, dim, dim)) != 0) return rc;
+    flyp::KPlan kplan = flyp::kplan_bf16();
+    if (dtype == FLYP_F32) {
+        const int dp = plane_cols(dim);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(A), n_m, dim, dp, w.planes_a, st);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(B), n_n, dim, dp, w.planes_b, st);
+        CUDA_OK(cudaGetLastError());
+        if ((rc = make_tmap(&tmA, w.planes_a, n_m, 3 * dp, 3 * dp)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, w.planes_b, n_n, 3 * dp, 3 * dp)) != 0) return rc;
+        kplan = flyp::kplan_f32(dp);
+    } else {
+        if ((rc = make_tmap(&tmA, A, n_m, dim, dim)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, B, n_n, dim, dim)) != 0) return rc;
+    }
     const int sms = num_sms();
     const float slack = shift_slack(n_m, n_n);
     CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(int), st));
 
     flyp::FwdParams p;
     memset(&p, 0, sizeof(p));
-    p.n_m = n_m; p.n_n = n_n; p.kc = ceil_div(dim, flyp::KCHUNK);
+    p.n_m = n_m; p.n_n = n_n; p.kc = ceil_div(dim, flyp::KCHUNK); p.kplan = kplan;
     p.m_tiles = w.m_tiles; p.n_tiles = w.n_tiles; p.m_split = w.m_split;
     p.ld_rows = w.ld_rows; p.ld_cols = w.ld_cols;
     p.scale = scale; p.shift_slack = slack;
@@ -244,24 +263,38 @@ void carve_vecs(Carver& c, int n_pad, VecSet& v) {
 int check_common(int n_m, int n_n, int dim, int dtype) {
     if (n_m <= 0 || n_n <= 0) return fail(FLYP_ERR_ARG, "empty operand (%d x %d)", n_m, n_n);
     if (dim <= 0 || dim % 8 != 0) return fail(FLYP_ERR_ARG, "dim=%d must be a positive multiple of 8", dim);
-    if (dtype != FLYP_BF16) return fail(FLYP_ERR_ARG, "dtype %d not supported by this build (bf16 only)", dtype);
+    if (dtype != FLYP_BF16 && dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "dtype %d not supported (bf16 / fp32)", dtype);
     return 0;
 }
 
-int run_sweep(const void* A, const void* B, const void* B_f16, const float* scale, int n_m, int n_n, int dim, const float* wr,
+// One backward sweep: gradient w.r.t. the rows of A.  bf16: A / B are the features, B_f16 the fp16 copy of B.
+// fp32: A_planes / B_planes are the 3-plane bf16 splits, B_f16 the 2-plane fp16 split of B; output is fp32.
+int run_sweep(const void* A, const void* B, const void* B_f16, int dtype, const void* A_planes, const void* B_planes,
+              const float* scale, int n_m, int n_n, int dim, const float* wr,
               const float* lr, const float* wc, const float* lc, const int* labr, const float* dr, const int* labc,
               const float* dc, const float* fa, const float* fb, const float* fast_info, const void* a_rows_for_dscale,
               void* out, int out_fp32, float out_mul, float* dscale_part, float* part_scratch, const uint32_t* gmax_bits,
               cudaStream_t st) {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmBd;
     int rc;
-    if ((rc = make_tmap(&tmA, A, n_m, dim, dim)) != 0) return rc;
-    if ((rc = make_tmap(&tmB, B, n_n, dim, dim)) != 0) return rc;
-    CUtensorMap tmBd;
-    if ((rc = make_tmap(&tmBd, B_f16, n_n, dim, dim, true)) != 0) return rc;
+    const bool f32 = dtype == FLYP_F32;
+    const int dp = plane_cols(dim);
+    flyp::KPlan kplan = flyp::kplan_bf16();
+    if (f32) {
+        if ((rc = make_tmap(&tmA, A_planes, n_m, 3 * dp, 3 * dp)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, B_planes, n_n, 3 * dp, 3 * dp)) != 0) return rc;
+        if ((rc = make_tmap(&tmBd, B_f16, n_n, 2 * dp, 2 * dp, true)) != 0) return rc;
+        kplan = flyp::kplan_f32(dp);
+        if (!out_fp32) return fail(FLYP_ERR_ARG, "fp32 features need fp32 gradients");
+    } else {
+        if ((rc = make_tmap(&tmA, A, n_m, dim, dim)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, B, n_n, dim, dim)) != 0) return rc;
+        if ((rc = make_tmap(&tmBd, B_f16, n_n, dim, dim, true)) != 0) return rc;
+    }
     flyp::BwdParams p;
     memset(&p, 0, sizeof(p));
-    p.n_m = n_m; p.n_n = n_n; p.kc = ceil_div(dim, flyp::KCHUNK);
+    p.n_m = n_m; p.n_n = n_n; p.kc = ceil_div(dim, flyp::KCHUNK); p.kplan = kplan;
+    p.f32_mode = f32 ? 1 : 0; p.bd_plane_cols = dp;
     p.m_tiles = ceil_div(n_m, flyp::TILE); p.n_tiles = ceil_div(n_n, flyp::TILE);
     p.d_out = dim; p.d_parts = ceil_div(dim, 256);
     p.scale = scale; p.wr = wr; p.lr = lr; p.wc = wc; p.lc = lc;
@@ -272,7 +305,7 @@ int run_sweep(const void* A, const void* B, const void* B_f16, const float* scal
     p.dscale_part = dscale_part;
     p.prof = g_prof_buf;
     p.full_items = p.m_tiles; p.split_k = 1; p.part_out = nullptr;
-    if (use_pair_kernel(dim)) {
+    if (use_pair_kernel(dim, dtype)) {
         CUtensorMap tmA64;
         if ((rc = make_tmap(&tmA64, A, n_m, dim, dim, false, 64)) != 0) return rc;
         const char* ns = getenv("FLYP_NO_SPLIT");          // A/B switch for measurements
@@ -311,23 +344,25 @@ struct ClipWs {
     uint16_t *img16, *txt16;  // fp16 staging copies of the features (backward only)
     size_t bytes;
 };
-static void carve_clip(void* base, int n_rows, int n_cols, int dim, ClipWs& w) {
+static void carve_clip(void* base, int n_rows, int n_cols, int dim, int dtype, ClipWs& w) {
     Carver c(base);
-    carve_stats(c, n_rows, n_cols, true, w.stats);
+    carve_stats(c, n_rows, n_cols, dim, dtype, true, w.stats);
     const int rp = ceil_div(n_rows, VEC_PAD) * VEC_PAD, cp = ceil_div(n_cols, VEC_PAD) * VEC_PAD;
     carve_vecs(c, rp, w.rows);
     carve_vecs(c, cp, w.cols);
-    w.n_dscale = sweep_dscale_slots(n_rows, n_cols, dim);
+    w.n_dscale = sweep_dscale_slots(n_rows, n_cols, dim, dtype);
     w.dscale_part = c.take<float>(w.n_dscale);
     {
-        const size_t a = sweep_part_floats(n_rows, n_cols, dim), b = sweep_part_floats(n_cols, n_rows, dim);
+        const size_t a = sweep_part_floats(n_rows, n_cols, dim, dtype), b = sweep_part_floats(n_cols, n_rows, dim, dtype);
         const size_t n = a > b ? a : b;
         w.part_scratch = n ? c.take<float>(n) : nullptr;
     }
     w.gmax_bits = c.take<uint32_t>(4);
     w.fast_info = c.take<float>(2);
-    w.img16 = c.take<uint16_t>((size_t)n_rows * dim);
-    w.txt16 = c.take<uint16_t>((size_t)n_cols * dim);
+    // fp16 staging copy (bf16 features) or two fp16 planes (fp32 features)
+    const size_t w16 = dtype == FLYP_F32 ? (size_t)2 * plane_cols(dim) : (size_t)dim;
+    w.img16 = c.take<uint16_t>((size_t)n_rows * w16);
+    w.txt16 = c.take<uint16_t>((size_t)n_cols * w16);
     w.bytes = align_up(c.off, 256);
 }
 
@@ -336,7 +371,7 @@ int flyp_clip_workspace_bytes(int n_rows, int n_cols, int dim, int dtype, size_t
     if (rc) return rc;
     if (!bytes) return fail(FLYP_ERR_ARG, "bytes is null");
     ClipWs w;
-    carve_clip(nullptr, n_rows, n_cols, dim, w);
+    carve_clip(nullptr, n_rows, n_cols, dim, dtype, w);
     *bytes = w.bytes;
     return 0;
 }
@@ -351,7 +386,7 @@ int flyp_clip_fwd_local(const void* img, const void* txt, const float* scale, in
     if (row_offset < 0 || row_offset + n_rows > n_cols)
         return fail(FLYP_ERR_ARG, "row_offset %d + n_rows %d exceeds n_cols %d", row_offset, n_rows, n_cols);
     ClipWs w;
-    carve_clip(workspace, n_rows, n_cols, dim, w);
+    carve_clip(workspace, n_rows, n_cols, dim, dtype, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return run_stats(img, txt, scale, n_rows, n_cols, dim, dtype, nullptr, row_offset, w.stats, row_lse, row_nll,
@@ -381,7 +416,7 @@ int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, in
     if (row_offset < 0 || row_offset + n_rows > n_cols)
         return fail(FLYP_ERR_ARG, "row_offset %d + n_rows %d exceeds n_cols %d", row_offset, n_rows, n_cols);
     ClipWs w;
-    carve_clip(workspace, n_rows, n_cols, dim, w);
+    carve_clip(workspace, n_rows, n_cols, dim, dtype, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int rp = ceil_div(n_rows, VEC_PAD) * VEC_PAD, cp = ceil_div(n_cols, VEC_PAD) * VEC_PAD;
@@ -396,12 +431,21 @@ int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, in
     flyp::launch_bwd_fast_vectors(w.gmax_bits, rp, w.rows.w, w.rows.l2, w.rows.f, cp, w.cols.w, w.cols.l2, w.cols.f,
                                   w.fast_info, st);
     CUDA_OK(cudaGetLastError());
-    if (d_img) {
-        flyp::launch_to_f16(txt, dtype, (size_t)n_cols * dim, w.txt16, st);
+    const bool f32 = dtype == FLYP_F32;
+    if (f32 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "fp32 features need grad_dtype = FLYP_F32");
+    const int dp = plane_cols(dim);
+    if (f32) {
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(img), n_rows, dim, dp, w.stats.planes_a, st);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(txt), n_cols, dim, dp, w.stats.planes_b, st);
         CUDA_OK(cudaGetLastError());
-        rc = run_sweep(img, txt, w.txt16, scale, n_rows, n_cols, dim, w.rows.w, w.rows.l2, w.cols.w, w.cols.l2, w.rows.lab,
-                       w.rows.d, nullptr, nullptr, w.rows.f, w.cols.f, w.fast_info, d_scale ? img : nullptr, d_img,
-                       grad_dtype, grad_mul,
+    }
+    if (d_img) {
+        if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(txt), n_cols, dim, dp, w.txt16, st);
+        else flyp::launch_to_f16(txt, dtype, (size_t)n_cols * dim, w.txt16, st);
+        CUDA_OK(cudaGetLastError());
+        rc = run_sweep(img, txt, w.txt16, dtype, w.stats.planes_a, w.stats.planes_b, scale, n_rows, n_cols, dim,
+                       w.rows.w, w.rows.l2, w.cols.w, w.cols.l2, w.rows.lab, w.rows.d, nullptr, nullptr, w.rows.f,
+                       w.cols.f, w.fast_info, d_scale ? img : nullptr, d_img, grad_dtype, grad_mul,
                        d_scale ? w.dscale_part : nullptr, w.part_scratch, w.gmax_bits, st);
         if (rc) return rc;
         if (d_scale) {
@@ -412,11 +456,13 @@ int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, in
         return fail(FLYP_ERR_ARG, "d_scale requires d_img");
     }
     if (d_txt) {
-        flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
+        if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(img), n_rows, dim, dp, w.img16, st);
+        else flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
         CUDA_OK(cudaGetLastError());
-        rc = run_sweep(txt, img, w.img16, scale, n_cols, n_rows, dim, w.cols.w, w.cols.l2, w.rows.w, w.rows.l2, w.cols.lab,
-                       w.cols.d, nullptr, nullptr, w.cols.f, w.rows.f, w.fast_info, nullptr, d_txt, grad_dtype, grad_mul,
-                       nullptr, w.part_scratch, w.gmax_bits, st);
+        rc = run_sweep(txt, img, w.img16, dtype, w.stats.planes_b, w.stats.planes_a, scale, n_cols, n_rows, dim,
+                       w.cols.w, w.cols.l2, w.rows.w, w.rows.l2, w.cols.lab, w.cols.d, nullptr, nullptr, w.cols.f,
+                       w.rows.f, w.fast_info, nullptr, d_txt, grad_dtype, grad_mul, nullptr, w.part_scratch, w.gmax_bits,
+                       st);
         if (rc) return rc;
     }
     return 0;
@@ -434,22 +480,23 @@ struct CeWs {
     uint16_t *a16, *b16;
     size_t bytes;
 };
-static void carve_ce(void* base, int n, int n_classes, int dim, CeWs& w) {
+static void carve_ce(void* base, int n, int n_classes, int dim, int dtype, CeWs& w) {
     Carver c(base);
-    carve_stats(c, n, n_classes, false, w.stats);
+    carve_stats(c, n, n_classes, dim, dtype, false, w.stats);
     const int np = ceil_div(n, VEC_PAD) * VEC_PAD;
     carve_vecs(c, np, w.v);
-    w.n_dscale = sweep_dscale_slots(n, n_classes, dim);
+    w.n_dscale = sweep_dscale_slots(n, n_classes, dim, dtype);
     w.dscale_part = c.take<float>(w.n_dscale);
     {
-        const size_t a = sweep_part_floats(n, n_classes, dim), b = sweep_part_floats(n_classes, n, dim);
+        const size_t a = sweep_part_floats(n, n_classes, dim, dtype), b = sweep_part_floats(n_classes, n, dim, dtype);
         const size_t nn = a > b ? a : b;
         w.part_scratch = nn ? c.take<float>(nn) : nullptr;
     }
     w.gmax_bits = c.take<uint32_t>(4);
     w.fast_info = c.take<float>(2);
-    w.a16 = c.take<uint16_t>((size_t)n * dim);
-    w.b16 = c.take<uint16_t>((size_t)n_classes * dim);
+    const size_t w16 = dtype == FLYP_F32 ? (size_t)2 * plane_cols(dim) : (size_t)dim;
+    w.a16 = c.take<uint16_t>((size_t)n * w16);
+    w.b16 = c.take<uint16_t>((size_t)n_classes * w16);
     w.bytes = align_up(c.off, 256);
 }
 
@@ -458,7 +505,7 @@ int flyp_ce_workspace_bytes(int n, int n_classes, int dim, int dtype, size_t* by
     if (rc) return rc;
     if (!bytes) return fail(FLYP_ERR_ARG, "bytes is null");
     CeWs w;
-    carve_ce(nullptr, n, n_classes, dim, w);
+    carve_ce(nullptr, n, n_classes, dim, dtype, w);
     *bytes = w.bytes;
     return 0;
 }
@@ -470,7 +517,7 @@ int flyp_ce_fwd(const void* a, const void* b, const float* scale, int n, int n_c
     if (rc) return rc;
     if (!a || !b || !scale || !loss || !lse || !workspace) return fail(FLYP_ERR_ARG, "null pointer argument");
     CeWs w;
-    carve_ce(workspace, n, n_classes, dim, w);
+    carve_ce(workspace, n, n_classes, dim, dtype, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     return run_stats(a, b, scale, n, n_classes, dim, dtype, labels, label_offset, w.stats, lse, loss, nullptr,
                      nullptr, nullptr, static_cast<cudaStream_t>(stream));
@@ -485,7 +532,7 @@ int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_c
     if (!a || !b || !scale || !lse || !loss || !g || !workspace) return fail(FLYP_ERR_ARG, "null pointer argument");
     if (grad_dtype != FLYP_BF16 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad grad_dtype %d", grad_dtype);
     CeWs w;
-    carve_ce(workspace, n, n_classes, dim, w);
+    carve_ce(workspace, n, n_classes, dim, dtype, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int np = ceil_div(n, VEC_PAD) * VEC_PAD;
@@ -496,12 +543,22 @@ int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_c
                           w.v.l2, w.v.lab, w.v.d, w.gmax_bits, st);
     flyp::launch_bwd_fast_vectors(w.gmax_bits, np, w.v.w, w.v.l2, w.v.f, 0, nullptr, nullptr, nullptr, w.fast_info, st);
     CUDA_OK(cudaGetLastError());
-    if (d_a) {
-        flyp::launch_to_f16(b, dtype, (size_t)n_classes * dim, w.b16, st);
+    const bool f32 = dtype == FLYP_F32;
+    if (f32 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "fp32 features need grad_dtype = FLYP_F32");
+    const int dp = plane_cols(dim);
+    if (f32) {
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(a), n, dim, dp, w.stats.planes_a, st);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(b), n_classes, dim, dp, w.stats.planes_b, st);
         CUDA_OK(cudaGetLastError());
-        rc = run_sweep(a, b, w.b16, scale, n, n_classes, dim, w.v.w, w.v.l2, nullptr, nullptr, w.v.lab, w.v.d, nullptr,
-                       nullptr, w.v.f, nullptr, w.fast_info, d_scale ? a : nullptr, d_a, grad_dtype, 1.0f,
-                       d_scale ? w.dscale_part : nullptr, w.part_scratch, w.gmax_bits, st);
+    }
+    if (d_a) {
+        if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(b), n_classes, dim, dp, w.b16, st);
+        else flyp::launch_to_f16(b, dtype, (size_t)n_classes * dim, w.b16, st);
+        CUDA_OK(cudaGetLastError());
+        rc = run_sweep(a, b, w.b16, dtype, w.stats.planes_a, w.stats.planes_b, scale, n, n_classes, dim, w.v.w, w.v.l2,
+                       nullptr, nullptr, w.v.lab, w.v.d, nullptr, nullptr, w.v.f, nullptr, w.fast_info,
+                       d_scale ? a : nullptr, d_a, grad_dtype, 1.0f, d_scale ? w.dscale_part : nullptr, w.part_scratch,
+                       w.gmax_bits, st);
         if (rc) return rc;
         if (d_scale) {
             flyp::launch_sum_parts(w.dscale_part, (int)w.n_dscale, d_scale, st);
@@ -512,11 +569,12 @@ int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_c
     }
     if (d_b) {
         // rows = classes, columns = samples: only the column (sample) softmax term exists
-        flyp::launch_to_f16(a, dtype, (size_t)n * dim, w.a16, st);
+        if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(a), n, dim, dp, w.a16, st);
+        else flyp::launch_to_f16(a, dtype, (size_t)n * dim, w.a16, st);
         CUDA_OK(cudaGetLastError());
-        rc = run_sweep(b, a, w.a16, scale, n_classes, n, dim, nullptr, nullptr, w.v.w, w.v.l2, nullptr, nullptr, w.v.lab,
-                       w.v.d, nullptr, w.v.f, w.fast_info, nullptr, d_b, grad_dtype, 1.0f, nullptr, w.part_scratch, w.gmax_bits,
-                       st);
+        rc = run_sweep(b, a, w.a16, dtype, w.stats.planes_b, w.stats.planes_a, scale, n_classes, n, dim, nullptr,
+                       nullptr, w.v.w, w.v.l2, nullptr, nullptr, w.v.lab, w.v.d, nullptr, w.v.f, w.fast_info, nullptr,
+                       d_b, grad_dtype, 1.0f, nullptr, w.part_scratch, w.gmax_bits, st);
         if (rc) return rc;
     }
     return 0;
@@ -554,7 +612,7 @@ int flyp_debug_logits(const void* a, const void* b, int n_m, int n_n, int dim, i
     if (rc) return rc;
     if (!a || !b || !out || !workspace) return fail(FLYP_ERR_ARG, "null pointer argument");
     ClipWs w;
-    carve_clip(workspace, n_m, n_n, dim, w);
+    carve_clip(workspace, n_m, n_n, dim, dtype, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     // scale is irrelevant for raw dot products but the kernel reads it: park a 1.0f in the (unused) d(scale) scratch
     float* one = w.dscale_part;

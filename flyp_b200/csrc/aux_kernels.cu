@@ -2,6 +2,7 @@
 #include "aux_kernels.cuh"
 #include "clip_kernels.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace flyp {
 
@@ -383,6 +384,41 @@ void launch_to_f16(const void* src, int dtype, size_t n_elems, void* dst, cudaSt
     const unsigned grid = (unsigned)((n8 + 255) / 256);
     if (dtype == 1) k_to_f16<true><<<grid, 256, 0, st>>>(src, n8, dst);
     else k_to_f16<false><<<grid, 256, 0, st>>>(src, n8, dst);
+}
+
+// ------------------------------------------------------------------------------------------------ fp32 -> planes
+// x (fp32 [n][dim]) -> NP planes of 16-bit floats side by side: out[n][NP * dp], plane p at columns [p*dp, p*dp+dim),
+// x = x_1 + x_2 (+ x_3) with x_1 = round(x), x_2 = round(x - x_1), ...  Columns [dim, dp) of every plane are zero.
+template <int NP, bool BF16>
+__global__ void k_split_planes(const float* __restrict__ x, int n, int dim, int dp, uint16_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per 8 columns of dp
+    const int cols8 = dp / 8;
+    if (i >= (size_t)n * cols8) return;
+    const int row = (int)(i / cols8), c0 = (int)(i - (size_t)row * cols8) * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (c0 + e < dim) ? x[(size_t)row * dim + c0 + e] : 0.f;
+#pragma unroll
+    for (int pl = 0; pl < NP; ++pl) {
+        uint4 u;
+        uint16_t* h = reinterpret_cast<uint16_t*>(&u);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float r;
+            if (BF16) { const __nv_bfloat16 b = __float2bfloat16_rn(v[e]); h[e] = *reinterpret_cast<const uint16_t*>(&b); r = __bfloat162float(b); }
+            else { const __half b = __float2half_rn(v[e]); h[e] = *reinterpret_cast<const uint16_t*>(&b); r = __half2float(b); }
+            v[e] -= r;
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)row * NP * dp + (size_t)pl * dp + c0) = u;
+    }
+}
+void launch_split_planes_bf16x3(const float* x, int n, int dim, int dp, void* out, cudaStream_t st) {
+    const size_t t = (size_t)n * (dp / 8);
+    if (t) k_split_planes<3, true><<<(unsigned)((t + 255) / 256), 256, 0, st>>>(x, n, dim, dp, static_cast<uint16_t*>(out));
+}
+void launch_split_planes_f16x2(const float* x, int n, int dim, int dp, void* out, cudaStream_t st) {
+    const size_t t = (size_t)n * (dp / 8);
+    if (t) k_split_planes<2, false><<<(unsigned)((t + 255) / 256), 256, 0, st>>>(x, n, dim, dp, static_cast<uint16_t*>(out));
 }
 
 // ------------------------------------------------------------------------------------------------ L2 normalise

@@ -46,6 +46,10 @@ void launch_reduce_parts(const float* part, int n_blocks, int split_k, int first
 // dst (fp16, n_elems) = saturating round-to-nearest of src (bf16 or fp32); n_elems % 8 == 0
 void launch_to_f16(const void* src, int dtype, size_t n_elems, void* dst, cudaStream_t st);
 
+// fp32 [n][dim] -> three bf16 planes / two fp16 planes side by side ([n][NP * dp], dp = dim rounded up to 64, zero pad)
+void launch_split_planes_bf16x3(const float* x, int n, int dim, int dp, void* out, cudaStream_t st);
+void launch_split_planes_f16x2(const float* x, int n, int dim, int dp, void* out, cudaStream_t st);
+
 void launch_l2norm_fwd(const void* x, int n, int dim, int dtype, void* y, float* inv_norm, cudaStream_t st);
 void launch_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n, int dim, int dtype, void* dx,
                        cudaStream_t st);

@@ -3,6 +3,7 @@
 #pragma once
 #include "clip_kernels.cuh"
 #include "sm100.cuh"
+#include <cuda_fp16.h>
 
 namespace flyp {
 
@@ -119,6 +120,16 @@ __device__ __forceinline__ void ds_tile(const uint32_t (&r0)[32], const uint32_t
 __device__ __forceinline__ void pack_ds(const float (&v)[64], uint32_t (&pk)[32]) {
 #pragma unroll
     for (int k = 0; k < 32; ++k) pk[k] = sm100::pack_f16x2(v[2 * k], v[2 * k + 1]);
+}
+// v -= float(fp16(v)) given the packed fp16 pairs of v
+__device__ __forceinline__ void residual_ds(float (&v)[64], const uint32_t (&pk)[32]) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const __half2 hh = *reinterpret_cast<const __half2*>(&pk[k]);
+        const float2 f = __half22float2(hh);
+        v[2 * k] -= f.x;
+        v[2 * k + 1] -= f.y;
+    }
 }
 // store this thread's 64 staged values as one 128-byte row segment of a K-major SWIZZLE_128B chunk
 __device__ __forceinline__ void store_ds_row(uint8_t* chunk_row, int rloc, const uint32_t (&pk)[32]) {

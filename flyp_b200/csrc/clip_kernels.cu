@@ -98,13 +98,17 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                         tma_load_2d(smem_u32(stat_b + c * CHUNK_BYTES), &tmB, BFULL, c * KCHUNK, nb * TILE);
                 }
                 for (int mt = mt0; mt < mt1; ++mt) {
-                    for (int c = 0; c < p.kc; ++c) {
-                        mbar_wait(EMPTY(stage), phase ^ 1);
-                        mbar_expect_tx(FULL(stage), Cfg::STAGE_BYTES);
-                        uint8_t* dst = ring + stage * Cfg::STAGE_BYTES;
-                        tma_load_2d(smem_u32(dst), &tmA, FULL(stage), c * KCHUNK, mt * TILE);
-                        if (!STAT) tma_load_2d(smem_u32(dst + CHUNK_BYTES), &tmB, FULL(stage), c * KCHUNK, nb * TILE);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    for (int term = 0; term < p.kplan.n_terms; ++term) {
+                        const int ca = p.kplan.pa[term] * p.kplan.plane_cols, cb = p.kplan.pb[term] * p.kplan.plane_cols;
+                        for (int c = 0; c < p.kc; ++c) {
+                            mbar_wait(EMPTY(stage), phase ^ 1);
+                            mbar_expect_tx(FULL(stage), Cfg::STAGE_BYTES);
+                            uint8_t* dst = ring + stage * Cfg::STAGE_BYTES;
+                            tma_load_2d(smem_u32(dst), &tmA, FULL(stage), ca + c * KCHUNK, mt * TILE);
+                            if (!STAT)
+                                tma_load_2d(smem_u32(dst + CHUNK_BYTES), &tmB, FULL(stage), cb + c * KCHUNK, nb * TILE);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
                     }
                 }
             }
@@ -123,7 +127,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     mbar_wait(TEMPTY(as), aphase ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + as * TILE;
-                    for (int c = 0; c < p.kc; ++c) {
+                    const int kc_total = p.kc * p.kplan.n_terms;
+                    for (int c = 0; c < kc_total; ++c) {
                         mbar_wait(FULL(stage), phase);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(ring + stage * Cfg::STAGE_BYTES);
@@ -265,7 +270,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
 void launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, bool robust, const int* gate,
                 int num_sms, cudaStream_t st) {
-    const bool stat = p.kc <= FwdCfg<true>::KC_MAX;
+    const bool stat = p.kplan.n_terms == 1 && p.kc <= FwdCfg<true>::KC_MAX;
     const int n_items = p.n_tiles * p.m_split;
     const int grid = n_items < num_sms ? n_items : num_sms;
     const size_t smem = fwd_smem_bytes(stat);
@@ -286,8 +291,9 @@ struct BwdCfg {
     static constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;   // A chunk + B chunk of the S contraction
     static constexpr int STAGES = 4;
     static constexpr int TB_BYTES = 4 * CHUNK_BYTES;      // B operand of the dA MMA: [128 n][256 d] as 4 MN-major boxes
-    static constexpr int DS_BYTES = 2 * CHUNK_BYTES;      // dS tile [128 m][128 n] bf16, K-major SW128
+    static constexpr int DS_BYTES = 2 * CHUNK_BYTES;      // dS tile [128 m][128 n] fp16, K-major SW128 (one plane)
     static constexpr int RED_BYTES = 64;
+    // bf16 features: 4 ring stages + 1 dS plane; fp32 features (f32_mode): 3 ring stages + 2 dS planes (hi, lo)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TB_BYTES + DS_BYTES + RED_BYTES + 256 + 1024;
     static constexpr int DPART = 256;
 };
@@ -301,10 +307,13 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
+    const bool f32m = p.f32_mode != 0;
+    const int nstages = f32m ? STAGES - 1 : STAGES;       // one ring stage is traded for the second dS plane
+    const int npass = f32m ? 3 : 1;                        // dA = dS_hi.B_hi + dS_hi.B_lo + dS_lo.B_hi
     uint8_t* ring = smem;
-    uint8_t* tb = ring + STAGES * Cfg::STAGE_BYTES;
+    uint8_t* tb = ring + nstages * Cfg::STAGE_BYTES;
     uint8_t* ds = tb + Cfg::TB_BYTES;
-    float* red = reinterpret_cast<float*>(ds + Cfg::DS_BYTES);
+    float* red = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::TB_BYTES + Cfg::DS_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red) + Cfg::RED_BYTES);
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -339,23 +348,30 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (elect_one()) {
-            int stage = 0; uint32_t phase = 0; uint32_t g = 0;  // g: running tile counter (TB buffer phase)
+            int stage = 0; uint32_t phase = 0; uint32_t g = 0;  // g: running TB-load counter (TB buffer phase)
             auto load_s = [&](int mb, int n) {
-                for (int c = 0; c < p.kc; ++c) {
-                    mbar_wait(EMPTY(stage), phase ^ 1);
-                    mbar_expect_tx(FULL(stage), Cfg::STAGE_BYTES);
-                    uint8_t* dst = ring + stage * Cfg::STAGE_BYTES;
-                    tma_load_2d(smem_u32(dst), &tmA, FULL(stage), c * KCHUNK, mb * TILE);
-                    tma_load_2d(smem_u32(dst + CHUNK_BYTES), &tmB, FULL(stage), c * KCHUNK, n * TILE);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                for (int term = 0; term < p.kplan.n_terms; ++term) {
+                    const int ca = p.kplan.pa[term] * p.kplan.plane_cols, cb = p.kplan.pb[term] * p.kplan.plane_cols;
+                    for (int c = 0; c < p.kc; ++c) {
+                        mbar_wait(EMPTY(stage), phase ^ 1);
+                        mbar_expect_tx(FULL(stage), Cfg::STAGE_BYTES);
+                        uint8_t* dst = ring + stage * Cfg::STAGE_BYTES;
+                        tma_load_2d(smem_u32(dst), &tmA, FULL(stage), ca + c * KCHUNK, mb * TILE);
+                        tma_load_2d(smem_u32(dst + CHUNK_BYTES), &tmB, FULL(stage), cb + c * KCHUNK, n * TILE);
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    }
                 }
             };
             auto load_tb = [&](int dp, int n) {
-                mbar_wait(TBEMPTY, (g & 1) ^ 1);
-                mbar_expect_tx(TBFULL, Cfg::TB_BYTES);
-                for (int j = 0; j < 4; ++j)
-                    tma_load_2d(smem_u32(tb + j * CHUNK_BYTES), &tmBd, TBFULL, dp * Cfg::DPART + j * KCHUNK, n * TILE);
-                ++g;
+                for (int pass = 0; pass < npass; ++pass) {
+                    const int pcol = (pass == 1) ? p.bd_plane_cols : 0;      // feature plane: hi, lo, hi
+                    mbar_wait(TBEMPTY, (g & 1) ^ 1);
+                    mbar_expect_tx(TBFULL, Cfg::TB_BYTES);
+                    for (int j = 0; j < 4; ++j)
+                        tma_load_2d(smem_u32(tb + j * CHUNK_BYTES), &tmBd, TBFULL,
+                                    pcol + dp * Cfg::DPART + j * KCHUNK, n * TILE);
+                    ++g;
+                }
             };
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int mb = item / p.d_parts, dp = item % p.d_parts;
@@ -371,13 +387,14 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             constexpr uint32_t IDESC_S = umma_idesc_bf16(TILE, TILE, 0, 0);
             // A = dS staged as scaled fp16, B = fp16 copy of the features (MN-major): a_format = b_format = 0 (F16)
             constexpr uint32_t IDESC_D = umma_idesc_bf16(TILE, Cfg::DPART, 0, 1) & ~((7u << 7) | (7u << 10));
-            int stage = 0; uint32_t phase = 0; uint32_t gs = 0, gd = 0, it = 0;
+            int stage = 0; uint32_t phase = 0; uint32_t gs = 0, gd = 0, gtb = 0, it = 0;
+            const int kc_total = p.kc * p.kplan.n_terms;
             auto mma_s = [&]() {
                 const int sb = gs & 1;
                 mbar_wait(SEMPTY(sb), ((gs >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = TM_S + sb * TILE;
-                for (int c = 0; c < p.kc; ++c) {
+                for (int c = 0; c < kc_total; ++c) {
                     mbar_wait(FULL(stage), phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(ring + stage * Cfg::STAGE_BYTES);
@@ -387,7 +404,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                         umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
                                   umma_desc_sw128(b_addr + k * 32, 16, 1024), IDESC_S, (c | k) != 0);
                     umma_commit(EMPTY(stage));
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(SFULL(sb));
                 ++gs;
@@ -395,18 +412,22 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             auto mma_d = [&](bool first) {
                 if (first) { mbar_wait(ACCEMPTY, (it & 1) ^ 1); }
                 mbar_wait(DSFULL, gd & 1);
-                mbar_wait(TBFULL, gd & 1);
-                tc_fence_after();
-                const uint32_t ds_addr = smem_u32(ds), tb_addr = smem_u32(tb);
+                const uint32_t tb_addr = smem_u32(tb);
+                for (int pass = 0; pass < npass; ++pass) {
+                    mbar_wait(TBFULL, gtb & 1);
+                    tc_fence_after();
+                    const uint32_t ds_addr = smem_u32(ds) + (pass == 2 ? Cfg::DS_BYTES : 0);   // dS plane: hi, hi, lo
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    // A: dS rows m, K = n (K-major, two 64-wide chunks). B: [K = n rows][N = d], MN-major boxes.
-                    const uint64_t ad = umma_desc_sw128(ds_addr + (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32, 16, 1024);
-                    const uint64_t bd = umma_desc_sw128(tb_addr + kk * 16 * 128, CHUNK_BYTES, 1024);
-                    umma_bf16(TM_ACC, ad, bd, IDESC_D, (!first) || (kk != 0));
+                    for (int kk = 0; kk < 8; ++kk) {
+                        // A: dS rows m, K = n (K-major, two 64-wide chunks). B: [K = n rows][N = d], MN-major boxes.
+                        const uint64_t ad = umma_desc_sw128(ds_addr + (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32, 16, 1024);
+                        const uint64_t bd = umma_desc_sw128(tb_addr + kk * 16 * 128, CHUNK_BYTES, 1024);
+                        umma_bf16(TM_ACC, ad, bd, IDESC_D, (!first) || (pass | kk) != 0);
+                    }
+                    umma_commit(TBEMPTY);
+                    ++gtb;
                 }
                 umma_commit(DSEMPTY);
-                umma_commit(TBEMPTY);
                 ++gd;
             };
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -455,6 +476,12 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 // dS buffer is free once the dA MMA of the previous tile has completed
                 mbar_wait(DSEMPTY, (gs & 1) ^ 1);
                 store_ds_row(ds + h * CHUNK_BYTES + rloc * 128, rloc, pk);
+                if (f32m) {
+                    // second plane: what the fp16 rounding of the first one lost
+                    residual_ds(v, pk);
+                    pack_ds(v, pk);
+                    store_ds_row(ds + Cfg::DS_BYTES + h * CHUNK_BYTES + rloc * 128, rloc, pk);
+                }
                 fence_proxy_async_smem();
                 mbar_arrive(DSFULL);
             }

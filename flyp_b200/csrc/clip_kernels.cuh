@@ -21,10 +21,28 @@ __host__ __device__ inline float fixed_shift(float c1, float slack) {
     return c0;
 }
 
+// K-plane schedule of the S contraction.  bf16 features: one term, plane 0.  fp32 features are held as three bf16
+// planes x = x1 + x2 + x3 side by side ([n][3 * plane_cols]) and S = sum over the six (p, q) products with p + q <= 4,
+// i.e. fp32-accurate logits from bf16 tensor-core products (fp32 accumulation).
+struct KPlan {
+    int n_terms;       // 1 or 6
+    int plane_cols;    // column offset between planes (multiple of 64)
+    int pa[6], pb[6];  // plane of the M-side / N-side operand used by term i
+};
+inline KPlan kplan_bf16() { KPlan k{}; k.n_terms = 1; k.plane_cols = 0; return k; }
+inline KPlan kplan_f32(int plane_cols) {
+    KPlan k{};
+    k.n_terms = 6; k.plane_cols = plane_cols;
+    const int a[6] = {0, 0, 1, 0, 1, 2}, b[6] = {0, 1, 0, 2, 1, 0};
+    for (int i = 0; i < 6; ++i) { k.pa[i] = a[i]; k.pb[i] = b[i]; }
+    return k;
+}
+
 // ---- forward: per-row / per-column sum of exp2(c1 * <a_m, b_n> - c0) -------------------------------------------
 struct FwdParams {
     int n_m, n_n;            // valid rows of the M-side / N-side operand
-    int kc;                  // number of 64-wide K chunks (ceil(K / 64))
+    int kc;                  // number of 64-wide K chunks per plane (ceil(D / 64))
+    KPlan kplan;             // total chunks of the contraction = kc * kplan.n_terms
     int m_tiles, n_tiles;    // ceil(n / 128)
     int m_split;             // each N block is swept by m_split work items
     int ld_rows;             // leading dimension (floats) of rowpart / rowmax  (>= m_tiles * 128)
@@ -46,7 +64,10 @@ struct FwdParams {
 //  x = c1 * <a_m, b_n>
 struct BwdParams {
     int n_m, n_n;
-    int kc;                  // K chunks of the S contraction
+    int kc;                  // K chunks per plane of the S contraction
+    KPlan kplan;
+    int f32_mode;            // 1: dS staged as two fp16 planes, features as two fp16 planes (fp32-accurate products)
+    int bd_plane_cols;       // column offset between the fp16 planes of the dA operand (f32_mode)
     int m_tiles, n_tiles;
     int d_out;               // number of output columns (= feature dim D)
     int d_parts;             // ceil(d_out / 256)

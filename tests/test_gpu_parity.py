@@ -344,3 +344,52 @@ def test_full_size_properties():
     r2, n2, c2, _ = ops.clip_fwd_local(Ic[perm].contiguous(), Tc[perm].contiguous(), sc)
     _, _, loss_p = ops.clip_fwd_finish(c2, 1, n2, n)
     assert rel(to_np(loss_p), to_np(loss[perm])) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- fp32 features
+# north star: fp32 inputs -> loss within 1e-5 relative, gradients within 1e-4 relative.  fp32 features are evaluated
+# as split bf16 / fp16 planes on the tensor cores (six-term products, fp32 accumulation).
+def check_fp32(I, T, s, g):
+    In, Tn, gn = to_np(I), to_np(T), to_np(g)
+    want = orc.clip_loss(In, Tn, s)
+    wdI, wdT, wds = orc.clip_loss_grads(In, Tn, s, gn)
+    loss, dI, dT, ds = run_module(I, T, s, g)
+    assert loss.dtype == torch.float32 and dI.dtype == torch.float32
+    assert rel(to_np(loss), want) < 1e-5, "loss"
+    assert rel(to_np(dI), wdI) < 1e-4, "d image_features"
+    assert rel(to_np(dT), wdT) < 1e-4, "d text_features"
+    assert abs(ds.item() - wds) <= 1e-4 * abs(wds), "d logit_scale"
+
+
+@pytest.mark.parametrize("name", ["clip_w1_n24_d16_f64.npz", "clip_w1_n37_d64_s100_f64.npz",
+                                  "clip_w1_n130_d72_f64.npz", "clip_w1_n24_d16_f32.npz"])
+def test_fp32_golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    I = torch.tensor(z["I"]).float(); T = torch.tensor(z["T"]).float(); g = torch.tensor(z["g"]).float()
+    check_fp32(I, T, float(z["scale"]), g)
+    # and directly against what the reference itself produced on (essentially) these inputs
+    loss, dI, dT, ds = run_module(I, T, float(z["scale"]), g)
+    assert rel(to_np(loss), z["loss"]) < 2e-5
+    assert rel(to_np(dI), z["dI"]) < 2e-4 and rel(to_np(dT), z["dT"]) < 2e-4
+
+
+@pytest.mark.parametrize("n,d,s", [(512, 512, 1 / 0.07), (300, 768, 100.0), (1024, 512, 1 / 0.07), (37, 520, 1 / 0.07)])
+def test_fp32_shapes(n, d, s):
+    # (at s = 100 the positives are kept weak so that the losses are O(1): a loss of 1e-5 on logits of magnitude 100 is
+    #  below what ANY fp32 evaluation, the reference's included, can resolve to 1e-5 relative)
+    I, T, g = make_inputs(n, d, seed=n + d + 1, mix=0.5 if s < 50 else 0.08, dtype=torch.float32)
+    check_fp32(I, T, s, g)
+
+
+def test_fp32_ce_head(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ce_n150_c182_d64.npz"))
+    s = float(z["scale"])
+    a = torch.tensor(z["imgn"]).float(); b = torch.tensor(z["txtn"]).float()
+    labels = torch.tensor(z["labels"]); g = torch.tensor(z["g"]).float()
+    ac = a.to(DEV).requires_grad_(True); bc = b.to(DEV).requires_grad_(True)
+    sc = torch.tensor(s, device=DEV, requires_grad=True)
+    loss = flyp_b200.contrastive_cross_entropy(ac, bc, sc, labels.to(DEV))
+    (loss * g.to(DEV)).sum().backward()
+    assert rel(to_np(loss), z["loss"]) < 1e-5
+    assert rel(to_np(ac.grad), z["d_imgn"]) < 1e-4 and rel(to_np(bc.grad), z["d_txtn"]) < 1e-4
+    assert abs(sc.grad.item() - float(z["ds"])) < 1e-4 * abs(float(z["ds"]))
