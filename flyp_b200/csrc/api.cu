@@ -149,6 +149,7 @@ struct Carver {
 // ---- workspace of one forward statistics pass over S = A . B^T ([n_m] x [n_n]) ------------------------------------
 struct StatsWs {
     int m_tiles, n_tiles, m_split, ld_rows, ld_cols;
+    bool use_mc;                         // multicast (2-CTA cluster) forward kernel
     float *rowpart, *rowmax, *colpart;   // fast pass + robust row pass
     float *rowpart2, *rowmax2;           // robust column pass (roles swapped): [m_tiles*2][ld_cols]
     float* t2;                           // [ld_rows] positive logit of each row, log2 units
@@ -161,7 +162,12 @@ struct StatsWs {
 void carve_stats(Carver& c, int n_m, int n_n, int dim, int dtype, bool want_cols, StatsWs& w) {
     w.m_tiles = ceil_div(n_m, flyp::TILE);
     w.n_tiles = ceil_div(n_n, flyp::TILE);
-    w.m_split = pick_m_split(w.m_tiles, w.n_tiles, 148);
+    {
+        const char* e = getenv("FLYP_FWD_MC");
+        w.use_mc = dtype == FLYP_BF16 && dim <= 512 && w.n_tiles >= 2 && !(e && e[0] == '0');
+    }
+    const int sms = num_sms();
+    w.m_split = w.use_mc ? pick_m_split(w.m_tiles, (w.n_tiles + 1) / 2, sms / 2) : pick_m_split(w.m_tiles, w.n_tiles, sms);
     w.ld_rows = w.m_tiles * flyp::TILE;
     w.ld_cols = w.n_tiles * flyp::TILE;
     w.rowpart = c.take<float>((size_t)w.n_tiles * 2 * w.ld_rows);
@@ -221,11 +227,17 @@ int run_stats(const void* A, const void* B, const float* scale, int n_m, int n_n
     p.rowpart = w.rowpart; p.colpart = w.colpart; p.rowmax = w.rowmax; p.colmax = nullptr;
     p.dbg_logits = dbg_logits;
     if (dbg_logits == nullptr) {
-        flyp::launch_pair_dot(A, B, dtype, scale, n_m, w.ld_rows, n_n, dim, labels, pos_offset, w.t2, w.pos, st);
+        flyp::launch_pair_dot(A, B, dtype, scale, n_m, w.ld_rows, n_n, dim, labels, pos_offset, w.t2, w.pos, nullptr, st);
         CUDA_OK(cudaGetLastError());
         p.pos = w.pos;
     }
-    flyp::launch_fwd(tmA, tmB, p, /*robust=*/false, nullptr, sms, st);
+    if (w.use_mc && dbg_logits == nullptr) {
+        CUtensorMap tmA64;
+        if ((rc = make_tmap(&tmA64, A, n_m, dim, dim, false, 64)) != 0) return rc;
+        flyp::launch_fwd_mc(tmA64, tmB, p, sms, st);
+    } else {
+        flyp::launch_fwd(tmA, tmB, p, /*robust=*/false, nullptr, sms, st);
+    }
     CUDA_OK(cudaGetLastError());
     if (dbg_logits != nullptr) return 0;
     flyp::launch_fwd_finalize(w.rowpart, w.n_tiles * 2, w.ld_rows, n_m, w.colpart, w.m_split, w.ld_cols, n_n, scale,
@@ -237,7 +249,8 @@ int run_stats(const void* A, const void* B, const float* scale, int n_m, int n_n
     CUDA_OK(cudaGetLastError());
     if (col_stat != nullptr) {
         // roles swapped: rows of S^T are the columns of S; the positive of column j is local row j - pos_offset
-        flyp::launch_pair_dot(B, A, dtype, scale, n_n, w.ld_cols, n_m, dim, nullptr, -pos_offset, w.t2_t, w.pos_t, st);
+        flyp::launch_pair_dot(B, A, dtype, scale, n_n, w.ld_cols, n_m, dim, nullptr, -pos_offset, w.t2_t, w.pos_t, w.flag,
+                              st);
         CUDA_OK(cudaGetLastError());
         flyp::FwdParams pt = p;
         pt.n_m = n_n; pt.n_n = n_m; pt.m_tiles = w.n_tiles; pt.n_tiles = w.m_tiles;

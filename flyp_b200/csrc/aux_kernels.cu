@@ -55,7 +55,8 @@ __device__ __forceinline__ void store8(void* base, size_t elem, const float (&v)
 template <bool F32>
 __global__ void k_pair_dot(const void* __restrict__ A, const void* __restrict__ B, const float* __restrict__ scale,
                            int n, int n_pad, int n_b, int dim, const int64_t* __restrict__ labels, int offset,
-                           float* __restrict__ t2, int* __restrict__ pos) {
+                           float* __restrict__ t2, int* __restrict__ pos, const int* __restrict__ gate) {
+    if (gate != nullptr && *gate == 0) return;      // helper of the robust path: nothing to do
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n_pad) return;
@@ -80,12 +81,14 @@ __global__ void k_pair_dot(const void* __restrict__ A, const void* __restrict__ 
 }
 
 void launch_pair_dot(const void* A, const void* B, int dtype, const float* scale, int n, int n_pad, int n_b, int dim,
-                     const int64_t* labels, int offset, float* t2, int* pos, cudaStream_t st) {
+                     const int64_t* labels, int offset, float* t2, int* pos, const int* gate, cudaStream_t st) {
     if (n_pad <= 0) return;
     const int wpb = 8;
     dim3 grid((n_pad + wpb - 1) / wpb), block(wpb * 32);
-    if (dtype == 1) k_pair_dot<true><<<grid, block, 0, st>>>(A, B, scale, n, n_pad, n_b, dim, labels, offset, t2, pos);
-    else k_pair_dot<false><<<grid, block, 0, st>>>(A, B, scale, n, n_pad, n_b, dim, labels, offset, t2, pos);
+    if (dtype == 1)
+        k_pair_dot<true><<<grid, block, 0, st>>>(A, B, scale, n, n_pad, n_b, dim, labels, offset, t2, pos, gate);
+    else
+        k_pair_dot<false><<<grid, block, 0, st>>>(A, B, scale, n, n_pad, n_b, dim, labels, offset, t2, pos, gate);
 }
 
 // log2-domain logaddexp of a (off-positive mass) and t (positive logit): returns lse2 and nll = ln2 * (lse2 - t)
@@ -106,21 +109,34 @@ __device__ __forceinline__ void lse_with_positive(float a, float t, float& lse2,
 // ------------------------------------------------------------------------------------------------ finalize (fast)
 // col_stat layout: [3][n_n] = (m_j log2 reference, sum_j of exp2(x - m_j) over the local rows EXCLUDING positives,
 //                              t_j log2 positive logit of column j if its row is local else -inf)
+// Block = 8 warps x 32 lanes: lane = row / column within a group of 32, the warps split the partials 8 ways
+// (coalesced 128-byte reads, 8x more loads in flight than one thread per row), then one smem reduction.
 __global__ void k_fwd_finalize(const float* __restrict__ rowpart, int n_rowparts, int ld_rows, int n_m,
                                const float* __restrict__ colpart, int n_colparts, int ld_cols, int n_n,
                                const float* __restrict__ scale, float slack, const float* __restrict__ t2,
                                const int* __restrict__ pos, int col_pos_offset, float* __restrict__ row_lse,
                                float* __restrict__ row_nll, float* __restrict__ col_stat, int* __restrict__ flag) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float sm_r[8][32], sm_c[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
     const float c1 = scale[0] * LOG2E_F;
     const float c0 = fixed_shift(c1, slack);
     // A sum is trustworthy when the mass lost to flush-to-zero (< n * 2^-126 in shifted units) is below fp32
     // resolution of either the sum itself or of the (exactly known) positive term it is added to.
     const float lg_r = log2f((float)n_n), lg_c = log2f((float)n_m);
+    float pr = 0.f, pc = 0.f;
+    if (i < n_m)
+        for (int p = w; p < n_rowparts; p += 8) pr += rowpart[(size_t)p * ld_rows + i];
+    if (i < n_n && col_stat != nullptr)
+        for (int p = w; p < n_colparts; p += 8) pc += colpart[(size_t)p * ld_cols + i];
+    sm_r[w][lane] = pr; sm_c[w][lane] = pc;
+    __syncthreads();
+    if (w != 0) return;
     bool bad = false;
     if (i < n_m) {
         float sum = 0.f;
-        for (int p = 0; p < n_rowparts; ++p) sum += rowpart[(size_t)p * ld_rows + i];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += sm_r[k][lane];
         const float t = t2 ? t2[i] : -INFINITY;
         const float a = sum > 0.f ? log2f(sum) + c0 : -INFINITY;
         float lse2, nll;
@@ -132,7 +148,8 @@ __global__ void k_fwd_finalize(const float* __restrict__ rowpart, int n_rowparts
     }
     if (i < n_n && col_stat != nullptr) {
         float sum = 0.f;
-        for (int p = 0; p < n_colparts; ++p) sum += colpart[(size_t)p * ld_cols + i];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += sm_c[k][lane];
         const int r = i - col_pos_offset;                    // local row whose positive is column i
         const float t = (r >= 0 && r < n_m && t2 && pos[r] == i) ? t2[r] : -INFINITY;
         col_stat[i] = c0;
@@ -149,7 +166,7 @@ void launch_fwd_finalize(const float* rowpart, int n_rowparts, int ld_rows, int 
                          const int* pos, int col_pos_offset, float* row_lse, float* row_nll, float* col_stat,
                          int* flag, cudaStream_t st) {
     const int n = n_m > n_n ? n_m : n_n;
-    k_fwd_finalize<<<(n + 255) / 256, 256, 0, st>>>(rowpart, n_rowparts, ld_rows, n_m, colpart, n_colparts, ld_cols,
+    k_fwd_finalize<<<(n + 31) / 32, 256, 0, st>>>(rowpart, n_rowparts, ld_rows, n_m, colpart, n_colparts, ld_cols,
                                                     n_n, scale, slack, t2, pos, col_pos_offset, row_lse, row_nll,
                                                     col_stat, flag);
 }

@@ -7,9 +7,10 @@
 namespace flyp {
 
 // t2[i] = scale * log2(e) * <A[i,:], B[idx(i),:]>, pos[i] = idx(i) (int32), idx(i) = labels ? labels[i] : offset + i;
-// rows without a valid positive (and padding rows [n, n_pad)) get t2 = -inf, pos = -1.
+// rows without a valid positive (and padding rows [n, n_pad)) get t2 = -inf, pos = -1.  gate (device int, may be null):
+// the kernel returns immediately when *gate == 0.
 void launch_pair_dot(const void* A, const void* B, int dtype, const float* scale, int n, int n_pad, int n_b, int dim,
-                     const int64_t* labels, int offset, float* t2, int* pos, cudaStream_t st);
+                     const int64_t* labels, int offset, float* t2, int* pos, const int* gate, cudaStream_t st);
 
 // Fast-path finalize: rowpart[P][ld_rows] -> row_lse (natural log) and row_nll (= lse - positive logit, computed
 // without cancellation); colpart[MS][ld_cols] -> col_stat[3][n_n].  Sets *flag = 1 when the fixed shift was inadequate.

@@ -43,10 +43,11 @@ size_t fwd_smem_bytes(bool stationary) {
     return stationary ? FwdCfg<true>::SMEM_BYTES : FwdCfg<false>::SMEM_BYTES;
 }
 
-template <bool STAT, bool ROBUST>
-__global__ void __launch_bounds__(NTHREADS, 1)
-fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p,
-           const int* __restrict__ gate) {
+// MC: clusters of two CTAs sweep two adjacent column blocks over the SAME stream of A tiles; each CTA fetches half of
+// every A chunk and multicasts it to both (halves the L2 -> SM traffic, the measured limiter of the 1-CTA kernel).
+template <bool STAT, bool ROBUST, bool MC>
+__device__ __forceinline__ void
+fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, const int* __restrict__ gate) {
     using Cfg = FwdCfg<STAT>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int ACC_STAGES = Cfg::ACC_STAGES;
@@ -68,10 +69,14 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 + 2 * ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = p.n_tiles * p.m_split;
+    const int cta = MC ? (int)cluster_ctarank() : 0;
+    const int worker = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nworkers = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // MC: a work item covers the column blocks (2 * nbp, 2 * nbp + 1); the second may lie beyond n_tiles (all-zero B)
+    const int n_items = (MC ? (p.n_tiles + 1) / 2 : p.n_tiles) * p.m_split;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), MC ? 2 : 1); }
         mbar_init(BFULL, 1); mbar_init(BFREE, 1);
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), EPI_THREADS); }
         fence_mbar_init();
@@ -79,7 +84,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     }
     if (warp == 2) { tmem_alloc(smem_u32(tmem_holder), 512); tmem_relinquish(); }
     tc_fence_before();
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
 
@@ -87,8 +92,8 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         // ------------------------------------------------------------------ TMA producer
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int nb = item / p.m_split, ms = item % p.m_split;
+            for (int item = worker; item < n_items; item += nworkers, ++it) {
+                const int nb = MC ? 2 * (item / p.m_split) + cta : item / p.m_split, ms = item % p.m_split;
                 const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
                 const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
                 if (STAT) {
@@ -104,7 +109,11 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                             mbar_wait(EMPTY(stage), phase ^ 1);
                             mbar_expect_tx(FULL(stage), Cfg::STAGE_BYTES);
                             uint8_t* dst = ring + stage * Cfg::STAGE_BYTES;
-                            tma_load_2d(smem_u32(dst), &tmA, FULL(stage), ca + c * KCHUNK, mt * TILE);
+                            if (MC)   // tmA has 64-row boxes: this CTA's half of the tile, delivered to both CTAs
+                                tma_load_2d_mc(smem_u32(dst + cta * (CHUNK_BYTES / 2)), &tmA, FULL(stage),
+                                               ca + c * KCHUNK, mt * TILE + cta * 64, (uint16_t)3);
+                            else
+                                tma_load_2d(smem_u32(dst), &tmA, FULL(stage), ca + c * KCHUNK, mt * TILE);
                             if (!STAT)
                                 tma_load_2d(smem_u32(dst + CHUNK_BYTES), &tmB, FULL(stage), cb + c * KCHUNK, nb * TILE);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -118,7 +127,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (elect_one()) {
             constexpr uint32_t IDESC = umma_idesc_bf16(TILE, TILE, 0, 0);
             int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0; uint32_t it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            for (int item = worker; item < n_items; item += nworkers, ++it) {
                 const int ms = item % p.m_split;
                 const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
                 const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
@@ -138,7 +147,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                             umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
                                       umma_desc_sw128(b_addr + k * 32, 16, 1024), IDESC, (c | k) != 0);
                         }
-                        umma_commit(EMPTY(stage));
+                        if (MC) umma_commit_mc(EMPTY(stage), (uint16_t)3); else umma_commit(EMPTY(stage));
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(TFULL(as));
@@ -155,8 +164,9 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const float c1 = s * LOG2E;
         const float c0 = fixed_shift(c1, p.shift_slack);
         int as = 0; uint32_t aphase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int nb = item / p.m_split, ms = item % p.m_split;
+        for (int item = worker; item < n_items; item += nworkers) {
+            const int nb = MC ? 2 * (item / p.m_split) + cta : item / p.m_split, ms = item % p.m_split;
+            const bool nb_live = nb < p.n_tiles;           // MC: the odd block of the last pair may not exist
             const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
             const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
             const int col0 = nb * TILE + h * 64;
@@ -234,8 +244,10 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 tc_fence_before();
                 mbar_arrive(TEMPTY(as));
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
-                p.rowpart[(size_t)(nb * 2 + h) * p.ld_rows + row] = rs;
-                if (ROBUST) p.rowmax[(size_t)(nb * 2 + h) * p.ld_rows + row] = rmax;
+                if (nb_live) {
+                    p.rowpart[(size_t)(nb * 2 + h) * p.ld_rows + row] = rs;
+                    if (ROBUST) p.rowmax[(size_t)(nb * 2 + h) * p.ld_rows + row] = rmax;
+                }
             }
 
             if (!ROBUST) {
@@ -255,7 +267,7 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 red[q * TILE + h * 64 + 2 * lane + 1] = ca[1];
                 epi_bar_sync();
                 const int et = threadIdx.x - 128;
-                if (et < TILE) {
+                if (et < TILE && nb_live) {
                     float v = (red[et] + red[TILE + et]) + (red[2 * TILE + et] + red[3 * TILE + et]);
                     p.colpart[(size_t)ms * p.ld_cols + nb * TILE + et] = v;
                 }
@@ -264,8 +276,30 @@ fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <bool STAT, bool ROBUST>
+__global__ void __launch_bounds__(NTHREADS, 1)
+fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p,
+           const int* __restrict__ gate) {
+    fwd_body<STAT, ROBUST, false>(tmA, tmB, p, gate);
+}
+
+// tmA64: the A operand with [64 rows][64 cols] boxes
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+fwd_kernel_mc(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
+    fwd_body<true, false, true>(tmA64, tmB, p, nullptr);
+}
+
+void launch_fwd_mc(const CUtensorMap& tmA64, const CUtensorMap& tmB, const FwdParams& p, int num_sms, cudaStream_t st) {
+    const int n_items = ((p.n_tiles + 1) / 2) * p.m_split;
+    int workers = num_sms / 2;
+    if (n_items < workers) workers = n_items;
+    const size_t smem = fwd_smem_bytes(true);
+    cudaFuncSetAttribute(fwd_kernel_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fwd_kernel_mc<<<workers * 2, NTHREADS, smem, st>>>(tmA64, tmB, p);
 }
 
 void launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, bool robust, const int* gate,

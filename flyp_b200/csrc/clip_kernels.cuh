@@ -102,6 +102,9 @@ struct BwdParams {
 // immediately when *gate == 0.
 void launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, bool robust, const int* gate,
                 int num_sms, cudaStream_t st);
+// Multicast variant of the fast forward (bf16, D <= 512, no debug logits): tmA64 has [64 rows][64 cols] boxes; the
+// m_split in p must have been chosen for (n_tiles + 1) / 2 column-block pairs on num_sms / 2 clusters.
+void launch_fwd_mc(const CUtensorMap& tmA64, const CUtensorMap& tmB, const FwdParams& p, int num_sms, cudaStream_t st);
 // tmBd: tensor map used for the N-side operand rows as the B operand of the dA MMA (box [64 d][128 n]).
 void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
                 int num_sms, cudaStream_t st);

@@ -214,6 +214,20 @@ DEVI void umma_commit_cg2(uint32_t bar) {
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n"
         ::"r"(bar) : "memory");
 }
+// TMA load multicast to the CTAs in `mask` (same smem offset and same mbarrier offset in every destination CTA)
+DEVI void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+// single-CTA UMMA commit that arrives on the barrier at the same offset in every CTA of `mask`
+DEVI void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(mask) : "memory");
+}
 // generic instruction descriptor for kind::f16: fmt 0 = F16, 1 = BF16
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_fmt, int b_fmt, int a_mn_major, int b_mn_major) {
     return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
