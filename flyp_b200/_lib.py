@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p, POINTER, Structure
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libflypclip.so")
@@ -17,6 +17,27 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 FLYP_BF16 = 0
 FLYP_F32 = 1
+
+IPC_HANDLE_BYTES = 64
+COMM_MAX_WORLD = 16
+
+
+class Ready(Structure):
+    """flyp_ready_t: device flag words that say which ranks' rows have arrived."""
+    _fields_ = [("flags", c_void_p), ("seq", c_uint32), ("n_flags", c_int), ("rows_per_flag", c_int), ("err", c_void_p)]
+
+
+class Gathered(Structure):
+    """flyp_gathered_t"""
+    _fields_ = [("img_all", c_void_p), ("txt_all", c_void_p), ("img16_all", c_void_p), ("txt16_all", c_void_p),
+                ("img_ready", Ready), ("txt_ready", Ready), ("img16_ready", Ready), ("txt16_ready", Ready),
+                ("seq", c_uint32)]
+
+
+class Stats(Structure):
+    """flyp_stats_t"""
+    _fields_ = [("col_stat_all", c_void_p), ("row_lse_all", c_void_p), ("row_nll_all", c_void_p), ("ready", Ready)]
+
 
 # name -> (restype, argtypes); must list every symbol declared in include/flyp_clip.h
 SIGNATURES = {
@@ -30,6 +51,27 @@ SIGNATURES = {
     "flyp_clip_bwd_local": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "flyp_clip_fwd_local_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(Ready), c_void_p]),
+    "flyp_clip_fwd_finish_ex": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                        POINTER(Ready), c_void_p]),
+    "flyp_clip_bwd_local_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, POINTER(Ready),
+                                       POINTER(Ready), c_void_p]),
+    "flyp_comm_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "flyp_comm_segment_bytes": (c_int, [c_void_p, POINTER(c_size_t)]),
+    "flyp_comm_ipc_handle": (c_int, [c_void_p, c_void_p]),
+    "flyp_comm_connect_ipc": (c_int, [c_void_p, c_void_p]),
+    "flyp_comm_connect_local": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "flyp_comm_error": (c_int, [c_void_p]),
+    "flyp_comm_destroy": (c_int, [c_void_p]),
+    "flyp_comm_gather_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(Gathered),
+                                          c_void_p]),
+    "flyp_comm_push_stats": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p, c_void_p, c_int, c_int, POINTER(Stats),
+                                     c_void_p]),
+    "flyp_comm_push_scalar": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p]),
+    "flyp_comm_sum_scalar": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p]),
     "flyp_ce_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "flyp_ce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                             c_void_p, c_void_p, c_size_t, c_void_p]),

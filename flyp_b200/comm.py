@@ -1,0 +1,219 @@
+"""Peer-memory exchange between the GPUs of one node - the host side of ``flyp_comm_*`` (include/flyp_clip.h).
+
+For the row-sharded loss this replaces the collectives of the reference's ``gather_features`` (clip/loss.py:19-69) and
+the statistics exchange: every rank owns an exchange segment that all peers map (CUDA IPC); features are pushed with the
+copy engines in ring order while the forward kernel already works on the local column block, and the tensor-core
+kernels poll per-rank flag words before they touch a peer's rows.  ``torch.distributed`` is used only once, to hand the
+64-byte IPC handles around.
+"""
+from __future__ import annotations
+
+import ctypes
+import socket
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import FlypError, Gathered, Ready, Stats
+
+
+class PeerComm:
+    """One rank's communicator: segment sized for blocks of up to ``max_rows x dim`` bf16 features."""
+
+    def __init__(self, rank: int, world: int, max_rows: int, dim: int, device: torch.device):
+        self.rank, self.world, self.max_rows, self.dim, self.device = rank, world, max_rows, dim, device
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().flyp_comm_create(rank, world, max_rows, dim, ctypes.byref(self._h)))
+        self.seq = 0                      # sequence number of the latest gather
+
+    # ---- wiring -----------------------------------------------------------------------------------------------
+    def ipc_handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        _lib.check(_lib.load().flyp_comm_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def connect_ipc(self, handles) -> None:
+        blob = b"".join(handles)
+        if len(blob) != self.world * _lib.IPC_HANDLE_BYTES:
+            raise FlypError("expected one IPC handle per rank")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().flyp_comm_connect_ipc(self._h, blob))
+
+    @staticmethod
+    def connect_local(comms) -> None:
+        """Wire communicators that live in this process (tests: several emulated ranks on one GPU)."""
+        arr = (ctypes.c_void_p * len(comms))(*[c._h for c in comms])
+        for c in comms:
+            _lib.check(_lib.load().flyp_comm_connect_local(c._h, arr))
+
+    @classmethod
+    def from_process_group(cls, rank: int, world: int, max_rows: int, dim: int, device: torch.device,
+                           group=None) -> Optional["PeerComm"]:
+        """Create + connect over ``torch.distributed``.  Returns None (on every rank alike) when the ranks do not all
+        sit on one node or a segment could not be created / mapped; the caller then uses the NCCL path."""
+        import torch.distributed as dist
+        comm, handle, err = None, b"", ""
+        try:
+            comm = cls(rank, world, max_rows, dim, device)
+            handle = comm.ipc_handle()
+        except Exception as e:  # noqa: BLE001 - any failure means "no peer path on this rank"
+            err = str(e)
+        infos = [None] * world
+        dist.all_gather_object(infos, (socket.gethostname(), handle, err), group=group)
+        ok = all(i[1] and not i[2] for i in infos) and len({i[0] for i in infos}) == 1
+        if ok:
+            try:
+                comm.connect_ipc([i[1] for i in infos])
+            except Exception as e:  # noqa: BLE001
+                err = str(e)
+        flags = [None] * world
+        dist.all_gather_object(flags, ok and not err, group=group)
+        if not all(flags):
+            if comm is not None:
+                comm.close()
+            return None
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)          # every segment is zeroed and mapped before anyone pushes
+        return comm
+
+    def close(self) -> None:
+        if self._h:
+            _lib.load().flyp_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- steps ------------------------------------------------------------------------------------------------
+    def check_error(self) -> None:
+        e = _lib.load().flyp_comm_error(self._h)
+        if e:
+            raise FlypError(f"a kernel timed out waiting for the rows of rank {e - 1} (peer-memory exchange)")
+
+    def alive(self, seq: int) -> bool:
+        """The buffers of gather ``seq`` stay intact until gather ``seq + 2`` is issued (double buffering)."""
+        return self.seq < seq + 2
+
+    def gather(self, img: torch.Tensor, txt: torch.Tensor) -> Gathered:
+        n, d = img.shape
+        out = Gathered()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().flyp_comm_gather_features(self._h, img.data_ptr(), txt.data_ptr(), n, d,
+                                                             _lib.dtype_code(img), ctypes.byref(out),
+                                                             _lib.stream_ptr(self.device)))
+        self.seq = int(out.seq)
+        return out
+
+    def push_stats(self, seq: int, col_stat: torch.Tensor, row_lse: torch.Tensor, row_nll: torch.Tensor) -> Stats:
+        out = Stats()
+        n_rows = row_lse.numel()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().flyp_comm_push_stats(self._h, seq, col_stat.data_ptr(), row_lse.data_ptr(),
+                                                        row_nll.data_ptr(), n_rows, col_stat.numel() // 3,
+                                                        ctypes.byref(out), _lib.stream_ptr(self.device)))
+        return out
+
+    def all_reduce_scalar(self, seq: int, value: torch.Tensor, out: torch.Tensor) -> None:
+        self.push_scalar(seq, value)
+        self.sum_scalar(seq, out)
+
+    def push_scalar(self, seq: int, value: torch.Tensor) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().flyp_comm_push_scalar(self._h, seq, value.data_ptr(), _lib.stream_ptr(self.device)))
+
+    def sum_scalar(self, seq: int, out: torch.Tensor) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().flyp_comm_sum_scalar(self._h, seq, out.data_ptr(), _lib.stream_ptr(self.device)))
+
+
+# ---------------------------------------------------------------------------------------------------- loss phases
+# The row-sharded symmetric loss over a communicator, split into the phases between which ranks exchange data; the
+# autograd function in loss.py runs them back to back, the single-GPU emulation test runs each phase for all ranks.
+
+class PeerStep:
+    """State of one forward (kept for the backward)."""
+    __slots__ = ("comm", "g", "st", "img", "txt", "s", "b", "B", "D", "off", "row_lse", "row_nll", "col_stat", "status",
+                 "col_lse", "col_nll", "loss", "ws")
+
+
+def fwd_gather(comm: PeerComm, img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor) -> PeerStep:
+    from . import ops
+    ops._check_features(img, txt)
+    if img.dtype != torch.bfloat16:
+        raise FlypError("the peer-memory path carries bf16 features")
+    st = PeerStep()
+    st.comm, st.img, st.txt, st.s = comm, img.contiguous(), txt.contiguous(), scale
+    st.b, st.D = img.shape
+    st.B, st.off = st.b * comm.world, comm.rank * st.b
+    st.g = comm.gather(st.img, st.txt)
+    return st
+
+
+def fwd_local(st: PeerStep) -> None:
+    from . import ops
+    dev = st.img.device
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        st.ws = ops.clip_workspace(st.b, st.B, st.D, _lib.FLYP_BF16, dev)
+        st.row_lse, st.row_nll, st.col_stat = ops._f32(st.b, dev), ops._f32(st.b, dev), ops._f32(3 * st.B, dev)
+        st.status = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.flyp_clip_fwd_local_ex(
+            st.img.data_ptr(), st.g.txt_all, st.s.data_ptr(), st.b, st.B, st.D, _lib.FLYP_BF16, st.off,
+            st.row_lse.data_ptr(), st.row_nll.data_ptr(), st.col_stat.data_ptr(), st.status.data_ptr(),
+            st.ws.data_ptr(), st.ws.numel(), ctypes.byref(st.g.txt_ready), _lib.stream_ptr(dev)))
+    st.st = st.comm.push_stats(st.g.seq, st.col_stat, st.row_lse, st.row_nll)
+
+
+def fwd_finish(st: PeerStep) -> torch.Tensor:
+    """Loss of every global row (the reference returns the full vector on every rank, clip/loss.py:113-114,208)."""
+    from . import ops
+    dev = st.img.device
+    with torch.cuda.device(dev):
+        st.col_lse, st.col_nll, st.loss = ops._f32(st.B, dev), ops._f32(st.B, dev), ops._f32(st.B, dev)
+        _lib.check(_lib.load().flyp_clip_fwd_finish_ex(
+            st.st.col_stat_all, st.comm.world, st.st.row_nll_all, st.B, st.B, 0, st.col_lse.data_ptr(),
+            st.col_nll.data_ptr(), st.loss.data_ptr(), ctypes.byref(st.st.ready), _lib.stream_ptr(dev)))
+    return st.loss
+
+
+def bwd_local(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_img: bool, need_txt: bool,
+              need_scale: bool):
+    """Returns (d_img, d_txt, d_scale_partial): complete gradients of the local rows, this rank's share of d(scale)."""
+    from . import ops
+    if not st.comm.alive(st.g.seq):
+        raise FlypError("the gathered features of this step were overwritten: with the peer-memory path at most one "
+                        "later forward may run before a step's backward (use ClipLoss(comm='nccl') otherwise)")
+    dev = st.img.device
+    lib = _lib.load()
+    gdt = st.img.dtype if grad_dtype is None else grad_dtype
+    gcode = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[gdt]
+    g = g.to(torch.float32).contiguous()
+    f4 = 4
+    d_img = d_txt = d_s = None
+    with torch.cuda.device(dev):
+        stream = _lib.stream_ptr(dev)
+        if need_img or need_scale:
+            d_img = torch.empty(st.b, st.D, dtype=gdt, device=dev)
+            d_s = ops._f32(1, dev) if need_scale else None
+            _lib.check(lib.flyp_clip_bwd_local_ex(
+                st.img.data_ptr(), st.g.txt_all, st.s.data_ptr(), st.b, st.B, st.D, _lib.FLYP_BF16, st.off,
+                st.row_lse.data_ptr(), st.row_nll.data_ptr(), st.col_lse.data_ptr(), st.col_nll.data_ptr(),
+                g.data_ptr() + st.off * f4, g.data_ptr(), float(grad_mul), gcode, d_img.data_ptr(), None, _lib.ptr(d_s),
+                st.ws.data_ptr(), st.ws.numel(), st.g.txt16_all, ctypes.byref(st.g.txt_ready),
+                ctypes.byref(st.g.txt16_ready), stream))
+        if need_txt:
+            # the transposed problem: text rows of this rank against all images
+            d_txt = torch.empty(st.b, st.D, dtype=gdt, device=dev)
+            _lib.check(lib.flyp_clip_bwd_local_ex(
+                st.txt.data_ptr(), st.g.img_all, st.s.data_ptr(), st.b, st.B, st.D, _lib.FLYP_BF16, st.off,
+                st.col_lse.data_ptr() + st.off * f4, st.col_nll.data_ptr() + st.off * f4, st.st.row_lse_all,
+                st.st.row_nll_all, g.data_ptr() + st.off * f4, g.data_ptr(), float(grad_mul), gcode, d_txt.data_ptr(),
+                None, None, st.ws.data_ptr(), st.ws.numel(), st.g.img16_all, ctypes.byref(st.g.img_ready),
+                ctypes.byref(st.g.img16_ready), stream))
+    # keep g alive until the kernels that read it through raw pointers are enqueued (they are, by now)
+    return d_img, d_txt, d_s

@@ -23,6 +23,16 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+flyp::PeerWait to_wait(const flyp_ready_t* r) {
+    flyp::PeerWait w;
+    memset(&w, 0, sizeof(w));
+    if (r != nullptr && r->flags != nullptr) {
+        w.flags = r->flags; w.seq = r->seq; w.n_flags = r->n_flags; w.rows_per_flag = r->rows_per_flag > 0 ? r->rows_per_flag : 1;
+        w.err = r->err;
+    }
+    return w;
+}
+
 #define CUDA_OK(expr)                                                                                   \
     do {                                                                                                \
         cudaError_t e__ = (expr);                                                                       \
@@ -198,7 +208,7 @@ void carve_stats(Carver& c, int n_m, int n_n, int dim, int dtype, bool want_cols
 //   exactly, so a loss much smaller than the logits keeps full relative accuracy.
 int run_stats(const void* A, const void* B, const float* scale, int n_m, int n_n, int dim, int dtype,
               const int64_t* labels, int pos_offset, const StatsWs& w, float* row_lse, float* row_nll,
-              float* col_stat, int* status, float* dbg_logits, cudaStream_t st) {
+              float* col_stat, int* status, float* dbg_logits, cudaStream_t st, const flyp_ready_t* b_ready = nullptr) {
     CUtensorMap tmA, tmB;
     int rc;
     flyp::KPlan kplan = flyp::kplan_bf16();
@@ -231,12 +241,19 @@ int run_stats(const void* A, const void* B, const float* scale, int n_m, int n_n
         CUDA_OK(cudaGetLastError());
         p.pos = w.pos;
     }
-    if (w.use_mc && dbg_logits == nullptr) {
-        CUtensorMap tmA64;
-        if ((rc = make_tmap(&tmA64, A, n_m, dim, dim, false, 64)) != 0) return rc;
-        flyp::launch_fwd_mc(tmA64, tmB, p, sms, st);
-    } else {
-        flyp::launch_fwd(tmA, tmB, p, /*robust=*/false, nullptr, sms, st);
+    {
+        // multi-GPU: rows of B owned by other ranks are still arriving; start at this rank's own column block
+        flyp::FwdParams pf = p;
+        const bool mc = w.use_mc && dbg_logits == nullptr;
+        pf.wait_b = to_wait(b_ready);
+        if (pf.wait_b.flags != nullptr) pf.nb_rot = mc ? pos_offset / (2 * flyp::TILE) : pos_offset / flyp::TILE;
+        if (mc) {
+            CUtensorMap tmA64;
+            if ((rc = make_tmap(&tmA64, A, n_m, dim, dim, false, 64)) != 0) return rc;
+            flyp::launch_fwd_mc(tmA64, tmB, pf, sms, st);
+        } else {
+            flyp::launch_fwd(tmA, tmB, pf, /*robust=*/false, nullptr, sms, st);
+        }
     }
     CUDA_OK(cudaGetLastError());
     if (dbg_logits != nullptr) return 0;
@@ -287,7 +304,7 @@ int run_sweep(const void* A, const void* B, const void* B_f16, int dtype, const 
               const float* lr, const float* wc, const float* lc, const int* labr, const float* dr, const int* labc,
               const float* dc, const float* fa, const float* fb, const float* fast_info, const void* a_rows_for_dscale,
               void* out, int out_fp32, float out_mul, float* dscale_part, float* part_scratch, const uint32_t* gmax_bits,
-              cudaStream_t st) {
+              cudaStream_t st, const flyp_ready_t* b_ready = nullptr, const flyp_ready_t* b16_ready = nullptr) {
     CUtensorMap tmA, tmB, tmBd;
     int rc;
     const bool f32 = dtype == FLYP_F32;
@@ -316,7 +333,9 @@ int run_sweep(const void* A, const void* B, const void* B_f16, int dtype, const 
     p.a_rows = a_rows_for_dscale; p.lda = dim;
     p.out = out; p.ld_out = dim; p.out_fp32 = out_fp32; p.out_mul = out_mul; p.gmax_bits = gmax_bits;
     p.dscale_part = dscale_part;
+    p.wait_b = to_wait(b_ready); p.wait_bd = to_wait(b16_ready);
     p.prof = g_prof_buf;
+    { const char* e = getenv("FLYP_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.full_items = p.m_tiles; p.split_k = 1; p.part_out = nullptr;
     if (use_pair_kernel(dim, dtype)) {
         CUtensorMap tmA64;
@@ -339,6 +358,17 @@ int run_sweep(const void* A, const void* B, const void* B_f16, int dtype, const 
 }
 
 }  // namespace
+
+namespace flyp {
+// used by comm.cu: same thread-local message buffer as the rest of the C ABI
+void set_error(int code, const char* fmt, ...) {
+    (void)code;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace flyp
 
 extern "C" {
 
@@ -392,6 +422,13 @@ int flyp_clip_workspace_bytes(int n_rows, int n_cols, int dim, int dtype, size_t
 int flyp_clip_fwd_local(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
                         int dtype, int row_offset, float* row_lse, float* row_nll, float* col_stat, int* status,
                         void* workspace, size_t workspace_bytes, void* stream) {
+    return flyp_clip_fwd_local_ex(img, txt, scale, n_rows, n_cols, dim, dtype, row_offset, row_lse, row_nll, col_stat,
+                                  status, workspace, workspace_bytes, nullptr, stream);
+}
+
+int flyp_clip_fwd_local_ex(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
+                           int dtype, int row_offset, float* row_lse, float* row_nll, float* col_stat, int* status,
+                           void* workspace, size_t workspace_bytes, const flyp_ready_t* txt_ready, void* stream) {
     int rc = check_common(n_rows, n_cols, dim, dtype);
     if (rc) return rc;
     if (!img || !txt || !scale || !row_lse || !row_nll || !col_stat || !workspace)
@@ -403,15 +440,22 @@ int flyp_clip_fwd_local(const void* img, const void* txt, const float* scale, in
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return run_stats(img, txt, scale, n_rows, n_cols, dim, dtype, nullptr, row_offset, w.stats, row_lse, row_nll,
-                     col_stat, status, nullptr, st);
+                     col_stat, status, nullptr, st, txt_ready);
 }
 
 int flyp_clip_fwd_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
                          int row_offset, float* col_lse, float* col_nll, float* loss, void* stream) {
+    return flyp_clip_fwd_finish_ex(col_stat_all, world, row_nll, n_rows, n_cols, row_offset, col_lse, col_nll, loss,
+                                   nullptr, stream);
+}
+
+int flyp_clip_fwd_finish_ex(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
+                            int row_offset, float* col_lse, float* col_nll, float* loss,
+                            const flyp_ready_t* stats_ready, void* stream) {
     if (!col_stat_all || !row_nll || !col_lse || !col_nll || !loss) return fail(FLYP_ERR_ARG, "null pointer argument");
     if (world < 1 || n_rows <= 0 || n_cols <= 0) return fail(FLYP_ERR_ARG, "bad sizes");
     flyp::launch_clip_finish(col_stat_all, world, row_nll, n_rows, n_cols, row_offset, col_lse, col_nll, loss,
-                             static_cast<cudaStream_t>(stream));
+                             to_wait(stats_ready), static_cast<cudaStream_t>(stream));
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -421,6 +465,17 @@ int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, in
                         const float* col_nll, const float* g_row, const float* g_col, float grad_mul, int grad_dtype,
                         void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
                         void* stream) {
+    return flyp_clip_bwd_local_ex(img, txt, scale, n_rows, n_cols, dim, dtype, row_offset, row_lse, row_nll, col_lse,
+                                  col_nll, g_row, g_col, grad_mul, grad_dtype, d_img, d_txt, d_scale, workspace,
+                                  workspace_bytes, nullptr, nullptr, nullptr, stream);
+}
+
+int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
+                           int dtype, int row_offset, const float* row_lse, const float* row_nll, const float* col_lse,
+                           const float* col_nll, const float* g_row, const float* g_col, float grad_mul, int grad_dtype,
+                           void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
+                           const void* txt16, const flyp_ready_t* txt_ready, const flyp_ready_t* txt16_ready,
+                           void* stream) {
     int rc = check_common(n_rows, n_cols, dim, dtype);
     if (rc) return rc;
     if (!img || !txt || !scale || !row_lse || !row_nll || !col_lse || !col_nll || !g_row || !g_col || !workspace)
@@ -452,14 +507,19 @@ int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, in
         flyp::launch_split_planes_bf16x3(static_cast<const float*>(txt), n_cols, dim, dp, w.stats.planes_b, st);
         CUDA_OK(cudaGetLastError());
     }
+    if (txt16 != nullptr && f32) return fail(FLYP_ERR_ARG, "a precomputed fp16 copy is only accepted for bf16 features");
     if (d_img) {
-        if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(txt), n_cols, dim, dp, w.txt16, st);
-        else flyp::launch_to_f16(txt, dtype, (size_t)n_cols * dim, w.txt16, st);
-        CUDA_OK(cudaGetLastError());
-        rc = run_sweep(img, txt, w.txt16, dtype, w.stats.planes_a, w.stats.planes_b, scale, n_rows, n_cols, dim,
+        const void* t16 = txt16;
+        if (t16 == nullptr) {
+            if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(txt), n_cols, dim, dp, w.txt16, st);
+            else flyp::launch_to_f16(txt, dtype, (size_t)n_cols * dim, w.txt16, st);
+            CUDA_OK(cudaGetLastError());
+            t16 = w.txt16;
+        }
+        rc = run_sweep(img, txt, t16, dtype, w.stats.planes_a, w.stats.planes_b, scale, n_rows, n_cols, dim,
                        w.rows.w, w.rows.l2, w.cols.w, w.cols.l2, w.rows.lab, w.rows.d, nullptr, nullptr, w.rows.f,
                        w.cols.f, w.fast_info, d_scale ? img : nullptr, d_img, grad_dtype, grad_mul,
-                       d_scale ? w.dscale_part : nullptr, w.part_scratch, w.gmax_bits, st);
+                       d_scale ? w.dscale_part : nullptr, w.part_scratch, w.gmax_bits, st, txt_ready, txt16_ready);
         if (rc) return rc;
         if (d_scale) {
             flyp::launch_sum_parts(w.dscale_part, (int)w.n_dscale, d_scale, st);

@@ -224,21 +224,27 @@ void launch_fwd_finalize_robust(const float* rowpart, const float* rowmax, int n
 
 // ------------------------------------------------------------------------------------------------ clip finish
 // col_stat_all[world][3 * n_cols] -> col_lse[n_cols]; loss[i] = 0.5 * (row_nll[i] + col_nll[row_offset + i])
-__global__ void k_clip_finish(const float* __restrict__ col_stat_all, int world, const float* __restrict__ row_nll,
-                              int n_rows, int n_cols, int row_offset, float* __restrict__ col_lse,
-                              float* __restrict__ col_nll, float* __restrict__ loss) {
+__global__ void k_clip_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
+                              int row_offset, float* __restrict__ col_lse, float* __restrict__ col_nll,
+                              float* __restrict__ loss, PeerWait wait) {
+    // multi-GPU: the triples / row statistics of the other ranks are pushed into this rank's memory over NVLink; poll
+    // their flags first, then read through L2 (__ldcg: no stale non-coherent lines)
+    if (wait.flags != nullptr) {
+        if (threadIdx.x == 0) peer_wait_all(wait);
+        __syncthreads();
+    }
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_cols) return;
     const size_t ldw = (size_t)3 * n_cols;
     float m = -INFINITY, t = -INFINITY;
     for (int w = 0; w < world; ++w) {
-        if (col_stat_all[w * ldw + n_cols + j] > 0.f) m = fmaxf(m, col_stat_all[w * ldw + j]);
-        t = fmaxf(t, col_stat_all[w * ldw + 2 * n_cols + j]);
+        if (__ldcg(col_stat_all + w * ldw + n_cols + j) > 0.f) m = fmaxf(m, __ldcg(col_stat_all + w * ldw + j));
+        t = fmaxf(t, __ldcg(col_stat_all + w * ldw + 2 * n_cols + j));
     }
     float s = 0.f;
     for (int w = 0; w < world; ++w) {
-        const float sw = col_stat_all[w * ldw + n_cols + j];
-        if (sw > 0.f) s += sw * exp2f(col_stat_all[w * ldw + j] - m);
+        const float sw = __ldcg(col_stat_all + w * ldw + n_cols + j);
+        if (sw > 0.f) s += sw * exp2f(__ldcg(col_stat_all + w * ldw + j) - m);
     }
     const float a = s > 0.f ? log2f(s) + m : -INFINITY;
     float lse2, nll;
@@ -246,13 +252,13 @@ __global__ void k_clip_finish(const float* __restrict__ col_stat_all, int world,
     col_lse[j] = lse2 * LN2_F;
     col_nll[j] = nll;
     const int i = j - row_offset;
-    if (i >= 0 && i < n_rows) loss[i] = 0.5f * (row_nll[i] + nll);
+    if (i >= 0 && i < n_rows) loss[i] = 0.5f * (__ldcg(row_nll + i) + nll);
 }
 
 void launch_clip_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
-                        int row_offset, float* col_lse, float* col_nll, float* loss, cudaStream_t st) {
+                        int row_offset, float* col_lse, float* col_nll, float* loss, PeerWait wait, cudaStream_t st) {
     k_clip_finish<<<(n_cols + 255) / 256, 256, 0, st>>>(col_stat_all, world, row_nll, n_rows, n_cols, row_offset,
-                                                        col_lse, col_nll, loss);
+                                                        col_lse, col_nll, loss, wait);
 }
 
 // ------------------------------------------------------------------------------------------------ bwd vectors

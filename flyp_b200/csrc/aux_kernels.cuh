@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "peer.cuh"
 
 namespace flyp {
 
@@ -24,8 +25,9 @@ void launch_fwd_finalize_robust(const float* rowpart, const float* rowmax, int n
                                 const float* t2, float* row_lse, float* row_nll, float* col_stat, const int* flag,
                                 cudaStream_t st);
 // col_stat_all[world][3*n_cols] -> col_lse; loss[i] = 0.5 (row_nll[i] + col_nll[off+i])
+// wait: readiness of col_stat_all / row_nll when other ranks push them (peer.cuh); flags == nullptr -> no waiting
 void launch_clip_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
-                        int row_offset, float* col_lse, float* col_nll, float* loss, cudaStream_t st);
+                        int row_offset, float* col_lse, float* col_nll, float* loss, PeerWait wait, cudaStream_t st);
 
 // Vectors consumed by bwd_kernel, padded with zeros / -1 to a multiple of 128 entries.
 //   w[i] = wmul * g[i]; l2[i] = lse[i] * log2(e); lab[i] = labels ? labels[i] : (i + lab_offset if in [0, lab_range) else -1)

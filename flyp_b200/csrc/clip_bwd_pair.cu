@@ -136,6 +136,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 if (prof) { const long long t0 = clock64(); mbar_wait(EMPTY(slot), ph ^ 1); w_empty += clock64() - t0; }
                 else mbar_wait(EMPTY(slot), ph ^ 1);
                 if (cta == 0) mbar_expect_tx(FULL(slot), 2 * Cfg::SLOT);
+                if (p.dbg & 1) { c0 = 0; c1 = 0; }
                 tma_load_2d_cg2(smem_u32(ring + slot * Cfg::SLOT), tm, mapa(FULL(slot), 0), c0, c1);
                 if (++slot == NSLOT) { slot = 0; ph ^= 1; }
             };
@@ -148,6 +149,8 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                         for (int dsub = 0; dsub < 2; ++dsub)
                             put(&tmBd, (dblk * 2 + (int)cta) * 128 + dsub * 64, t * Cfg::NSTEP + jh * 128);
             };
+            peer_wait_all(p.wait_b);      // multi-GPU: the N-side rows (and their fp16 copy) of every rank have arrived
+            peer_wait_all(p.wait_bd);
             for (int item = pair; item < n_items; item += npairs, ++it) {
                 const ItemInfo ii = item_info(item, p, NJ);
                 mbar_wait(IFREE, (it & 1) ^ 1);

@@ -43,6 +43,16 @@ size_t fwd_smem_bytes(bool stationary) {
     return stationary ? FwdCfg<true>::SMEM_BYTES : FwdCfg<false>::SMEM_BYTES;
 }
 
+// Column block of a work item.  The schedule starts at block / block pair p.nb_rot and wraps around (multi-GPU: own rows
+// first, then the other ranks' rows in the order in which they arrive).
+template <bool MC>
+__device__ __forceinline__ int fwd_block(const FwdParams& p, int item, int cta) {
+    const int units = MC ? (p.n_tiles + 1) / 2 : p.n_tiles;
+    int u = item / p.m_split + p.nb_rot;
+    if (u >= units) u -= units;
+    return MC ? 2 * u + cta : u;
+}
+
 // MC: clusters of two CTAs sweep two adjacent column blocks over the SAME stream of A tiles; each CTA fetches half of
 // every A chunk and multicasts it to both (halves the L2 -> SM traffic, the measured limiter of the 1-CTA kernel).
 template <bool STAT, bool ROBUST, bool MC>
@@ -93,9 +103,10 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
             for (int item = worker; item < n_items; item += nworkers, ++it) {
-                const int nb = MC ? 2 * (item / p.m_split) + cta : item / p.m_split, ms = item % p.m_split;
+                const int nb = fwd_block<MC>(p, item, cta), ms = item % p.m_split;
                 const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
                 const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
+                peer_wait_rows(p.wait_b, nb * TILE, min((nb + 1) * TILE, p.n_n));
                 if (STAT) {
                     mbar_wait(BFREE, (it & 1) ^ 1);
                     mbar_expect_tx(BFULL, p.kc * CHUNK_BYTES);
@@ -165,7 +176,7 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
         const float c0 = fixed_shift(c1, p.shift_slack);
         int as = 0; uint32_t aphase = 0;
         for (int item = worker; item < n_items; item += nworkers) {
-            const int nb = MC ? 2 * (item / p.m_split) + cta : item / p.m_split, ms = item % p.m_split;
+            const int nb = fwd_block<MC>(p, item, cta), ms = item % p.m_split;
             const bool nb_live = nb < p.n_tiles;           // MC: the odd block of the last pair may not exist
             const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
             const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
@@ -407,6 +418,8 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     ++g;
                 }
             };
+            peer_wait_all(p.wait_b);      // multi-GPU: the N-side rows (and their fp16 copy) of every rank have arrived
+            peer_wait_all(p.wait_bd);
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int mb = item / p.d_parts, dp = item % p.d_parts;
                 // same order as the MMA issuer consumes: S(0), S(1), dA(0), S(2), dA(1), ...

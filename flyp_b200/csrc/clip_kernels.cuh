@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include "peer.cuh"
 
 namespace flyp {
 
@@ -56,6 +57,11 @@ struct FwdParams {
     float* rowmax;           // robust mode only: running log2-domain max paired with rowpart
     float* colmax;           // robust mode only
     float* dbg_logits;       // optional [n_m][n_n] fp32 raw dot products (debug / argmax path), may be null
+    // row-sharded multi-GPU: the N-side rows of other ranks arrive over NVLink while the kernel runs.  Column blocks are
+    // visited starting at block nb_rot (this rank's own rows) so that work proceeds in arrival order, and the producer
+    // polls wait_b before the first TMA read of a block.
+    int nb_rot;              // first column block (MC kernel: first column-block pair) of the static schedule
+    PeerWait wait_b;
 };
 
 // ---- backward sweep: dA[m, :] = s * sum_n dS[m, n] * B[n, :]  with dS recomputed from the S tile ------------------
@@ -94,6 +100,8 @@ struct BwdParams {
     // split_k work items over disjoint column ranges that write fp32 partials to part_out[idx][128][d_out]
     int full_items, split_k;
     float* part_out;
+    PeerWait wait_b, wait_bd; // readiness of the N-side operand rows (tmB) / of their fp16 copy (tmBd), see peer.cuh
+    int dbg;                 // debug experiments (FLYP_DBG env): bit 0 = every streamed load reads box (0, 0)
     unsigned long long* prof; // optional debug: per-role wait-cycle counters of cluster 0 (see tools/pair_prof.py)
     float* dscale_part;      // [m_tiles * max(d_parts, 2)] partial sums of <acc, a> (unscaled), may be null
 };

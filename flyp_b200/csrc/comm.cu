@@ -1,0 +1,453 @@
+// comm.cu — peer-memory exchange between the GPUs of one node (NVLink 5 / NVSwitch), C ABI flyp_comm_*.
+//
+// Replaces, for the row-sharded loss, the collectives of the reference: the two feature all-gathers of
+// clip/loss.py:19-69 (gather_features) and - because no rank ever holds the B x B logits here - the exchange of the
+// per-column softmax statistics, of the per-row statistics and of the d(logit_scale) partial sums.
+//
+// Every rank owns one exchange segment (cudaMalloc, exported with cudaIpcGetMemHandle and mapped by all peers).  The
+// segment holds, double-buffered by step parity, the GATHERED matrices of this rank: text / image features in bf16 and
+// their fp16 copies (the operand format of the backward's second GEMM), [world * rows, dim] rank-major - the ordering of
+// clip/loss.py:66-67.  A step is
+//   pack   (kernel, caller's stream)  local rows -> own slots of the four gathered matrices (+ fp16 conversion)
+//   push   (copy engines, side stream) own slots -> the same slots in every peer's segment, peer (rank - k) in round k
+//                                     so that every rank receives from one peer at a time at full link rate; after
+//                                     each block a 4-byte sequence number lands in the peer's flag word
+//   the tensor-core kernels poll those flag words (peer.cuh) right before their first TMA read of a rank's rows: the
+//   forward starts on its own column block while the other blocks are still in flight.
+// The small vectors (column triples, row statistics, d(scale)) are pushed by a kernel with remote stores and flagged
+// the same way.  No NCCL call is on this path.
+#include "../../include/flyp_clip.h"
+#include "aux_kernels.cuh"
+#include "peer.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+
+namespace flyp {
+void set_error(int code, const char* fmt, ...);   // api.cu: thread-local message returned by flyp_last_error()
+}
+
+namespace {
+
+constexpr int MAXW = 16;
+enum { ARR_TXT = 0, ARR_TXT16 = 1, ARR_IMG = 2, ARR_IMG16 = 3, N_ARR = 4 };
+enum { FLAG_STAT = N_ARR, FLAG_DS = N_ARR + 1, N_FLAGSETS = N_ARR + 2 };
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+#define COMM_CUDA_OK(expr)                                                                       \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            flyp::set_error(FLYP_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__));            \
+            return FLYP_ERR_CUDA;                                                                \
+        }                                                                                        \
+    } while (0)
+
+struct SegPtrs { uint8_t* seg[MAXW]; };
+
+}  // namespace
+
+struct flyp_comm {
+    int rank, world, dev, max_rows, dim;
+    size_t seg_bytes;
+    uint8_t* seg[MAXW];
+    bool ipc_mapped[MAXW];
+    bool connected;
+    cudaStream_t side;
+    cudaEvent_t ev_packed, ev_pushed;
+    cudaGraphExec_t push_exec[2];
+    int push_rows, push_dim;
+    bool use_graph;
+    uint32_t seq;
+    uint32_t* err_host;
+    uint32_t* err_dev;
+    // byte offsets inside a segment (identical on every rank)
+    size_t off_feat[2][N_ARR], off_colstat[2], off_rowstat[2], off_dscale[2], off_flags, off_seqword[2], off_counter;
+};
+
+namespace {
+
+void layout(flyp_comm* c) {
+    const size_t cap = (size_t)c->world * c->max_rows;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { off = align_up(off, 1024); const size_t r = off; off += bytes; return r; };
+    for (int par = 0; par < 2; ++par) {
+        for (int a = 0; a < N_ARR; ++a) c->off_feat[par][a] = take(cap * c->dim * 2);
+        c->off_colstat[par] = take((size_t)c->world * 3 * cap * sizeof(float));
+        c->off_rowstat[par] = take(2 * cap * sizeof(float));
+        c->off_dscale[par] = take(MAXW * sizeof(float));
+    }
+    c->off_flags = take((size_t)N_FLAGSETS * MAXW * sizeof(uint32_t));
+    c->off_seqword[0] = take(sizeof(uint32_t));
+    c->off_seqword[1] = take(sizeof(uint32_t));
+    c->off_counter = take(sizeof(uint32_t));
+    c->seg_bytes = align_up(off, 1 << 20);
+}
+
+inline uint32_t* flag_ptr(const flyp_comm* c, int q, int set, int k) {
+    return reinterpret_cast<uint32_t*>(c->seg[q] + c->off_flags) + set * MAXW + k;
+}
+
+// ---- pack: local bf16 rows -> own slots (bf16 copy + fp16 conversion), sequence word, own flags ---------------------
+__global__ void k_pack(const uint4* __restrict__ img, const uint4* __restrict__ txt, size_t n8, uint4* __restrict__ img_bf,
+                       uint4* __restrict__ img_h, uint4* __restrict__ txt_bf, uint4* __restrict__ txt_h,
+                       uint32_t* seqword, uint32_t* own_flags, int rank, uint32_t seq) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        *seqword = seq;
+        for (int a = 0; a < N_ARR; ++a) own_flags[a * MAXW + rank] = seq;
+    }
+    if (i >= n8) return;
+    auto conv = [](uint4 v) {
+        uint4 u;
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+        uint32_t* d = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float lo = __uint_as_float(s[e] << 16), hi = __uint_as_float(s[e] & 0xffff0000u);
+            uint32_t r;
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+            d[e] = r;
+        }
+        return u;
+    };
+    const uint4 a = img[i], b = txt[i];
+    img_bf[i] = a; txt_bf[i] = b;
+    img_h[i] = conv(a); txt_h[i] = conv(b);
+}
+
+// ---- statistics push: this rank's column triples and row statistics -> every rank's segment, then the flag ----------
+__global__ void k_push_stats(SegPtrs ptrs, int world, int rank, size_t off_colstat, size_t off_rowstat, size_t off_flags,
+                             size_t off_counter, const float* __restrict__ col_stat, const float* __restrict__ row_lse,
+                             const float* __restrict__ row_nll, int n_rows, int n_cols, size_t cap, uint32_t seq) {
+    const int q = blockIdx.y;
+    float* cs = reinterpret_cast<float*>(ptrs.seg[q] + off_colstat) + (size_t)rank * 3 * n_cols;
+    float* rl = reinterpret_cast<float*>(ptrs.seg[q] + off_rowstat) + (size_t)rank * n_rows;
+    float* rn = rl + cap;
+    const int n_cs = 3 * n_cols;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cs; i += gridDim.x * blockDim.x) cs[i] = col_stat[i];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
+        rl[i] = row_lse[i];
+        rn[i] = row_nll[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t* counter = reinterpret_cast<uint32_t*>(ptrs.seg[rank] + off_counter);
+        const uint32_t total = gridDim.x * gridDim.y;
+        if (atomicInc(counter, total - 1) == total - 1) {      // last block: everything above is visible system-wide
+            __threadfence_system();
+            for (int p = 0; p < world; ++p)
+                flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(ptrs.seg[p] + off_flags) + FLAG_STAT * MAXW + rank, seq);
+        }
+    }
+}
+
+__global__ void k_push_scalar(SegPtrs ptrs, int world, int rank, size_t off_dscale, size_t off_flags,
+                              const float* __restrict__ value, uint32_t seq) {
+    const int q = threadIdx.x;
+    if (q < world) {
+        reinterpret_cast<float*>(ptrs.seg[q] + off_dscale)[rank] = value[0];
+        __threadfence_system();
+        flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(ptrs.seg[q] + off_flags) + FLAG_DS * MAXW + rank, seq);
+    }
+}
+
+__global__ void k_sum_scalar(const float* parts, int world, flyp::PeerWait w, float* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    flyp::peer_wait_all(w);
+    float s = 0.f;
+    for (int q = 0; q < world; ++q) s += __ldcg(parts + q);      // fixed rank order: identical bits on every rank
+    out[0] = s;
+}
+
+int check_comm(const flyp_comm* c, bool need_connected) {
+    if (c == nullptr) { flyp::set_error(FLYP_ERR_ARG, "comm is null"); return FLYP_ERR_ARG; }
+    if (need_connected && !c->connected) { flyp::set_error(FLYP_ERR_ARG, "comm is not connected"); return FLYP_ERR_ARG; }
+    return 0;
+}
+
+// The copy-engine schedule of one gather: for each of the four matrices, W - 1 block copies (own slot -> same slot of
+// peer (rank - k)), each followed by the 4-byte flag copy.  Text first: it is what the forward waits for.
+struct PushOp { void* dst; const void* src; size_t bytes; };
+int build_push_ops(const flyp_comm* c, int par, int n_rows, int dim, PushOp* ops) {
+    int n = 0;
+    const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
+    for (int a = 0; a < N_ARR; ++a) {
+        for (int k = 1; k < c->world; ++k) {
+            const int q = (c->rank - k + c->world) % c->world;
+            ops[n++] = {c->seg[q] + c->off_feat[par][a] + slot_off, c->seg[c->rank] + c->off_feat[par][a] + slot_off,
+                        slot_bytes};
+            ops[n++] = {flag_ptr(c, q, a, c->rank), c->seg[c->rank] + c->off_seqword[par], sizeof(uint32_t)};
+        }
+    }
+    return n;
+}
+
+int build_push_graphs(flyp_comm* c, int n_rows, int dim) {
+    for (int par = 0; par < 2; ++par) {
+        if (c->push_exec[par]) { cudaGraphExecDestroy(c->push_exec[par]); c->push_exec[par] = nullptr; }
+    }
+    c->push_rows = n_rows; c->push_dim = dim;
+    if (!c->use_graph || c->world == 1) return 0;
+    for (int par = 0; par < 2; ++par) {
+        PushOp ops[2 * N_ARR * MAXW];
+        const int n = build_push_ops(c, par, n_rows, dim, ops);
+        cudaGraph_t g;
+        COMM_CUDA_OK(cudaGraphCreate(&g, 0));
+        cudaGraphNode_t prev = nullptr;
+        for (int i = 0; i < n; ++i) {
+            cudaGraphNode_t node;
+            cudaError_t e = cudaGraphAddMemcpyNode1D(&node, g, prev ? &prev : nullptr, prev ? 1 : 0, ops[i].dst, ops[i].src,
+                                                     ops[i].bytes, cudaMemcpyDefault);
+            if (e != cudaSuccess) {                  // e.g. peer memcpy nodes unsupported: plain async copies instead
+                cudaGraphDestroy(g);
+                cudaGetLastError();
+                c->use_graph = false;
+                return 0;
+            }
+            prev = node;
+        }
+        cudaError_t e = cudaGraphInstantiate(&c->push_exec[par], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { cudaGetLastError(); c->push_exec[par] = nullptr; c->use_graph = false; return 0; }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int flyp_comm_create(int rank, int world, int max_rows, int dim, flyp_comm** out) {
+    if (!out) { flyp::set_error(FLYP_ERR_ARG, "out is null"); return FLYP_ERR_ARG; }
+    if (world < 1 || world > MAXW || rank < 0 || rank >= world || max_rows <= 0 || dim <= 0 || dim % 8 != 0) {
+        flyp::set_error(FLYP_ERR_ARG, "bad comm shape: rank %d world %d (max %d) rows %d dim %d", rank, world, MAXW, max_rows,
+                        dim);
+        return FLYP_ERR_ARG;
+    }
+    flyp_comm* c = new flyp_comm();
+    memset(c, 0, sizeof(*c));
+    c->rank = rank; c->world = world; c->max_rows = max_rows; c->dim = dim;
+    COMM_CUDA_OK(cudaGetDevice(&c->dev));
+    layout(c);
+    uint8_t* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, c->seg_bytes);
+    if (e != cudaSuccess) {
+        flyp::set_error(FLYP_ERR_CUDA, "cudaMalloc of the %zu-byte exchange segment: %s", c->seg_bytes, cudaGetErrorString(e));
+        delete c;
+        return FLYP_ERR_CUDA;
+    }
+    c->seg[rank] = p;
+    COMM_CUDA_OK(cudaMemset(p, 0, c->seg_bytes));
+    COMM_CUDA_OK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
+    COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_pushed, cudaEventDisableTiming));
+    COMM_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&c->err_host), sizeof(uint32_t), cudaHostAllocMapped));
+    *c->err_host = 0;
+    COMM_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->err_dev), c->err_host, 0));
+    const char* g = getenv("FLYP_COMM_GRAPH");
+    c->use_graph = !(g && g[0] == '0');
+    c->connected = (world == 1);
+    COMM_CUDA_OK(cudaDeviceSynchronize());
+    *out = c;
+    return 0;
+}
+
+int flyp_comm_segment_bytes(const flyp_comm* c, size_t* bytes) {
+    int rc = check_comm(c, false);
+    if (rc) return rc;
+    if (bytes) *bytes = c->seg_bytes;
+    return 0;
+}
+
+int flyp_comm_ipc_handle(flyp_comm* c, void* handle_out) {
+    int rc = check_comm(c, false);
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == FLYP_IPC_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    COMM_CUDA_OK(cudaSetDevice(c->dev));
+    COMM_CUDA_OK(cudaIpcGetMemHandle(&h, c->seg[c->rank]));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int flyp_comm_connect_ipc(flyp_comm* c, const void* all_handles) {
+    int rc = check_comm(c, false);
+    if (rc) return rc;
+    COMM_CUDA_OK(cudaSetDevice(c->dev));
+    for (int q = 0; q < c->world; ++q) {
+        if (q == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const uint8_t*>(all_handles) + (size_t)q * FLYP_IPC_HANDLE_BYTES, sizeof(h));
+        void* p = nullptr;
+        COMM_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->seg[q] = static_cast<uint8_t*>(p);
+        c->ipc_mapped[q] = true;
+    }
+    c->connected = true;
+    return 0;
+}
+
+int flyp_comm_connect_local(flyp_comm* c, flyp_comm* const* peers) {
+    int rc = check_comm(c, false);
+    if (rc) return rc;
+    for (int q = 0; q < c->world; ++q) {
+        if (q == c->rank) continue;
+        if (!peers[q] || peers[q]->rank != q || peers[q]->world != c->world || peers[q]->seg_bytes != c->seg_bytes) {
+            flyp::set_error(FLYP_ERR_ARG, "peer %d does not match this communicator", q);
+            return FLYP_ERR_ARG;
+        }
+        c->seg[q] = peers[q]->seg[q];
+    }
+    c->connected = true;
+    return 0;
+}
+
+int flyp_comm_error(const flyp_comm* c) {
+    if (!c) return 0;
+    return (int)*reinterpret_cast<volatile uint32_t*>(c->err_host);
+}
+
+int flyp_comm_destroy(flyp_comm* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->dev);
+    cudaDeviceSynchronize();
+    for (int par = 0; par < 2; ++par)
+        if (c->push_exec[par]) cudaGraphExecDestroy(c->push_exec[par]);
+    for (int q = 0; q < c->world; ++q)
+        if (c->ipc_mapped[q]) cudaIpcCloseMemHandle(c->seg[q]);
+    if (c->seg[c->rank]) cudaFree(c->seg[c->rank]);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_packed) cudaEventDestroy(c->ev_packed);
+    if (c->ev_pushed) cudaEventDestroy(c->ev_pushed);
+    if (c->err_host) cudaFreeHost(c->err_host);
+    cudaGetLastError();
+    delete c;
+    return 0;
+}
+
+int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, int n_rows, int dim, int dtype,
+                              flyp_gathered_t* out, void* stream) {
+    int rc = check_comm(c, true);
+    if (rc) return rc;
+    if (!img || !txt || !out) { flyp::set_error(FLYP_ERR_ARG, "null pointer argument"); return FLYP_ERR_ARG; }
+    if (dtype != FLYP_BF16) { flyp::set_error(FLYP_ERR_ARG, "the peer-memory gather carries bf16 features only"); return FLYP_ERR_ARG; }
+    if (n_rows <= 0 || dim != c->dim || n_rows > c->max_rows) {
+        flyp::set_error(FLYP_ERR_ARG, "gather shape [%d, %d] does not fit the communicator (max rows %d, dim %d)", n_rows, dim,
+                        c->max_rows, c->dim);
+        return FLYP_ERR_ARG;
+    }
+    if (((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(txt)) & 15) != 0) {
+        flyp::set_error(FLYP_ERR_ARG, "feature pointers must be 16-byte aligned");
+        return FLYP_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    COMM_CUDA_OK(cudaSetDevice(c->dev));
+    if (c->push_rows != n_rows || c->push_dim != dim) {
+        // a shape change invalidates the slot offsets peers poll for: the caller must not change it mid-flight
+        if ((rc = build_push_graphs(c, n_rows, dim)) != 0) return rc;
+    }
+    const uint32_t seq = ++c->seq;
+    const int par = (int)(seq & 1u);
+    uint8_t* own = c->seg[c->rank];
+    const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
+    // the copy engines may still be reading the own slots / sequence word of the previous step
+    COMM_CUDA_OK(cudaStreamWaitEvent(st, c->ev_pushed, 0));
+    const size_t n8 = (size_t)n_rows * dim / 8;
+    k_pack<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
+        static_cast<const uint4*>(img), static_cast<const uint4*>(txt), n8,
+        reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_IMG] + slot_off),
+        reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_IMG16] + slot_off),
+        reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_TXT] + slot_off),
+        reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_TXT16] + slot_off),
+        reinterpret_cast<uint32_t*>(own + c->off_seqword[par]), reinterpret_cast<uint32_t*>(own + c->off_flags), c->rank, seq);
+    COMM_CUDA_OK(cudaGetLastError());
+    if (c->world > 1) {
+        COMM_CUDA_OK(cudaEventRecord(c->ev_packed, st));
+        COMM_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_packed, 0));
+        if (c->use_graph && c->push_exec[par]) {
+            COMM_CUDA_OK(cudaGraphLaunch(c->push_exec[par], c->side));
+        } else {
+            PushOp ops[2 * N_ARR * MAXW];
+            const int n = build_push_ops(c, par, n_rows, dim, ops);
+            for (int i = 0; i < n; ++i)
+                COMM_CUDA_OK(cudaMemcpyAsync(ops[i].dst, ops[i].src, ops[i].bytes, cudaMemcpyDefault, c->side));
+        }
+        COMM_CUDA_OK(cudaEventRecord(c->ev_pushed, c->side));
+    }
+    memset(out, 0, sizeof(*out));
+    out->txt_all = own + c->off_feat[par][ARR_TXT];
+    out->txt16_all = own + c->off_feat[par][ARR_TXT16];
+    out->img_all = own + c->off_feat[par][ARR_IMG];
+    out->img16_all = own + c->off_feat[par][ARR_IMG16];
+    flyp_ready_t* r[N_ARR] = {&out->txt_ready, &out->txt16_ready, &out->img_ready, &out->img16_ready};
+    for (int a = 0; a < N_ARR; ++a) {
+        r[a]->flags = flag_ptr(c, c->rank, a, 0);
+        r[a]->seq = seq; r[a]->n_flags = c->world; r[a]->rows_per_flag = n_rows; r[a]->err = c->err_dev;
+    }
+    out->seq = seq;
+    return 0;
+}
+
+int flyp_comm_push_stats(flyp_comm* c, uint32_t seq, const float* col_stat, const float* row_lse, const float* row_nll,
+                         int n_rows, int n_cols, flyp_stats_t* out, void* stream) {
+    int rc = check_comm(c, true);
+    if (rc) return rc;
+    if (!col_stat || !row_lse || !row_nll || !out) { flyp::set_error(FLYP_ERR_ARG, "null pointer argument"); return FLYP_ERR_ARG; }
+    const size_t cap = (size_t)c->world * c->max_rows;
+    if (n_rows <= 0 || n_rows > c->max_rows || n_cols != n_rows * c->world) {
+        flyp::set_error(FLYP_ERR_ARG, "statistics shape (%d rows, %d columns) does not fit the communicator", n_rows, n_cols);
+        return FLYP_ERR_ARG;
+    }
+    COMM_CUDA_OK(cudaSetDevice(c->dev));
+    const int par = (int)(seq & 1u);
+    SegPtrs ptrs;
+    for (int q = 0; q < MAXW; ++q) ptrs.seg[q] = q < c->world ? c->seg[q] : nullptr;
+    int bx = (3 * n_cols + 1023) / 1024;
+    if (bx > 16) bx = 16;
+    if (bx < 1) bx = 1;
+    k_push_stats<<<dim3(bx, c->world), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        ptrs, c->world, c->rank, c->off_colstat[par], c->off_rowstat[par], c->off_flags, c->off_counter, col_stat, row_lse,
+        row_nll, n_rows, n_cols, cap, seq);
+    COMM_CUDA_OK(cudaGetLastError());
+    uint8_t* own = c->seg[c->rank];
+    out->col_stat_all = reinterpret_cast<const float*>(own + c->off_colstat[par]);
+    out->row_lse_all = reinterpret_cast<const float*>(own + c->off_rowstat[par]);
+    out->row_nll_all = out->row_lse_all + cap;
+    out->ready.flags = flag_ptr(c, c->rank, FLAG_STAT, 0);
+    out->ready.seq = seq; out->ready.n_flags = c->world; out->ready.rows_per_flag = n_rows; out->ready.err = c->err_dev;
+    return 0;
+}
+
+int flyp_comm_push_scalar(flyp_comm* c, uint32_t seq, const float* value, void* stream) {
+    int rc = check_comm(c, true);
+    if (rc) return rc;
+    if (!value) { flyp::set_error(FLYP_ERR_ARG, "null pointer argument"); return FLYP_ERR_ARG; }
+    COMM_CUDA_OK(cudaSetDevice(c->dev));
+    SegPtrs ptrs;
+    for (int q = 0; q < MAXW; ++q) ptrs.seg[q] = q < c->world ? c->seg[q] : nullptr;
+    k_push_scalar<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(ptrs, c->world, c->rank, c->off_dscale[seq & 1u],
+                                                                  c->off_flags, value, seq);
+    COMM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int flyp_comm_sum_scalar(flyp_comm* c, uint32_t seq, float* out, void* stream) {
+    int rc = check_comm(c, true);
+    if (rc) return rc;
+    if (!out) { flyp::set_error(FLYP_ERR_ARG, "null pointer argument"); return FLYP_ERR_ARG; }
+    COMM_CUDA_OK(cudaSetDevice(c->dev));
+    flyp::PeerWait w;
+    w.flags = flag_ptr(c, c->rank, FLAG_DS, 0); w.seq = seq; w.n_flags = c->world; w.rows_per_flag = 1; w.err = c->err_dev;
+    k_sum_scalar<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float*>(c->seg[c->rank] + c->off_dscale[seq & 1u]), c->world, w, out);
+    COMM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

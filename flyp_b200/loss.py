@@ -230,11 +230,49 @@ class _ClipLossFn(torch.autograd.Function):
         return (d_img if need_img else None), (d_txt if need_txt else None), gs, None, None, None, None, None
 
 
+class _ClipLossPeerFn(torch.autograd.Function):
+    """The same row-sharded symmetric loss with every exchange done over peer memory (flyp_b200/comm.py): copy-engine
+    feature pushes that overlap the forward kernel, flag-polling tensor-core kernels, remote-store statistics."""
+
+    @staticmethod
+    def forward(ctx, img, txt, scale, comm, gather_with_grad, grad_dtype):
+        from . import comm as peer
+        s = ops._scale_tensor(scale, img.device)
+        st = peer.fwd_gather(comm, img, txt, s)
+        peer.fwd_local(st)
+        loss = peer.fwd_finish(st)
+        ctx.st = st
+        ctx.meta = (gather_with_grad, grad_dtype, torch.is_tensor(scale), scale.shape if torch.is_tensor(scale) else None,
+                    scale.dtype if torch.is_tensor(scale) else None)
+        return loss.to(img.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import comm as peer
+        st = ctx.st
+        gwg, grad_dtype, s_is_tensor, s_shape, s_dtype = ctx.meta
+        need_img, need_txt, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        mul = float(st.comm.world) if gwg else 1.0
+        d_img, d_txt, d_s = peer.bwd_local(st, g, mul, grad_dtype, need_img, need_txt, need_s)
+        gs = None
+        if need_s:
+            # every rank differentiates the same replicated loss: d(scale) sums the row blocks of all ranks
+            tot = torch.empty(1, dtype=torch.float32, device=st.img.device)
+            st.comm.all_reduce_scalar(st.g.seq, d_s, tot)
+            if s_is_tensor:
+                gs = torch.zeros(s_shape, dtype=torch.float32, device=st.img.device).reshape(-1)
+                gs[:1] = tot
+                gs = gs.reshape(s_shape).to(s_dtype)
+        st.comm.check_error()
+        return (d_img if need_img else None), (d_txt if need_txt else None), gs, None, None, None
+
+
 class ClipLoss(nn.Module):
     """clip/loss.py:72-211 with the same constructor and forward signature."""
 
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
-                 use_horovod=False, normalize=False, grad_dtype: Optional[torch.dtype] = None, group=None):
+                 use_horovod=False, normalize=False, grad_dtype: Optional[torch.dtype] = None, group=None,
+                 comm: str = "auto"):
         super().__init__()
         self.local_loss = local_loss
         self.gather_with_grad = gather_with_grad
@@ -246,6 +284,13 @@ class ClipLoss(nn.Module):
         self.normalize = normalize
         self.grad_dtype = grad_dtype
         self.group = group
+        # multi-rank exchange: "peer" = NVLink peer memory (one node, bf16, the default loss), "nccl" = torch.distributed
+        # collectives, "auto" = peer when it can be set up on every rank, else nccl
+        if comm not in ("auto", "peer", "nccl"):
+            raise ValueError(f"comm must be 'auto', 'peer' or 'nccl', got {comm!r}")
+        self.comm = comm
+        self._peer = None          # PeerComm, or False once the set-up was tried and refused
+        self._peer_shape = None
 
         # cache state (kept for attribute compatibility; the kernels need no label tensor)
         self.prev_num_logits = 0
@@ -263,6 +308,25 @@ class ClipLoss(nn.Module):
         else:
             labels = self.labels[device]
         return labels
+
+    def _peer_comm(self, feats):
+        """The peer-memory communicator for blocks shaped like ``feats`` (created collectively on first use; every rank
+        takes the same decision).  None -> use the NCCL path."""
+        if self.comm == "nccl" or feats.dtype != torch.bfloat16:
+            return None
+        shape = (feats.shape[0], feats.shape[1])
+        if self._peer is not None and self._peer_shape == shape:
+            return self._peer or None
+        if self._peer:
+            self._peer.close()
+        from .comm import PeerComm
+        self._peer_shape = shape
+        self._peer = PeerComm.from_process_group(self.rank, self.world_size, shape[0], shape[1], feats.device,
+                                                 self.group) or False
+        if not self._peer and self.comm == "peer":
+            raise FlypError("comm='peer' was requested but the peer-memory exchange could not be set up on every rank "
+                            "(ranks on several nodes, or no CUDA IPC between the GPUs)")
+        return self._peer or None
 
     def forward(self, image_features, text_features, logit_scale, ground_labels=None, ignore=False,
                 google_sup_loss=False):
@@ -292,8 +356,13 @@ class ClipLoss(nn.Module):
                                            grad_dtype=self.grad_dtype)
             return (li + lt) / 2
 
-        loss = _ClipLossFn.apply(image_features, text_features, logit_scale, self.rank, self.world_size, self.group,
-                                 self.gather_with_grad, self.grad_dtype)
+        peer = self._peer_comm(image_features) if self.world_size > 1 else None
+        if peer is not None:
+            loss = _ClipLossPeerFn.apply(image_features, text_features, logit_scale, peer, self.gather_with_grad,
+                                         self.grad_dtype)
+        else:
+            loss = _ClipLossFn.apply(image_features, text_features, logit_scale, self.rank, self.world_size, self.group,
+                                     self.gather_with_grad, self.grad_dtype)
         if self.cache_labels:
             self._labels(device, loss.shape[0])
         return loss

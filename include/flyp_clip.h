@@ -91,6 +91,87 @@ int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_c
                 void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Peer-memory exchange between the GPUs of one node (NVLink / NVSwitch).  Replaces the collectives of the row-sharded
+ * loss: the two feature all-gathers of clip/loss.py:19-69 (gather_features; rank-major ordering of :66-67) and the
+ * O(B) statistics this implementation exchanges instead of replicating logits (clip/loss.py:103-114).
+ * One communicator per (rank, process); its exchange segment is device memory owned by the library (the only
+ * allocation the library makes, at creation time, never on the hot path).  All calls must be made by every rank in the
+ * same order.  Readiness of remotely written rows is signalled through device flag words described by flyp_ready_t;
+ * the *_ex entry points below make the tensor-core kernels poll them right before the first read of a rank's rows, so
+ * the transfers overlap the kernels.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct flyp_comm flyp_comm;
+#define FLYP_IPC_HANDLE_BYTES 64
+#define FLYP_COMM_MAX_WORLD 16
+
+/* Rows [k * rows_per_flag, (k + 1) * rows_per_flag) are valid once (int32)(flags[k] - seq) >= 0.  flags == NULL: ready. */
+typedef struct {
+    const uint32_t* flags; /* device */
+    uint32_t seq;
+    int n_flags;
+    int rows_per_flag;
+    uint32_t* err;         /* device-visible word set to 1 + k if waiting for flags[k] timed out (4 s); may be NULL */
+} flyp_ready_t;
+
+/* The gathered matrices of one step, [world * n_rows, dim] rank-major, in this rank's exchange segment. */
+typedef struct {
+    const void *img_all, *txt_all;      /* bf16 */
+    const void *img16_all, *txt16_all;  /* fp16 copies (operands of the backward's second GEMM) */
+    flyp_ready_t img_ready, txt_ready, img16_ready, txt16_ready;
+    uint32_t seq;                       /* sequence number of this step (pass it to the push / sum calls) */
+} flyp_gathered_t;
+
+/* The gathered statistics of one step. */
+typedef struct {
+    const float* col_stat_all;          /* [world][3 * n_cols] column triples of every rank (flyp_clip_fwd_local) */
+    const float *row_lse_all, *row_nll_all; /* [world * n_rows] */
+    flyp_ready_t ready;
+} flyp_stats_t;
+
+/* Create the communicator of `rank` on the current device for blocks of at most max_rows x dim bf16 features. */
+int flyp_comm_create(int rank, int world, int max_rows, int dim, flyp_comm** comm);
+int flyp_comm_segment_bytes(const flyp_comm* comm, size_t* bytes);
+/* handle_out: FLYP_IPC_HANDLE_BYTES host bytes to be all-gathered by the caller (e.g. through torch.distributed). */
+int flyp_comm_ipc_handle(flyp_comm* comm, void* handle_out);
+/* all_handles: world x FLYP_IPC_HANDLE_BYTES host bytes, rank-major.  The caller must barrier before the first step. */
+int flyp_comm_connect_ipc(flyp_comm* comm, const void* all_handles);
+/* Same-process peers (single-process multi-GPU, or several emulated ranks on one GPU in tests). */
+int flyp_comm_connect_local(flyp_comm* comm, flyp_comm* const* peers);
+/* 0, or 1 + k if a kernel gave up waiting for rank k (host read of a mapped word; no synchronisation). */
+int flyp_comm_error(const flyp_comm* comm);
+int flyp_comm_destroy(flyp_comm* comm);
+
+/* clip/loss.py:59-67 without torch.cat: pack the local rows (and their fp16 copies) into the own slots on `stream`,
+ * then push them to every peer with the copy engines on the communicator's side stream (text first, peers in ring
+ * order), each block followed by its flag.  Returns at once; `out` describes where the gathered matrices will be. */
+int flyp_comm_gather_features(flyp_comm* comm, const void* img, const void* txt, int n_rows, int dim, int dtype,
+                              flyp_gathered_t* out, void* stream);
+/* Push this rank's column triples / row statistics (outputs of flyp_clip_fwd_local) into every rank's segment. */
+int flyp_comm_push_stats(flyp_comm* comm, uint32_t seq, const float* col_stat, const float* row_lse,
+                         const float* row_nll, int n_rows, int n_cols, flyp_stats_t* out, void* stream);
+/* All-reduce (sum, fixed rank order) of one fp32 device scalar: push, then sum once every rank's value has arrived. */
+int flyp_comm_push_scalar(flyp_comm* comm, uint32_t seq, const float* value, void* stream);
+int flyp_comm_sum_scalar(flyp_comm* comm, uint32_t seq, float* out, void* stream);
+
+/* Variants of the loss entry points for operands that other ranks are still writing.
+ *   txt_ready        readiness of the rows of `txt` (forward: the schedule starts at this rank's own column block and
+ *                    follows the ring order of the push)
+ *   txt16 (may be NULL -> converted here), txt16_ready: the fp16 copy of `txt` and its readiness
+ *   stats_ready      readiness of col_stat_all / row_nll (all ranks) */
+int flyp_clip_fwd_local_ex(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
+                           int dtype, int row_offset, float* row_lse, float* row_nll, float* col_stat, int* status,
+                           void* workspace, size_t workspace_bytes, const flyp_ready_t* txt_ready, void* stream);
+int flyp_clip_fwd_finish_ex(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
+                            int row_offset, float* col_lse, float* col_nll, float* loss,
+                            const flyp_ready_t* stats_ready, void* stream);
+int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
+                           int dtype, int row_offset, const float* row_lse, const float* row_nll, const float* col_lse,
+                           const float* col_nll, const float* g_row, const float* g_col, float grad_mul, int grad_dtype,
+                           void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
+                           const void* txt16, const flyp_ready_t* txt_ready, const flyp_ready_t* txt16_ready,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Row-wise L2 normalisation x / ||x||_2 (no epsilon), clip/model.py:375-376, src/models/ce_ablation.py:115-118.
  * ------------------------------------------------------------------------------------------------------------------ */
 /* y[n, dim] = x / ||x||; inv_norm[n] = 1 / ||x|| (fp32, saved for backward). */
