@@ -161,10 +161,10 @@ def fwd_local(st: PeerStep) -> None:
     with torch.cuda.device(dev):
         st.ws = ops.clip_workspace(st.b, st.B, st.D, _lib.FLYP_BF16, dev)
         st.row_lse, st.row_nll, st.col_stat = ops._f32(st.b, dev), ops._f32(st.b, dev), ops._f32(3 * st.B, dev)
-        st.status = torch.empty(1, dtype=torch.int32, device=dev)
+        st.status = None
         _lib.check(lib.flyp_clip_fwd_local_ex(
             st.img.data_ptr(), st.g.txt_all, st.s.data_ptr(), st.b, st.B, st.D, _lib.FLYP_BF16, st.off,
-            st.row_lse.data_ptr(), st.row_nll.data_ptr(), st.col_stat.data_ptr(), st.status.data_ptr(),
+            st.row_lse.data_ptr(), st.row_nll.data_ptr(), st.col_stat.data_ptr(), None,
             st.ws.data_ptr(), st.ws.numel(), ctypes.byref(st.g.txt_ready), _lib.stream_ptr(dev)))
     st.st = st.comm.push_stats(st.g.seq, st.col_stat, st.row_lse, st.row_nll)
 
@@ -193,27 +193,18 @@ def bwd_local(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_i
     gdt = st.img.dtype if grad_dtype is None else grad_dtype
     gcode = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[gdt]
     g = g.to(torch.float32).contiguous()
-    f4 = 4
     d_img = d_txt = d_s = None
+    need_img = need_img or need_scale
     with torch.cuda.device(dev):
-        stream = _lib.stream_ptr(dev)
-        if need_img or need_scale:
-            d_img = torch.empty(st.b, st.D, dtype=gdt, device=dev)
-            d_s = ops._f32(1, dev) if need_scale else None
-            _lib.check(lib.flyp_clip_bwd_local_ex(
-                st.img.data_ptr(), st.g.txt_all, st.s.data_ptr(), st.b, st.B, st.D, _lib.FLYP_BF16, st.off,
-                st.row_lse.data_ptr(), st.row_nll.data_ptr(), st.col_lse.data_ptr(), st.col_nll.data_ptr(),
-                g.data_ptr() + st.off * f4, g.data_ptr(), float(grad_mul), gcode, d_img.data_ptr(), None, _lib.ptr(d_s),
-                st.ws.data_ptr(), st.ws.numel(), st.g.txt16_all, ctypes.byref(st.g.txt_ready),
-                ctypes.byref(st.g.txt16_ready), stream))
-        if need_txt:
-            # the transposed problem: text rows of this rank against all images
-            d_txt = torch.empty(st.b, st.D, dtype=gdt, device=dev)
-            _lib.check(lib.flyp_clip_bwd_local_ex(
-                st.txt.data_ptr(), st.g.img_all, st.s.data_ptr(), st.b, st.B, st.D, _lib.FLYP_BF16, st.off,
-                st.col_lse.data_ptr() + st.off * f4, st.col_nll.data_ptr() + st.off * f4, st.st.row_lse_all,
-                st.st.row_nll_all, g.data_ptr() + st.off * f4, g.data_ptr(), float(grad_mul), gcode, d_txt.data_ptr(),
-                None, None, st.ws.data_ptr(), st.ws.numel(), st.g.img16_all, ctypes.byref(st.g.img_ready),
-                ctypes.byref(st.g.img16_ready), stream))
+        d_img = torch.empty(st.b, st.D, dtype=gdt, device=dev) if need_img else None
+        d_txt = torch.empty(st.b, st.D, dtype=gdt, device=dev) if need_txt else None
+        d_s = ops._f32(1, dev) if need_scale else None
+        gg = st.g
+        _lib.check(lib.flyp_clip_bwd_sharded(
+            st.img.data_ptr(), st.txt.data_ptr(), gg.img_all, gg.txt_all, gg.img16_all, gg.txt16_all, st.s.data_ptr(),
+            st.b, st.B, st.D, _lib.FLYP_BF16, st.off, st.st.row_lse_all, st.st.row_nll_all, st.col_lse.data_ptr(),
+            st.col_nll.data_ptr(), g.data_ptr(), float(grad_mul), gcode, _lib.ptr(d_img), _lib.ptr(d_txt), _lib.ptr(d_s),
+            st.ws.data_ptr(), st.ws.numel(), ctypes.byref(gg.img_ready), ctypes.byref(gg.txt_ready),
+            ctypes.byref(gg.img16_ready), ctypes.byref(gg.txt16_ready), _lib.stream_ptr(dev)))
     # keep g alive until the kernels that read it through raw pointers are enqueued (they are, by now)
     return d_img, d_txt, d_s

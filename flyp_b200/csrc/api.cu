@@ -106,16 +106,12 @@ int num_sms();
 size_t sweep_dscale_slots(int n_m, int n_n, int dim, int dtype) {
     const int m_tiles = ceil_div(n_m, flyp::TILE);
     if (!use_pair_kernel(dim, dtype)) return (size_t)m_tiles * ceil_div(dim, 256);
-    int full = m_tiles;
-    const int k = flyp::bwd_pair_tail_split(m_tiles, n_n, num_sms(), &full);
-    return (size_t)(full + (m_tiles - full) * k) * 2;
+    return (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles, n_n, num_sms());
 }
 size_t sweep_part_floats(int n_m, int n_n, int dim, int dtype) {
     if (!use_pair_kernel(dim, dtype)) return 0;
     const int m_tiles = ceil_div(n_m, flyp::TILE);
-    int full = m_tiles;
-    const int k = flyp::bwd_pair_tail_split(m_tiles, n_n, num_sms(), &full);
-    return k > 1 ? (size_t)(m_tiles - full) * k * flyp::TILE * dim : 0;
+    return (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles, n_n, num_sms()) * flyp::TILE * dim;
 }
 constexpr int VEC_PAD = 256;   // per-row / per-column vectors are padded to this many entries
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -336,20 +332,16 @@ int run_sweep(const void* A, const void* B, const void* B_f16, int dtype, const 
     p.wait_b = to_wait(b_ready); p.wait_bd = to_wait(b16_ready);
     p.prof = g_prof_buf;
     { const char* e = getenv("FLYP_DBG"); p.dbg = e ? atoi(e) : 0; }
-    p.full_items = p.m_tiles; p.split_k = 1; p.part_out = nullptr;
     if (use_pair_kernel(dim, dtype)) {
         CUtensorMap tmA64;
         if ((rc = make_tmap(&tmA64, A, n_m, dim, dim, false, 64)) != 0) return rc;
-        const char* ns = getenv("FLYP_NO_SPLIT");          // A/B switch for measurements
-        if (part_scratch != nullptr && !(ns && ns[0] == '1')) {
-            p.split_k = flyp::bwd_pair_tail_split(p.m_tiles, n_n, num_sms(), &p.full_items);
-            p.part_out = part_scratch;
-        }
+        if (part_scratch == nullptr) return fail(FLYP_ERR_ARG, "the pair sweep needs its partial-sum scratch");
+        p.sched_pairs = flyp::bwd_pair_sched_pairs(p.m_tiles, n_n, num_sms());
+        p.part_out = part_scratch;
         flyp::launch_bwd_pair(tmA64, tmB, tmBd, p, num_sms(), st);
         CUDA_OK(cudaGetLastError());
-        if (p.split_k > 1)
-            flyp::launch_reduce_parts(part_scratch, p.m_tiles - p.full_items, p.split_k, p.full_items, n_m, dim, out,
-                                      dim, out_fp32, st);
+        flyp::launch_reduce_parts(part_scratch, p.m_tiles, ceil_div(n_n, flyp::PAIR_NSTEP), p.sched_pairs, n_m, dim, out,
+                                  dim, out_fp32, st);
     } else {
         flyp::launch_bwd(tmA, tmB, tmBd, p, num_sms(), st);
     }
@@ -536,6 +528,60 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
                        w.cols.w, w.cols.l2, w.rows.w, w.rows.l2, w.cols.lab, w.cols.d, nullptr, nullptr, w.cols.f,
                        w.rows.f, w.fast_info, nullptr, d_txt, grad_dtype, grad_mul, nullptr, w.part_scratch, w.gmax_bits,
                        st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all, const void* txt_all,
+                          const void* img16_all, const void* txt16_all, const float* scale, int n_rows, int n_cols,
+                          int dim, int dtype, int row_offset, const float* row_lse_all, const float* row_nll_all,
+                          const float* col_lse, const float* col_nll, const float* g, float grad_mul, int grad_dtype,
+                          void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
+                          const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready, const flyp_ready_t* img16_ready,
+                          const flyp_ready_t* txt16_ready, void* stream) {
+    int rc = check_common(n_rows, n_cols, dim, dtype);
+    if (rc) return rc;
+    if (dtype != FLYP_BF16) return fail(FLYP_ERR_ARG, "the sharded backward takes bf16 features");
+    if (!img || !txt || !scale || !row_lse_all || !row_nll_all || !col_lse || !col_nll || !g || !workspace)
+        return fail(FLYP_ERR_ARG, "null pointer argument");
+    if ((d_img || d_scale) && (!txt_all || !txt16_all)) return fail(FLYP_ERR_ARG, "d_img needs the gathered text features");
+    if (d_txt && (!img_all || !img16_all)) return fail(FLYP_ERR_ARG, "d_txt needs the gathered image features");
+    if (d_scale && !d_img) return fail(FLYP_ERR_ARG, "d_scale requires d_img");
+    if (grad_dtype != FLYP_BF16 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad grad_dtype %d", grad_dtype);
+    if (row_offset < 0 || row_offset + n_rows > n_cols)
+        return fail(FLYP_ERR_ARG, "row_offset %d + n_rows %d exceeds n_cols %d", row_offset, n_rows, n_cols);
+    ClipWs w;
+    carve_clip(workspace, n_rows, n_cols, dim, dtype, w);
+    if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cp = ceil_div(n_cols, VEC_PAD) * VEC_PAD;
+    // global vectors live in the column set (its d / lab arrays hold the row-statistics l2 / f), local ones in the row set
+    float *wg = w.cols.w, *l2c = w.cols.l2, *fc = w.cols.f, *l2r = w.cols.d, *fr = reinterpret_cast<float*>(w.cols.lab);
+    CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, 2 * sizeof(uint32_t), st));
+    CUDA_OK(cudaMemsetAsync(w.gmax_bits + 2, 0xff, sizeof(uint32_t), st));
+    flyp::launch_bwd_prep_sharded(n_cols, cp, row_offset, n_rows, g, row_lse_all, row_nll_all, col_lse, col_nll, wg, l2c,
+                                  l2r, w.rows.lab, w.rows.d, w.gmax_bits, st);
+    flyp::launch_bwd_fast_vectors(w.gmax_bits, cp, wg, l2c, fc, cp, wg, l2r, fr, w.fast_info, st);
+    CUDA_OK(cudaGetLastError());
+    const int off = row_offset;
+    if (d_img) {
+        // image rows of this rank against all texts: complete d_img and this row block's share of d(scale)
+        rc = run_sweep(img, txt_all, txt16_all, dtype, nullptr, nullptr, scale, n_rows, n_cols, dim, wg + off, l2r + off, wg,
+                       l2c, w.rows.lab, w.rows.d, nullptr, nullptr, fr + off, fc, w.fast_info, d_scale ? img : nullptr,
+                       d_img, grad_dtype, grad_mul, d_scale ? w.dscale_part : nullptr, w.part_scratch, w.gmax_bits, st,
+                       txt_ready, txt16_ready);
+        if (rc) return rc;
+        if (d_scale) {
+            flyp::launch_sum_parts(w.dscale_part, (int)w.n_dscale, d_scale, st);
+            CUDA_OK(cudaGetLastError());
+        }
+    }
+    if (d_txt) {
+        // the transposed problem: text rows of this rank against all images (no B x D reduce-scatter)
+        rc = run_sweep(txt, img_all, img16_all, dtype, nullptr, nullptr, scale, n_rows, n_cols, dim, wg + off, l2c + off, wg,
+                       l2r, w.rows.lab, w.rows.d, nullptr, nullptr, fc + off, fr, w.fast_info, nullptr, d_txt, grad_dtype,
+                       grad_mul, nullptr, w.part_scratch, w.gmax_bits, st, img_ready, img16_ready);
         if (rc) return rc;
     }
     return 0;

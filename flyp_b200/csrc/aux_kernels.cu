@@ -311,6 +311,52 @@ void launch_bwd_prep(int n, int n_pad, const float* g, float wmul, const float* 
                                                     nll2, dmul, w, l2, lab, d, gmax_bits);
 }
 
+// Row-sharded symmetric loss: one pass prepares the vectors of BOTH backward sweeps of a rank.  Global (padded) vectors:
+// w = g / 2, l2c = col_lse log2 e, l2r = row_lse_all log2 e; local: lab[i] = off + i, d[i] = exact dS at the positive of
+// local row i (the same value serves the transposed sweep).
+__global__ void k_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const float* __restrict__ g,
+                                   const float* row_lse_all, const float* row_nll_all, const float* __restrict__ col_lse,
+                                   const float* __restrict__ col_nll, float* __restrict__ w, float* __restrict__ l2c,
+                                   float* __restrict__ l2r, int* __restrict__ lab, float* __restrict__ d,
+                                   uint32_t* __restrict__ words) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t gb = 0u, khi = 0u, klo = 0xffffffffu;
+    float wi = 0.f, lc = 0.f, lr = 0.f;
+    if (i < n) {
+        const float gi = g[i];
+        gb = __float_as_uint(fabsf(gi));
+        wi = 0.5f * gi;
+        lc = col_lse[i] * LOG2E_F;
+        lr = __ldcg(row_lse_all + i) * LOG2E_F;
+        if (gi != 0.f) {
+            const uint32_t u = __float_as_uint(lc), v = __float_as_uint(lr);
+            const uint32_t ku = (u & 0x80000000u) ? ~u : (u | 0x80000000u), kv = (v & 0x80000000u) ? ~v : (v | 0x80000000u);
+            khi = ku > kv ? ku : kv;
+            klo = ku < kv ? ku : kv;
+        }
+        const int r = i - off;
+        if (r >= 0 && r < n_loc) {
+            lab[r] = i;
+            d[r] = 0.5f * gi * (expm1f(-__ldcg(row_nll_all + i)) + expm1f(-col_nll[i]));
+        }
+    }
+    gb = __reduce_max_sync(0xffffffffu, gb);
+    khi = __reduce_max_sync(0xffffffffu, khi);
+    klo = __reduce_min_sync(0xffffffffu, klo);
+    if ((threadIdx.x & 31) == 0) {
+        if (gb != 0u) atomicMax(words, gb);
+        if (khi != 0u) atomicMax(words + 1, khi);
+        if (klo != 0xffffffffu) atomicMin(words + 2, klo);
+    }
+    if (i < n_pad) { w[i] = wi; l2c[i] = lc; l2r[i] = lr; }
+}
+void launch_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const float* g, const float* row_lse_all,
+                             const float* row_nll_all, const float* col_lse, const float* col_nll, float* w, float* l2c,
+                             float* l2r, int* lab, float* d, uint32_t* words, cudaStream_t st) {
+    k_bwd_prep_sharded<<<(n_pad + 255) / 256, 256, 0, st>>>(n, n_pad, off, n_loc, g, row_lse_all, row_nll_all, col_lse,
+                                                            col_nll, w, l2c, l2r, lab, d, words);
+}
+
 // Fast (single-exponential) form of the backward epilogue: c0 = centre of the lse range, valid when the range is at
 // most 200 log2 units wide; f[i] = w[i] * 2^(c0 - l2[i]).
 __device__ __forceinline__ float key_to_float(uint32_t k) {
@@ -355,31 +401,45 @@ void launch_sum_parts(const float* parts, int n, float* out, cudaStream_t st) {
     k_sum_parts<<<1, 256, 0, st>>>(parts, n, out);
 }
 
-// ------------------------------------------------------------------------------------------------ tail partial sums
-// out[(first_blk + blk) * 128 + r][d] = sum_k part[(blk * split_k + k)][r][d]   (bwd pair kernel, split tail blocks)
+// ------------------------------------------------------------------------------------------------ flat-schedule partials
+// Sums, for every row block that the flat schedule of the pair backward sweep cut into several ranges, the fp32 partial
+// accumulators of those ranges (in pair order: deterministic) into `out`.  Blocks swept by one item were written directly.
 template <bool F32OUT>
-__global__ void k_reduce_parts(const float* __restrict__ part, int n_blocks, int split_k, int first_blk, int n_m,
-                               int d_out, void* __restrict__ out, int ld_out) {
-    const size_t per_blk = (size_t)128 * d_out;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)n_blocks * per_blk) return;
-    const int blk = (int)(i / per_blk);
-    const size_t rem = i - (size_t)blk * per_blk;
-    const int r = (int)(rem / d_out), d = (int)(rem - (size_t)r * d_out);
-    const int m = (first_blk + blk) * 128 + r;
+__global__ void k_reduce_parts(const float* __restrict__ part, int m_tiles, int NJ, int pairs, int n_m, int d_out,
+                               void* __restrict__ out, int ld_out) {
+    const int mb = blockIdx.y;
+    const long long S = (long long)m_tiles * NJ, lo = (long long)mb * NJ, hi = lo + NJ;
+    int q = (int)(lo * pairs / S);
+    while (q + 1 < pairs && flat_start(q + 1, S, pairs) <= lo) ++q;
+    while (q > 0 && flat_start(q, S, pairs) > lo) --q;
+    if (flat_start(q, S, pairs) <= lo && flat_start(q + 1, S, pairs) >= hi) return;      // swept whole
+    const int d4 = d_out / 4;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 128 * d4) return;
+    const int r = i / d4, d = (i - r * d4) * 4;
+    const int m = mb * 128 + r;
     if (m >= n_m) return;
-    float acc = 0.f;
-    for (int k = 0; k < split_k; ++k) acc += part[((size_t)(blk * split_k + k) * 128 + r) * d_out + d];
-    if (F32OUT) reinterpret_cast<float*>(out)[(size_t)m * ld_out + d] = acc;
-    else reinterpret_cast<__nv_bfloat16*>(out)[(size_t)m * ld_out + d] = __float2bfloat16_rn(acc);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (; q < pairs && flat_start(q, S, pairs) < hi; ++q) {
+        const int slot = 2 * q + (flat_start(q, S, pairs) >= lo ? 0 : 1);
+        const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)slot * 128 + r) * d_out + d);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (F32OUT) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)m * ld_out + d) = acc;
+    } else {
+        __nv_bfloat162 lo2 = __floats2bfloat162_rn(acc.x, acc.y), hi2 = __floats2bfloat162_rn(acc.z, acc.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&lo2); u.y = *reinterpret_cast<uint32_t*>(&hi2);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)m * ld_out + d) = u;
+    }
 }
-void launch_reduce_parts(const float* part, int n_blocks, int split_k, int first_blk, int n_m, int d_out, void* out,
-                         int ld_out, int out_fp32, cudaStream_t st) {
-    const size_t n = (size_t)n_blocks * 128 * d_out;
-    if (n == 0) return;
-    const unsigned grid = (unsigned)((n + 255) / 256);
-    if (out_fp32) k_reduce_parts<true><<<grid, 256, 0, st>>>(part, n_blocks, split_k, first_blk, n_m, d_out, out, ld_out);
-    else k_reduce_parts<false><<<grid, 256, 0, st>>>(part, n_blocks, split_k, first_blk, n_m, d_out, out, ld_out);
+void launch_reduce_parts(const float* part, int m_tiles, int NJ, int pairs, int n_m, int d_out, void* out, int ld_out,
+                         int out_fp32, cudaStream_t st) {
+    if (m_tiles <= 0 || pairs <= 0) return;
+    const dim3 grid((unsigned)((128 * (d_out / 4) + 255) / 256), (unsigned)m_tiles);
+    if (out_fp32) k_reduce_parts<true><<<grid, 256, 0, st>>>(part, m_tiles, NJ, pairs, n_m, d_out, out, ld_out);
+    else k_reduce_parts<false><<<grid, 256, 0, st>>>(part, m_tiles, NJ, pairs, n_m, d_out, out, ld_out);
 }
 
 // ------------------------------------------------------------------------------------------------ fp16 staging copy

@@ -36,6 +36,11 @@ void launch_clip_finish(const float* col_stat_all, int world, const float* row_n
 void launch_bwd_prep(int n, int n_pad, const float* g, float wmul, const float* lse, const float* nll,
                      const int64_t* labels, int lab_offset, int lab_range, const float* g2, const float* nll2,
                      float dmul, float* w, float* l2, int* lab, float* d, uint32_t* gmax_bits, cudaStream_t st);
+// Row-sharded symmetric loss (n = global batch, rows [off, off + n_loc) are local): the vectors of both sweeps in one
+// pass - w = g / 2, l2c / l2r = column / row logsumexp in log2 units (padded to n_pad), lab[n_loc], d[n_loc].
+void launch_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const float* g, const float* row_lse_all,
+                             const float* row_nll_all, const float* col_lse, const float* col_nll, float* w, float* l2c,
+                             float* l2r, int* lab, float* d, uint32_t* words, cudaStream_t st);
 // words = {bits(max|g|), key(max lse2), key(min lse2)} as accumulated by launch_bwd_prep; computes the centre c0 of the
 // lse range, info = {c0, valid}, and f_x[i] = w_x[i] * 2^(c0 - l_x[i]) for both vector sets (f_b may be null).
 void launch_bwd_fast_vectors(const uint32_t* words, int n_a, const float* w_a, const float* l_a, float* f_a, int n_b,
@@ -43,9 +48,10 @@ void launch_bwd_fast_vectors(const uint32_t* words, int n_a, const float* w_a, c
 // out[0] = sum(parts[0..n))   (single block, fixed order -> deterministic)
 void launch_sum_parts(const float* parts, int n, float* out, cudaStream_t st);
 
-// sums the fp32 partial outputs of the split tail blocks of the pair backward sweep into `out`
-void launch_reduce_parts(const float* part, int n_blocks, int split_k, int first_blk, int n_m, int d_out, void* out,
-                         int ld_out, int out_fp32, cudaStream_t st);
+// sums the fp32 partial accumulators of the row blocks that the flat schedule of the pair backward sweep (m_tiles row
+// blocks x NJ column steps over `pairs` CTA pairs, clip_kernels.cuh) cut into several ranges
+void launch_reduce_parts(const float* part, int m_tiles, int NJ, int pairs, int n_m, int d_out, void* out, int ld_out,
+                         int out_fp32, cudaStream_t st);
 // dst (fp16, n_elems) = saturating round-to-nearest of src (bf16 or fp32); n_elems % 8 == 0
 void launch_to_f16(const void* src, int dtype, size_t n_elems, void* dst, cudaStream_t st);
 

@@ -19,6 +19,7 @@
 #include "clip_kernels.cuh"
 #include "sm100.cuh"
 #include "bwd_common.cuh"
+#include <cstdlib>
 
 namespace flyp {
 using namespace sm100;
@@ -44,36 +45,42 @@ DEVI uint8_t* align1024p(uint8_t* p) {
 DEVI void epi_bar_sync2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct ItemInfo { int mb, t0, t1, part; };
-DEVI ItemInfo item_info(int item, const BwdParams& p, int NJ) {
-    ItemInfo r;
-    if (item < p.full_items) { r.mb = item; r.t0 = 0; r.t1 = NJ; r.part = -1; return r; }
-    const int idx = item - p.full_items;
-    const int blk = idx / p.split_k, prt = idx - blk * p.split_k;
-    r.mb = p.full_items + blk;
-    r.t0 = (int)((long long)prt * NJ / p.split_k);
-    r.t1 = (int)((long long)(prt + 1) * NJ / p.split_k);
-    r.part = idx;
-    return r;
-}
+// Work items of one CTA pair under the flat schedule: its contiguous range of (row block, column step) units, cut at
+// row-block boundaries.  part = -1: the item covers its whole row block and writes the output directly; otherwise the
+// index of the fp32 partial slot it accumulates into.
+struct ItemIter {
+    long long pos, end;
+    int NJ, pair, ord;
+    DEVI ItemIter(const BwdParams& p, int pair_, int NJ_) {
+        const long long S = (long long)p.m_tiles * NJ_;
+        pos = flat_start(pair_, S, p.sched_pairs);
+        end = flat_start(pair_ + 1, S, p.sched_pairs);
+        NJ = NJ_; pair = pair_; ord = 0;
+    }
+    DEVI bool next(ItemInfo& r) {
+        if (pos >= end) return false;
+        r.mb = (int)(pos / NJ);
+        r.t0 = (int)(pos - (long long)r.mb * NJ);
+        const long long room = NJ - r.t0, len = end - pos;
+        r.t1 = r.t0 + (int)(len < room ? len : room);
+        r.part = (r.t0 == 0 && r.t1 == NJ) ? -1 : 2 * pair + (ord == 0 ? 0 : 1);
+        pos += r.t1 - r.t0;
+        ++ord;
+        return true;
+    }
+};
 }  // namespace
 
-// The row blocks that do not fill a whole wave of CTA pairs are split into k column ranges each, so that the last
-// wave costs ceil(rem * k / npairs) / k of a full one instead of 1 (k <= 8; each part adds a fill + drain, ~2 %).
-int bwd_pair_tail_split(int m_tiles, int n_cols, int num_sms, int* full_items) {
-    const int npairs = num_sms / 2;
-    const int NJ = (n_cols + PairCfg::NSTEP - 1) / PairCfg::NSTEP;
-    const int rem = npairs > 0 ? m_tiles % npairs : 0;
-    int best_k = 1;
-    if (rem > 0) {
-        double best = 1.0;
-        for (int k = 2; k <= 8 && k <= NJ; ++k) {
-            const int waves = (rem * k + npairs - 1) / npairs;
-            const double cost = (double)waves / k + 0.02 * k;
-            if (cost < best - 1e-9) { best = cost; best_k = k; }
-        }
+// The flat schedule keeps every pair equally loaded whatever the number of row blocks (a per-row-block schedule idles
+// 14 % of the pairs when a rank owns 32 or 64 row blocks, i.e. B = 32768 on 8 or 4 GPUs).
+int bwd_pair_sched_pairs(int m_tiles, int n_cols, int num_sms) {
+    int npairs = num_sms / 2;
+    if (const char* e = getenv("FLYP_SCHED_PAIRS")) {          // A/B switch for measurements
+        const int v = atoi(e);
+        if (v > 0 && v < npairs) npairs = v;
     }
-    *full_items = (best_k > 1) ? m_tiles - rem : m_tiles;
-    return best_k;
+    const long long S = (long long)m_tiles * ((n_cols + PairCfg::NSTEP - 1) / PairCfg::NSTEP);
+    return (int)(S < npairs ? S : npairs);
 }
 
 size_t bwd_pair_smem_bytes() { return PairCfg::SMEM_BYTES; }
@@ -103,8 +110,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int n_items = p.full_items + (p.m_tiles - p.full_items) * p.split_k;
+    const int pair = blockIdx.x >> 1;
     const int NJ = (p.n_n + Cfg::NSTEP - 1) / Cfg::NSTEP;
     const int KC = p.kc;                         // 64-wide K chunks of the S contraction (even)
     const int ND = (p.d_out + 255) / 256;        // pair MMAs of the dA^T product (256 feature columns each)
@@ -151,8 +157,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             };
             peer_wait_all(p.wait_b);      // multi-GPU: the N-side rows (and their fp16 copy) of every rank have arrived
             peer_wait_all(p.wait_bd);
-            for (int item = pair; item < n_items; item += npairs, ++it) {
-                const ItemInfo ii = item_info(item, p, NJ);
+            ItemIter iter(p, pair, NJ);
+            ItemInfo ii;
+            for (; iter.next(ii); ++it) {
                 mbar_wait(IFREE, (it & 1) ^ 1);
                 if (cta == 0) mbar_expect_tx(IFULL, 2 * KC * 8192);
                 for (int c = 0; c < KC; ++c)
@@ -226,8 +233,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 umma_commit_cg2(DSEMPTY);
                 ++gd;
             };
-            for (int item = pair; item < n_items; item += npairs, ++it) {
-                const ItemInfo ii = item_info(item, p, NJ);
+            ItemIter iter(p, pair, NJ);
+            ItemInfo ii;
+            for (; iter.next(ii); ++it) {
                 const int nj = ii.t1 - ii.t0;
                 twait(IFULL, it & 1, w_ifull);
                 tc_fence_after();
@@ -261,12 +269,13 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
         const bool prof = p.prof != nullptr && pair == 0 && cta == 0 && threadIdx.x == 128;
         long long w_sfull = 0, w_dsempty = 0, w_accfull = 0;
         const long long t_begin = clock64();
-        for (int item = pair; item < n_items; item += npairs, ++it) {
-            const ItemInfo ii = item_info(item, p, NJ);
+        const bool want_ds = p.dscale_part != nullptr;
+        float dsum = 0.f;                           // d(scale) share of this thread over all items of the pair
+        ItemIter iter(p, pair, NJ);
+        ItemInfo ii;
+        for (; iter.next(ii); ++it) {
             const int m = ii.mb * TILE + (int)cta * 64 + rloc;
             const RowCtx rc = load_row_ctx<ROW_TERM>(p, m, fast, G);
-            const bool want_ds = p.dscale_part != nullptr;
-            float dsum = 0.f;
             for (int t = ii.t0; t < ii.t1; ++t, ++gs) {
                 const int sb = gs & 1;
                 { const long long t0 = clock64(); mbar_wait(SFULL(sb), (gs >> 1) & 1); w_sfull += clock64() - t0; }
@@ -321,17 +330,16 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             }
             tc_fence_before();
             mbar_arrive_cluster(R_ACCEMPTY);
-            if (p.dscale_part != nullptr) {
+        }
+        if (want_ds) {
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
-                if (lane == 0) red[warp - 4] = dsum;
-                epi_bar_sync2();
-                if (et == 0) {
-                    float tot = 0.f;
-                    for (int w = 0; w < 8; ++w) tot += red[w];
-                    p.dscale_part[item * 2 + (int)cta] = tot * invG;
-                }
-                epi_bar_sync2();
+            for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
+            if (lane == 0) red[warp - 4] = dsum;
+            epi_bar_sync2();
+            if (et == 0) {
+                float tot = 0.f;
+                for (int w = 0; w < 8; ++w) tot += red[w];
+                p.dscale_part[pair * 2 + (int)cta] = tot * invG;
             }
         }
         if (prof) {
@@ -346,10 +354,8 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
 
 void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
                      int num_sms, cudaStream_t st) {
-    const int n_items = p.full_items + (p.m_tiles - p.full_items) * p.split_k;
-    int npairs = num_sms / 2;
-    if (n_items < npairs) npairs = n_items;
-    const int grid = npairs * 2;
+    (void)num_sms;
+    const int grid = p.sched_pairs * 2;
     const size_t smem = bwd_pair_smem_bytes();
     const bool row_term = p.wr != nullptr, col_term = p.wc != nullptr;
 #define FLYP_LAUNCH_BWD2(R, C)                                                                                 \

@@ -96,14 +96,17 @@ struct BwdParams {
     const float* fa;         // [m] fast form: wr 2^(c0 - lr)      (see bwd_common.cuh)
     const float* fb;         // [n] fast form: wc 2^(c0 - lc)
     const float* fast_info;  // device {c0, valid}: valid != 0 -> single-exponential epilogue
-    // tail splitting (pair kernel): M blocks [0, full_items) are swept whole; each of the remaining blocks is swept by
-    // split_k work items over disjoint column ranges that write fp32 partials to part_out[idx][128][d_out]
-    int full_items, split_k;
+    // flat schedule (pair kernel): the S = m_tiles * ceil(n_n / 256) (row block, column step) units, row-block-major,
+    // are cut into sched_pairs equal contiguous ranges, one per CTA pair (flat_start).  A range that covers a row block
+    // only partly accumulates that part into part_out[2 * pair + (0: the range starts inside the block, 1: it ends
+    // inside it)][128][d_out] (fp32), summed per block by launch_reduce_parts.
+    int sched_pairs;
     float* part_out;
     PeerWait wait_b, wait_bd; // readiness of the N-side operand rows (tmB) / of their fp16 copy (tmBd), see peer.cuh
     int dbg;                 // debug experiments (FLYP_DBG env): bit 0 = every streamed load reads box (0, 0)
     unsigned long long* prof; // optional debug: per-role wait-cycle counters of cluster 0 (see tools/pair_prof.py)
-    float* dscale_part;      // [m_tiles * max(d_parts, 2)] partial sums of <acc, a> (unscaled), may be null
+    float* dscale_part;      // partial sums of dS * <a, b> (unscaled), may be null: [m_tiles * d_parts] (bwd_kernel) or
+                             // [2 * sched_pairs] (pair kernel: one per CTA)
 };
 
 // robust = exact per-tile (max, sum) row statistics only; gate (device int, may be null): the robust kernel returns
@@ -121,8 +124,11 @@ void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
                      int num_sms, cudaStream_t st);
 size_t bwd_pair_smem_bytes();
-// how launch_bwd_pair splits the tail: returns split_k (1 = no split) and sets full_items
-int bwd_pair_tail_split(int m_tiles, int n_cols, int num_sms, int* full_items);
+// number of CTA pairs the flat schedule of launch_bwd_pair uses (<= num_sms / 2)
+int bwd_pair_sched_pairs(int m_tiles, int n_cols, int num_sms);
+constexpr int PAIR_NSTEP = 256;      // columns per step of the pair kernel
+// first flat unit of pair q
+__host__ __device__ inline long long flat_start(int q, long long S, int pairs) { return (long long)q * S / pairs; }
 size_t fwd_smem_bytes(bool stationary);
 size_t bwd_smem_bytes();
 

@@ -129,10 +129,17 @@ __global__ void k_push_stats(SegPtrs ptrs, int world, int rank, size_t off_colst
     float* rl = reinterpret_cast<float*>(ptrs.seg[q] + off_rowstat) + (size_t)rank * n_rows;
     float* rn = rl + cap;
     const int n_cs = 3 * n_cols;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cs; i += gridDim.x * blockDim.x) cs[i] = col_stat[i];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
-        rl[i] = row_lse[i];
-        rn[i] = row_nll[i];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if ((n_cols & 3) == 0 && (n_rows & 3) == 0 && (cap & 3) == 0) {      // 16-byte remote stores
+        const float4* s4 = reinterpret_cast<const float4*>(col_stat);
+        float4* d4 = reinterpret_cast<float4*>(cs);
+        for (int i = tid; i < n_cs / 4; i += nth) d4[i] = s4[i];
+        const float4 *l4 = reinterpret_cast<const float4*>(row_lse), *n4 = reinterpret_cast<const float4*>(row_nll);
+        float4 *dl = reinterpret_cast<float4*>(rl), *dn = reinterpret_cast<float4*>(rn);
+        for (int i = tid; i < n_rows / 4; i += nth) { dl[i] = l4[i]; dn[i] = n4[i]; }
+    } else {
+        for (int i = tid; i < n_cs; i += nth) cs[i] = col_stat[i];
+        for (int i = tid; i < n_rows; i += nth) { rl[i] = row_lse[i]; rn[i] = row_nll[i]; }
     }
     __threadfence_system();
     __syncthreads();

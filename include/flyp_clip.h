@@ -171,6 +171,19 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
                            const void* txt16, const flyp_ready_t* txt_ready, const flyp_ready_t* txt16_ready,
                            void* stream);
 
+/* Both backward sweeps of a rank of the row-sharded symmetric loss with one shared preparation pass: d_img from the
+ * row block img . txt_all^T, d_txt from the transposed block txt . img_all^T (complete gradients of the local rows,
+ * no B x D reduce-scatter), d_scale = this rank's share.  *_all / *16_all: gathered features and their fp16 copies
+ * (flyp_gathered_t); row_lse_all / row_nll_all / col_lse / col_nll: statistics of all n_cols global rows / columns;
+ * g[n_cols]: upstream gradient on the (replicated) loss vector.  Any of d_img, d_txt, d_scale may be NULL. */
+int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all, const void* txt_all,
+                          const void* img16_all, const void* txt16_all, const float* scale, int n_rows, int n_cols,
+                          int dim, int dtype, int row_offset, const float* row_lse_all, const float* row_nll_all,
+                          const float* col_lse, const float* col_nll, const float* g, float grad_mul, int grad_dtype,
+                          void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
+                          const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready, const flyp_ready_t* img16_ready,
+                          const flyp_ready_t* txt16_ready, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Row-wise L2 normalisation x / ||x||_2 (no epsilon), clip/model.py:375-376, src/models/ce_ablation.py:115-118.
  * ------------------------------------------------------------------------------------------------------------------ */
