@@ -54,14 +54,14 @@ SIGNATURES = {
     "flyp_clip_fwd_local_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(Ready), c_void_p]),
     "flyp_clip_fwd_finish_ex": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                        POINTER(Ready), c_void_p]),
+                                        c_int, POINTER(Ready), c_void_p]),
     "flyp_clip_bwd_local_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, POINTER(Ready),
                                        POINTER(Ready), c_void_p]),
     "flyp_clip_bwd_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                      c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
-                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(Ready),
+                                      c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                      c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(Ready),
                                       POINTER(Ready), POINTER(Ready), POINTER(Ready), c_void_p]),
     "flyp_comm_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
     "flyp_comm_segment_bytes": (c_int, [c_void_p, POINTER(c_size_t)]),

@@ -137,8 +137,24 @@ class PeerComm:
 
 class PeerStep:
     """State of one forward (kept for the backward)."""
-    __slots__ = ("comm", "g", "st", "img", "txt", "s", "b", "B", "D", "off", "row_lse", "row_nll", "col_stat", "status",
+    __slots__ = ("comm", "g", "st", "img", "txt", "s", "b", "B", "D", "off", "buf", "row_lse", "row_nll", "col_stat",
                  "col_lse", "col_nll", "loss", "ws")
+
+
+_WS_CACHE = {}
+
+
+def _workspace(b: int, B: int, D: int, dev) -> torch.Tensor:
+    """Scratch of the kernels of one rank.  Cached per shape and device: every use is stream-ordered on the current
+    stream and nothing in it outlives a call, so consecutive steps share it."""
+    key = (b, B, D, dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        from . import ops
+        if len(_WS_CACHE) > 8:
+            _WS_CACHE.clear()
+        ws = _WS_CACHE[key] = ops.clip_workspace(b, B, D, _lib.FLYP_BF16, dev)
+    return ws
 
 
 def fwd_gather(comm: PeerComm, img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor) -> PeerStep:
@@ -155,36 +171,41 @@ def fwd_gather(comm: PeerComm, img: torch.Tensor, txt: torch.Tensor, scale: torc
 
 
 def fwd_local(st: PeerStep) -> None:
-    from . import ops
     dev = st.img.device
     lib = _lib.load()
+    b, B = st.b, st.B
     with torch.cuda.device(dev):
-        st.ws = ops.clip_workspace(st.b, st.B, st.D, _lib.FLYP_BF16, dev)
-        st.row_lse, st.row_nll, st.col_stat = ops._f32(st.b, dev), ops._f32(st.b, dev), ops._f32(3 * st.B, dev)
-        st.status = None
+        st.ws = _workspace(b, B, st.D, dev)
+        # one allocation for every fp32 vector of the step (each slice 16-byte aligned)
+        bp = (b + 3) & ~3
+        Bp = (B + 3) & ~3
+        st.buf = torch.empty(2 * bp + 5 * Bp, dtype=torch.float32, device=dev)
+        st.row_lse, st.row_nll = st.buf[0:b], st.buf[bp:bp + b]
+        o = 2 * bp
+        st.col_stat = st.buf[o:o + 3 * B]
+        st.col_lse, st.col_nll = st.buf[o + 3 * Bp:o + 3 * Bp + B], st.buf[o + 4 * Bp:o + 4 * Bp + B]
         _lib.check(lib.flyp_clip_fwd_local_ex(
-            st.img.data_ptr(), st.g.txt_all, st.s.data_ptr(), st.b, st.B, st.D, _lib.FLYP_BF16, st.off,
+            st.img.data_ptr(), st.g.txt_all, st.s.data_ptr(), b, B, st.D, _lib.FLYP_BF16, st.off,
             st.row_lse.data_ptr(), st.row_nll.data_ptr(), st.col_stat.data_ptr(), None,
             st.ws.data_ptr(), st.ws.numel(), ctypes.byref(st.g.txt_ready), _lib.stream_ptr(dev)))
     st.st = st.comm.push_stats(st.g.seq, st.col_stat, st.row_lse, st.row_nll)
 
 
-def fwd_finish(st: PeerStep) -> torch.Tensor:
+def fwd_finish(st: PeerStep, loss_dtype=torch.float32) -> torch.Tensor:
     """Loss of every global row (the reference returns the full vector on every rank, clip/loss.py:113-114,208)."""
-    from . import ops
     dev = st.img.device
+    code = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[loss_dtype]
     with torch.cuda.device(dev):
-        st.col_lse, st.col_nll, st.loss = ops._f32(st.B, dev), ops._f32(st.B, dev), ops._f32(st.B, dev)
+        st.loss = torch.empty(st.B, dtype=loss_dtype, device=dev)
         _lib.check(_lib.load().flyp_clip_fwd_finish_ex(
             st.st.col_stat_all, st.comm.world, st.st.row_nll_all, st.B, st.B, 0, st.col_lse.data_ptr(),
-            st.col_nll.data_ptr(), st.loss.data_ptr(), ctypes.byref(st.st.ready), _lib.stream_ptr(dev)))
+            st.col_nll.data_ptr(), st.loss.data_ptr(), code, ctypes.byref(st.st.ready), _lib.stream_ptr(dev)))
     return st.loss
 
 
 def bwd_local(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_img: bool, need_txt: bool,
               need_scale: bool):
     """Returns (d_img, d_txt, d_scale_partial): complete gradients of the local rows, this rank's share of d(scale)."""
-    from . import ops
     if not st.comm.alive(st.g.seq):
         raise FlypError("the gathered features of this step were overwritten: with the peer-memory path at most one "
                         "later forward may run before a step's backward (use ClipLoss(comm='nccl') otherwise)")
@@ -192,19 +213,20 @@ def bwd_local(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_i
     lib = _lib.load()
     gdt = st.img.dtype if grad_dtype is None else grad_dtype
     gcode = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[gdt]
-    g = g.to(torch.float32).contiguous()
-    d_img = d_txt = d_s = None
+    if g.dtype not in (torch.float32, torch.bfloat16):
+        g = g.to(torch.float32)
+    g = g.contiguous()
+    g_code = _lib.FLYP_BF16 if g.dtype == torch.bfloat16 else _lib.FLYP_F32
     need_img = need_img or need_scale
     with torch.cuda.device(dev):
         d_img = torch.empty(st.b, st.D, dtype=gdt, device=dev) if need_img else None
         d_txt = torch.empty(st.b, st.D, dtype=gdt, device=dev) if need_txt else None
-        d_s = ops._f32(1, dev) if need_scale else None
+        d_s = torch.empty(1, dtype=torch.float32, device=dev) if need_scale else None
         gg = st.g
         _lib.check(lib.flyp_clip_bwd_sharded(
             st.img.data_ptr(), st.txt.data_ptr(), gg.img_all, gg.txt_all, gg.img16_all, gg.txt16_all, st.s.data_ptr(),
             st.b, st.B, st.D, _lib.FLYP_BF16, st.off, st.st.row_lse_all, st.st.row_nll_all, st.col_lse.data_ptr(),
-            st.col_nll.data_ptr(), g.data_ptr(), float(grad_mul), gcode, _lib.ptr(d_img), _lib.ptr(d_txt), _lib.ptr(d_s),
-            st.ws.data_ptr(), st.ws.numel(), ctypes.byref(gg.img_ready), ctypes.byref(gg.txt_ready),
+            st.col_nll.data_ptr(), g.data_ptr(), g_code, float(grad_mul), gcode, _lib.ptr(d_img), _lib.ptr(d_txt),
+            _lib.ptr(d_s), st.ws.data_ptr(), st.ws.numel(), ctypes.byref(gg.img_ready), ctypes.byref(gg.txt_ready),
             ctypes.byref(gg.img16_ready), ctypes.byref(gg.txt16_ready), _lib.stream_ptr(dev)))
-    # keep g alive until the kernels that read it through raw pointers are enqueued (they are, by now)
     return d_img, d_txt, d_s

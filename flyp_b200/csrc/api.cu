@@ -438,16 +438,17 @@ int flyp_clip_fwd_local_ex(const void* img, const void* txt, const float* scale,
 int flyp_clip_fwd_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
                          int row_offset, float* col_lse, float* col_nll, float* loss, void* stream) {
     return flyp_clip_fwd_finish_ex(col_stat_all, world, row_nll, n_rows, n_cols, row_offset, col_lse, col_nll, loss,
-                                   nullptr, stream);
+                                   FLYP_F32, nullptr, stream);
 }
 
 int flyp_clip_fwd_finish_ex(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
-                            int row_offset, float* col_lse, float* col_nll, float* loss,
+                            int row_offset, float* col_lse, float* col_nll, void* loss, int loss_dtype,
                             const flyp_ready_t* stats_ready, void* stream) {
     if (!col_stat_all || !row_nll || !col_lse || !col_nll || !loss) return fail(FLYP_ERR_ARG, "null pointer argument");
     if (world < 1 || n_rows <= 0 || n_cols <= 0) return fail(FLYP_ERR_ARG, "bad sizes");
+    if (loss_dtype != FLYP_BF16 && loss_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad loss_dtype %d", loss_dtype);
     flyp::launch_clip_finish(col_stat_all, world, row_nll, n_rows, n_cols, row_offset, col_lse, col_nll, loss,
-                             to_wait(stats_ready), static_cast<cudaStream_t>(stream));
+                             loss_dtype == FLYP_BF16, to_wait(stats_ready), static_cast<cudaStream_t>(stream));
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -536,11 +537,12 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
 int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all, const void* txt_all,
                           const void* img16_all, const void* txt16_all, const float* scale, int n_rows, int n_cols,
                           int dim, int dtype, int row_offset, const float* row_lse_all, const float* row_nll_all,
-                          const float* col_lse, const float* col_nll, const float* g, float grad_mul, int grad_dtype,
-                          void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
-                          const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready, const flyp_ready_t* img16_ready,
-                          const flyp_ready_t* txt16_ready, void* stream) {
+                          const float* col_lse, const float* col_nll, const void* g, int g_dtype, float grad_mul,
+                          int grad_dtype, void* d_img, void* d_txt, float* d_scale, void* workspace,
+                          size_t workspace_bytes, const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready,
+                          const flyp_ready_t* img16_ready, const flyp_ready_t* txt16_ready, void* stream) {
     int rc = check_common(n_rows, n_cols, dim, dtype);
+    if (g_dtype != FLYP_BF16 && g_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad g_dtype %d", g_dtype);
     if (rc) return rc;
     if (dtype != FLYP_BF16) return fail(FLYP_ERR_ARG, "the sharded backward takes bf16 features");
     if (!img || !txt || !scale || !row_lse_all || !row_nll_all || !col_lse || !col_nll || !g || !workspace)
@@ -560,7 +562,7 @@ int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all,
     float *wg = w.cols.w, *l2c = w.cols.l2, *fc = w.cols.f, *l2r = w.cols.d, *fr = reinterpret_cast<float*>(w.cols.lab);
     CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, 2 * sizeof(uint32_t), st));
     CUDA_OK(cudaMemsetAsync(w.gmax_bits + 2, 0xff, sizeof(uint32_t), st));
-    flyp::launch_bwd_prep_sharded(n_cols, cp, row_offset, n_rows, g, row_lse_all, row_nll_all, col_lse, col_nll, wg, l2c,
+    flyp::launch_bwd_prep_sharded(n_cols, cp, row_offset, n_rows, g, g_dtype == FLYP_BF16, row_lse_all, row_nll_all, col_lse, col_nll, wg, l2c,
                                   l2r, w.rows.lab, w.rows.d, w.gmax_bits, st);
     flyp::launch_bwd_fast_vectors(w.gmax_bits, cp, wg, l2c, fc, cp, wg, l2r, fr, w.fast_info, st);
     CUDA_OK(cudaGetLastError());

@@ -226,7 +226,7 @@ void launch_fwd_finalize_robust(const float* rowpart, const float* rowmax, int n
 // col_stat_all[world][3 * n_cols] -> col_lse[n_cols]; loss[i] = 0.5 * (row_nll[i] + col_nll[row_offset + i])
 __global__ void k_clip_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
                               int row_offset, float* __restrict__ col_lse, float* __restrict__ col_nll,
-                              float* __restrict__ loss, PeerWait wait) {
+                              void* __restrict__ loss, int loss_bf16, PeerWait wait) {
     // multi-GPU: the triples / row statistics of the other ranks are pushed into this rank's memory over NVLink; poll
     // their flags first, then read through L2 (__ldcg: no stale non-coherent lines)
     if (wait.flags != nullptr) {
@@ -252,13 +252,18 @@ __global__ void k_clip_finish(const float* col_stat_all, int world, const float*
     col_lse[j] = lse2 * LN2_F;
     col_nll[j] = nll;
     const int i = j - row_offset;
-    if (i >= 0 && i < n_rows) loss[i] = 0.5f * (__ldcg(row_nll + i) + nll);
+    if (i >= 0 && i < n_rows) {
+        const float v = 0.5f * (__ldcg(row_nll + i) + nll);
+        if (loss_bf16) reinterpret_cast<__nv_bfloat16*>(loss)[i] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(loss)[i] = v;
+    }
 }
 
 void launch_clip_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
-                        int row_offset, float* col_lse, float* col_nll, float* loss, PeerWait wait, cudaStream_t st) {
+                        int row_offset, float* col_lse, float* col_nll, void* loss, int loss_bf16, PeerWait wait,
+                        cudaStream_t st) {
     k_clip_finish<<<(n_cols + 255) / 256, 256, 0, st>>>(col_stat_all, world, row_nll, n_rows, n_cols, row_offset,
-                                                        col_lse, col_nll, loss, wait);
+                                                        col_lse, col_nll, loss, loss_bf16, wait);
 }
 
 // ------------------------------------------------------------------------------------------------ bwd vectors
@@ -314,7 +319,7 @@ void launch_bwd_prep(int n, int n_pad, const float* g, float wmul, const float* 
 // Row-sharded symmetric loss: one pass prepares the vectors of BOTH backward sweeps of a rank.  Global (padded) vectors:
 // w = g / 2, l2c = col_lse log2 e, l2r = row_lse_all log2 e; local: lab[i] = off + i, d[i] = exact dS at the positive of
 // local row i (the same value serves the transposed sweep).
-__global__ void k_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const float* __restrict__ g,
+__global__ void k_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const void* __restrict__ g, int g_bf16,
                                    const float* row_lse_all, const float* row_nll_all, const float* __restrict__ col_lse,
                                    const float* __restrict__ col_nll, float* __restrict__ w, float* __restrict__ l2c,
                                    float* __restrict__ l2r, int* __restrict__ lab, float* __restrict__ d,
@@ -323,7 +328,8 @@ __global__ void k_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const f
     uint32_t gb = 0u, khi = 0u, klo = 0xffffffffu;
     float wi = 0.f, lc = 0.f, lr = 0.f;
     if (i < n) {
-        const float gi = g[i];
+        const float gi = g_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g)[i])
+                                : reinterpret_cast<const float*>(g)[i];
         gb = __float_as_uint(fabsf(gi));
         wi = 0.5f * gi;
         lc = col_lse[i] * LOG2E_F;
@@ -350,10 +356,10 @@ __global__ void k_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const f
     }
     if (i < n_pad) { w[i] = wi; l2c[i] = lc; l2r[i] = lr; }
 }
-void launch_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const float* g, const float* row_lse_all,
+void launch_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const void* g, int g_bf16, const float* row_lse_all,
                              const float* row_nll_all, const float* col_lse, const float* col_nll, float* w, float* l2c,
                              float* l2r, int* lab, float* d, uint32_t* words, cudaStream_t st) {
-    k_bwd_prep_sharded<<<(n_pad + 255) / 256, 256, 0, st>>>(n, n_pad, off, n_loc, g, row_lse_all, row_nll_all, col_lse,
+    k_bwd_prep_sharded<<<(n_pad + 255) / 256, 256, 0, st>>>(n, n_pad, off, n_loc, g, g_bf16, row_lse_all, row_nll_all, col_lse,
                                                             col_nll, w, l2c, l2r, lab, d, words);
 }
 

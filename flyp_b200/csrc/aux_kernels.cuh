@@ -27,7 +27,8 @@ void launch_fwd_finalize_robust(const float* rowpart, const float* rowmax, int n
 // col_stat_all[world][3*n_cols] -> col_lse; loss[i] = 0.5 (row_nll[i] + col_nll[off+i])
 // wait: readiness of col_stat_all / row_nll when other ranks push them (peer.cuh); flags == nullptr -> no waiting
 void launch_clip_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
-                        int row_offset, float* col_lse, float* col_nll, float* loss, PeerWait wait, cudaStream_t st);
+                        int row_offset, float* col_lse, float* col_nll, void* loss, int loss_bf16, PeerWait wait,
+                        cudaStream_t st);
 
 // Vectors consumed by bwd_kernel, padded with zeros / -1 to a multiple of 128 entries.
 //   w[i] = wmul * g[i]; l2[i] = lse[i] * log2(e); lab[i] = labels ? labels[i] : (i + lab_offset if in [0, lab_range) else -1)
@@ -38,7 +39,7 @@ void launch_bwd_prep(int n, int n_pad, const float* g, float wmul, const float* 
                      float dmul, float* w, float* l2, int* lab, float* d, uint32_t* gmax_bits, cudaStream_t st);
 // Row-sharded symmetric loss (n = global batch, rows [off, off + n_loc) are local): the vectors of both sweeps in one
 // pass - w = g / 2, l2c / l2r = column / row logsumexp in log2 units (padded to n_pad), lab[n_loc], d[n_loc].
-void launch_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const float* g, const float* row_lse_all,
+void launch_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const void* g, int g_bf16, const float* row_lse_all,
                              const float* row_nll_all, const float* col_lse, const float* col_nll, float* w, float* l2c,
                              float* l2r, int* lab, float* d, uint32_t* words, cudaStream_t st);
 // words = {bits(max|g|), key(max lse2), key(min lse2)} as accumulated by launch_bwd_prep; computes the centre c0 of the

@@ -178,22 +178,28 @@ int check_comm(const flyp_comm* c, bool need_connected) {
     return 0;
 }
 
-// The copy-engine schedule of one gather: for each of the four matrices, W - 1 block copies (own slot -> same slot of
-// peer (rank - k)), each followed by the 4-byte flag copy.  Text first: it is what the forward waits for.
-struct PushOp { void* dst; const void* src; size_t bytes; };
+// The copy-engine schedule of one gather: one independent chain per peer (the chains run on different copy engines and
+// share the NVLink egress), each chain in the order the consumer needs the data - text (forward), its fp16 copy (first
+// backward sweep), image + fp16 copy (second sweep) - with the 4-byte sequence number written behind each stage.
+struct PushOp { void* dst; const void* src; size_t bytes; int chain; };
 int build_push_ops(const flyp_comm* c, int par, int n_rows, int dim, PushOp* ops) {
     int n = 0;
     const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
-    for (int a = 0; a < N_ARR; ++a) {
-        for (int k = 1; k < c->world; ++k) {
-            const int q = (c->rank - k + c->world) % c->world;
-            ops[n++] = {c->seg[q] + c->off_feat[par][a] + slot_off, c->seg[c->rank] + c->off_feat[par][a] + slot_off,
-                        slot_bytes};
-            ops[n++] = {flag_ptr(c, q, a, c->rank), c->seg[c->rank] + c->off_seqword[par], sizeof(uint32_t)};
-        }
+    uint8_t* own = c->seg[c->rank];
+    const void* seqword = own + c->off_seqword[par];
+    for (int k = 1; k < c->world; ++k) {
+        const int q = (c->rank - k + c->world) % c->world, ch = k - 1;
+        auto data = [&](int a) {
+            ops[n++] = {c->seg[q] + c->off_feat[par][a] + slot_off, own + c->off_feat[par][a] + slot_off, slot_bytes, ch};
+        };
+        auto flag = [&](int a) { ops[n++] = {flag_ptr(c, q, a, c->rank), seqword, sizeof(uint32_t), ch}; };
+        data(ARR_TXT); flag(ARR_TXT);
+        data(ARR_TXT16); flag(ARR_TXT16);
+        data(ARR_IMG); data(ARR_IMG16); flag(ARR_IMG16);      // the image matrices share the flag of the fp16 copy
     }
     return n;
 }
+constexpr int MAX_PUSH_OPS = 8 * MAXW;
 
 int build_push_graphs(flyp_comm* c, int n_rows, int dim) {
     for (int par = 0; par < 2; ++par) {
@@ -202,22 +208,24 @@ int build_push_graphs(flyp_comm* c, int n_rows, int dim) {
     c->push_rows = n_rows; c->push_dim = dim;
     if (!c->use_graph || c->world == 1) return 0;
     for (int par = 0; par < 2; ++par) {
-        PushOp ops[2 * N_ARR * MAXW];
+        PushOp ops[MAX_PUSH_OPS];
         const int n = build_push_ops(c, par, n_rows, dim, ops);
         cudaGraph_t g;
         COMM_CUDA_OK(cudaGraphCreate(&g, 0));
-        cudaGraphNode_t prev = nullptr;
+        cudaGraphNode_t prev[MAXW];
+        for (int i = 0; i < MAXW; ++i) prev[i] = nullptr;
         for (int i = 0; i < n; ++i) {
             cudaGraphNode_t node;
-            cudaError_t e = cudaGraphAddMemcpyNode1D(&node, g, prev ? &prev : nullptr, prev ? 1 : 0, ops[i].dst, ops[i].src,
-                                                     ops[i].bytes, cudaMemcpyDefault);
+            cudaGraphNode_t* dep = prev[ops[i].chain] ? &prev[ops[i].chain] : nullptr;
+            cudaError_t e = cudaGraphAddMemcpyNode1D(&node, g, dep, dep ? 1 : 0, ops[i].dst, ops[i].src, ops[i].bytes,
+                                                     cudaMemcpyDefault);
             if (e != cudaSuccess) {                  // e.g. peer memcpy nodes unsupported: plain async copies instead
                 cudaGraphDestroy(g);
                 cudaGetLastError();
                 c->use_graph = false;
                 return 0;
             }
-            prev = node;
+            prev[ops[i].chain] = node;
         }
         cudaError_t e = cudaGraphInstantiate(&c->push_exec[par], g, 0);
         cudaGraphDestroy(g);
@@ -380,7 +388,7 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
         if (c->use_graph && c->push_exec[par]) {
             COMM_CUDA_OK(cudaGraphLaunch(c->push_exec[par], c->side));
         } else {
-            PushOp ops[2 * N_ARR * MAXW];
+            PushOp ops[MAX_PUSH_OPS];
             const int n = build_push_ops(c, par, n_rows, dim, ops);
             for (int i = 0; i < n; ++i)
                 COMM_CUDA_OK(cudaMemcpyAsync(ops[i].dst, ops[i].src, ops[i].bytes, cudaMemcpyDefault, c->side));
@@ -394,7 +402,7 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     out->img16_all = own + c->off_feat[par][ARR_IMG16];
     flyp_ready_t* r[N_ARR] = {&out->txt_ready, &out->txt16_ready, &out->img_ready, &out->img16_ready};
     for (int a = 0; a < N_ARR; ++a) {
-        r[a]->flags = flag_ptr(c, c->rank, a, 0);
+        r[a]->flags = flag_ptr(c, c->rank, a == ARR_IMG ? ARR_IMG16 : a, 0);
         r[a]->seq = seq; r[a]->n_flags = c->world; r[a]->rows_per_flag = n_rows; r[a]->err = c->err_dev;
     }
     out->seq = seq;

@@ -240,11 +240,11 @@ class _ClipLossPeerFn(torch.autograd.Function):
         s = ops._scale_tensor(scale, img.device)
         st = peer.fwd_gather(comm, img, txt, s)
         peer.fwd_local(st)
-        loss = peer.fwd_finish(st)
+        loss = peer.fwd_finish(st, img.dtype)       # the kernel writes the loss in the feature dtype (no cast pass)
         ctx.st = st
         ctx.meta = (gather_with_grad, grad_dtype, torch.is_tensor(scale), scale.shape if torch.is_tensor(scale) else None,
                     scale.dtype if torch.is_tensor(scale) else None)
-        return loss.to(img.dtype)
+        return loss
 
     @staticmethod
     def backward(ctx, g):
@@ -260,9 +260,12 @@ class _ClipLossPeerFn(torch.autograd.Function):
             tot = torch.empty(1, dtype=torch.float32, device=st.img.device)
             st.comm.all_reduce_scalar(st.g.seq, d_s, tot)
             if s_is_tensor:
-                gs = torch.zeros(s_shape, dtype=torch.float32, device=st.img.device).reshape(-1)
-                gs[:1] = tot
-                gs = gs.reshape(s_shape).to(s_dtype)
+                if s_dtype == torch.float32 and len(s_shape) <= 1 and (len(s_shape) == 0 or s_shape[0] == 1):
+                    gs = tot.view(s_shape)
+                else:
+                    gs = torch.zeros(s_shape, dtype=torch.float32, device=st.img.device).reshape(-1)
+                    gs[:1] = tot
+                    gs = gs.reshape(s_shape).to(s_dtype)
         st.comm.check_error()
         return (d_img if need_img else None), (d_txt if need_txt else None), gs, None, None, None
 

@@ -30,8 +30,10 @@ def _scale_tensor(scale, device) -> torch.Tensor:
     src/models/flyp_loss_few_shot.py:156-159 does for DataParallel outputs)."""
     if not torch.is_tensor(scale):
         return torch.tensor([float(scale)], dtype=torch.float32, device=device)
-    s = scale.detach().reshape(-1)[:1]
-    return s.to(device=device, dtype=torch.float32).contiguous()
+    s = scale.detach()
+    if s.dtype == torch.float32 and s.device == device and s.numel() == 1:
+        return s.view(1)                                    # the usual case: exp() of the fp32 parameter, no copy
+    return s.reshape(-1)[:1].to(device=device, dtype=torch.float32).contiguous()
 
 
 def _f32(n: int, device) -> torch.Tensor:

@@ -157,12 +157,14 @@ int flyp_comm_sum_scalar(flyp_comm* comm, uint32_t seq, float* out, void* stream
  *   txt_ready        readiness of the rows of `txt` (forward: the schedule starts at this rank's own column block and
  *                    follows the ring order of the push)
  *   txt16 (may be NULL -> converted here), txt16_ready: the fp16 copy of `txt` and its readiness
- *   stats_ready      readiness of col_stat_all / row_nll (all ranks) */
+ *   stats_ready      readiness of col_stat_all / row_nll (all ranks)
+ *   loss_dtype       FLYP_F32 or FLYP_BF16: element type of the loss vector written by the finish step
+ *   (g_dtype of flyp_clip_bwd_sharded likewise: element type of the upstream gradient vector) */
 int flyp_clip_fwd_local_ex(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
                            int dtype, int row_offset, float* row_lse, float* row_nll, float* col_stat, int* status,
                            void* workspace, size_t workspace_bytes, const flyp_ready_t* txt_ready, void* stream);
 int flyp_clip_fwd_finish_ex(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
-                            int row_offset, float* col_lse, float* col_nll, float* loss,
+                            int row_offset, float* col_lse, float* col_nll, void* loss, int loss_dtype,
                             const flyp_ready_t* stats_ready, void* stream);
 int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
                            int dtype, int row_offset, const float* row_lse, const float* row_nll, const float* col_lse,
@@ -179,10 +181,10 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
 int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all, const void* txt_all,
                           const void* img16_all, const void* txt16_all, const float* scale, int n_rows, int n_cols,
                           int dim, int dtype, int row_offset, const float* row_lse_all, const float* row_nll_all,
-                          const float* col_lse, const float* col_nll, const float* g, float grad_mul, int grad_dtype,
-                          void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
-                          const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready, const flyp_ready_t* img16_ready,
-                          const flyp_ready_t* txt16_ready, void* stream);
+                          const float* col_lse, const float* col_nll, const void* g, int g_dtype, float grad_mul,
+                          int grad_dtype, void* d_img, void* d_txt, float* d_scale, void* workspace,
+                          size_t workspace_bytes, const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready,
+                          const flyp_ready_t* img16_ready, const flyp_ready_t* txt16_ready, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Row-wise L2 normalisation x / ||x||_2 (no epsilon), clip/model.py:375-376, src/models/ce_ablation.py:115-118.
