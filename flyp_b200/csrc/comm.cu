@@ -9,9 +9,13 @@
 // their fp16 copies (the operand format of the backward's second GEMM), [world * rows, dim] rank-major - the ordering of
 // clip/loss.py:66-67.  A step is
 //   pack   (kernel, caller's stream)  local rows -> own slots of the four gathered matrices (+ fp16 conversion)
-//   push   (copy engines, side stream) own slots -> the same slots in every peer's segment, peer (rank - k) in round k
-//                                     so that every rank receives from one peer at a time at full link rate; after
-//                                     each block a 4-byte sequence number lands in the peer's flag word
+//   push   (copy engines, side streams) own slots -> the same slots in every peer's segment, peer (rank - k) in round k
+//                                     so that every rank receives from one peer at a time; after each block a 4-byte
+//                                     sequence number lands in the peer's flag word.  Five chains on three side
+//                                     streams: text to odd / even rounds and the fp16 text copy start with the
+//                                     forward; the two image matrices (needed by the second backward sweep only)
+//                                     start after the statistics exchange so that its small remote stores do not
+//                                     queue behind bulk traffic
 //   the tensor-core kernels poll those flag words (peer.cuh) right before their first TMA read of a rank's rows: the
 //   forward starts on its own column block while the other blocks are still in flight.
 // The small vectors (column triples, row statistics, d(scale)) are pushed by a kernel with remote stores and flagged
@@ -57,9 +61,9 @@ struct flyp_comm {
     uint8_t* seg[MAXW];
     bool ipc_mapped[MAXW];
     bool connected;
-    cudaStream_t side;
-    cudaEvent_t ev_packed, ev_pushed;
-    cudaGraphExec_t push_exec[2];
+    cudaStream_t side[3];
+    cudaEvent_t ev_packed, ev_stats, ev_pushed[3];
+    cudaGraphExec_t push_exec[2][5];
     int push_rows, push_dim;
     bool use_graph;
     uint32_t seq;
@@ -178,59 +182,75 @@ int check_comm(const flyp_comm* c, bool need_connected) {
     return 0;
 }
 
-// The copy-engine schedule of one gather: one independent chain per peer (the chains run on different copy engines and
-// share the NVLink egress), each chain in the order the consumer needs the data - text (forward), its fp16 copy (first
-// backward sweep), image + fp16 copy (second sweep) - with the 4-byte sequence number written behind each stage.
-struct PushOp { void* dst; const void* src; size_t bytes; int chain; };
-int build_push_ops(const flyp_comm* c, int par, int n_rows, int dim, PushOp* ops) {
+// The copy-engine schedule of one gather, as chains of (block copy, 4-byte flag copy) pairs.  Copies cost ~4 us + bytes
+// at ~750 GB/s each and a chain is serial, so the work is spread over chains that run on different copy engines:
+//   chain 0 / 1  text, odd / even ring rounds        (stream 0 / 1, start with the forward kernel)
+//   chain 2      fp16 text copy, all rounds          (stream 2, same start; needed by the first backward sweep)
+//   chain 3 / 4  image / fp16 image copy, all rounds (stream 0 / 1, start after the statistics exchange)
+constexpr int N_CHAIN = 5;
+constexpr int CHAIN_STREAM[N_CHAIN] = {0, 1, 2, 0, 1};
+struct PushOp { void* dst; const void* src; size_t bytes; };
+int build_chain_ops(const flyp_comm* c, int par, int chain, int n_rows, int dim, PushOp* ops) {
     int n = 0;
     const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
     uint8_t* own = c->seg[c->rank];
     const void* seqword = own + c->off_seqword[par];
+    const int arr = chain <= 1 ? ARR_TXT : chain == 2 ? ARR_TXT16 : chain == 3 ? ARR_IMG : ARR_IMG16;
     for (int k = 1; k < c->world; ++k) {
-        const int q = (c->rank - k + c->world) % c->world, ch = k - 1;
-        auto data = [&](int a) {
-            ops[n++] = {c->seg[q] + c->off_feat[par][a] + slot_off, own + c->off_feat[par][a] + slot_off, slot_bytes, ch};
-        };
-        auto flag = [&](int a) { ops[n++] = {flag_ptr(c, q, a, c->rank), seqword, sizeof(uint32_t), ch}; };
-        data(ARR_TXT); flag(ARR_TXT);
-        data(ARR_TXT16); flag(ARR_TXT16);
-        data(ARR_IMG); data(ARR_IMG16); flag(ARR_IMG16);      // the image matrices share the flag of the fp16 copy
+        if (chain == 0 && (k & 1) == 0) continue;
+        if (chain == 1 && (k & 1) == 1) continue;
+        const int q = (c->rank - k + c->world) % c->world;
+        ops[n++] = {c->seg[q] + c->off_feat[par][arr] + slot_off, own + c->off_feat[par][arr] + slot_off, slot_bytes};
+        ops[n++] = {flag_ptr(c, q, arr, c->rank), seqword, sizeof(uint32_t)};
     }
     return n;
 }
-constexpr int MAX_PUSH_OPS = 8 * MAXW;
+constexpr int MAX_CHAIN_OPS = 2 * MAXW;
 
 int build_push_graphs(flyp_comm* c, int n_rows, int dim) {
-    for (int par = 0; par < 2; ++par) {
-        if (c->push_exec[par]) { cudaGraphExecDestroy(c->push_exec[par]); c->push_exec[par] = nullptr; }
-    }
+    for (int par = 0; par < 2; ++par)
+        for (int ch = 0; ch < N_CHAIN; ++ch)
+            if (c->push_exec[par][ch]) { cudaGraphExecDestroy(c->push_exec[par][ch]); c->push_exec[par][ch] = nullptr; }
     c->push_rows = n_rows; c->push_dim = dim;
     if (!c->use_graph || c->world == 1) return 0;
     for (int par = 0; par < 2; ++par) {
-        PushOp ops[MAX_PUSH_OPS];
-        const int n = build_push_ops(c, par, n_rows, dim, ops);
-        cudaGraph_t g;
-        COMM_CUDA_OK(cudaGraphCreate(&g, 0));
-        cudaGraphNode_t prev[MAXW];
-        for (int i = 0; i < MAXW; ++i) prev[i] = nullptr;
-        for (int i = 0; i < n; ++i) {
-            cudaGraphNode_t node;
-            cudaGraphNode_t* dep = prev[ops[i].chain] ? &prev[ops[i].chain] : nullptr;
-            cudaError_t e = cudaGraphAddMemcpyNode1D(&node, g, dep, dep ? 1 : 0, ops[i].dst, ops[i].src, ops[i].bytes,
-                                                     cudaMemcpyDefault);
-            if (e != cudaSuccess) {                  // e.g. peer memcpy nodes unsupported: plain async copies instead
-                cudaGraphDestroy(g);
-                cudaGetLastError();
-                c->use_graph = false;
-                return 0;
+        for (int ch = 0; ch < N_CHAIN; ++ch) {
+            PushOp ops[MAX_CHAIN_OPS];
+            const int n = build_chain_ops(c, par, ch, n_rows, dim, ops);
+            if (n == 0) continue;
+            cudaGraph_t g;
+            COMM_CUDA_OK(cudaGraphCreate(&g, 0));
+            cudaGraphNode_t prev = nullptr;
+            for (int i = 0; i < n; ++i) {
+                cudaGraphNode_t node;
+                cudaError_t e = cudaGraphAddMemcpyNode1D(&node, g, prev ? &prev : nullptr, prev ? 1 : 0, ops[i].dst,
+                                                         ops[i].src, ops[i].bytes, cudaMemcpyDefault);
+                if (e != cudaSuccess) {              // e.g. peer memcpy nodes unsupported: plain async copies instead
+                    cudaGraphDestroy(g);
+                    cudaGetLastError();
+                    c->use_graph = false;
+                    return 0;
+                }
+                prev = node;
             }
-            prev[ops[i].chain] = node;
+            cudaError_t e = cudaGraphInstantiate(&c->push_exec[par][ch], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { cudaGetLastError(); c->push_exec[par][ch] = nullptr; c->use_graph = false; return 0; }
         }
-        cudaError_t e = cudaGraphInstantiate(&c->push_exec[par], g, 0);
-        cudaGraphDestroy(g);
-        if (e != cudaSuccess) { cudaGetLastError(); c->push_exec[par] = nullptr; c->use_graph = false; return 0; }
     }
+    return 0;
+}
+
+// enqueue one chain on its side stream
+int launch_chain(flyp_comm* c, int par, int ch) {
+    cudaStream_t ss = c->side[CHAIN_STREAM[ch]];
+    if (c->use_graph) {
+        if (c->push_exec[par][ch]) COMM_CUDA_OK(cudaGraphLaunch(c->push_exec[par][ch], ss));
+        return 0;
+    }
+    PushOp ops[MAX_CHAIN_OPS];
+    const int n = build_chain_ops(c, par, ch, c->push_rows, c->push_dim, ops);
+    for (int i = 0; i < n; ++i) COMM_CUDA_OK(cudaMemcpyAsync(ops[i].dst, ops[i].src, ops[i].bytes, cudaMemcpyDefault, ss));
     return 0;
 }
 
@@ -259,9 +279,12 @@ int flyp_comm_create(int rank, int world, int max_rows, int dim, flyp_comm** out
     }
     c->seg[rank] = p;
     COMM_CUDA_OK(cudaMemset(p, 0, c->seg_bytes));
-    COMM_CUDA_OK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) {
+        COMM_CUDA_OK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+        COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_pushed[i], cudaEventDisableTiming));
+    }
     COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
-    COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_pushed, cudaEventDisableTiming));
+    COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming));
     COMM_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&c->err_host), sizeof(uint32_t), cudaHostAllocMapped));
     *c->err_host = 0;
     COMM_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->err_dev), c->err_host, 0));
@@ -333,13 +356,17 @@ int flyp_comm_destroy(flyp_comm* c) {
     cudaSetDevice(c->dev);
     cudaDeviceSynchronize();
     for (int par = 0; par < 2; ++par)
-        if (c->push_exec[par]) cudaGraphExecDestroy(c->push_exec[par]);
+        for (int ch = 0; ch < N_CHAIN; ++ch)
+            if (c->push_exec[par][ch]) cudaGraphExecDestroy(c->push_exec[par][ch]);
     for (int q = 0; q < c->world; ++q)
         if (c->ipc_mapped[q]) cudaIpcCloseMemHandle(c->seg[q]);
     if (c->seg[c->rank]) cudaFree(c->seg[c->rank]);
-    if (c->side) cudaStreamDestroy(c->side);
+    for (int i = 0; i < 3; ++i) {
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->ev_pushed[i]) cudaEventDestroy(c->ev_pushed[i]);
+    }
     if (c->ev_packed) cudaEventDestroy(c->ev_packed);
-    if (c->ev_pushed) cudaEventDestroy(c->ev_pushed);
+    if (c->ev_stats) cudaEventDestroy(c->ev_stats);
     if (c->err_host) cudaFreeHost(c->err_host);
     cudaGetLastError();
     delete c;
@@ -372,7 +399,7 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     uint8_t* own = c->seg[c->rank];
     const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
     // the copy engines may still be reading the own slots / sequence word of the previous step
-    COMM_CUDA_OK(cudaStreamWaitEvent(st, c->ev_pushed, 0));
+    for (int i = 0; i < 3; ++i) COMM_CUDA_OK(cudaStreamWaitEvent(st, c->ev_pushed[i], 0));
     const size_t n8 = (size_t)n_rows * dim / 8;
     k_pack<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
         static_cast<const uint4*>(img), static_cast<const uint4*>(txt), n8,
@@ -384,16 +411,12 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     COMM_CUDA_OK(cudaGetLastError());
     if (c->world > 1) {
         COMM_CUDA_OK(cudaEventRecord(c->ev_packed, st));
-        COMM_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_packed, 0));
-        if (c->use_graph && c->push_exec[par]) {
-            COMM_CUDA_OK(cudaGraphLaunch(c->push_exec[par], c->side));
-        } else {
-            PushOp ops[MAX_PUSH_OPS];
-            const int n = build_push_ops(c, par, n_rows, dim, ops);
-            for (int i = 0; i < n; ++i)
-                COMM_CUDA_OK(cudaMemcpyAsync(ops[i].dst, ops[i].src, ops[i].bytes, cudaMemcpyDefault, c->side));
+        for (int ch = 0; ch < 3; ++ch) {            // text (two chains) and its fp16 copy; the image chains follow the
+            cudaStream_t ss = c->side[CHAIN_STREAM[ch]];   // statistics exchange (flyp_comm_push_stats)
+            COMM_CUDA_OK(cudaStreamWaitEvent(ss, c->ev_packed, 0));
+            if ((rc = launch_chain(c, par, ch)) != 0) return rc;
+            COMM_CUDA_OK(cudaEventRecord(c->ev_pushed[CHAIN_STREAM[ch]], ss));
         }
-        COMM_CUDA_OK(cudaEventRecord(c->ev_pushed, c->side));
     }
     memset(out, 0, sizeof(*out));
     out->txt_all = own + c->off_feat[par][ARR_TXT];
@@ -402,7 +425,7 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     out->img16_all = own + c->off_feat[par][ARR_IMG16];
     flyp_ready_t* r[N_ARR] = {&out->txt_ready, &out->txt16_ready, &out->img_ready, &out->img16_ready};
     for (int a = 0; a < N_ARR; ++a) {
-        r[a]->flags = flag_ptr(c, c->rank, a == ARR_IMG ? ARR_IMG16 : a, 0);
+        r[a]->flags = flag_ptr(c, c->rank, a, 0);
         r[a]->seq = seq; r[a]->n_flags = c->world; r[a]->rows_per_flag = n_rows; r[a]->err = c->err_dev;
     }
     out->seq = seq;
@@ -430,6 +453,18 @@ int flyp_comm_push_stats(flyp_comm* c, uint32_t seq, const float* col_stat, cons
         ptrs, c->world, c->rank, c->off_colstat[par], c->off_rowstat[par], c->off_flags, c->off_counter, col_stat, row_lse,
         row_nll, n_rows, n_cols, cap, seq);
     COMM_CUDA_OK(cudaGetLastError());
+    if (c->world > 1 && seq == c->seq) {
+        // the image matrices of this step (second backward sweep) go out now that the latency-critical stores are queued
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        COMM_CUDA_OK(cudaEventRecord(c->ev_stats, st));
+        for (int ch = 3; ch < N_CHAIN; ++ch) {
+            cudaStream_t ss = c->side[CHAIN_STREAM[ch]];
+            COMM_CUDA_OK(cudaStreamWaitEvent(ss, c->ev_stats, 0));
+            int rc2 = launch_chain(c, par, ch);
+            if (rc2) return rc2;
+            COMM_CUDA_OK(cudaEventRecord(c->ev_pushed[CHAIN_STREAM[ch]], ss));
+        }
+    }
     uint8_t* own = c->seg[c->rank];
     out->col_stat_all = reinterpret_cast<const float*>(own + c->off_colstat[par]);
     out->row_lse_all = reinterpret_cast<const float*>(own + c->off_rowstat[par]);
