@@ -24,7 +24,8 @@ COMM_MAX_WORLD = 16
 
 class Ready(Structure):
     """flyp_ready_t: device flag words that say which ranks' rows have arrived."""
-    _fields_ = [("flags", c_void_p), ("seq", c_uint32), ("n_flags", c_int), ("rows_per_flag", c_int), ("err", c_void_p)]
+    _fields_ = [("flags", c_void_p), ("seq", c_uint32), ("n_flags", c_int), ("rows_per_flag", c_int), ("sub", c_int),
+                ("stride", c_int), ("reserved_sms", c_int), ("err", c_void_p)]
 
 
 class Gathered(Structure):

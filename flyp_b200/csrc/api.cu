@@ -28,7 +28,7 @@ flyp::PeerWait to_wait(const flyp_ready_t* r) {
     memset(&w, 0, sizeof(w));
     if (r != nullptr && r->flags != nullptr) {
         w.flags = r->flags; w.seq = r->seq; w.n_flags = r->n_flags; w.rows_per_flag = r->rows_per_flag > 0 ? r->rows_per_flag : 1;
-        w.err = r->err;
+        w.sub = r->sub > 0 ? r->sub : 1; w.stride = r->stride > 0 ? r->stride : w.sub; w.err = r->err;
     }
     return w;
 }
@@ -75,6 +75,16 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, bool
 
 unsigned long long* g_prof_buf = nullptr;   // debug only (flyp_debug_profile)
 
+// SMs left to a concurrently running push kernel (comm.cu) by the kernels this thread is about to launch
+thread_local int g_reserved_sms = 0;
+struct ReserveSms {
+    int saved;
+    explicit ReserveSms(const flyp_ready_t* r) : saved(g_reserved_sms) {
+        if (r != nullptr && r->flags != nullptr && r->reserved_sms > g_reserved_sms) g_reserved_sms = r->reserved_sms;
+    }
+    ~ReserveSms() { g_reserved_sms = saved; }
+};
+
 int num_sms() {
     static int cached[64] = {0};
     int dev = 0;
@@ -85,7 +95,8 @@ int num_sms() {
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
         cached[dev] = v > 0 ? v : 148;
     }
-    return cached[dev];
+    const int avail = cached[dev] - g_reserved_sms;
+    return avail >= 4 ? avail : 4;
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -421,6 +432,7 @@ int flyp_clip_fwd_local(const void* img, const void* txt, const float* scale, in
 int flyp_clip_fwd_local_ex(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
                            int dtype, int row_offset, float* row_lse, float* row_nll, float* col_stat, int* status,
                            void* workspace, size_t workspace_bytes, const flyp_ready_t* txt_ready, void* stream) {
+    ReserveSms reserve(txt_ready);
     int rc = check_common(n_rows, n_cols, dim, dtype);
     if (rc) return rc;
     if (!img || !txt || !scale || !row_lse || !row_nll || !col_stat || !workspace)
@@ -469,6 +481,7 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
                            void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
                            const void* txt16, const flyp_ready_t* txt_ready, const flyp_ready_t* txt16_ready,
                            void* stream) {
+    ReserveSms reserve(txt_ready);
     int rc = check_common(n_rows, n_cols, dim, dtype);
     if (rc) return rc;
     if (!img || !txt || !scale || !row_lse || !row_nll || !col_lse || !col_nll || !g_row || !g_col || !workspace)
@@ -541,6 +554,7 @@ int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all,
                           int grad_dtype, void* d_img, void* d_txt, float* d_scale, void* workspace,
                           size_t workspace_bytes, const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready,
                           const flyp_ready_t* img16_ready, const flyp_ready_t* txt16_ready, void* stream) {
+    ReserveSms reserve(txt_ready ? txt_ready : img_ready);
     int rc = check_common(n_rows, n_cols, dim, dtype);
     if (g_dtype != FLYP_BF16 && g_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad g_dtype %d", g_dtype);
     if (rc) return rc;

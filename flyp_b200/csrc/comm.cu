@@ -9,13 +9,16 @@
 // their fp16 copies (the operand format of the backward's second GEMM), [world * rows, dim] rank-major - the ordering of
 // clip/loss.py:66-67.  A step is
 //   pack   (kernel, caller's stream)  local rows -> own slots of the four gathered matrices (+ fp16 conversion)
-//   push   (copy engines, side streams) own slots -> the same slots in every peer's segment, peer (rank - k) in round k
-//                                     so that every rank receives from one peer at a time; after each block a 4-byte
-//                                     sequence number lands in the peer's flag word.  Five chains on three side
-//                                     streams: text to odd / even rounds and the fp16 text copy start with the
-//                                     forward; the two image matrices (needed by the second backward sweep only)
-//                                     start after the statistics exchange so that its small remote stores do not
-//                                     queue behind bulk traffic
+//   push   (kernel, side stream)      a small persistent kernel (PUSH_CTAS CTAs as 2-CTA clusters, i.e. whole TPCs)
+//                                     streams the own slots to the same slots of every peer's segment with 16-byte
+//                                     remote stores: matrices in the order the consumers need them (text, its fp16
+//                                     copy, image, its fp16 copy), peers in ring order (rank - k in round k) so that
+//                                     every rank receives from one peer at a time at link rate.  Each CTA owns a
+//                                     slice of every block and releases its flag word at the peer as soon as the
+//                                     slice is out.  (Copy engines were measured first: ~4 us + bytes / 750 GB/s per
+//                                     copy, one engine for all peer copies of a GPU, 3.5 us per 4-byte flag copy and
+//                                     ~2.5 us of host time per call: 560 us of engine time and 140 us of host time
+//                                     for the 56 operations of a step on 8 GPUs.)
 //   the tensor-core kernels poll those flag words (peer.cuh) right before their first TMA read of a rank's rows: the
 //   forward starts on its own column block while the other blocks are still in flight.
 // The small vectors (column triples, row statistics, d(scale)) are pushed by a kernel with remote stores and flagged
@@ -37,6 +40,7 @@ void set_error(int code, const char* fmt, ...);   // api.cu: thread-local messag
 namespace {
 
 constexpr int MAXW = 16;
+constexpr int MAXG = 8;             // flag words per (matrix, rank): one per CTA of the push kernel
 enum { ARR_TXT = 0, ARR_TXT16 = 1, ARR_IMG = 2, ARR_IMG16 = 3, N_ARR = 4 };
 enum { FLAG_STAT = N_ARR, FLAG_DS = N_ARR + 1, N_FLAGSETS = N_ARR + 2 };
 
@@ -61,11 +65,9 @@ struct flyp_comm {
     uint8_t* seg[MAXW];
     bool ipc_mapped[MAXW];
     bool connected;
-    cudaStream_t side[3];
-    cudaEvent_t ev_packed, ev_stats, ev_pushed[3];
-    cudaGraphExec_t push_exec[2][5];
-    int push_rows, push_dim;
-    bool use_graph;
+    cudaStream_t side;
+    cudaEvent_t ev_packed, ev_pushed;
+    int push_ctas;              // CTAs of the push kernel (even, <= MAXG)
     uint32_t seq;
     uint32_t* err_host;
     uint32_t* err_dev;
@@ -85,15 +87,16 @@ void layout(flyp_comm* c) {
         c->off_rowstat[par] = take(2 * cap * sizeof(float));
         c->off_dscale[par] = take(MAXW * sizeof(float));
     }
-    c->off_flags = take((size_t)N_FLAGSETS * MAXW * sizeof(uint32_t));
+    c->off_flags = take((size_t)N_FLAGSETS * MAXW * MAXG * sizeof(uint32_t));
     c->off_seqword[0] = take(sizeof(uint32_t));
     c->off_seqword[1] = take(sizeof(uint32_t));
     c->off_counter = take(sizeof(uint32_t));
     c->seg_bytes = align_up(off, 1 << 20);
 }
 
+// flag word j of producer k in flag set `set` of rank q's segment
 inline uint32_t* flag_ptr(const flyp_comm* c, int q, int set, int k) {
-    return reinterpret_cast<uint32_t*>(c->seg[q] + c->off_flags) + set * MAXW + k;
+    return reinterpret_cast<uint32_t*>(c->seg[q] + c->off_flags) + ((size_t)set * MAXW + k) * MAXG;
 }
 
 // ---- pack: local bf16 rows -> own slots (bf16 copy + fp16 conversion), sequence word, own flags ---------------------
@@ -103,7 +106,8 @@ __global__ void k_pack(const uint4* __restrict__ img, const uint4* __restrict__ 
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         *seqword = seq;
-        for (int a = 0; a < N_ARR; ++a) own_flags[a * MAXW + rank] = seq;
+        for (int a = 0; a < N_ARR; ++a)
+            for (int j = 0; j < MAXG; ++j) own_flags[(a * MAXW + rank) * MAXG + j] = seq;
     }
     if (i >= n8) return;
     auto conv = [](uint4 v) {
@@ -153,7 +157,7 @@ __global__ void k_push_stats(SegPtrs ptrs, int world, int rank, size_t off_colst
         if (atomicInc(counter, total - 1) == total - 1) {      // last block: everything above is visible system-wide
             __threadfence_system();
             for (int p = 0; p < world; ++p)
-                flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(ptrs.seg[p] + off_flags) + FLAG_STAT * MAXW + rank, seq);
+                flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(ptrs.seg[p] + off_flags) + (FLAG_STAT * MAXW + rank) * MAXG, seq);
         }
     }
 }
@@ -164,7 +168,7 @@ __global__ void k_push_scalar(SegPtrs ptrs, int world, int rank, size_t off_dsca
     if (q < world) {
         reinterpret_cast<float*>(ptrs.seg[q] + off_dscale)[rank] = value[0];
         __threadfence_system();
-        flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(ptrs.seg[q] + off_flags) + FLAG_DS * MAXW + rank, seq);
+        flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(ptrs.seg[q] + off_flags) + (FLAG_DS * MAXW + rank) * MAXG, seq);
     }
 }
 
@@ -182,76 +186,40 @@ int check_comm(const flyp_comm* c, bool need_connected) {
     return 0;
 }
 
-// The copy-engine schedule of one gather, as chains of (block copy, 4-byte flag copy) pairs.  Copies cost ~4 us + bytes
-// at ~750 GB/s each and a chain is serial, so the work is spread over chains that run on different copy engines:
-//   chain 0 / 1  text, odd / even ring rounds        (stream 0 / 1, start with the forward kernel)
-//   chain 2      fp16 text copy, all rounds          (stream 2, same start; needed by the first backward sweep)
-//   chain 3 / 4  image / fp16 image copy, all rounds (stream 0 / 1, start after the statistics exchange)
-constexpr int N_CHAIN = 5;
-constexpr int CHAIN_STREAM[N_CHAIN] = {0, 1, 2, 0, 1};
-struct PushOp { void* dst; const void* src; size_t bytes; };
-int build_chain_ops(const flyp_comm* c, int par, int chain, int n_rows, int dim, PushOp* ops) {
-    int n = 0;
-    const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
-    uint8_t* own = c->seg[c->rank];
-    const void* seqword = own + c->off_seqword[par];
-    const int arr = chain <= 1 ? ARR_TXT : chain == 2 ? ARR_TXT16 : chain == 3 ? ARR_IMG : ARR_IMG16;
-    for (int k = 1; k < c->world; ++k) {
-        if (chain == 0 && (k & 1) == 0) continue;
-        if (chain == 1 && (k & 1) == 1) continue;
-        const int q = (c->rank - k + c->world) % c->world;
-        ops[n++] = {c->seg[q] + c->off_feat[par][arr] + slot_off, own + c->off_feat[par][arr] + slot_off, slot_bytes};
-        ops[n++] = {flag_ptr(c, q, arr, c->rank), seqword, sizeof(uint32_t)};
-    }
-    return n;
-}
-constexpr int MAX_CHAIN_OPS = 2 * MAXW;
-
-int build_push_graphs(flyp_comm* c, int n_rows, int dim) {
-    for (int par = 0; par < 2; ++par)
-        for (int ch = 0; ch < N_CHAIN; ++ch)
-            if (c->push_exec[par][ch]) { cudaGraphExecDestroy(c->push_exec[par][ch]); c->push_exec[par][ch] = nullptr; }
-    c->push_rows = n_rows; c->push_dim = dim;
-    if (!c->use_graph || c->world == 1) return 0;
-    for (int par = 0; par < 2; ++par) {
-        for (int ch = 0; ch < N_CHAIN; ++ch) {
-            PushOp ops[MAX_CHAIN_OPS];
-            const int n = build_chain_ops(c, par, ch, n_rows, dim, ops);
-            if (n == 0) continue;
-            cudaGraph_t g;
-            COMM_CUDA_OK(cudaGraphCreate(&g, 0));
-            cudaGraphNode_t prev = nullptr;
-            for (int i = 0; i < n; ++i) {
-                cudaGraphNode_t node;
-                cudaError_t e = cudaGraphAddMemcpyNode1D(&node, g, prev ? &prev : nullptr, prev ? 1 : 0, ops[i].dst,
-                                                         ops[i].src, ops[i].bytes, cudaMemcpyDefault);
-                if (e != cudaSuccess) {              // e.g. peer memcpy nodes unsupported: plain async copies instead
-                    cudaGraphDestroy(g);
-                    cudaGetLastError();
-                    c->use_graph = false;
-                    return 0;
-                }
-                prev = node;
+// ---- feature push: own slots -> the same slots of every peer, remote stores, ring order, per-CTA flags -------------
+struct PushArgs {
+    SegPtrs ptrs;
+    size_t off_feat[N_ARR];     // byte offsets of the four gathered matrices (this parity)
+    size_t off_flags;
+    size_t slot_off, slot_bytes;
+    int world, rank;
+    uint32_t seq;
+};
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) k_push_features(const PushArgs a) {
+    const int G = gridDim.x, j = blockIdx.x;
+    // CTA j owns the j-th slice (whole uint4 words) of every block
+    const size_t n16 = a.slot_bytes / 16;
+    const size_t lo = n16 * j / G, hi = n16 * (j + 1) / G;
+    for (int arr = 0; arr < N_ARR; ++arr) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.ptrs.seg[a.rank] + a.off_feat[arr] + a.slot_off);
+        for (int k = 1; k < a.world; ++k) {
+            const int q = (a.rank - k + a.world) % a.world;
+            uint4* dst = reinterpret_cast<uint4*>(a.ptrs.seg[q] + a.off_feat[arr] + a.slot_off);
+            size_t i = lo + threadIdx.x;
+            for (; i + 3 * 512 < hi; i += 4 * 512) {          // four independent 16-byte loads in flight per thread
+                const uint4 v0 = __ldcg(src + i), v1 = __ldcg(src + i + 512), v2 = __ldcg(src + i + 1024),
+                            v3 = __ldcg(src + i + 1536);
+                dst[i] = v0; dst[i + 512] = v1; dst[i + 1024] = v2; dst[i + 1536] = v3;
             }
-            cudaError_t e = cudaGraphInstantiate(&c->push_exec[par][ch], g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) { cudaGetLastError(); c->push_exec[par][ch] = nullptr; c->use_graph = false; return 0; }
+            for (; i < hi; i += 512) dst[i] = __ldcg(src + i);
+            __syncthreads();                                   // the slice is issued by every thread of this CTA
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(a.ptrs.seg[q] + a.off_flags) +
+                                             ((size_t)arr * MAXW + a.rank) * MAXG + j, a.seq);
+            }
         }
     }
-    return 0;
-}
-
-// enqueue one chain on its side stream
-int launch_chain(flyp_comm* c, int par, int ch) {
-    cudaStream_t ss = c->side[CHAIN_STREAM[ch]];
-    if (c->use_graph) {
-        if (c->push_exec[par][ch]) COMM_CUDA_OK(cudaGraphLaunch(c->push_exec[par][ch], ss));
-        return 0;
-    }
-    PushOp ops[MAX_CHAIN_OPS];
-    const int n = build_chain_ops(c, par, ch, c->push_rows, c->push_dim, ops);
-    for (int i = 0; i < n; ++i) COMM_CUDA_OK(cudaMemcpyAsync(ops[i].dst, ops[i].src, ops[i].bytes, cudaMemcpyDefault, ss));
-    return 0;
 }
 
 }  // namespace
@@ -279,17 +247,17 @@ int flyp_comm_create(int rank, int world, int max_rows, int dim, flyp_comm** out
     }
     c->seg[rank] = p;
     COMM_CUDA_OK(cudaMemset(p, 0, c->seg_bytes));
-    for (int i = 0; i < 3; ++i) {
-        COMM_CUDA_OK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
-        COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_pushed[i], cudaEventDisableTiming));
-    }
+    COMM_CUDA_OK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
-    COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming));
+    COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_pushed, cudaEventDisableTiming));
     COMM_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&c->err_host), sizeof(uint32_t), cudaHostAllocMapped));
     *c->err_host = 0;
     COMM_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->err_dev), c->err_host, 0));
-    const char* g = getenv("FLYP_COMM_GRAPH");
-    c->use_graph = !(g && g[0] == '0');
+    c->push_ctas = MAXG;
+    if (const char* g = getenv("FLYP_PUSH_CTAS")) {           // measurement knob: 2, 4, 6 or 8
+        const int v = atoi(g);
+        if (v >= 2 && v <= MAXG && (v & 1) == 0) c->push_ctas = v;
+    }
     c->connected = (world == 1);
     COMM_CUDA_OK(cudaDeviceSynchronize());
     *out = c;
@@ -355,18 +323,12 @@ int flyp_comm_destroy(flyp_comm* c) {
     if (!c) return 0;
     cudaSetDevice(c->dev);
     cudaDeviceSynchronize();
-    for (int par = 0; par < 2; ++par)
-        for (int ch = 0; ch < N_CHAIN; ++ch)
-            if (c->push_exec[par][ch]) cudaGraphExecDestroy(c->push_exec[par][ch]);
     for (int q = 0; q < c->world; ++q)
         if (c->ipc_mapped[q]) cudaIpcCloseMemHandle(c->seg[q]);
     if (c->seg[c->rank]) cudaFree(c->seg[c->rank]);
-    for (int i = 0; i < 3; ++i) {
-        if (c->side[i]) cudaStreamDestroy(c->side[i]);
-        if (c->ev_pushed[i]) cudaEventDestroy(c->ev_pushed[i]);
-    }
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->ev_packed) cudaEventDestroy(c->ev_packed);
-    if (c->ev_stats) cudaEventDestroy(c->ev_stats);
+    if (c->ev_pushed) cudaEventDestroy(c->ev_pushed);
     if (c->err_host) cudaFreeHost(c->err_host);
     cudaGetLastError();
     delete c;
@@ -390,16 +352,12 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     COMM_CUDA_OK(cudaSetDevice(c->dev));
-    if (c->push_rows != n_rows || c->push_dim != dim) {
-        // a shape change invalidates the slot offsets peers poll for: the caller must not change it mid-flight
-        if ((rc = build_push_graphs(c, n_rows, dim)) != 0) return rc;
-    }
     const uint32_t seq = ++c->seq;
     const int par = (int)(seq & 1u);
     uint8_t* own = c->seg[c->rank];
     const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
     // the copy engines may still be reading the own slots / sequence word of the previous step
-    for (int i = 0; i < 3; ++i) COMM_CUDA_OK(cudaStreamWaitEvent(st, c->ev_pushed[i], 0));
+    COMM_CUDA_OK(cudaStreamWaitEvent(st, c->ev_pushed, 0));
     const size_t n8 = (size_t)n_rows * dim / 8;
     k_pack<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
         static_cast<const uint4*>(img), static_cast<const uint4*>(txt), n8,
@@ -411,12 +369,15 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     COMM_CUDA_OK(cudaGetLastError());
     if (c->world > 1) {
         COMM_CUDA_OK(cudaEventRecord(c->ev_packed, st));
-        for (int ch = 0; ch < 3; ++ch) {            // text (two chains) and its fp16 copy; the image chains follow the
-            cudaStream_t ss = c->side[CHAIN_STREAM[ch]];   // statistics exchange (flyp_comm_push_stats)
-            COMM_CUDA_OK(cudaStreamWaitEvent(ss, c->ev_packed, 0));
-            if ((rc = launch_chain(c, par, ch)) != 0) return rc;
-            COMM_CUDA_OK(cudaEventRecord(c->ev_pushed[CHAIN_STREAM[ch]], ss));
-        }
+        COMM_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_packed, 0));
+        PushArgs a;
+        for (int q = 0; q < MAXW; ++q) a.ptrs.seg[q] = q < c->world ? c->seg[q] : nullptr;
+        for (int arr = 0; arr < N_ARR; ++arr) a.off_feat[arr] = c->off_feat[par][arr];
+        a.off_flags = c->off_flags; a.slot_off = slot_off; a.slot_bytes = slot_bytes;
+        a.world = c->world; a.rank = c->rank; a.seq = seq;
+        k_push_features<<<c->push_ctas, 512, 0, c->side>>>(a);
+        COMM_CUDA_OK(cudaGetLastError());
+        COMM_CUDA_OK(cudaEventRecord(c->ev_pushed, c->side));
     }
     memset(out, 0, sizeof(*out));
     out->txt_all = own + c->off_feat[par][ARR_TXT];
@@ -427,6 +388,8 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     for (int a = 0; a < N_ARR; ++a) {
         r[a]->flags = flag_ptr(c, c->rank, a, 0);
         r[a]->seq = seq; r[a]->n_flags = c->world; r[a]->rows_per_flag = n_rows; r[a]->err = c->err_dev;
+        r[a]->sub = c->push_ctas; r[a]->stride = MAXG;
+        r[a]->reserved_sms = c->world > 1 ? c->push_ctas : 0;   // the push kernel runs beside the consumers
     }
     out->seq = seq;
     return 0;
@@ -453,24 +416,13 @@ int flyp_comm_push_stats(flyp_comm* c, uint32_t seq, const float* col_stat, cons
         ptrs, c->world, c->rank, c->off_colstat[par], c->off_rowstat[par], c->off_flags, c->off_counter, col_stat, row_lse,
         row_nll, n_rows, n_cols, cap, seq);
     COMM_CUDA_OK(cudaGetLastError());
-    if (c->world > 1 && seq == c->seq) {
-        // the image matrices of this step (second backward sweep) go out now that the latency-critical stores are queued
-        cudaStream_t st = static_cast<cudaStream_t>(stream);
-        COMM_CUDA_OK(cudaEventRecord(c->ev_stats, st));
-        for (int ch = 3; ch < N_CHAIN; ++ch) {
-            cudaStream_t ss = c->side[CHAIN_STREAM[ch]];
-            COMM_CUDA_OK(cudaStreamWaitEvent(ss, c->ev_stats, 0));
-            int rc2 = launch_chain(c, par, ch);
-            if (rc2) return rc2;
-            COMM_CUDA_OK(cudaEventRecord(c->ev_pushed[CHAIN_STREAM[ch]], ss));
-        }
-    }
     uint8_t* own = c->seg[c->rank];
     out->col_stat_all = reinterpret_cast<const float*>(own + c->off_colstat[par]);
     out->row_lse_all = reinterpret_cast<const float*>(own + c->off_rowstat[par]);
     out->row_nll_all = out->row_lse_all + cap;
     out->ready.flags = flag_ptr(c, c->rank, FLAG_STAT, 0);
     out->ready.seq = seq; out->ready.n_flags = c->world; out->ready.rows_per_flag = n_rows; out->ready.err = c->err_dev;
+    out->ready.sub = 1; out->ready.stride = MAXG; out->ready.reserved_sms = 0;
     return 0;
 }
 
@@ -494,6 +446,7 @@ int flyp_comm_sum_scalar(flyp_comm* c, uint32_t seq, float* out, void* stream) {
     COMM_CUDA_OK(cudaSetDevice(c->dev));
     flyp::PeerWait w;
     w.flags = flag_ptr(c, c->rank, FLAG_DS, 0); w.seq = seq; w.n_flags = c->world; w.rows_per_flag = 1; w.err = c->err_dev;
+    w.sub = 1; w.stride = MAXG;
     k_sum_scalar<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float*>(c->seg[c->rank] + c->off_dscale[seq & 1u]), c->world, w, out);
     COMM_CUDA_OK(cudaGetLastError());

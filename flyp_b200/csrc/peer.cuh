@@ -10,10 +10,12 @@ namespace flyp {
 // Rows [k * rows_per_flag, (k + 1) * rows_per_flag) of the operand are valid once (int)(flags[k] - seq) >= 0.
 // flags == nullptr: nothing to wait for (single rank, or data already known to be complete).
 struct PeerWait {
-    const uint32_t* flags;
+    const uint32_t* flags;  // producer k is done when its words flags[k * stride + j], j < sub, have all reached seq
     uint32_t seq;
     int n_flags;
     int rows_per_flag;
+    int sub;                // flag words per producer (one per CTA of the pushing kernel); 0 is read as 1
+    int stride;             // distance in words between the flag groups of consecutive producers; 0 is read as sub
     uint32_t* err;          // optional (host-mapped) word set to 1 + k when waiting for flags[k] timed out
 };
 
@@ -33,14 +35,17 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 
 // Bounded spin (4 s): a peer that never arrives must not hang the GPU; the error word tells the host.
 __device__ __forceinline__ void peer_wait_flag(const PeerWait& w, int k) {
-    const uint32_t* f = w.flags + k;
-    if ((int)(ld_acquire_sys_u32(f) - w.seq) >= 0) return;
-    const unsigned long long t0 = global_timer_ns();
-    while ((int)(ld_acquire_sys_u32(f) - w.seq) < 0) {
-        __nanosleep(100);
-        if (global_timer_ns() - t0 > 4000000000ull) {
-            if (w.err != nullptr) *reinterpret_cast<volatile uint32_t*>(w.err) = 1u + (uint32_t)k;
-            break;
+    const int sub = w.sub > 0 ? w.sub : 1, stride = w.stride > 0 ? w.stride : sub;
+    for (int j = 0; j < sub; ++j) {
+        const uint32_t* f = w.flags + k * stride + j;
+        if ((int)(ld_acquire_sys_u32(f) - w.seq) >= 0) continue;
+        const unsigned long long t0 = global_timer_ns();
+        while ((int)(ld_acquire_sys_u32(f) - w.seq) < 0) {
+            __nanosleep(100);
+            if (global_timer_ns() - t0 > 4000000000ull) {
+                if (w.err != nullptr) *reinterpret_cast<volatile uint32_t*>(w.err) = 1u + (uint32_t)k;
+                return;
+            }
         }
     }
 }

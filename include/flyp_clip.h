@@ -104,12 +104,16 @@ typedef struct flyp_comm flyp_comm;
 #define FLYP_IPC_HANDLE_BYTES 64
 #define FLYP_COMM_MAX_WORLD 16
 
-/* Rows [k * rows_per_flag, (k + 1) * rows_per_flag) are valid once (int32)(flags[k] - seq) >= 0.  flags == NULL: ready. */
+/* Rows [k * rows_per_flag, (k + 1) * rows_per_flag) are valid once (int32)(flags[k * stride + j] - seq) >= 0, j < sub.
+ * flags == NULL: ready. */
 typedef struct {
-    const uint32_t* flags; /* device */
+    const uint32_t* flags; /* device: producer k is done when flags[k * stride + j], j < sub, all reached seq */
     uint32_t seq;
     int n_flags;
     int rows_per_flag;
+    int sub;               /* flag words per producer (0 is read as 1) */
+    int stride;            /* words between the flag groups of consecutive producers (0 is read as sub) */
+    int reserved_sms;      /* SMs the consuming kernels must leave free for the concurrently running push kernel */
     uint32_t* err;         /* device-visible word set to 1 + k if waiting for flags[k] timed out (4 s); may be NULL */
 } flyp_ready_t;
 
@@ -142,8 +146,10 @@ int flyp_comm_error(const flyp_comm* comm);
 int flyp_comm_destroy(flyp_comm* comm);
 
 /* clip/loss.py:59-67 without torch.cat: pack the local rows (and their fp16 copies) into the own slots on `stream`,
- * then push them to every peer with the copy engines on the communicator's side stream (text first, peers in ring
- * order), each block followed by its flag.  Returns at once; `out` describes where the gathered matrices will be. */
+ * then push them to every peer with a small persistent kernel (remote 16-byte stores over NVLink, a few SMs, on the
+ * communicator's side stream): text first, peers in ring order so that every rank receives from one peer at a time,
+ * each CTA flagging its slice of a block as soon as it is out.  Returns at once; `out` describes where the gathered
+ * matrices will be and how many SMs the consumers must leave to the push kernel. */
 int flyp_comm_gather_features(flyp_comm* comm, const void* img, const void* txt, int n_rows, int dim, int dtype,
                               flyp_gathered_t* out, void* stream);
 /* Push this rank's column triples / row statistics (outputs of flyp_clip_fwd_local) into every rank's segment. */
