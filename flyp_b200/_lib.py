@@ -65,6 +65,9 @@ SIGNATURES = {
                                       c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(Ready),
                                       POINTER(Ready), POINTER(Ready), POINTER(Ready), c_void_p]),
     "flyp_comm_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    "flyp_comm_layout_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
+    "flyp_comm_create_external": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p), c_void_p, POINTER(c_void_p)]),
+    "flyp_comm_has_multicast": (c_int, [c_void_p]),
     "flyp_comm_segment_bytes": (c_int, [c_void_p, POINTER(c_size_t)]),
     "flyp_comm_ipc_handle": (c_int, [c_void_p, c_void_p]),
     "flyp_comm_connect_ipc": (c_int, [c_void_p, c_void_p]),

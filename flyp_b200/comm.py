@@ -21,14 +21,32 @@ from ._lib import FlypError, Gathered, Ready, Stats
 class PeerComm:
     """One rank's communicator: segment sized for blocks of up to ``max_rows x dim`` bf16 features."""
 
-    def __init__(self, rank: int, world: int, max_rows: int, dim: int, device: torch.device):
+    def __init__(self, rank: int, world: int, max_rows: int, dim: int, device: torch.device, segments=None,
+                 multicast: int = 0, keepalive=None):
+        """Without ``segments``: the library allocates the segment (wire it with connect_ipc / connect_local).
+        With ``segments`` (addresses of every rank's zeroed segment, own one included) and optionally the address of a
+        multicast mapping of them: nothing is allocated; ``keepalive`` holds whatever owns that memory."""
         self.rank, self.world, self.max_rows, self.dim, self.device = rank, world, max_rows, dim, device
         self._h = ctypes.c_void_p()
+        self._keepalive = keepalive
+        lib = _lib.load()
         with torch.cuda.device(device):
-            _lib.check(_lib.load().flyp_comm_create(rank, world, max_rows, dim, ctypes.byref(self._h)))
+            if segments is None:
+                _lib.check(lib.flyp_comm_create(rank, world, max_rows, dim, ctypes.byref(self._h)))
+            else:
+                arr = (ctypes.c_void_p * world)(*[int(p) for p in segments])
+                _lib.check(lib.flyp_comm_create_external(rank, world, max_rows, dim, arr, int(multicast) or None,
+                                                         ctypes.byref(self._h)))
         self.seq = 0                      # sequence number of the latest gather
+        self.multicast = bool(lib.flyp_comm_has_multicast(self._h))
 
     # ---- wiring -----------------------------------------------------------------------------------------------
+    @staticmethod
+    def layout_bytes(world: int, max_rows: int, dim: int) -> int:
+        sz = ctypes.c_size_t()
+        _lib.check(_lib.load().flyp_comm_layout_bytes(world, max_rows, dim, ctypes.byref(sz)))
+        return sz.value
+
     def ipc_handle(self) -> bytes:
         buf = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
         _lib.check(_lib.load().flyp_comm_ipc_handle(self._h, buf))
@@ -49,39 +67,81 @@ class PeerComm:
             _lib.check(_lib.load().flyp_comm_connect_local(c._h, arr))
 
     @classmethod
+    def _from_symmetric_memory(cls, rank, world, max_rows, dim, device, group):
+        """Segments from torch.distributed._symmetric_memory: peer-mapped by torch, with an NVSwitch multicast mapping
+        when the fabric offers one (then every push is one copy that the switch replicates)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        nbytes = cls.layout_bytes(world, max_rows, dim)
+        with torch.cuda.device(device):
+            buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        off = int(getattr(hdl, "offset", 0) or 0)          # position of `buf` inside the rendezvoused allocation
+        ptrs = [int(p) + off for p in hdl.buffer_ptrs]
+        if len(ptrs) != world or ptrs[rank] != buf.data_ptr():
+            raise FlypError("unexpected symmetric-memory layout")
+        mc = int(hdl.multicast_ptr or 0)
+        return cls(rank, world, max_rows, dim, device, segments=ptrs, multicast=(mc + off) if mc else 0,
+                   keepalive=(buf, hdl))
+
+    @classmethod
     def from_process_group(cls, rank: int, world: int, max_rows: int, dim: int, device: torch.device,
                            group=None) -> Optional["PeerComm"]:
-        """Create + connect over ``torch.distributed``.  Returns None (on every rank alike) when the ranks do not all
-        sit on one node or a segment could not be created / mapped; the caller then uses the NCCL path."""
+        """Create + connect over ``torch.distributed``: symmetric memory (multicast) first, CUDA IPC segments second.
+        Returns None (on every rank alike) when the ranks do not all sit on one node or no segment could be mapped;
+        the caller then uses the NCCL path."""
+        import os
         import torch.distributed as dist
-        comm, handle, err = None, b"", ""
+
+        def agree(ok: bool) -> bool:
+            flags = [None] * world
+            dist.all_gather_object(flags, bool(ok), group=group)
+            return all(flags)
+
+        hosts = [None] * world
+        dist.all_gather_object(hosts, socket.gethostname(), group=group)
+        if len(set(hosts)) != 1:
+            return None
+        comm = None
+        if os.environ.get("FLYP_COMM_SYMM", "1") != "0":
+            try:
+                comm = cls._from_symmetric_memory(rank, world, max_rows, dim, device, group)
+            except Exception:  # noqa: BLE001 - any failure means "no symmetric memory on this rank"
+                comm = None
+            if agree(comm is not None):
+                torch.cuda.synchronize(device)
+                dist.barrier(group=group)      # every segment is zeroed and mapped before anyone pushes
+                return comm
+            if comm is not None:
+                comm.close()
+        comm, handle = None, b""
         try:
             comm = cls(rank, world, max_rows, dim, device)
             handle = comm.ipc_handle()
-        except Exception as e:  # noqa: BLE001 - any failure means "no peer path on this rank"
-            err = str(e)
+        except Exception:  # noqa: BLE001
+            comm = None
         infos = [None] * world
-        dist.all_gather_object(infos, (socket.gethostname(), handle, err), group=group)
-        ok = all(i[1] and not i[2] for i in infos) and len({i[0] for i in infos}) == 1
+        dist.all_gather_object(infos, handle, group=group)
+        ok = all(infos)
         if ok:
             try:
-                comm.connect_ipc([i[1] for i in infos])
-            except Exception as e:  # noqa: BLE001
-                err = str(e)
-        flags = [None] * world
-        dist.all_gather_object(flags, ok and not err, group=group)
-        if not all(flags):
+                comm.connect_ipc(infos)
+            except Exception:  # noqa: BLE001
+                ok = False
+        if not agree(ok):
             if comm is not None:
                 comm.close()
             return None
         torch.cuda.synchronize(device)
-        dist.barrier(group=group)          # every segment is zeroed and mapped before anyone pushes
+        dist.barrier(group=group)
         return comm
 
     def close(self) -> None:
         if self._h:
             _lib.load().flyp_comm_destroy(self._h)
             self._h = ctypes.c_void_p()
+        self._keepalive = None
 
     def __del__(self):
         try:

@@ -9,20 +9,19 @@
 // their fp16 copies (the operand format of the backward's second GEMM), [world * rows, dim] rank-major - the ordering of
 // clip/loss.py:66-67.  A step is
 //   pack   (kernel, caller's stream)  local rows -> own slots of the four gathered matrices (+ fp16 conversion)
-//   push   (kernel, side stream)      a small persistent kernel (PUSH_CTAS CTAs as 2-CTA clusters, i.e. whole TPCs)
-//                                     streams the own slots to the same slots of every peer's segment with 16-byte
-//                                     remote stores: matrices in the order the consumers need them (text, its fp16
-//                                     copy, image, its fp16 copy), peers in ring order (rank - k in round k) so that
-//                                     every rank receives from one peer at a time at link rate.  Each CTA owns a
-//                                     slice of every block and releases its flag word at the peer as soon as the
-//                                     slice is out.  (Copy engines were measured first: ~4 us + bytes / 750 GB/s per
-//                                     copy, one engine for all peer copies of a GPU, 3.5 us per 4-byte flag copy and
-//                                     ~2.5 us of host time per call: 560 us of engine time and 140 us of host time
-//                                     for the 56 operations of a step on 8 GPUs.)
+//   push   (copy engines, side stream) own slots -> the same slots of every rank.  With an NVSwitch multicast mapping of
+//                                     the segments (torch symmetric memory, flyp_comm_create_external) ONE copy per
+//                                     matrix to the multicast address reaches all ranks, followed by ONE 4-byte copy
+//                                     of the sequence number to the multicast address of the flag word: 8 copy-engine
+//                                     operations per step, text first.  Without multicast (CUDA IPC segments) the
+//                                     same is done peer by peer in ring order (W - 1 times the operations; measured
+//                                     on 8 GPUs: ~4 us + bytes / 750 GB/s per copy on one engine, 3.5 us per flag copy).
+//                                     A push by remote stores from a few SMs was also measured and rejected (36 GB/s
+//                                     per CTA, and it slows the concurrent tensor-core kernels by 15 %).
 //   the tensor-core kernels poll those flag words (peer.cuh) right before their first TMA read of a rank's rows: the
 //   forward starts on its own column block while the other blocks are still in flight.
-// The small vectors (column triples, row statistics, d(scale)) are pushed by a kernel with remote stores and flagged
-// the same way.  No NCCL call is on this path.
+// The small vectors (column triples, row statistics, d(scale)) are pushed by a kernel with remote stores (to the
+// multicast address when there is one) and flagged the same way.  No NCCL call is on this path.
 #include "../../include/flyp_clip.h"
 #include "aux_kernels.cuh"
 #include "peer.cuh"
@@ -65,9 +64,10 @@ struct flyp_comm {
     uint8_t* seg[MAXW];
     bool ipc_mapped[MAXW];
     bool connected;
+    uint8_t* mc;                // multicast mapping of all segments (NVSwitch), or nullptr
+    bool owns_seg;              // the own segment was cudaMalloc'ed here (else it belongs to the caller)
     cudaStream_t side;
     cudaEvent_t ev_packed, ev_pushed;
-    int push_ctas;              // CTAs of the push kernel (even, <= MAXG)
     uint32_t seq;
     uint32_t* err_host;
     uint32_t* err_dev;
@@ -129,7 +129,8 @@ __global__ void k_pack(const uint4* __restrict__ img, const uint4* __restrict__ 
 }
 
 // ---- statistics push: this rank's column triples and row statistics -> every rank's segment, then the flag ----------
-__global__ void k_push_stats(SegPtrs ptrs, int world, int rank, size_t off_colstat, size_t off_rowstat, size_t off_flags,
+// ptrs.seg[0 .. n_dst): the destinations (every rank's segment, or the single multicast mapping); own_seg: this rank's
+__global__ void k_push_stats(SegPtrs ptrs, int n_dst, uint8_t* own_seg, int rank, size_t off_colstat, size_t off_rowstat, size_t off_flags,
                              size_t off_counter, const float* __restrict__ col_stat, const float* __restrict__ row_lse,
                              const float* __restrict__ row_nll, int n_rows, int n_cols, size_t cap, uint32_t seq) {
     const int q = blockIdx.y;
@@ -152,23 +153,25 @@ __global__ void k_push_stats(SegPtrs ptrs, int world, int rank, size_t off_colst
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t* counter = reinterpret_cast<uint32_t*>(ptrs.seg[rank] + off_counter);
+        uint32_t* counter = reinterpret_cast<uint32_t*>(own_seg + off_counter);
         const uint32_t total = gridDim.x * gridDim.y;
         if (atomicInc(counter, total - 1) == total - 1) {      // last block: everything above is visible system-wide
             __threadfence_system();
-            for (int p = 0; p < world; ++p)
-                flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(ptrs.seg[p] + off_flags) + (FLAG_STAT * MAXW + rank) * MAXG, seq);
+            for (int p = 0; p < n_dst; ++p)
+                *reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint32_t*>(ptrs.seg[p] + off_flags) +
+                                                      (FLAG_STAT * MAXW + rank) * MAXG) = seq;
         }
     }
 }
 
-__global__ void k_push_scalar(SegPtrs ptrs, int world, int rank, size_t off_dscale, size_t off_flags,
+__global__ void k_push_scalar(SegPtrs ptrs, int n_dst, int rank, size_t off_dscale, size_t off_flags,
                               const float* __restrict__ value, uint32_t seq) {
     const int q = threadIdx.x;
-    if (q < world) {
+    if (q < n_dst) {
         reinterpret_cast<float*>(ptrs.seg[q] + off_dscale)[rank] = value[0];
         __threadfence_system();
-        flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(ptrs.seg[q] + off_flags) + (FLAG_DS * MAXW + rank) * MAXG, seq);
+        *reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint32_t*>(ptrs.seg[q] + off_flags) +
+                                              (FLAG_DS * MAXW + rank) * MAXG) = seq;
     }
 }
 
@@ -186,47 +189,39 @@ int check_comm(const flyp_comm* c, bool need_connected) {
     return 0;
 }
 
-// ---- feature push: own slots -> the same slots of every peer, remote stores, ring order, per-CTA flags -------------
-struct PushArgs {
-    SegPtrs ptrs;
-    size_t off_feat[N_ARR];     // byte offsets of the four gathered matrices (this parity)
-    size_t off_flags;
-    size_t slot_off, slot_bytes;
-    int world, rank;
-    uint32_t seq;
-};
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) k_push_features(const PushArgs a) {
-    const int G = gridDim.x, j = blockIdx.x;
-    // CTA j owns the j-th slice (whole uint4 words) of every block
-    const size_t n16 = a.slot_bytes / 16;
-    const size_t lo = n16 * j / G, hi = n16 * (j + 1) / G;
-    for (int arr = 0; arr < N_ARR; ++arr) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.ptrs.seg[a.rank] + a.off_feat[arr] + a.slot_off);
-        for (int k = 1; k < a.world; ++k) {
-            const int q = (a.rank - k + a.world) % a.world;
-            uint4* dst = reinterpret_cast<uint4*>(a.ptrs.seg[q] + a.off_feat[arr] + a.slot_off);
-            size_t i = lo + threadIdx.x;
-            for (; i + 3 * 512 < hi; i += 4 * 512) {          // four independent 16-byte loads in flight per thread
-                const uint4 v0 = __ldcg(src + i), v1 = __ldcg(src + i + 512), v2 = __ldcg(src + i + 1024),
-                            v3 = __ldcg(src + i + 1536);
-                dst[i] = v0; dst[i + 512] = v1; dst[i + 1024] = v2; dst[i + 1536] = v3;
-            }
-            for (; i < hi; i += 512) dst[i] = __ldcg(src + i);
-            __syncthreads();                                   // the slice is issued by every thread of this CTA
-            if (threadIdx.x == 0) {
-                __threadfence_system();
-                flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(a.ptrs.seg[q] + a.off_flags) +
-                                             ((size_t)arr * MAXW + a.rank) * MAXG + j, a.seq);
+// ---- feature push schedule (copy engines) ------------------------------------------------------------------------
+// Matrices in the order the consumers need them: text (forward), its fp16 copy (first backward sweep), image and its
+// fp16 copy (second sweep).  Each block copy is followed by the 4-byte copy of the sequence number into the flag word.
+struct PushOp { void* dst; const void* src; size_t bytes; };
+constexpr int MAX_PUSH_OPS = 2 * N_ARR * MAXW;
+int build_push_ops(const flyp_comm* c, int par, int n_rows, int dim, PushOp* ops) {
+    int n = 0;
+    const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
+    uint8_t* own = c->seg[c->rank];
+    const void* seqword = own + c->off_seqword[par];
+    const size_t flag_stride = (size_t)MAXG * sizeof(uint32_t);
+    for (int a = 0; a < N_ARR; ++a) {
+        const size_t off_data = c->off_feat[par][a] + slot_off;
+        const size_t off_flag = c->off_flags + ((size_t)a * MAXW + c->rank) * flag_stride;
+        if (c->mc != nullptr) {                                  // one multicast copy reaches every rank
+            ops[n++] = {c->mc + off_data, own + off_data, slot_bytes};
+            ops[n++] = {c->mc + off_flag, seqword, sizeof(uint32_t)};
+        } else {
+            for (int k = 1; k < c->world; ++k) {                 // ring order: one sender per receiver at a time
+                const int q = (c->rank - k + c->world) % c->world;
+                ops[n++] = {c->seg[q] + off_data, own + off_data, slot_bytes};
+                ops[n++] = {c->seg[q] + off_flag, seqword, sizeof(uint32_t)};
             }
         }
     }
+    return n;
 }
 
 }  // namespace
 
 extern "C" {
 
-int flyp_comm_create(int rank, int world, int max_rows, int dim, flyp_comm** out) {
+static int comm_new(int rank, int world, int max_rows, int dim, flyp_comm** out) {
     if (!out) { flyp::set_error(FLYP_ERR_ARG, "out is null"); return FLYP_ERR_ARG; }
     if (world < 1 || world > MAXW || rank < 0 || rank >= world || max_rows <= 0 || dim <= 0 || dim % 8 != 0) {
         flyp::set_error(FLYP_ERR_ARG, "bad comm shape: rank %d world %d (max %d) rows %d dim %d", rank, world, MAXW, max_rows,
@@ -238,31 +233,69 @@ int flyp_comm_create(int rank, int world, int max_rows, int dim, flyp_comm** out
     c->rank = rank; c->world = world; c->max_rows = max_rows; c->dim = dim;
     COMM_CUDA_OK(cudaGetDevice(&c->dev));
     layout(c);
-    uint8_t* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, c->seg_bytes);
-    if (e != cudaSuccess) {
-        flyp::set_error(FLYP_ERR_CUDA, "cudaMalloc of the %zu-byte exchange segment: %s", c->seg_bytes, cudaGetErrorString(e));
-        delete c;
-        return FLYP_ERR_CUDA;
-    }
-    c->seg[rank] = p;
-    COMM_CUDA_OK(cudaMemset(p, 0, c->seg_bytes));
     COMM_CUDA_OK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming));
     COMM_CUDA_OK(cudaEventCreateWithFlags(&c->ev_pushed, cudaEventDisableTiming));
     COMM_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&c->err_host), sizeof(uint32_t), cudaHostAllocMapped));
     *c->err_host = 0;
     COMM_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->err_dev), c->err_host, 0));
-    c->push_ctas = MAXG;
-    if (const char* g = getenv("FLYP_PUSH_CTAS")) {           // measurement knob: 2, 4, 6 or 8
-        const int v = atoi(g);
-        if (v >= 2 && v <= MAXG && (v & 1) == 0) c->push_ctas = v;
-    }
-    c->connected = (world == 1);
-    COMM_CUDA_OK(cudaDeviceSynchronize());
     *out = c;
     return 0;
 }
+
+int flyp_comm_layout_bytes(int world, int max_rows, int dim, size_t* bytes) {
+    if (!bytes || world < 1 || world > MAXW || max_rows <= 0 || dim <= 0 || dim % 8 != 0) {
+        flyp::set_error(FLYP_ERR_ARG, "bad comm shape");
+        return FLYP_ERR_ARG;
+    }
+    flyp_comm tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    tmp.world = world; tmp.max_rows = max_rows; tmp.dim = dim;
+    layout(&tmp);
+    *bytes = tmp.seg_bytes;
+    return 0;
+}
+
+int flyp_comm_create(int rank, int world, int max_rows, int dim, flyp_comm** out) {
+    int rc = comm_new(rank, world, max_rows, dim, out);
+    if (rc) return rc;
+    flyp_comm* c = *out;
+    uint8_t* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, c->seg_bytes);
+    if (e != cudaSuccess) {
+        flyp::set_error(FLYP_ERR_CUDA, "cudaMalloc of the %zu-byte exchange segment: %s", c->seg_bytes, cudaGetErrorString(e));
+        flyp_comm_destroy(c);
+        *out = nullptr;
+        return FLYP_ERR_CUDA;
+    }
+    c->seg[rank] = p;
+    c->owns_seg = true;
+    COMM_CUDA_OK(cudaMemset(p, 0, c->seg_bytes));
+    c->connected = (world == 1);
+    COMM_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int flyp_comm_create_external(int rank, int world, int max_rows, int dim, void* const* segments, void* multicast,
+                              flyp_comm** out) {
+    if (!segments) { flyp::set_error(FLYP_ERR_ARG, "segments is null"); return FLYP_ERR_ARG; }
+    int rc = comm_new(rank, world, max_rows, dim, out);
+    if (rc) return rc;
+    flyp_comm* c = *out;
+    for (int q = 0; q < world; ++q) {
+        if (!segments[q]) { flyp_comm_destroy(c); *out = nullptr; flyp::set_error(FLYP_ERR_ARG, "segment %d is null", q); return FLYP_ERR_ARG; }
+        c->seg[q] = static_cast<uint8_t*>(segments[q]);
+    }
+    c->mc = static_cast<uint8_t*>(multicast);
+    if (const char* e = getenv("FLYP_COMM_MULTICAST")) {       // measurement knob: 0 = ignore the multicast mapping
+        if (e[0] == '0') c->mc = nullptr;
+    }
+    c->owns_seg = false;
+    c->connected = true;
+    return 0;
+}
+
+int flyp_comm_has_multicast(const flyp_comm* c) { return (c != nullptr && c->mc != nullptr) ? 1 : 0; }
 
 int flyp_comm_segment_bytes(const flyp_comm* c, size_t* bytes) {
     int rc = check_comm(c, false);
@@ -325,7 +358,7 @@ int flyp_comm_destroy(flyp_comm* c) {
     cudaDeviceSynchronize();
     for (int q = 0; q < c->world; ++q)
         if (c->ipc_mapped[q]) cudaIpcCloseMemHandle(c->seg[q]);
-    if (c->seg[c->rank]) cudaFree(c->seg[c->rank]);
+    if (c->owns_seg && c->seg[c->rank]) cudaFree(c->seg[c->rank]);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->ev_packed) cudaEventDestroy(c->ev_packed);
     if (c->ev_pushed) cudaEventDestroy(c->ev_pushed);
@@ -370,13 +403,10 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     if (c->world > 1) {
         COMM_CUDA_OK(cudaEventRecord(c->ev_packed, st));
         COMM_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_packed, 0));
-        PushArgs a;
-        for (int q = 0; q < MAXW; ++q) a.ptrs.seg[q] = q < c->world ? c->seg[q] : nullptr;
-        for (int arr = 0; arr < N_ARR; ++arr) a.off_feat[arr] = c->off_feat[par][arr];
-        a.off_flags = c->off_flags; a.slot_off = slot_off; a.slot_bytes = slot_bytes;
-        a.world = c->world; a.rank = c->rank; a.seq = seq;
-        k_push_features<<<c->push_ctas, 512, 0, c->side>>>(a);
-        COMM_CUDA_OK(cudaGetLastError());
+        PushOp ops[MAX_PUSH_OPS];
+        const int n = build_push_ops(c, par, n_rows, dim, ops);
+        for (int i = 0; i < n; ++i)
+            COMM_CUDA_OK(cudaMemcpyAsync(ops[i].dst, ops[i].src, ops[i].bytes, cudaMemcpyDefault, c->side));
         COMM_CUDA_OK(cudaEventRecord(c->ev_pushed, c->side));
     }
     memset(out, 0, sizeof(*out));
@@ -388,8 +418,7 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     for (int a = 0; a < N_ARR; ++a) {
         r[a]->flags = flag_ptr(c, c->rank, a, 0);
         r[a]->seq = seq; r[a]->n_flags = c->world; r[a]->rows_per_flag = n_rows; r[a]->err = c->err_dev;
-        r[a]->sub = c->push_ctas; r[a]->stride = MAXG;
-        r[a]->reserved_sms = c->world > 1 ? c->push_ctas : 0;   // the push kernel runs beside the consumers
+        r[a]->sub = 1; r[a]->stride = MAXG; r[a]->reserved_sms = 0;
     }
     out->seq = seq;
     return 0;
@@ -408,12 +437,14 @@ int flyp_comm_push_stats(flyp_comm* c, uint32_t seq, const float* col_stat, cons
     COMM_CUDA_OK(cudaSetDevice(c->dev));
     const int par = (int)(seq & 1u);
     SegPtrs ptrs;
+    int n_dst = c->world;
     for (int q = 0; q < MAXW; ++q) ptrs.seg[q] = q < c->world ? c->seg[q] : nullptr;
+    if (c->mc != nullptr) { n_dst = 1; ptrs.seg[0] = c->mc; }      // one store stream reaches every rank
     int bx = (3 * n_cols + 1023) / 1024;
     if (bx > 16) bx = 16;
     if (bx < 1) bx = 1;
-    k_push_stats<<<dim3(bx, c->world), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        ptrs, c->world, c->rank, c->off_colstat[par], c->off_rowstat[par], c->off_flags, c->off_counter, col_stat, row_lse,
+    k_push_stats<<<dim3(bx, n_dst), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        ptrs, n_dst, c->seg[c->rank], c->rank, c->off_colstat[par], c->off_rowstat[par], c->off_flags, c->off_counter, col_stat, row_lse,
         row_nll, n_rows, n_cols, cap, seq);
     COMM_CUDA_OK(cudaGetLastError());
     uint8_t* own = c->seg[c->rank];
@@ -432,8 +463,10 @@ int flyp_comm_push_scalar(flyp_comm* c, uint32_t seq, const float* value, void* 
     if (!value) { flyp::set_error(FLYP_ERR_ARG, "null pointer argument"); return FLYP_ERR_ARG; }
     COMM_CUDA_OK(cudaSetDevice(c->dev));
     SegPtrs ptrs;
+    int n_dst = c->world;
     for (int q = 0; q < MAXW; ++q) ptrs.seg[q] = q < c->world ? c->seg[q] : nullptr;
-    k_push_scalar<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(ptrs, c->world, c->rank, c->off_dscale[seq & 1u],
+    if (c->mc != nullptr) { n_dst = 1; ptrs.seg[0] = c->mc; }
+    k_push_scalar<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(ptrs, n_dst, c->rank, c->off_dscale[seq & 1u],
                                                                   c->off_flags, value, seq);
     COMM_CUDA_OK(cudaGetLastError());
     return 0;

@@ -135,6 +135,15 @@ typedef struct {
 /* Create the communicator of `rank` on the current device for blocks of at most max_rows x dim bf16 features. */
 int flyp_comm_create(int rank, int world, int max_rows, int dim, flyp_comm** comm);
 int flyp_comm_segment_bytes(const flyp_comm* comm, size_t* bytes);
+/* Size of the exchange segment a communicator of this shape needs (for callers that allocate it themselves). */
+int flyp_comm_layout_bytes(int world, int max_rows, int dim, size_t* bytes);
+/* Communicator over caller-owned, ZEROED segments that are already mapped in this process: segments[q] = address of
+ * rank q's segment (segments[rank] = the own one), multicast = address of an NVSwitch multicast mapping that aliases all
+ * of them (or NULL).  This is what torch.distributed._symmetric_memory hands out (buffer_ptrs, multicast_ptr); with a
+ * multicast mapping every push is ONE copy / store stream that the switch replicates to all ranks. */
+int flyp_comm_create_external(int rank, int world, int max_rows, int dim, void* const* segments, void* multicast,
+                              flyp_comm** comm);
+int flyp_comm_has_multicast(const flyp_comm* comm);
 /* handle_out: FLYP_IPC_HANDLE_BYTES host bytes to be all-gathered by the caller (e.g. through torch.distributed). */
 int flyp_comm_ipc_handle(flyp_comm* comm, void* handle_out);
 /* all_handles: world x FLYP_IPC_HANDLE_BYTES host bytes, rank-major.  The caller must barrier before the first step. */
