@@ -147,4 +147,26 @@ def ptr(t) -> int | None:
 
 def stream_ptr(device) -> int:
     import torch
-    return torch.cuda.current_stream(device).cuda_stream
+    try:
+        return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+    except AttributeError:  # pragma: no cover - older torch
+        return torch.cuda.current_stream(device).cuda_stream
+
+
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device):
+    """``torch.cuda.device(device)`` only when ``device`` is not already current (the context manager costs ~5 us)."""
+    import torch
+    if device.index is None or torch.cuda.current_device() == device.index:
+        return _NO_GUARD
+    return torch.cuda.device(device)

@@ -30,7 +30,7 @@ class PeerComm:
         self._h = ctypes.c_void_p()
         self._keepalive = keepalive
         lib = _lib.load()
-        with torch.cuda.device(device):
+        with _lib.device_guard(device):
             if segments is None:
                 _lib.check(lib.flyp_comm_create(rank, world, max_rows, dim, ctypes.byref(self._h)))
             else:
@@ -56,7 +56,7 @@ class PeerComm:
         blob = b"".join(handles)
         if len(blob) != self.world * _lib.IPC_HANDLE_BYTES:
             raise FlypError("expected one IPC handle per rank")
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(_lib.load().flyp_comm_connect_ipc(self._h, blob))
 
     @staticmethod
@@ -73,7 +73,7 @@ class PeerComm:
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         nbytes = cls.layout_bytes(world, max_rows, dim)
-        with torch.cuda.device(device):
+        with _lib.device_guard(device):
             buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
             buf.zero_()
             hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
@@ -162,7 +162,7 @@ class PeerComm:
     def gather(self, img: torch.Tensor, txt: torch.Tensor) -> Gathered:
         n, d = img.shape
         out = Gathered()
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(_lib.load().flyp_comm_gather_features(self._h, img.data_ptr(), txt.data_ptr(), n, d,
                                                              _lib.dtype_code(img), ctypes.byref(out),
                                                              _lib.stream_ptr(self.device)))
@@ -172,7 +172,7 @@ class PeerComm:
     def push_stats(self, seq: int, col_stat: torch.Tensor, row_lse: torch.Tensor, row_nll: torch.Tensor) -> Stats:
         out = Stats()
         n_rows = row_lse.numel()
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(_lib.load().flyp_comm_push_stats(self._h, seq, col_stat.data_ptr(), row_lse.data_ptr(),
                                                         row_nll.data_ptr(), n_rows, col_stat.numel() // 3,
                                                         ctypes.byref(out), _lib.stream_ptr(self.device)))
@@ -183,11 +183,11 @@ class PeerComm:
         self.sum_scalar(seq, out)
 
     def push_scalar(self, seq: int, value: torch.Tensor) -> None:
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(_lib.load().flyp_comm_push_scalar(self._h, seq, value.data_ptr(), _lib.stream_ptr(self.device)))
 
     def sum_scalar(self, seq: int, out: torch.Tensor) -> None:
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(_lib.load().flyp_comm_sum_scalar(self._h, seq, out.data_ptr(), _lib.stream_ptr(self.device)))
 
 
@@ -234,7 +234,7 @@ def fwd_local(st: PeerStep) -> None:
     dev = st.img.device
     lib = _lib.load()
     b, B = st.b, st.B
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         st.ws = _workspace(b, B, st.D, dev)
         # one allocation for every fp32 vector of the step (each slice 16-byte aligned)
         bp = (b + 3) & ~3
@@ -255,7 +255,7 @@ def fwd_finish(st: PeerStep, loss_dtype=torch.float32) -> torch.Tensor:
     """Loss of every global row (the reference returns the full vector on every rank, clip/loss.py:113-114,208)."""
     dev = st.img.device
     code = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[loss_dtype]
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         st.loss = torch.empty(st.B, dtype=loss_dtype, device=dev)
         _lib.check(_lib.load().flyp_clip_fwd_finish_ex(
             st.st.col_stat_all, st.comm.world, st.st.row_nll_all, st.B, st.B, 0, st.col_lse.data_ptr(),
@@ -278,7 +278,7 @@ def bwd_local(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_i
     g = g.contiguous()
     g_code = _lib.FLYP_BF16 if g.dtype == torch.bfloat16 else _lib.FLYP_F32
     need_img = need_img or need_scale
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         d_img = torch.empty(st.b, st.D, dtype=gdt, device=dev) if need_img else None
         d_txt = torch.empty(st.b, st.D, dtype=gdt, device=dev) if need_txt else None
         d_s = torch.empty(1, dtype=torch.float32, device=dev) if need_scale else None

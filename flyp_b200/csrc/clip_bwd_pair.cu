@@ -360,7 +360,8 @@ void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUt
     const bool row_term = p.wr != nullptr, col_term = p.wc != nullptr;
 #define FLYP_LAUNCH_BWD2(R, C)                                                                                 \
     do {                                                                                                       \
-        cudaFuncSetAttribute(bwd_pair_kernel<R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        static bool attr_done[64] = {false};                                                                  \
+        ensure_smem_attr(bwd_pair_kernel<R, C>, smem, attr_done);                                              \
         bwd_pair_kernel<R, C><<<grid, NTHREADS2, smem, st>>>(tmA64, tmB, tmBd, p);                             \
     } while (0)
     if (row_term && col_term) FLYP_LAUNCH_BWD2(true, true);

@@ -309,7 +309,8 @@ void launch_fwd_mc(const CUtensorMap& tmA64, const CUtensorMap& tmB, const FwdPa
     int workers = num_sms / 2;
     if (n_items < workers) workers = n_items;
     const size_t smem = fwd_smem_bytes(true);
-    cudaFuncSetAttribute(fwd_kernel_mc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static bool attr_done[64] = {false};
+    ensure_smem_attr(fwd_kernel_mc, smem, attr_done);
     fwd_kernel_mc<<<workers * 2, NTHREADS, smem, st>>>(tmA64, tmB, p);
 }
 
@@ -321,7 +322,8 @@ void launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams&
     const size_t smem = fwd_smem_bytes(stat);
 #define FLYP_LAUNCH_FWD(S, R)                                                                                  \
     do {                                                                                                       \
-        cudaFuncSetAttribute(fwd_kernel<S, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        static bool attr_done[64] = {false};                                                                   \
+        ensure_smem_attr(fwd_kernel<S, R>, smem, attr_done);                                                   \
         fwd_kernel<S, R><<<grid, NTHREADS, smem, st>>>(tmA, tmB, p, gate);                                     \
     } while (0)
     if (stat) { if (robust) FLYP_LAUNCH_FWD(true, true); else FLYP_LAUNCH_FWD(true, false); }
@@ -599,7 +601,8 @@ void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     const bool row_term = p.wr != nullptr, col_term = p.wc != nullptr;
 #define FLYP_LAUNCH_BWD(R, C)                                                                                  \
     do {                                                                                                       \
-        cudaFuncSetAttribute(bwd_kernel<R, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        static bool attr_done[64] = {false};                                                                   \
+        ensure_smem_attr(bwd_kernel<R, C>, smem, attr_done);                                                   \
         bwd_kernel<R, C><<<grid, NTHREADS, smem, st>>>(tmA, tmB, tmBd, p);                                     \
     } while (0)
     if (row_term && col_term) FLYP_LAUNCH_BWD(true, true);

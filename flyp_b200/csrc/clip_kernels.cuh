@@ -130,6 +130,17 @@ constexpr int PAIR_NSTEP = 256;      // columns per step of the pair kernel
 // first flat unit of pair q
 __host__ __device__ inline long long flat_start(int q, long long S, int pairs) { return (long long)q * S / pairs; }
 size_t fwd_smem_bytes(bool stationary);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is needed once per kernel and device, not once per launch
+template <typename K>
+inline void ensure_smem_attr(K kernel, size_t smem, bool (&done)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!done[dev]) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        done[dev] = true;
+    }
+}
 size_t bwd_smem_bytes();
 
 }  // namespace flyp

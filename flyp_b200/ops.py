@@ -62,7 +62,7 @@ def clip_fwd_local(img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor, ro
     n_cols = txt.shape[0]
     dev = img.device
     code = _lib.dtype_code(img)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         ws = workspace if workspace is not None else clip_workspace(n_rows, n_cols, dim, code, dev)
         row_lse, row_nll, col_stat = _f32(n_rows, dev), _f32(n_rows, dev), _f32(3 * n_cols, dev)
         status = torch.empty(1, dtype=torch.int32, device=dev)
@@ -80,7 +80,7 @@ def clip_fwd_finish(col_stat_all: torch.Tensor, world: int, row_nll: torch.Tenso
     col_stat_all = col_stat_all.contiguous()
     if col_stat_all.numel() != world * 3 * n_cols:
         raise FlypError("col_stat_all has the wrong size")
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         col_lse, col_nll, loss = _f32(n_cols, dev), _f32(n_cols, dev), _f32(n_rows, dev)
         _lib.check(_lib.load().flyp_clip_fwd_finish(col_stat_all.data_ptr(), world, row_nll.data_ptr(), n_rows, n_cols,
                                                     row_offset, col_lse.data_ptr(), col_nll.data_ptr(),
@@ -100,7 +100,7 @@ def clip_bwd_local(img, txt, scale, row_offset, row_lse, row_nll, col_lse, col_n
     gdt = img.dtype if grad_dtype is None else grad_dtype
     gcode = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[gdt]
     need_img = need_img or need_scale
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         ws = workspace if workspace is not None else clip_workspace(n_rows, n_cols, dim, code, dev)
         d_img = torch.empty(n_rows, dim, dtype=gdt, device=dev) if need_img else None
         d_txt = torch.empty(n_cols, dim, dtype=gdt, device=dev) if need_txt else None
@@ -127,7 +127,7 @@ def ce_fwd(a: torch.Tensor, b: torch.Tensor, scale: torch.Tensor, labels: Option
         if labels.numel() != n:
             raise FlypError("labels must have one entry per row of a")
         labels = labels.to(device=dev, dtype=torch.int64).contiguous()
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         ws = workspace if workspace is not None else ce_workspace(n, c, dim, code, dev)
         loss, lse = _f32(n, dev), _f32(n, dev)
         _lib.check(_lib.load().flyp_ce_fwd(a.data_ptr(), b.data_ptr(), scale.data_ptr(), n, c, dim, code,
@@ -149,7 +149,7 @@ def ce_bwd(a, b, scale, labels, label_offset, lse, loss, g, grad_dtype=None, nee
     need_a = need_a or need_scale
     if labels is not None:
         labels = labels.to(device=dev, dtype=torch.int64).contiguous()
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         ws = workspace if workspace is not None else ce_workspace(n, c, dim, code, dev)
         d_a = torch.empty(n, dim, dtype=gdt, device=dev) if need_a else None
         d_b = torch.empty(c, dim, dtype=gdt, device=dev) if need_b else None
@@ -170,7 +170,7 @@ def l2norm_fwd(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     x = x.contiguous()
     n, dim = x.shape
     dev = x.device
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         y = torch.empty_like(x)
         inv = _f32(n, dev)
         _lib.check(_lib.load().flyp_l2norm_fwd(x.data_ptr(), n, dim, _lib.dtype_code(x), y.data_ptr(), inv.data_ptr(),
@@ -182,7 +182,7 @@ def l2norm_bwd(y: torch.Tensor, dy: torch.Tensor, inv: torch.Tensor) -> torch.Te
     y = y.contiguous(); dy = dy.to(y.dtype).contiguous()
     n, dim = y.shape
     dev = y.device
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         dx = torch.empty_like(y)
         _lib.check(_lib.load().flyp_l2norm_bwd(y.data_ptr(), dy.data_ptr(), inv.data_ptr(), n, dim, _lib.dtype_code(y),
                                                dx.data_ptr(), _lib.stream_ptr(dev)))
@@ -197,7 +197,7 @@ def debug_logits(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     n_n = b.shape[0]
     dev = a.device
     code = _lib.dtype_code(a)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         ws = clip_workspace(n_m, n_n, dim, code, dev)
         out = torch.empty(n_m, n_n, dtype=torch.float32, device=dev)
         _lib.check(_lib.load().flyp_debug_logits(a.data_ptr(), b.data_ptr(), n_m, n_n, dim, code, out.data_ptr(),
