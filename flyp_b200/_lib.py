@@ -40,6 +40,11 @@ class Stats(Structure):
     _fields_ = [("col_stat_all", c_void_p), ("row_lse_all", c_void_p), ("row_nll_all", c_void_p), ("ready", Ready)]
 
 
+class Step(Structure):
+    """flyp_step_t"""
+    _fields_ = [("gathered", Gathered), ("stats", Stats)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/flyp_clip.h
 SIGNATURES = {
     "flyp_last_error": (c_char_p, []),
@@ -64,6 +69,12 @@ SIGNATURES = {
                                       c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                       c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(Ready),
                                       POINTER(Ready), POINTER(Ready), POINTER(Ready), c_void_p]),
+    "flyp_clip_fwd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                   POINTER(Step), c_void_p]),
+    "flyp_clip_bwd_step": (c_int, [c_void_p, POINTER(Step), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "flyp_comm_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
     "flyp_comm_layout_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
     "flyp_comm_create_external": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p), c_void_p, POINTER(c_void_p)]),

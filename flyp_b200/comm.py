@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import FlypError, Gathered, Ready, Stats
+from ._lib import FlypError, Gathered, Ready, Stats, Step
 
 
 class PeerComm:
@@ -290,3 +290,68 @@ def bwd_local(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_i
             _lib.ptr(d_s), st.ws.data_ptr(), st.ws.numel(), ctypes.byref(gg.img_ready), ctypes.byref(gg.txt_ready),
             ctypes.byref(gg.img16_ready), ctypes.byref(gg.txt16_ready), _lib.stream_ptr(dev)))
     return d_img, d_txt, d_s
+
+
+# ---------------------------------------------------------------------------------------------------- whole steps
+# What the drop-in module calls: one C call per direction (flyp_clip_fwd_step / flyp_clip_bwd_step).
+
+class FusedStep:
+    """State of one forward through flyp_clip_fwd_step (kept for the backward)."""
+    __slots__ = ("comm", "step", "img", "txt", "s", "b", "B", "D", "buf", "col_lse", "col_nll", "ws", "seq")
+
+
+def step_forward(comm: PeerComm, img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor, loss_dtype):
+    """Returns (loss[B] in loss_dtype, FusedStep)."""
+    from . import ops
+    ops._check_features(img, txt)
+    if img.dtype != torch.bfloat16:
+        raise FlypError("the peer-memory path carries bf16 features")
+    dev = img.device
+    st = FusedStep()
+    st.comm, st.img, st.txt, st.s = comm, img.contiguous(), txt.contiguous(), scale
+    b, D = img.shape
+    B = b * comm.world
+    st.b, st.B, st.D = b, B, D
+    st.step = Step()
+    code = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[loss_dtype]
+    with _lib.device_guard(dev):
+        st.ws = _workspace(b, B, D, dev)
+        bp, Bp = (b + 3) & ~3, (B + 3) & ~3
+        st.buf = buf = torch.empty(2 * bp + 5 * Bp, dtype=torch.float32, device=dev)
+        loss = torch.empty(B, dtype=loss_dtype, device=dev)
+        base, f4 = buf.data_ptr(), 4
+        o = 2 * bp
+        st.col_lse, st.col_nll = base + (o + 3 * Bp) * f4, base + (o + 4 * Bp) * f4
+        _lib.check(_lib.load().flyp_clip_fwd_step(
+            comm._h, st.img.data_ptr(), st.txt.data_ptr(), scale.data_ptr(), b, D, _lib.FLYP_BF16, comm.rank, comm.world,
+            base, base + bp * f4, base + o * f4, st.col_lse, st.col_nll, loss.data_ptr(), code, st.ws.data_ptr(),
+            st.ws.numel(), ctypes.byref(st.step), _lib.stream_ptr(dev)))
+    st.seq = comm.seq = int(st.step.gathered.seq)
+    return loss, st
+
+
+def step_backward(st: FusedStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_img: bool, need_txt: bool,
+                  need_scale: bool):
+    """Returns (d_img, d_txt, d_scale): complete gradients of the local rows and the all-reduced d(logit_scale)."""
+    comm = st.comm
+    if not comm.alive(st.seq):
+        raise FlypError("the gathered features of this step were overwritten: with the peer-memory path at most one "
+                        "later forward may run before a step's backward (use ClipLoss(comm='nccl') otherwise)")
+    dev = st.img.device
+    gdt = st.img.dtype if grad_dtype is None else grad_dtype
+    gcode = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[gdt]
+    if g.dtype not in (torch.float32, torch.bfloat16):
+        g = g.to(torch.float32)
+    g = g.contiguous()
+    g_code = _lib.FLYP_BF16 if g.dtype == torch.bfloat16 else _lib.FLYP_F32
+    need_img = need_img or need_scale
+    with _lib.device_guard(dev):
+        d_img = torch.empty(st.b, st.D, dtype=gdt, device=dev) if need_img else None
+        d_txt = torch.empty(st.b, st.D, dtype=gdt, device=dev) if need_txt else None
+        ds = torch.empty(2, dtype=torch.float32, device=dev) if need_scale else None      # [total, partial]
+        _lib.check(_lib.load().flyp_clip_bwd_step(
+            comm._h, ctypes.byref(st.step), st.img.data_ptr(), st.txt.data_ptr(), st.s.data_ptr(), st.b, st.D,
+            _lib.FLYP_BF16, comm.rank, comm.world, st.col_lse, st.col_nll, g.data_ptr(), g_code, float(grad_mul), gcode,
+            _lib.ptr(d_img), _lib.ptr(d_txt), (ds.data_ptr() + 4) if need_scale else None,
+            ds.data_ptr() if need_scale else None, st.ws.data_ptr(), st.ws.numel(), _lib.stream_ptr(dev)))
+    return d_img, d_txt, (ds[:1] if need_scale else None)

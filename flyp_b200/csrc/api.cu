@@ -547,13 +547,14 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
     return 0;
 }
 
-int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all, const void* txt_all,
-                          const void* img16_all, const void* txt16_all, const float* scale, int n_rows, int n_cols,
-                          int dim, int dtype, int row_offset, const float* row_lse_all, const float* row_nll_all,
-                          const float* col_lse, const float* col_nll, const void* g, int g_dtype, float grad_mul,
-                          int grad_dtype, void* d_img, void* d_txt, float* d_scale, void* workspace,
-                          size_t workspace_bytes, const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready,
-                          const flyp_ready_t* img16_ready, const flyp_ready_t* txt16_ready, void* stream) {
+static int bwd_sharded_impl(const void* img, const void* txt, const void* img_all, const void* txt_all,
+                            const void* img16_all, const void* txt16_all, const float* scale, int n_rows, int n_cols,
+                            int dim, int dtype, int row_offset, const float* row_lse_all, const float* row_nll_all,
+                            const float* col_lse, const float* col_nll, const void* g, int g_dtype, float grad_mul,
+                            int grad_dtype, void* d_img, void* d_txt, float* d_scale, void* workspace,
+                            size_t workspace_bytes, const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready,
+                            const flyp_ready_t* img16_ready, const flyp_ready_t* txt16_ready, void* stream,
+                            flyp_comm* comm, uint32_t seq, float* d_scale_total) {
     ReserveSms reserve(txt_ready ? txt_ready : img_ready);
     int rc = check_common(n_rows, n_cols, dim, dtype);
     if (g_dtype != FLYP_BF16 && g_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad g_dtype %d", g_dtype);
@@ -591,6 +592,8 @@ int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all,
         if (d_scale) {
             flyp::launch_sum_parts(w.dscale_part, (int)w.n_dscale, d_scale, st);
             CUDA_OK(cudaGetLastError());
+            // the partial goes out now; the other ranks' partials arrive while the second sweep runs
+            if (comm != nullptr && (rc = flyp_comm_push_scalar(comm, seq, d_scale, stream)) != 0) return rc;
         }
     }
     if (d_txt) {
@@ -600,7 +603,57 @@ int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all,
                        grad_mul, nullptr, w.part_scratch, w.gmax_bits, st, img_ready, img16_ready);
         if (rc) return rc;
     }
+    if (comm != nullptr && d_scale != nullptr && d_scale_total != nullptr)
+        return flyp_comm_sum_scalar(comm, seq, d_scale_total, stream);
     return 0;
+}
+
+int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all, const void* txt_all,
+                          const void* img16_all, const void* txt16_all, const float* scale, int n_rows, int n_cols,
+                          int dim, int dtype, int row_offset, const float* row_lse_all, const float* row_nll_all,
+                          const float* col_lse, const float* col_nll, const void* g, int g_dtype, float grad_mul,
+                          int grad_dtype, void* d_img, void* d_txt, float* d_scale, void* workspace,
+                          size_t workspace_bytes, const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready,
+                          const flyp_ready_t* img16_ready, const flyp_ready_t* txt16_ready, void* stream) {
+    return bwd_sharded_impl(img, txt, img_all, txt_all, img16_all, txt16_all, scale, n_rows, n_cols, dim, dtype,
+                            row_offset, row_lse_all, row_nll_all, col_lse, col_nll, g, g_dtype, grad_mul, grad_dtype,
+                            d_img, d_txt, d_scale, workspace, workspace_bytes, img_ready, txt_ready, img16_ready,
+                            txt16_ready, stream, nullptr, 0, nullptr);
+}
+
+// ---- whole-step entry points over a communicator: what ClipLoss.forward / backward of a rank call -------------------
+int flyp_clip_fwd_step(flyp_comm* comm, const void* img, const void* txt, const float* scale, int n_rows, int dim,
+                       int dtype, int rank, int world, float* row_lse, float* row_nll, float* col_stat, float* col_lse,
+                       float* col_nll, void* loss, int loss_dtype, void* workspace, size_t workspace_bytes,
+                       flyp_step_t* step, void* stream) {
+    if (!comm || !step) return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(FLYP_ERR_ARG, "bad rank %d / world %d", rank, world);
+    const int n_cols = n_rows * world, off = rank * n_rows;
+    int rc = flyp_comm_gather_features(comm, img, txt, n_rows, dim, dtype, &step->gathered, stream);
+    if (rc) return rc;
+    rc = flyp_clip_fwd_local_ex(img, step->gathered.txt_all, scale, n_rows, n_cols, dim, dtype, off, row_lse, row_nll,
+                                col_stat, nullptr, workspace, workspace_bytes, &step->gathered.txt_ready, stream);
+    if (rc) return rc;
+    rc = flyp_comm_push_stats(comm, step->gathered.seq, col_stat, row_lse, row_nll, n_rows, n_cols, &step->stats, stream);
+    if (rc) return rc;
+    return flyp_clip_fwd_finish_ex(step->stats.col_stat_all, world, step->stats.row_nll_all, n_cols, n_cols, 0, col_lse,
+                                   col_nll, loss, loss_dtype, &step->stats.ready, stream);
+}
+
+int flyp_clip_bwd_step(flyp_comm* comm, const flyp_step_t* step, const void* img, const void* txt, const float* scale,
+                       int n_rows, int dim, int dtype, int rank, int world, const float* col_lse, const float* col_nll,
+                       const void* g, int g_dtype, float grad_mul, int grad_dtype, void* d_img, void* d_txt,
+                       float* d_scale_partial, float* d_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!comm || !step) return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(FLYP_ERR_ARG, "bad rank %d / world %d", rank, world);
+    if ((d_scale != nullptr) != (d_scale_partial != nullptr))
+        return fail(FLYP_ERR_ARG, "d_scale and d_scale_partial go together");
+    const flyp_gathered_t& gg = step->gathered;
+    return bwd_sharded_impl(img, txt, gg.img_all, gg.txt_all, gg.img16_all, gg.txt16_all, scale, n_rows, n_rows * world,
+                            dim, dtype, rank * n_rows, step->stats.row_lse_all, step->stats.row_nll_all, col_lse, col_nll,
+                            g, g_dtype, grad_mul, grad_dtype, d_img, d_txt, d_scale_partial, workspace, workspace_bytes,
+                            &gg.img_ready, &gg.txt_ready, &gg.img16_ready, &gg.txt16_ready, stream, comm, gg.seq,
+                            d_scale);
 }
 
 // ------------------------------------------------------------------------------------------------ ce head

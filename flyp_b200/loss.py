@@ -231,16 +231,15 @@ class _ClipLossFn(torch.autograd.Function):
 
 
 class _ClipLossPeerFn(torch.autograd.Function):
-    """The same row-sharded symmetric loss with every exchange done over peer memory (flyp_b200/comm.py): copy-engine
-    feature pushes that overlap the forward kernel, flag-polling tensor-core kernels, remote-store statistics."""
+    """The same row-sharded symmetric loss with every exchange done over peer memory (flyp_b200/comm.py): feature
+    pushes by the copy engines (one multicast copy per matrix on NVSwitch) that overlap the forward kernel,
+    flag-polling tensor-core kernels, statistics and d(scale) by (multicast) remote stores.  One C call per direction."""
 
     @staticmethod
     def forward(ctx, img, txt, scale, comm, gather_with_grad, grad_dtype):
         from . import comm as peer
         s = ops._scale_tensor(scale, img.device)
-        st = peer.fwd_gather(comm, img, txt, s)
-        peer.fwd_local(st)
-        loss = peer.fwd_finish(st, img.dtype)       # the kernel writes the loss in the feature dtype (no cast pass)
+        loss, st = peer.step_forward(comm, img, txt, s, img.dtype)   # the loss is written in the feature dtype
         ctx.st = st
         ctx.meta = (gather_with_grad, grad_dtype, torch.is_tensor(scale), scale.shape if torch.is_tensor(scale) else None,
                     scale.dtype if torch.is_tensor(scale) else None)
@@ -253,19 +252,16 @@ class _ClipLossPeerFn(torch.autograd.Function):
         gwg, grad_dtype, s_is_tensor, s_shape, s_dtype = ctx.meta
         need_img, need_txt, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         mul = float(st.comm.world) if gwg else 1.0
-        d_img, d_txt, d_s = peer.bwd_local(st, g, mul, grad_dtype, need_img, need_txt, need_s)
+        # every rank differentiates the same replicated loss: d(scale) is the sum over the row blocks of all ranks
+        d_img, d_txt, tot = peer.step_backward(st, g, mul, grad_dtype, need_img, need_txt, need_s)
         gs = None
-        if need_s:
-            # every rank differentiates the same replicated loss: d(scale) sums the row blocks of all ranks
-            tot = torch.empty(1, dtype=torch.float32, device=st.img.device)
-            st.comm.all_reduce_scalar(st.g.seq, d_s, tot)
-            if s_is_tensor:
-                if s_dtype == torch.float32 and len(s_shape) <= 1 and (len(s_shape) == 0 or s_shape[0] == 1):
-                    gs = tot.view(s_shape)
-                else:
-                    gs = torch.zeros(s_shape, dtype=torch.float32, device=st.img.device).reshape(-1)
-                    gs[:1] = tot
-                    gs = gs.reshape(s_shape).to(s_dtype)
+        if need_s and s_is_tensor:
+            if s_dtype == torch.float32 and len(s_shape) <= 1 and (len(s_shape) == 0 or s_shape[0] == 1):
+                gs = tot.view(s_shape)
+            else:
+                gs = torch.zeros(s_shape, dtype=torch.float32, device=st.img.device).reshape(-1)
+                gs[:1] = tot
+                gs = gs.reshape(s_shape).to(s_dtype)
         st.comm.check_error()
         return (d_img if need_img else None), (d_txt if need_txt else None), gs, None, None, None
 

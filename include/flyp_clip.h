@@ -201,6 +201,27 @@ int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all,
                           size_t workspace_bytes, const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready,
                           const flyp_ready_t* img16_ready, const flyp_ready_t* txt16_ready, void* stream);
 
+/* Whole-step entry points of a rank over a communicator - what the drop-in module's forward / backward call.
+ * flyp_clip_fwd_step = flyp_comm_gather_features + flyp_clip_fwd_local_ex + flyp_comm_push_stats +
+ * flyp_clip_fwd_finish_ex: loss[world * n_rows] (the full per-item vector on every rank, clip/loss.py:113-114,208) and
+ * the statistics the backward needs; `step` keeps where the gathered data lives (valid until the second-next
+ * flyp_clip_fwd_step on this communicator).  flyp_clip_bwd_step = flyp_clip_bwd_sharded with the d(logit_scale)
+ * all-reduce folded in: this rank's partial is pushed right after the first sweep and summed (fixed rank order) after
+ * the second, so the exchange hides behind the second sweep.  d_scale (the global sum) and d_scale_partial (scratch,
+ * 1 float) are both NULL or both given. */
+typedef struct {
+    flyp_gathered_t gathered;
+    flyp_stats_t stats;
+} flyp_step_t;
+int flyp_clip_fwd_step(flyp_comm* comm, const void* img, const void* txt, const float* scale, int n_rows, int dim,
+                       int dtype, int rank, int world, float* row_lse, float* row_nll, float* col_stat, float* col_lse,
+                       float* col_nll, void* loss, int loss_dtype, void* workspace, size_t workspace_bytes,
+                       flyp_step_t* step, void* stream);
+int flyp_clip_bwd_step(flyp_comm* comm, const flyp_step_t* step, const void* img, const void* txt, const float* scale,
+                       int n_rows, int dim, int dtype, int rank, int world, const float* col_lse, const float* col_nll,
+                       const void* g, int g_dtype, float grad_mul, int grad_dtype, void* d_img, void* d_txt,
+                       float* d_scale_partial, float* d_scale, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Row-wise L2 normalisation x / ||x||_2 (no epsilon), clip/model.py:375-376, src/models/ce_ablation.py:115-118.
  * ------------------------------------------------------------------------------------------------------------------ */
