@@ -413,8 +413,10 @@ void launch_sum_parts(const float* parts, int n, float* out, cudaStream_t st) {
 template <bool F32OUT>
 __global__ void k_reduce_parts(const float* __restrict__ part, int m_tiles, int NJ, int pairs, int n_m, int d_out,
                                void* __restrict__ out, int ld_out) {
-    const int mb = blockIdx.y;
-    const long long S = (long long)m_tiles * NJ, lo = (long long)mb * NJ, hi = lo + NJ;
+    // only the flat tail (row blocks beyond the whole-block rounds) can be split
+    const int first = (m_tiles / pairs) * pairs;
+    const int tb = blockIdx.y, mb = first + tb;
+    const long long S = (long long)(m_tiles - first) * NJ, lo = (long long)tb * NJ, hi = lo + NJ;
     int q = (int)(lo * pairs / S);
     while (q + 1 < pairs && flat_start(q + 1, S, pairs) <= lo) ++q;
     while (q > 0 && flat_start(q, S, pairs) > lo) --q;
@@ -443,7 +445,9 @@ __global__ void k_reduce_parts(const float* __restrict__ part, int m_tiles, int 
 void launch_reduce_parts(const float* part, int m_tiles, int NJ, int pairs, int n_m, int d_out, void* out, int ld_out,
                          int out_fp32, cudaStream_t st) {
     if (m_tiles <= 0 || pairs <= 0) return;
-    const dim3 grid((unsigned)((128 * (d_out / 4) + 255) / 256), (unsigned)m_tiles);
+    const int tail = m_tiles - (m_tiles / pairs) * pairs;
+    if (tail == 0) return;
+    const dim3 grid((unsigned)((128 * (d_out / 4) + 255) / 256), (unsigned)tail);
     if (out_fp32) k_reduce_parts<true><<<grid, 256, 0, st>>>(part, m_tiles, NJ, pairs, n_m, d_out, out, ld_out);
     else k_reduce_parts<false><<<grid, 256, 0, st>>>(part, m_tiles, NJ, pairs, n_m, d_out, out, ld_out);
 }

@@ -50,17 +50,24 @@ struct ItemInfo { int mb, t0, t1, part; };
 // index of the fp32 partial slot it accumulates into.
 struct ItemIter {
     long long pos, end;
-    int NJ, pair, ord;
+    int NJ, pair, ord, round, full_rounds, P;
     DEVI ItemIter(const BwdParams& p, int pair_, int NJ_) {
-        const long long S = (long long)p.m_tiles * NJ_;
-        pos = flat_start(pair_, S, p.sched_pairs);
-        end = flat_start(pair_ + 1, S, p.sched_pairs);
-        NJ = NJ_; pair = pair_; ord = 0;
+        P = p.sched_pairs; NJ = NJ_; pair = pair_; ord = 0; round = 0;
+        full_rounds = p.m_tiles / P;                         // whole row blocks, one per pair and round, in lockstep
+        const long long S = (long long)(p.m_tiles - full_rounds * P) * NJ;   // units of the flat tail
+        pos = flat_start(pair_, S, P);
+        end = flat_start(pair_ + 1, S, P);
     }
     DEVI bool next(ItemInfo& r) {
+        if (round < full_rounds) {
+            r.mb = round * P + pair; r.t0 = 0; r.t1 = NJ; r.part = -1;
+            ++round;
+            return true;
+        }
         if (pos >= end) return false;
-        r.mb = (int)(pos / NJ);
-        r.t0 = (int)(pos - (long long)r.mb * NJ);
+        const int tb = (int)(pos / NJ);
+        r.mb = full_rounds * P + tb;
+        r.t0 = (int)(pos - (long long)tb * NJ);
         const long long room = NJ - r.t0, len = end - pos;
         r.t1 = r.t0 + (int)(len < room ? len : room);
         r.part = (r.t0 == 0 && r.t1 == NJ) ? -1 : 2 * pair + (ord == 0 ? 0 : 1);
@@ -71,8 +78,11 @@ struct ItemIter {
 };
 }  // namespace
 
-// The flat schedule keeps every pair equally loaded whatever the number of row blocks (a per-row-block schedule idles
-// 14 % of the pairs when a rank owns 32 or 64 row blocks, i.e. B = 32768 on 8 or 4 GPUs).
+// Schedule of a sweep over m_tiles row blocks on P CTA pairs: floor(m_tiles / P) rounds of whole row blocks (all pairs
+// walk the columns in lockstep: one stream of B tiles through L2 serves them all), then the remaining blocks as a FLAT
+// tail - their (row block, column step) units cut into P equal contiguous ranges - so that the last, partial wave keeps
+// every pair busy (a per-row-block schedule idles 14 % of the pairs when a rank owns 32 or 64 row blocks, i.e.
+// B = 32768 on 8 or 4 GPUs).
 int bwd_pair_sched_pairs(int m_tiles, int n_cols, int num_sms) {
     int npairs = num_sms / 2;
     if (const char* e = getenv("FLYP_SCHED_PAIRS")) {          // A/B switch for measurements

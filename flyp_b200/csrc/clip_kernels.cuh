@@ -96,10 +96,10 @@ struct BwdParams {
     const float* fa;         // [m] fast form: wr 2^(c0 - lr)      (see bwd_common.cuh)
     const float* fb;         // [n] fast form: wc 2^(c0 - lc)
     const float* fast_info;  // device {c0, valid}: valid != 0 -> single-exponential epilogue
-    // flat schedule (pair kernel): the S = m_tiles * ceil(n_n / 256) (row block, column step) units, row-block-major,
-    // are cut into sched_pairs equal contiguous ranges, one per CTA pair (flat_start).  A range that covers a row block
-    // only partly accumulates that part into part_out[2 * pair + (0: the range starts inside the block, 1: it ends
-    // inside it)][128][d_out] (fp32), summed per block by launch_reduce_parts.
+    // schedule (pair kernel): floor(m_tiles / sched_pairs) rounds of whole row blocks, then the remaining row blocks as a
+    // flat tail: their (row block, column step) units, row-block-major, cut into sched_pairs equal contiguous ranges
+    // (flat_start).  A range that covers a row block only partly accumulates that part into part_out[2 * pair + (0: the
+    // range starts inside the block, 1: it ends inside it)][128][d_out] (fp32), summed by launch_reduce_parts.
     int sched_pairs;
     float* part_out;
     PeerWait wait_b, wait_bd; // readiness of the N-side operand rows (tmB) / of their fp16 copy (tmBd), see peer.cuh
