@@ -306,7 +306,10 @@ def run_ours(args):
                 "h2d_bytes_per_step": 2 * b * D * 2, "d2h_bytes_per_step": B * 2,
                 "how": "pinned host inputs, H2D of step k+1 overlapped with step k on a copy stream, loss vector D2H; "
                        "one timed region over all steps"},
-        "gpu_launches": 15 * args.steps,
+        # own kernels per step (profiles/r01c_launches_step_B32768.csv, r01_timeline_*): 1 GPU 8 forward + 10 backward;
+        # peer path 10 forward (pack, pair_dot, forward, finalize, 4 gated robust helpers, statistics push, finish) +
+        # 9 backward (prep, fast vectors, 2 sweeps, 2 partial reductions, d(scale) sum / push / all-rank sum)
+        "gpu_launches": (18 if world == 1 else 19) * args.steps,
         "roofline": {"bound": "tensor", "kernel": "bwd_kernel (dI sweep: S recompute + dS.T), per launch",
                      "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": ach / pk["sustained"],
                      "peak_kind": "sustained bf16, " + pk["source"], "frac_of_burst": ach / pk["burst"],
