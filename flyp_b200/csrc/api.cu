@@ -793,6 +793,49 @@ int flyp_debug_profile(void* device_buffer_16_u64) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ fused argmax
+int flyp_argmax(const void* a, const void* b, int n_m, int n_n, int dim, int dtype, int64_t* out_index, float* out_max,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(n_m, n_n, dim, dtype);
+    if (rc) return rc;
+    if (!a || !b || !out_index || !workspace) return fail(FLYP_ERR_ARG, "null pointer argument");
+    ClipWs w;
+    carve_clip(workspace, n_m, n_n, dim, dtype, w);
+    if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* one = w.dscale_part;                       // the kernel multiplies by scale * log2(e) > 0: order-preserving
+    static const float h_one = 1.0f;
+    CUDA_OK(cudaMemcpyAsync(one, &h_one, sizeof(float), cudaMemcpyHostToDevice, st));
+    CUtensorMap tmA, tmB;
+    flyp::KPlan kplan = flyp::kplan_bf16();
+    if (dtype == FLYP_F32) {
+        const int dp = plane_cols(dim);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(a), n_m, dim, dp, w.stats.planes_a, st);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(b), n_n, dim, dp, w.stats.planes_b, st);
+        CUDA_OK(cudaGetLastError());
+        if ((rc = make_tmap(&tmA, w.stats.planes_a, n_m, 3 * dp, 3 * dp)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, w.stats.planes_b, n_n, 3 * dp, 3 * dp)) != 0) return rc;
+        kplan = flyp::kplan_f32(dp);
+    } else {
+        if ((rc = make_tmap(&tmA, a, n_m, dim, dim)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, b, n_n, dim, dim)) != 0) return rc;
+    }
+    flyp::FwdParams p;
+    memset(&p, 0, sizeof(p));
+    const StatsWs& s = w.stats;
+    p.n_m = n_m; p.n_n = n_n; p.kc = ceil_div(dim, flyp::KCHUNK); p.kplan = kplan;
+    p.m_tiles = s.m_tiles; p.n_tiles = s.n_tiles; p.m_split = s.m_split; p.ld_rows = s.ld_rows; p.ld_cols = s.ld_cols;
+    p.scale = one; p.shift_slack = shift_slack(n_m, n_n);
+    p.rowpart = s.rowpart; p.rowmax = s.rowmax; p.colpart = nullptr; p.colmax = nullptr; p.pos = nullptr;
+    p.argidx = reinterpret_cast<int*>(s.rowpart);     // the sums are not needed: their buffer carries the columns
+    flyp::launch_fwd(tmA, tmB, p, /*robust=*/true, nullptr, num_sms(), st);
+    CUDA_OK(cudaGetLastError());
+    flyp::launch_argmax_finalize(s.rowmax, p.argidx, s.n_tiles * 2, s.ld_rows, n_m, reinterpret_cast<long long*>(out_index),
+                                 out_max, st);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ debug logits
 int flyp_debug_logits(const void* a, const void* b, int n_m, int n_n, int dim, int dtype, float* out,
                       void* workspace, size_t workspace_bytes, void* stream) {

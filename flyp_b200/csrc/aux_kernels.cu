@@ -222,6 +222,27 @@ void launch_fwd_finalize_robust(const float* rowpart, const float* rowmax, int n
                                                            flag);
 }
 
+// ------------------------------------------------------------------------------------------------ argmax finalize
+// out[i] = column of the maximum of row i over all (column block, half) partials; partials are in increasing column
+// order and a later one wins only when strictly greater, so ties go to the lowest index like torch.argmax.
+__global__ void k_argmax_finalize(const float* __restrict__ pmax, const int* __restrict__ pidx, int n_parts, int ld,
+                                  int n_m, long long* __restrict__ out, float* __restrict__ out_max) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_m) return;
+    float best = pmax[i];
+    int bi = pidx[i];
+    for (int p = 1; p < n_parts; ++p) {
+        const float v = pmax[(size_t)p * ld + i];
+        if (v > best) { best = v; bi = pidx[(size_t)p * ld + i]; }
+    }
+    out[i] = bi;
+    if (out_max != nullptr) out_max[i] = best;
+}
+void launch_argmax_finalize(const float* pmax, const int* pidx, int n_parts, int ld, int n_m, long long* out,
+                            float* out_max, cudaStream_t st) {
+    k_argmax_finalize<<<(n_m + 255) / 256, 256, 0, st>>>(pmax, pidx, n_parts, ld, n_m, out, out_max);
+}
+
 // ------------------------------------------------------------------------------------------------ clip finish
 // col_stat_all[world][3 * n_cols] -> col_lse[n_cols]; loss[i] = 0.5 * (row_nll[i] + col_nll[row_offset + i])
 __global__ void k_clip_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,

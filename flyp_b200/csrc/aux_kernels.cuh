@@ -25,6 +25,9 @@ void launch_fwd_finalize_robust(const float* rowpart, const float* rowmax, int n
                                 const float* t2, float* row_lse, float* row_nll, float* col_stat, const int* flag,
                                 cudaStream_t st);
 // col_stat_all[world][3*n_cols] -> col_lse; loss[i] = 0.5 (row_nll[i] + col_nll[off+i])
+// fused argmax: reduce the per-(column block, half) row maxima / columns written by the forward kernel's argmax mode
+void launch_argmax_finalize(const float* pmax, const int* pidx, int n_parts, int ld, int n_m, long long* out,
+                            float* out_max, cudaStream_t st);
 // wait: readiness of col_stat_all / row_nll when other ranks push them (peer.cuh); flags == nullptr -> no waiting
 void launch_clip_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
                         int row_offset, float* col_lse, float* col_nll, void* loss, int loss_bf16, PeerWait wait,

@@ -236,10 +236,11 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
                     tmem_ld_32x32b_x32(taddr + 32, r1);
                     tmem_ld_wait();
                     float x[64];
+                    const float cx = (p.argidx != nullptr) ? 1.f : c1;      // argmax mode works on the raw dot products
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
-                        x[k] = __uint_as_float(r0[k]) * c1;
-                        x[32 + k] = __uint_as_float(r1[k]) * c1;
+                        x[k] = __uint_as_float(r0[k]) * cx;
+                        x[32 + k] = __uint_as_float(r1[k]) * cx;
                     }
                     if (edge || has_pos) {
 #pragma unroll
@@ -248,15 +249,23 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
                     }
 #pragma unroll
                     for (int k = 0; k < 64; ++k) rmax = fmaxf(rmax, x[k]);
-                    const float mref = (rmax == -INFINITY) ? 0.f : rmax;
+                    if (p.argidx != nullptr) {
+                        // fused argmax: first column (lowest index) that attains the maximum of this thread's 64 columns
+                        int bi = 63;
 #pragma unroll
-                    for (int k = 0; k < 64; ++k) rs += ex2f(x[k] - mref);
+                        for (int k = 62; k >= 0; --k) bi = (x[k] == rmax) ? k : bi;
+                        if (nb_live) p.argidx[(size_t)(nb * 2 + h) * p.ld_rows + row] = col0 + bi;
+                    } else {
+                        const float mref = (rmax == -INFINITY) ? 0.f : rmax;
+#pragma unroll
+                        for (int k = 0; k < 64; ++k) rs += ex2f(x[k] - mref);
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(TEMPTY(as));
                 if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
                 if (nb_live) {
-                    p.rowpart[(size_t)(nb * 2 + h) * p.ld_rows + row] = rs;
+                    if (!ROBUST || p.argidx == nullptr) p.rowpart[(size_t)(nb * 2 + h) * p.ld_rows + row] = rs;
                     if (ROBUST) p.rowmax[(size_t)(nb * 2 + h) * p.ld_rows + row] = rmax;
                 }
             }

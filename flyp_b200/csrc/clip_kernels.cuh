@@ -56,7 +56,9 @@ struct FwdParams {
     float* colpart;          // [m_split][ld_cols]      partial column sums, one per M split
     float* rowmax;           // robust mode only: running log2-domain max paired with rowpart
     float* colmax;           // robust mode only
-    float* dbg_logits;       // optional [n_m][n_n] fp32 raw dot products (debug / argmax path), may be null
+    float* dbg_logits;       // optional [n_m][n_n] fp32 raw dot products (debug path), may be null
+    int* argidx;             // robust mode, optional [n_tiles * 2][ld_rows]: column of the per-tile row maximum (lowest
+                             // index among equals), written next to rowmax INSTEAD of the sums (fused zero-shot argmax)
     // row-sharded multi-GPU: the N-side rows of other ranks arrive over NVLink while the kernel runs.  Column blocks are
     // visited starting at block nb_rot (this rank's own rows) so that work proceeds in arrival order, and the producer
     // polls wait_b before the first TMA read of a block.

@@ -203,3 +203,21 @@ def debug_logits(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         _lib.check(_lib.load().flyp_debug_logits(a.data_ptr(), b.data_ptr(), n_m, n_n, dim, code, out.data_ptr(),
                                                  ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)))
     return out
+
+
+def argmax(a: torch.Tensor, b: torch.Tensor, return_max: bool = False):
+    """argmax_j <a_i, b_j> per row of a (int64, ties -> lowest index), fused into the tensor-core kernel's epilogue: the
+    [n_m, n_n] logits are never materialised."""
+    _check_features(a, b)
+    a = a.contiguous(); b = b.contiguous()
+    n_m, dim = a.shape
+    n_n = b.shape[0]
+    dev = a.device
+    code = _lib.dtype_code(a)
+    with _lib.device_guard(dev):
+        ws = clip_workspace(n_m, n_n, dim, code, dev)
+        idx = torch.empty(n_m, dtype=torch.int64, device=dev)
+        mx = _f32(n_m, dev) if return_max else None
+        _lib.check(_lib.load().flyp_argmax(a.data_ptr(), b.data_ptr(), n_m, n_n, dim, code, idx.data_ptr(), _lib.ptr(mx),
+                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)))
+    return (idx, mx) if return_max else idx

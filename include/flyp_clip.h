@@ -232,8 +232,17 @@ int flyp_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n,
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Zero-shot prediction, src/models/eval.py:150-158 (`logits = ...; pred = logits.argmax(dim=1)`) and
+ * src/models/zeroshot.py:56-81: out_index[i] = argmax_j <a_i, b_j> (ties -> lowest j, like torch.argmax), fused into the
+ * forward kernel's epilogue - the [n_m, n_n] logits are never written.  out_max (optional) = the maximal dot product.
+ * Workspace: flyp_clip_workspace_bytes(n_m, n_n, dim, dtype).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int flyp_argmax(const void* a, const void* b, int n_m, int n_n, int dim, int dtype, int64_t* out_index, float* out_max,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Debug / evaluation: raw dot products <a_i, b_j> as fp32 [n_m, n_n] through the same tensor-core path (used by the
- * argmax-parity tests and the zero-shot argmax, src/models/eval.py:158).  Not used by the loss.
+ * parity tests).  Not used by the loss.
  * ------------------------------------------------------------------------------------------------------------------ */
 int flyp_debug_logits(const void* a, const void* b, int n_m, int n_n, int dim, int dtype, float* out,
                       void* workspace, size_t workspace_bytes, void* stream);

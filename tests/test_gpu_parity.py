@@ -307,6 +307,28 @@ def test_argmax_predictions_are_bit_exact():
     assert np.array_equal(L.argmax(0).cpu().numpy(), S.argmax(0))
 
 
+@pytest.mark.parametrize("n,c,d,dtype", [(37, 182, 512, torch.bfloat16), (1000, 1000, 768, torch.bfloat16),
+                                         (300, 129, 64, torch.bfloat16), (513, 1000, 512, torch.float32),
+                                         (8192, 1000, 512, torch.bfloat16)])
+def test_fused_argmax_equals_argmax_of_logits(n, c, d, dtype):
+    """flyp_argmax (epilogue argmax, logits never written) == torch.argmax of the same kernel's dot products and of the
+    float64 oracle, including exact ties (lowest index) and ragged shapes; src/models/eval.py:150-158."""
+    gen = torch.Generator().manual_seed(n + c)
+    img = torch.nn.functional.normalize(torch.randn(n, d, generator=gen), dim=-1).to(dtype)
+    cls = torch.nn.functional.normalize(torch.randn(c, d, generator=gen), dim=-1).to(dtype)
+    cls[c - 1] = cls[2]                   # ties across different column blocks / halves
+    cls[70 % c] = cls[2]
+    img[n // 2] = cls[2]
+    idx, mx = ops.argmax(img.to(DEV), cls.to(DEV), return_max=True)
+    L = ops.debug_logits(img.to(DEV), cls.to(DEV))
+    assert torch.equal(idx, L.argmax(dim=1))
+    assert torch.equal(mx, L.max(dim=1).values)
+    assert idx[n // 2].item() == min(2, 70 % c)
+    if dtype == torch.bfloat16:
+        want = orc.argmax_predictions(to_np(img), to_np(cls))
+        assert np.array_equal(idx.cpu().numpy(), want)
+
+
 # ---------------------------------------------------------------------------------------------- full size properties
 def test_full_size_properties():
     """BASELINE config B = 32768, D = 512 bf16: size-independent checks (the oracle cannot form 32768^2 logits)."""
