@@ -101,28 +101,32 @@ int num_sms() {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// The CTA-pair backward sweep handles feature dims that are multiples of 128 up to 512; FLYP_BWD_IMPL=1 forces the
+// The CTA-pair backward sweep handles feature dims that are multiples of 128 up to 1024; FLYP_BWD_IMPL=1 forces the
 // single-CTA kernel (kept for other dims and for A/B measurements).
-bool use_pair_kernel(int dim, int dtype = FLYP_BF16) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("FLYP_BWD_IMPL");
-        forced = (e && e[0] == '1') ? 1 : 0;
-    }
-    return forced == 0 && dtype == FLYP_BF16 && dim % 128 == 0 && dim <= 512;
+bool use_pair_kernel(int dim, int dtype, int n_m, int n_n) {
+    const char* e = getenv("FLYP_BWD_IMPL");                              // A/B switch, read on every call
+    const int forced = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;   // 1: never, 2: whenever the shape allows
+    if (forced == 1 || dtype != FLYP_BF16 || dim % 128 != 0 || dim > 1024) return false;
+    if (dim <= 512 || forced == 2) return true;
+    // two passes over the column halves: pays off once the sweep is long enough to amortise the extra pipeline fills and
+    // partial sums (measured: B = 8192, D = 1024 1.02 ms vs 1.35 ms; B = 4096, D = 768 0.42 ms vs 0.35 ms)
+    return (long long)ceil_div(n_m, flyp::TILE) * ceil_div(n_n, flyp::TILE) >= 2048;
 }
+// passes over the output columns of the pair sweep and columns per pass (a multiple of 128, <= 512)
+inline int pair_n_dh(int dim) { return dim > 512 ? 2 : 1; }
+inline int pair_d_half(int dim) { const int n = pair_n_dh(dim); return ((dim + n - 1) / n + 127) / 128 * 128; }
 // number of d(scale) partial slots / fp32 tail-partial blocks a sweep over m_tiles row blocks may use
 int num_sms();
 // d(scale) partial slots and fp32 tail-partial floats a backward sweep over n_m rows x n_n columns may use
 size_t sweep_dscale_slots(int n_m, int n_n, int dim, int dtype) {
     const int m_tiles = ceil_div(n_m, flyp::TILE);
-    if (!use_pair_kernel(dim, dtype)) return (size_t)m_tiles * ceil_div(dim, 256);
-    return (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles, n_n, num_sms());
+    if (!use_pair_kernel(dim, dtype, n_m, n_n)) return (size_t)m_tiles * ceil_div(dim, 256);
+    return (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles * pair_n_dh(dim), n_n, num_sms());
 }
 size_t sweep_part_floats(int n_m, int n_n, int dim, int dtype) {
-    if (!use_pair_kernel(dim, dtype)) return 0;
+    if (!use_pair_kernel(dim, dtype, n_m, n_n)) return 0;
     const int m_tiles = ceil_div(n_m, flyp::TILE);
-    return (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles, n_n, num_sms()) * flyp::TILE * dim;
+    return (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles * pair_n_dh(dim), n_n, num_sms()) * flyp::TILE * pair_d_half(dim);
 }
 constexpr int VEC_PAD = 256;   // per-row / per-column vectors are padded to this many entries
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -343,16 +347,17 @@ int run_sweep(const void* A, const void* B, const void* B_f16, int dtype, const 
     p.wait_b = to_wait(b_ready); p.wait_bd = to_wait(b16_ready);
     p.prof = g_prof_buf;
     { const char* e = getenv("FLYP_DBG"); p.dbg = e ? atoi(e) : 0; }
-    if (use_pair_kernel(dim, dtype)) {
+    if (use_pair_kernel(dim, dtype, n_m, n_n)) {
         CUtensorMap tmA64;
         if ((rc = make_tmap(&tmA64, A, n_m, dim, dim, false, 64)) != 0) return rc;
         if (part_scratch == nullptr) return fail(FLYP_ERR_ARG, "the pair sweep needs its partial-sum scratch");
-        p.sched_pairs = flyp::bwd_pair_sched_pairs(p.m_tiles, n_n, num_sms());
+        p.n_dh = pair_n_dh(dim); p.d_half = pair_d_half(dim);
+        p.sched_pairs = flyp::bwd_pair_sched_pairs(p.m_tiles * p.n_dh, n_n, num_sms());
         p.part_out = part_scratch;
         flyp::launch_bwd_pair(tmA64, tmB, tmBd, p, num_sms(), st);
         CUDA_OK(cudaGetLastError());
-        flyp::launch_reduce_parts(part_scratch, p.m_tiles, ceil_div(n_n, flyp::PAIR_NSTEP), p.sched_pairs, n_m, dim, out,
-                                  dim, out_fp32, st);
+        flyp::launch_reduce_parts(part_scratch, p.m_tiles * p.n_dh, ceil_div(n_n, flyp::PAIR_NSTEP), p.sched_pairs, p.n_dh,
+                                  p.d_half, n_m, dim, out, dim, out_fp32, st);
     } else {
         flyp::launch_bwd(tmA, tmB, tmBd, p, num_sms(), st);
     }

@@ -432,26 +432,27 @@ void launch_sum_parts(const float* parts, int n, float* out, cudaStream_t st) {
 // Sums, for every row block that the flat schedule of the pair backward sweep cut into several ranges, the fp32 partial
 // accumulators of those ranges (in pair order: deterministic) into `out`.  Blocks swept by one item were written directly.
 template <bool F32OUT>
-__global__ void k_reduce_parts(const float* __restrict__ part, int m_tiles, int NJ, int pairs, int n_m, int d_out,
-                               void* __restrict__ out, int ld_out) {
-    // only the flat tail (row blocks beyond the whole-block rounds) can be split
-    const int first = (m_tiles / pairs) * pairs;
-    const int tb = blockIdx.y, mb = first + tb;
-    const long long S = (long long)(m_tiles - first) * NJ, lo = (long long)tb * NJ, hi = lo + NJ;
+__global__ void k_reduce_parts(const float* __restrict__ part, int v_tiles, int NJ, int pairs, int n_dh, int d_half,
+                               int n_m, int d_out, void* __restrict__ out, int ld_out) {
+    // only the flat tail (virtual row blocks beyond the whole-block rounds) can be split
+    const int first = (v_tiles / pairs) * pairs;
+    const int tb = blockIdx.y, vb = first + tb;
+    const int mb = vb / n_dh, dh = vb - mb * n_dh;
+    const long long S = (long long)(v_tiles - first) * NJ, lo = (long long)tb * NJ, hi = lo + NJ;
     int q = (int)(lo * pairs / S);
     while (q + 1 < pairs && flat_start(q + 1, S, pairs) <= lo) ++q;
     while (q > 0 && flat_start(q, S, pairs) > lo) --q;
     if (flat_start(q, S, pairs) <= lo && flat_start(q + 1, S, pairs) >= hi) return;      // swept whole
-    const int d4 = d_out / 4;
+    const int d4 = d_half / 4;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 128 * d4) return;
-    const int r = i / d4, d = (i - r * d4) * 4;
+    const int r = i / d4, dl = (i - r * d4) * 4, d = dh * d_half + dl;
     const int m = mb * 128 + r;
-    if (m >= n_m) return;
+    if (m >= n_m || d >= d_out) return;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (; q < pairs && flat_start(q, S, pairs) < hi; ++q) {
         const int slot = 2 * q + (flat_start(q, S, pairs) >= lo ? 0 : 1);
-        const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)slot * 128 + r) * d_out + d);
+        const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)slot * 128 + r) * d_half + dl);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     if (F32OUT) {
@@ -463,14 +464,14 @@ __global__ void k_reduce_parts(const float* __restrict__ part, int m_tiles, int 
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)m * ld_out + d) = u;
     }
 }
-void launch_reduce_parts(const float* part, int m_tiles, int NJ, int pairs, int n_m, int d_out, void* out, int ld_out,
-                         int out_fp32, cudaStream_t st) {
-    if (m_tiles <= 0 || pairs <= 0) return;
-    const int tail = m_tiles - (m_tiles / pairs) * pairs;
+void launch_reduce_parts(const float* part, int v_tiles, int NJ, int pairs, int n_dh, int d_half, int n_m, int d_out,
+                         void* out, int ld_out, int out_fp32, cudaStream_t st) {
+    if (v_tiles <= 0 || pairs <= 0) return;
+    const int tail = v_tiles - (v_tiles / pairs) * pairs;
     if (tail == 0) return;
-    const dim3 grid((unsigned)((128 * (d_out / 4) + 255) / 256), (unsigned)tail);
-    if (out_fp32) k_reduce_parts<true><<<grid, 256, 0, st>>>(part, m_tiles, NJ, pairs, n_m, d_out, out, ld_out);
-    else k_reduce_parts<false><<<grid, 256, 0, st>>>(part, m_tiles, NJ, pairs, n_m, d_out, out, ld_out);
+    const dim3 grid((unsigned)((128 * (d_half / 4) + 255) / 256), (unsigned)tail);
+    if (out_fp32) k_reduce_parts<true><<<grid, 256, 0, st>>>(part, v_tiles, NJ, pairs, n_dh, d_half, n_m, d_out, out, ld_out);
+    else k_reduce_parts<false><<<grid, 256, 0, st>>>(part, v_tiles, NJ, pairs, n_dh, d_half, n_m, d_out, out, ld_out);
 }
 
 // ------------------------------------------------------------------------------------------------ fp16 staging copy

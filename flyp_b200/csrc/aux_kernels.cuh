@@ -52,10 +52,10 @@ void launch_bwd_fast_vectors(const uint32_t* words, int n_a, const float* w_a, c
 // out[0] = sum(parts[0..n))   (single block, fixed order -> deterministic)
 void launch_sum_parts(const float* parts, int n, float* out, cudaStream_t st);
 
-// sums the fp32 partial accumulators of the row blocks that the flat schedule of the pair backward sweep (m_tiles row
-// blocks x NJ column steps over `pairs` CTA pairs, clip_kernels.cuh) cut into several ranges
-void launch_reduce_parts(const float* part, int m_tiles, int NJ, int pairs, int n_m, int d_out, void* out, int ld_out,
-                         int out_fp32, cudaStream_t st);
+// sums the fp32 partial accumulators of the virtual row blocks (row block, d-half) that the flat tail of the pair backward
+// sweep's schedule (v_tiles virtual blocks x NJ column steps over `pairs` CTA pairs, clip_kernels.cuh) cut into ranges
+void launch_reduce_parts(const float* part, int v_tiles, int NJ, int pairs, int n_dh, int d_half, int n_m, int d_out,
+                         void* out, int ld_out, int out_fp32, cudaStream_t st);
 // dst (fp16, n_elems) = saturating round-to-nearest of src (bf16 or fp32); n_elems % 8 == 0
 void launch_to_f16(const void* src, int dtype, size_t n_elems, void* dst, cudaStream_t st);
 

@@ -1,4 +1,10 @@
-// clip_bwd_pair.cu — backward sweep on CTA pairs (tcgen05 cta_group::2), feature dim <= 512 and a multiple of 128.
+// clip_bwd_pair.cu — backward sweep on CTA pairs (tcgen05 cta_group::2), feature dim a multiple of 128 up to 1024.
+//
+// dim > 512: the dA^T accumulators of a 128-row block (128 x dim fp32) exceed the pair's tensor memory, so a row block is
+// swept once per HALF of the output columns ("virtual row blocks" (row block, d-half), p.n_dh = 2, p.d_half columns each),
+// S being recomputed per pass (6 B^2 D executed per sweep instead of the 10 B^2 D of the single-CTA kernel at D = 1024);
+// and only the first 8 of the kc K-chunks of the A half-block are stationary - the others are streamed through the ring,
+// two 8 KiB chunks per slot, right before the B chunks they multiply.
 //
 // One cluster of two CTAs (an SM pair) owns a block of 128 M-rows and walks over the N side in steps of 256 columns.
 // Per step
@@ -44,29 +50,33 @@ DEVI uint8_t* align1024p(uint8_t* p) {
 }
 DEVI void epi_bar_sync2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-struct ItemInfo { int mb, t0, t1, part; };
+struct ItemInfo { int mb, dh, t0, t1, part; };
 // Work items of one CTA pair under the flat schedule: its contiguous range of (row block, column step) units, cut at
 // row-block boundaries.  part = -1: the item covers its whole row block and writes the output directly; otherwise the
 // index of the fp32 partial slot it accumulates into.
 struct ItemIter {
     long long pos, end;
-    int NJ, pair, ord, round, full_rounds, P;
+    int NJ, pair, ord, round, full_rounds, P, n_dh;
     DEVI ItemIter(const BwdParams& p, int pair_, int NJ_) {
         P = p.sched_pairs; NJ = NJ_; pair = pair_; ord = 0; round = 0;
-        full_rounds = p.m_tiles / P;                         // whole row blocks, one per pair and round, in lockstep
-        const long long S = (long long)(p.m_tiles - full_rounds * P) * NJ;   // units of the flat tail
+        n_dh = p.n_dh;
+        const int vtiles = p.m_tiles * n_dh;                 // virtual row blocks: (row block, d-half), d-half fastest
+        full_rounds = vtiles / P;                            // whole blocks, one per pair and round, in lockstep
+        const long long S = (long long)(vtiles - full_rounds * P) * NJ;      // units of the flat tail
         pos = flat_start(pair_, S, P);
         end = flat_start(pair_ + 1, S, P);
     }
     DEVI bool next(ItemInfo& r) {
         if (round < full_rounds) {
-            r.mb = round * P + pair; r.t0 = 0; r.t1 = NJ; r.part = -1;
+            const int vb = round * P + pair;
+            r.mb = vb / n_dh; r.dh = vb - r.mb * n_dh; r.t0 = 0; r.t1 = NJ; r.part = -1;
             ++round;
             return true;
         }
         if (pos >= end) return false;
         const int tb = (int)(pos / NJ);
-        r.mb = full_rounds * P + tb;
+        const int vb = full_rounds * P + tb;
+        r.mb = vb / n_dh; r.dh = vb - r.mb * n_dh;
         r.t0 = (int)(pos - (long long)tb * NJ);
         const long long room = NJ - r.t0, len = end - pos;
         r.t1 = r.t0 + (int)(len < room ? len : room);
@@ -122,8 +132,12 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
     const uint32_t cta = cluster_ctarank();
     const int pair = blockIdx.x >> 1;
     const int NJ = (p.n_n + Cfg::NSTEP - 1) / Cfg::NSTEP;
-    const int KC = p.kc;                         // 64-wide K chunks of the S contraction (even)
-    const int ND = (p.d_out + 255) / 256;        // pair MMAs of the dA^T product (256 feature columns each)
+    const int KC = p.kc;                         // 64-wide K chunks of the S contraction (even, <= 16)
+    const int KCS = KC < 8 ? KC : 8;             // ... of which the first KCS are stationary, the others streamed
+    const int ND = (p.d_half + 255) / 256;       // pair MMAs of the dA^T product (256 feature columns each) per pass
+    // the dA^T operand boxes are consumed as ADJACENT slot pairs (even, odd): when the streamed A chunks take an odd
+    // number of slots per step (dim = 640, 896) an empty bubble slot restores the alignment
+    const bool pad_slot = (((KC - KCS) / 2) & 1) != 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLOT; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
@@ -156,14 +170,31 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 tma_load_2d_cg2(smem_u32(ring + slot * Cfg::SLOT), tm, mapa(FULL(slot), 0), c0, c1);
                 if (++slot == NSLOT) { slot = 0; ph ^= 1; }
             };
-            auto load_s = [&](int t) {
-                for (int c = 0; c < KC; ++c) put(&tmB, c * KCHUNK, t * Cfg::NSTEP + (int)cta * 128);
+            // two streamed K-chunks (c, c + 1) of this CTA's 64 A rows share one slot (2 x 8 KiB)
+            auto put_a2 = [&](int c, int mb) {
+                mbar_wait(EMPTY(slot), ph ^ 1);
+                if (cta == 0) mbar_expect_tx(FULL(slot), 2 * Cfg::SLOT);
+                const uint32_t dst = smem_u32(ring + slot * Cfg::SLOT), bar = mapa(FULL(slot), 0);
+                tma_load_2d_cg2(dst, &tmA64, bar, c * KCHUNK, mb * TILE + (int)cta * 64);
+                tma_load_2d_cg2(dst + 8192, &tmA64, bar, (c + 1) * KCHUNK, mb * TILE + (int)cta * 64);
+                if (++slot == NSLOT) { slot = 0; ph ^= 1; }
             };
-            auto load_t = [&](int t) {
+            auto load_s = [&](int t, int mb) {
+                for (int c = 0; c < KC; ++c) {
+                    if (c >= KCS && (c & 1) == 0) put_a2(c, mb);
+                    put(&tmB, c * KCHUNK, t * Cfg::NSTEP + (int)cta * 128);
+                }
+                if (pad_slot) {                                // bubble: no data, the slot just changes hands
+                    mbar_wait(EMPTY(slot), ph ^ 1);
+                    if (cta == 0) mbar_arrive(FULL(slot));
+                    if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+                }
+            };
+            auto load_t = [&](int t, int dcol0) {
                 for (int dblk = 0; dblk < ND; ++dblk)
                     for (int jh = 0; jh < 2; ++jh)
                         for (int dsub = 0; dsub < 2; ++dsub)
-                            put(&tmBd, (dblk * 2 + (int)cta) * 128 + dsub * 64, t * Cfg::NSTEP + jh * 128);
+                            put(&tmBd, dcol0 + (dblk * 2 + (int)cta) * 128 + dsub * 64, t * Cfg::NSTEP + jh * 128);
             };
             peer_wait_all(p.wait_b);      // multi-GPU: the N-side rows (and their fp16 copy) of every rank have arrived
             peer_wait_all(p.wait_bd);
@@ -171,13 +202,14 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             ItemInfo ii;
             for (; iter.next(ii); ++it) {
                 mbar_wait(IFREE, (it & 1) ^ 1);
-                if (cta == 0) mbar_expect_tx(IFULL, 2 * KC * 8192);
-                for (int c = 0; c < KC; ++c)
+                if (cta == 0) mbar_expect_tx(IFULL, 2 * KCS * 8192);
+                for (int c = 0; c < KCS; ++c)
                     tma_load_2d_cg2(smem_u32(ist + c * 8192), &tmA64, mapa(IFULL, 0), c * KCHUNK,
                                     ii.mb * TILE + (int)cta * 64);
-                load_s(ii.t0);
-                for (int t = ii.t0 + 1; t < ii.t1; ++t) { load_s(t); load_t(t - 1); }
-                load_t(ii.t1 - 1);
+                const int dcol0 = ii.dh * p.d_half;
+                load_s(ii.t0, ii.mb);
+                for (int t = ii.t0 + 1; t < ii.t1; ++t) { load_s(t, ii.mb); load_t(t - 1, dcol0); }
+                load_t(ii.t1 - 1, dcol0);
             }
             if (prof) { p.prof[8 + cta * 2] = (unsigned long long)(clock64() - t_begin); p.prof[9 + cta * 2] = w_empty; }
         }
@@ -200,15 +232,32 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 twait(SEMPTY(sb), ((gs >> 1) & 1) ^ 1, w_sempty);
                 tc_fence_after();
                 const uint32_t d_tmem = TM_S + sb * 128;
+                int a_slot = 0;
                 for (int c = 0; c < KC; ++c) {
+                    uint32_t a_addr;
+                    if (c < KCS) {
+                        a_addr = smem_u32(ist + c * 8192);
+                    } else {
+                        if ((c & 1) == 0) {                    // the slot holding the streamed A chunks c and c + 1
+                            twait(FULL(slot), ph, w_full_s);
+                            a_slot = slot;
+                            adv();
+                        }
+                        a_addr = smem_u32(ring + a_slot * Cfg::SLOT + (c & 1) * 8192);
+                    }
                     twait(FULL(slot), ph, w_full_s);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(ist + c * 8192);
                     const uint32_t b_addr = smem_u32(ring + slot * Cfg::SLOT);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_f16_cg2(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
                                      umma_desc_sw128(b_addr + k * 32, 16, 1024), IDESC_S, (c | k) != 0);
+                    umma_commit_cg2(EMPTY(slot));
+                    if (c >= KCS && (c & 1) == 1) umma_commit_cg2(EMPTY(a_slot));
+                    adv();
+                }
+                if (pad_slot) {
+                    twait(FULL(slot), ph, w_full_s);
                     umma_commit_cg2(EMPTY(slot));
                     adv();
                 }
@@ -299,7 +348,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 mbar_arrive_cluster(sb ? R_SEMPTY1 : R_SEMPTY0);
                 const int n0 = t * Cfg::NSTEP + jq * 128 + h * 64;
                 float v[64];
-                ds_tile<ROW_TERM, COL_TERM>(r0, r1, p, rc, n0, c1, fast, c0, G, v, want_ds, dsum);
+                ds_tile<ROW_TERM, COL_TERM>(r0, r1, p, rc, n0, c1, fast, c0, G, v, want_ds && ii.dh == 0, dsum);
                 uint32_t pk[32];
                 pack_ds(v, pk);
                 { const long long t0 = clock64(); mbar_wait(DSEMPTY, (gs & 1) ^ 1); w_dsempty += clock64() - t0; }
@@ -312,8 +361,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             tc_fence_after();
             const float omul = s * p.out_mul * invG;
             for (int dblk = 0; dblk < ND; ++dblk) {
-                const int d = (dblk * 2 + (int)cta) * 128 + q * 32 + lane;
-                const bool dvalid = d < p.d_out;
+                const int dl = (dblk * 2 + (int)cta) * 128 + q * 32 + lane;      // column within this pass
+                const int d = ii.dh * p.d_half + dl;
+                const bool dvalid = dl < p.d_half && d < p.d_out;
 #pragma unroll 1
                 for (int cc = 0; cc < 2; ++cc) {
                     uint32_t r[32];
@@ -327,7 +377,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                             if (mi < p.n_m) {
                                 const float a = __uint_as_float(r[k]);
                                 if (ii.part >= 0)
-                                    p.part_out[((size_t)ii.part * TILE + ri) * p.d_out + d] = a * omul;
+                                    p.part_out[((size_t)ii.part * TILE + ri) * p.d_half + dl] = a * omul;
                                 else if (p.out_fp32)
                                     reinterpret_cast<float*>(p.out)[(size_t)mi * p.ld_out + d] = a * omul;
                                 else

@@ -103,6 +103,8 @@ struct BwdParams {
     // (flat_start).  A range that covers a row block only partly accumulates that part into part_out[2 * pair + (0: the
     // range starts inside the block, 1: it ends inside it)][128][d_out] (fp32), summed by launch_reduce_parts.
     int sched_pairs;
+    int n_dh, d_half;        // pair kernel: passes over the output columns (1, or 2 when d_out > 512) and columns per pass;
+                             // the schedule runs over the m_tiles * n_dh virtual row blocks (row block, d-half)
     float* part_out;
     PeerWait wait_b, wait_bd; // readiness of the N-side operand rows (tmB) / of their fp16 copy (tmBd), see peer.cuh
     int dbg;                 // debug experiments (FLYP_DBG env): bit 0 = every streamed load reads box (0, 0)
@@ -121,12 +123,12 @@ void launch_fwd_mc(const CUtensorMap& tmA64, const CUtensorMap& tmB, const FwdPa
 // tmBd: tensor map used for the N-side operand rows as the B operand of the dA MMA (box [64 d][128 n]).
 void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
                 int num_sms, cudaStream_t st);
-// CTA-pair variant (clip_bwd_pair.cu): requires d_out % 128 == 0, d_out <= 512; tmA64 has box [64 rows][64 cols];
+// CTA-pair variant (clip_bwd_pair.cu): requires d_out % 128 == 0, d_out <= 1024; tmA64 has box [64 rows][64 cols];
 // column vectors padded to a multiple of 256; dscale_part has 2 entries per M tile.
 void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
                      int num_sms, cudaStream_t st);
 size_t bwd_pair_smem_bytes();
-// number of CTA pairs the flat schedule of launch_bwd_pair uses (<= num_sms / 2)
+// number of CTA pairs the schedule of launch_bwd_pair uses (<= num_sms / 2); m_tiles counts VIRTUAL row blocks
 int bwd_pair_sched_pairs(int m_tiles, int n_cols, int num_sms);
 constexpr int PAIR_NSTEP = 256;      // columns per step of the pair kernel
 // first flat unit of pair q

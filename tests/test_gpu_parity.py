@@ -288,6 +288,16 @@ def test_normalize_flag_of_the_module():
     assert rel(to_np(got), orc.clip_loss(In, Tn, 1 / 0.07)) < 2.0 ** -8 + TOL
 
 
+@pytest.mark.parametrize("n,d", [(300, 640), (640, 768), (257, 896), (1024, 1024)])
+@pytest.mark.parametrize("impl", ["1", "2"])
+def test_wide_features_both_sweep_kernels(n, d, impl, monkeypatch):
+    """D > 512: the single-CTA sweep (FLYP_BWD_IMPL=1) and the two-pass CTA-pair sweep with streamed A chunks (=2; chosen
+    automatically only for long sweeps) must both meet the bar, incl. the bubble-slot cases D = 640 / 896."""
+    monkeypatch.setenv("FLYP_BWD_IMPL", impl)
+    I, T, g = make_inputs(n, d, seed=n + d)
+    check_against_oracle(I, T, 1 / 0.07, g)
+
+
 # ---------------------------------------------------------------------------------------------- argmax (bit-exact)
 def test_argmax_predictions_are_bit_exact():
     gen = torch.Generator().manual_seed(4)
