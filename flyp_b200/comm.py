@@ -201,20 +201,9 @@ class PeerStep:
                  "col_lse", "col_nll", "loss", "ws")
 
 
-_WS_CACHE = {}
-
-
 def _workspace(b: int, B: int, D: int, dev) -> torch.Tensor:
-    """Scratch of the kernels of one rank.  Cached per shape and device: every use is stream-ordered on the current
-    stream and nothing in it outlives a call, so consecutive steps share it."""
-    key = (b, B, D, dev.index, torch.cuda.current_stream(dev).cuda_stream)
-    ws = _WS_CACHE.get(key)
-    if ws is None:
-        from . import ops
-        if len(_WS_CACHE) > 8:
-            _WS_CACHE.clear()
-        ws = _WS_CACHE[key] = ops.clip_workspace(b, B, D, _lib.FLYP_BF16, dev)
-    return ws
+    from . import ops
+    return ops.cached_clip_workspace(b, B, D, _lib.FLYP_BF16, dev)
 
 
 def fwd_gather(comm: PeerComm, img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor) -> PeerStep:

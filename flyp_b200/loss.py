@@ -185,13 +185,13 @@ class _ClipLossFn(torch.autograd.Function):
         else:
             col_stat_all, row_lse_all, row_nll_all = col_stat, row_lse, row_nll
         # loss of every global row (the reference returns the full vector on every rank, clip/loss.py:113-114,208)
-        col_lse, col_nll, loss = ops.clip_fwd_finish(col_stat_all, world_size, row_nll_all, n, 0)
+        col_lse, col_nll, loss = ops.clip_fwd_finish(col_stat_all, world_size, row_nll_all, n, 0, loss_dtype=img.dtype)
         ctx.save_for_backward(img, txt, img_all, txt_all, s, row_lse_all, row_nll_all, col_lse, col_nll)
         ctx.meta = (rank, world_size, group, gather_with_grad, grad_dtype, off, b,
                     torch.is_tensor(scale), scale.shape if torch.is_tensor(scale) else None,
                     scale.dtype if torch.is_tensor(scale) else None)
         ctx.status = status
-        return loss.to(img.dtype)
+        return loss
 
     @staticmethod
     def backward(ctx, g):
@@ -224,9 +224,12 @@ class _ClipLossFn(torch.autograd.Function):
                 dist.all_reduce(d_s, op=dist.ReduceOp.SUM, group=group)
         gs = None
         if need_s and s_is_tensor:
-            gs = torch.zeros(s_shape, dtype=torch.float32, device=img.device).reshape(-1)
-            gs[:1] = d_s
-            gs = gs.reshape(s_shape).to(s_dtype)
+            if s_dtype == torch.float32 and len(s_shape) <= 1 and (len(s_shape) == 0 or s_shape[0] == 1):
+                gs = d_s.view(s_shape)
+            else:
+                gs = torch.zeros(s_shape, dtype=torch.float32, device=img.device).reshape(-1)
+                gs[:1] = d_s
+                gs = gs.reshape(s_shape).to(s_dtype)
         return (d_img if need_img else None), (d_txt if need_txt else None), gs, None, None, None, None, None
 
 

@@ -46,6 +46,23 @@ def clip_workspace(n_rows: int, n_cols: int, dim: int, dtype_code: int, device) 
     return torch.empty(sz.value, dtype=torch.uint8, device=device)
 
 
+_WS_CACHE = {}
+
+
+def cached_clip_workspace(n_rows: int, n_cols: int, dim: int, dtype_code: int, device) -> torch.Tensor:
+    """Kernel scratch, cached per shape, device and stream.  Nothing in it outlives a C call and every use is
+    stream-ordered, so consecutive calls (forward and backward, consecutive steps) share it."""
+    key = (n_rows, n_cols, dim, dtype_code, device.index, _lib.stream_ptr(device))
+    sz = ctypes.c_size_t()
+    _lib.check(_lib.load().flyp_clip_workspace_bytes(n_rows, n_cols, dim, dtype_code, ctypes.byref(sz)))
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < sz.value:        # the size also depends on the kernel choice (FLYP_BWD_IMPL)
+        if len(_WS_CACHE) > 8:
+            _WS_CACHE.clear()
+        ws = _WS_CACHE[key] = torch.empty(sz.value, dtype=torch.uint8, device=device)
+    return ws
+
+
 def ce_workspace(n: int, n_classes: int, dim: int, dtype_code: int, device) -> torch.Tensor:
     sz = ctypes.c_size_t()
     _lib.check(_lib.load().flyp_ce_workspace_bytes(n, n_classes, dim, dtype_code, ctypes.byref(sz)))
@@ -63,7 +80,7 @@ def clip_fwd_local(img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor, ro
     dev = img.device
     code = _lib.dtype_code(img)
     with _lib.device_guard(dev):
-        ws = workspace if workspace is not None else clip_workspace(n_rows, n_cols, dim, code, dev)
+        ws = workspace if workspace is not None else cached_clip_workspace(n_rows, n_cols, dim, code, dev)
         row_lse, row_nll, col_stat = _f32(n_rows, dev), _f32(n_rows, dev), _f32(3 * n_cols, dev)
         status = torch.empty(1, dtype=torch.int32, device=dev)
         _lib.check(_lib.load().flyp_clip_fwd_local(
@@ -73,18 +90,22 @@ def clip_fwd_local(img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor, ro
     return row_lse, row_nll, col_stat, status
 
 
-def clip_fwd_finish(col_stat_all: torch.Tensor, world: int, row_nll: torch.Tensor, n_cols: int, row_offset: int = 0):
-    """Merge the column statistics of all ranks.  Returns (col_lse[n_cols], col_nll[n_cols], loss[n_rows])."""
+def clip_fwd_finish(col_stat_all: torch.Tensor, world: int, row_nll: torch.Tensor, n_cols: int, row_offset: int = 0,
+                    loss_dtype=torch.float32):
+    """Merge the column statistics of all ranks.  Returns (col_lse[n_cols], col_nll[n_cols], loss[n_rows]); the loss is
+    written by the kernel in ``loss_dtype`` (fp32 or bf16)."""
     dev = row_nll.device
     n_rows = row_nll.numel()
     col_stat_all = col_stat_all.contiguous()
     if col_stat_all.numel() != world * 3 * n_cols:
         raise FlypError("col_stat_all has the wrong size")
+    code = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[loss_dtype]
     with _lib.device_guard(dev):
-        col_lse, col_nll, loss = _f32(n_cols, dev), _f32(n_cols, dev), _f32(n_rows, dev)
-        _lib.check(_lib.load().flyp_clip_fwd_finish(col_stat_all.data_ptr(), world, row_nll.data_ptr(), n_rows, n_cols,
-                                                    row_offset, col_lse.data_ptr(), col_nll.data_ptr(),
-                                                    loss.data_ptr(), _lib.stream_ptr(dev)))
+        col_lse, col_nll = _f32(n_cols, dev), _f32(n_cols, dev)
+        loss = torch.empty(n_rows, dtype=loss_dtype, device=dev)
+        _lib.check(_lib.load().flyp_clip_fwd_finish_ex(col_stat_all.data_ptr(), world, row_nll.data_ptr(), n_rows, n_cols,
+                                                       row_offset, col_lse.data_ptr(), col_nll.data_ptr(),
+                                                       loss.data_ptr(), code, None, _lib.stream_ptr(dev)))
     return col_lse, col_nll, loss
 
 
@@ -101,7 +122,7 @@ def clip_bwd_local(img, txt, scale, row_offset, row_lse, row_nll, col_lse, col_n
     gcode = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[gdt]
     need_img = need_img or need_scale
     with _lib.device_guard(dev):
-        ws = workspace if workspace is not None else clip_workspace(n_rows, n_cols, dim, code, dev)
+        ws = workspace if workspace is not None else cached_clip_workspace(n_rows, n_cols, dim, code, dev)
         d_img = torch.empty(n_rows, dim, dtype=gdt, device=dev) if need_img else None
         d_txt = torch.empty(n_cols, dim, dtype=gdt, device=dev) if need_txt else None
         d_scale = _f32(1, dev) if need_scale else None

@@ -43,7 +43,7 @@ def clip_fwd_local(img, txt, scale, row_offset=0, workspace=None):
     return f(row_lse), f(row_nll), f(col_stat), torch.zeros(1, dtype=torch.int32)
 
 
-def clip_fwd_finish(col_stat_all, world, row_nll, n_cols, row_offset=0):
+def clip_fwd_finish(col_stat_all, world, row_nll, n_cols, row_offset=0, loss_dtype=torch.float32):
     cs = _np(col_stat_all).reshape(world, 3, n_cols)
     m = np.max(cs[:, 0], axis=0)
     ssum = np.sum(cs[:, 1] * np.exp2(cs[:, 0] - m[None, :]), axis=0)
@@ -55,7 +55,7 @@ def clip_fwd_finish(col_stat_all, world, row_nll, n_cols, row_offset=0):
     n_rows = row_nll.numel()
     loss = 0.5 * (_np(row_nll) + col_nll[row_offset:row_offset + n_rows])
     f = lambda a: torch.tensor(a, dtype=torch.float32)
-    return f(col_lse), f(col_nll), f(loss)
+    return f(col_lse), f(col_nll), f(loss).to(loss_dtype)
 
 
 def clip_bwd_local(img, txt, scale, row_offset, row_lse, row_nll, col_lse, col_nll, g_row, g_col, grad_mul=1.0,
