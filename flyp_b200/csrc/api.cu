@@ -859,3 +859,9 @@ int flyp_debug_logits(const void* a, const void* b, int n_m, int n_n, int dim, i
 }
 
 }  // extern "C"
+
+// the ctypes mirrors in flyp_b200/_lib.py assume these layouts (tests/test_comm_cpu.py pins the Python side)
+static_assert(sizeof(flyp_ready_t) == 40, "flyp_ready_t layout");
+static_assert(sizeof(flyp_gathered_t) == 4 * 8 + 4 * 40 + 8, "flyp_gathered_t layout");
+static_assert(sizeof(flyp_stats_t) == 3 * 8 + 40, "flyp_stats_t layout");
+static_assert(sizeof(flyp_step_t) == sizeof(flyp_gathered_t) + sizeof(flyp_stats_t), "flyp_step_t layout");
