@@ -88,6 +88,18 @@ class ClockSampler:
         return out
 
 
+def synthetic_pairs(n, d, seed=0):
+    """BASELINE.md section 3 inputs: I = normalize(randn), T = normalize(0.5 I + 0.5 normalize(randn)), bf16."""
+    import torch
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, d, generator=gen)
+    y = torch.randn(n, d, generator=gen)
+    I = F.normalize(x, dim=-1)
+    T = F.normalize(0.5 * I + 0.5 * F.normalize(y, dim=-1), dim=-1)
+    return I.bfloat16(), T.bfloat16()
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_port_measure(batch, dim, steps, warmup, budget_s=150.0):
     """Time the CPU port on a bounded sample.  Returns dict(value=pairs/s at `batch`, sample=..., cores=..., sec=...)."""
@@ -134,7 +146,6 @@ def run_ours(args):
     import torch.distributed as dist
     import flyp_b200
     from flyp_b200 import ops
-    from oracle import torch_port
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -151,7 +162,7 @@ def run_ours(args):
     B, D = args.batch, args.dim
     assert B % world == 0
     b = B // world
-    I_all, T_all = torch_port.synthetic_pairs(B, D, seed=0, dtype=torch.bfloat16)
+    I_all, T_all = synthetic_pairs(B, D, seed=0)                   # the oracle is only used by the cpu_baseline leg
     I_host = I_all[rank * b:(rank + 1) * b].contiguous().pin_memory()
     T_host = T_all[rank * b:(rank + 1) * b].contiguous().pin_memory()
     I_dev = I_host.to(dev).requires_grad_(True)

@@ -2,9 +2,10 @@
 CUDA events, L2 flushed between iterations.  Prints one JSON line per configuration."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import flyp_b200
-from oracle import torch_port
+import _inputs as torch_port
 
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

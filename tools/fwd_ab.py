@@ -1,9 +1,10 @@
 """A/B timing of the forward statistics pass: multicast cluster kernel vs single-CTA kernel (same process)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from flyp_b200 import ops
-from oracle import torch_port
+import _inputs as torch_port
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 dev = torch.device("cuda:0")

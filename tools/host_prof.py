@@ -1,9 +1,10 @@
 """Host-side cost of one ClipLoss fwd+bwd call (cProfile over many small steps; the GPU is never the bottleneck here)."""
 import cProfile, os, pstats, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import flyp_b200
-from oracle import torch_port
+import _inputs as torch_port
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 dev = torch.device("cuda:0")

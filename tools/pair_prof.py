@@ -1,9 +1,10 @@
 """Wait-cycle breakdown of the CTA-pair backward sweep (cluster 0) - debugging aid, see flyp_debug_profile."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from flyp_b200 import ops, _lib
-from oracle import torch_port
+import _inputs as torch_port
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 D = 512
 dev = torch.device("cuda:0")

@@ -3,9 +3,10 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from flyp_b200 import ops
-from oracle import torch_port
+import _inputs as torch_port
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 512

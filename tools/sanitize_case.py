@@ -1,10 +1,11 @@
 """Small end-to-end cases for compute-sanitizer (memcheck): every kernel family once, ragged shapes."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import flyp_b200
 from flyp_b200 import ops
-from oracle import torch_port
+import _inputs as torch_port
 
 dev = torch.device("cuda:0")
 for (n, d, dt, impl) in [(300, 512, torch.bfloat16, "0"), (257, 640, torch.bfloat16, "2"), (200, 1024, torch.bfloat16, "2"),

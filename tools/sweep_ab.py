@@ -1,9 +1,10 @@
 """A/B timing of one backward sweep (dI + d(scale)) under different FLYP_SCHED_PAIRS settings, same process."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from flyp_b200 import ops
-from oracle import torch_port
+import _inputs as torch_port
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 b = int(sys.argv[2]) if len(sys.argv) > 2 else B
 settings = sys.argv[3].split(",") if len(sys.argv) > 3 else ["0", "64", "0", "64"]

@@ -9,12 +9,13 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import torch.distributed as dist
 from torch.profiler import ProfilerActivity, profile
 
 import flyp_b200
-from oracle import torch_port
+import _inputs as torch_port
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 512
