@@ -4,7 +4,8 @@
 // clip/loss.py:19-69 (gather_features) and - because no rank ever holds the B x B logits here - the exchange of the
 // per-column softmax statistics, of the per-row statistics and of the d(logit_scale) partial sums.
 //
-// Every rank owns one exchange segment (cudaMalloc, exported with cudaIpcGetMemHandle and mapped by all peers).  The
+// Every rank owns one exchange segment that all peers map (torch symmetric memory with an NVSwitch multicast mapping
+// through flyp_comm_create_external, or cudaMalloc + CUDA IPC through flyp_comm_create / connect_ipc).  The
 // segment holds, double-buffered by step parity, the GATHERED matrices of this rank: text / image features in bf16 and
 // their fp16 copies (the operand format of the backward's second GEMM), [world * rows, dim] rank-major - the ordering of
 // clip/loss.py:66-67.  A step is
@@ -39,7 +40,7 @@ void set_error(int code, const char* fmt, ...);   // api.cu: thread-local messag
 namespace {
 
 constexpr int MAXW = 16;
-constexpr int MAXG = 8;             // flag words per (matrix, rank): one per CTA of the push kernel
+constexpr int MAXG = 8;             // flag words are spaced MAXG words (32 bytes) apart: one word per (flag set, rank)
 enum { ARR_TXT = 0, ARR_TXT16 = 1, ARR_IMG = 2, ARR_IMG16 = 3, N_ARR = 4 };
 enum { FLAG_STAT = N_ARR, FLAG_DS = N_ARR + 1, N_FLAGSETS = N_ARR + 2 };
 
@@ -106,8 +107,7 @@ __global__ void k_pack(const uint4* __restrict__ img, const uint4* __restrict__ 
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         *seqword = seq;
-        for (int a = 0; a < N_ARR; ++a)
-            for (int j = 0; j < MAXG; ++j) own_flags[(a * MAXW + rank) * MAXG + j] = seq;
+        for (int a = 0; a < N_ARR; ++a) own_flags[(a * MAXW + rank) * MAXG] = seq;
     }
     if (i >= n8) return;
     auto conv = [](uint4 v) {
