@@ -1,6 +1,7 @@
 // aux_kernels.cu — the HBM-bound helper kernels of the ClipLoss path (see aux_kernels.cuh).
 #include "aux_kernels.cuh"
 #include "clip_kernels.cuh"
+#include <cstring>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -537,71 +538,215 @@ void launch_split_planes_f16x2(const float* x, int n, int dim, int dp, void* out
 }
 
 // ------------------------------------------------------------------------------------------------ L2 normalise
-// One warp per row, 128-bit accesses.  The row is read twice (second read is an L1/L2 hit), written once.
+// One warp per RPW rows, 128-bit accesses.  Rows of up to CH * 256 elements (CH <= 4) stay in registers - in their
+// STORAGE format (a bf16 chunk of 8 elements is one uint4) - between the reduction and the scaling, so every operand
+// crosses HBM exactly once: 2 n D e bytes forward (read x, write y), 3 n D e bytes backward (read y and dy, write dx).
+// RPW is chosen so that every lane keeps >= 64 bytes per operand in flight (short bf16 rows: four rows per warp); rows
+// longer than 1024 elements re-read the tail (L2 hit).
+template <bool F32> struct Pk8;
+template <> struct Pk8<true> { float4 a, b; };
+template <> struct Pk8<false> { uint4 u; };
 template <bool F32>
-__global__ void k_l2norm_fwd(const void* __restrict__ x, int n, int dim, void* __restrict__ y,
-                             float* __restrict__ inv_norm) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= n) return;
-    float ss = 0.f;
-    for (int d = lane * 8; d < dim; d += 256) {
-        float v[8];
-        load8<F32>(x, (size_t)row * dim + d, v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) ss = fmaf(v[e], v[e], ss);
-    }
-    ss = warp_sum(ss);
-    const float inv = 1.0f / sqrtf(ss);   // no epsilon: matches x / x.norm(dim=-1, keepdim=True)
-    if (lane == 0 && inv_norm) inv_norm[row] = inv;
-    for (int d = lane * 8; d < dim; d += 256) {
-        float v[8];
-        load8<F32>(x, (size_t)row * dim + d, v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] *= inv;
-        store8<F32>(y, (size_t)row * dim + d, v);
-    }
+__device__ __forceinline__ Pk8<F32> pk_load(const void* base, size_t elem);
+template <>
+__device__ __forceinline__ Pk8<true> pk_load<true>(const void* base, size_t elem) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
+    Pk8<true> r; r.a = __ldg(p); r.b = __ldg(p + 1); return r;
 }
-void launch_l2norm_fwd(const void* x, int n, int dim, int dtype, void* y, float* inv_norm, cudaStream_t st) {
-    if (n <= 0) return;
-    const int wpb = 8;
-    dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
-    if (dtype == 1) k_l2norm_fwd<true><<<grid, block, 0, st>>>(x, n, dim, y, inv_norm);
-    else k_l2norm_fwd<false><<<grid, block, 0, st>>>(x, n, dim, y, inv_norm);
+template <>
+__device__ __forceinline__ Pk8<false> pk_load<false>(const void* base, size_t elem) {
+    Pk8<false> r; r.u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem)); return r;
+}
+__device__ __forceinline__ void pk_unpack(const Pk8<true>& p, float (&v)[8]) {
+    v[0] = p.a.x; v[1] = p.a.y; v[2] = p.a.z; v[3] = p.a.w; v[4] = p.b.x; v[5] = p.b.y; v[6] = p.b.z; v[7] = p.b.w;
+}
+__device__ __forceinline__ void pk_unpack(const Pk8<false>& p, float (&v)[8]) {
+    const uint32_t w[4] = {p.u.x, p.u.y, p.u.z, p.u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(w[e] << 16); v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+}
+template <bool F32>
+__device__ __forceinline__ Pk8<F32> pk_zero() { Pk8<F32> r; memset(&r, 0, sizeof(r)); return r; }
+
+template <bool F32, int CH, int RPW>
+__global__ void __launch_bounds__(256) k_l2norm_fwd(const void* __restrict__ x, int n, int dim, void* __restrict__ y,
+                                                    float* __restrict__ inv_norm) {
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+    const int lane = threadIdx.x & 31;
+    if (row0 >= n) return;
+    Pk8<F32> v[RPW][CH];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const bool live = row0 + r < n;
+        const size_t base = (size_t)(row0 + r) * dim;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int d = c * 256 + lane * 8;
+            v[r][c] = (live && d < dim) ? pk_load<F32>(x, base + d) : pk_zero<F32>();
+        }
+    }
+    float ss[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        ss[r] = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            float t[8];
+            pk_unpack(v[r][c], t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss[r] = fmaf(t[e], t[e], ss[r]);
+        }
+        if (row0 + r < n)
+            for (int d = CH * 256 + lane * 8; d < dim; d += 256) {       // rows longer than CH * 256 (CH == 4 only)
+                float t[8];
+                load8<F32>(x, (size_t)(row0 + r) * dim + d, t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) ss[r] = fmaf(t[e], t[e], ss[r]);
+            }
+        ss[r] = warp_sum(ss[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        if (row0 + r >= n) break;
+        const size_t base = (size_t)(row0 + r) * dim;
+        const float inv = 1.0f / sqrtf(ss[r]);   // no epsilon: matches x / x.norm(dim=-1, keepdim=True)
+        if (lane == 0 && inv_norm) inv_norm[row0 + r] = inv;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int d = c * 256 + lane * 8;
+            if (d < dim) {
+                float t[8];
+                pk_unpack(v[r][c], t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t[e] *= inv;
+                store8<F32>(y, base + d, t);
+            }
+        }
+        for (int d = CH * 256 + lane * 8; d < dim; d += 256) {
+            float t[8];
+            load8<F32>(x, base + d, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] *= inv;
+            store8<F32>(y, base + d, t);
+        }
+    }
 }
 
-template <bool F32>
-__global__ void k_l2norm_bwd(const void* __restrict__ y, const void* __restrict__ dy,
-                             const float* __restrict__ inv_norm, int n, int dim, void* __restrict__ dx) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+template <bool F32, int CH, int RPW>
+__global__ void __launch_bounds__(256) k_l2norm_bwd(const void* __restrict__ y, const void* __restrict__ dy,
+                                                    const float* __restrict__ inv_norm, int n, int dim,
+                                                    void* __restrict__ dx) {
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
     const int lane = threadIdx.x & 31;
-    if (row >= n) return;
-    float dot = 0.f;
-    for (int d = lane * 8; d < dim; d += 256) {
-        float a[8], b[8];
-        load8<F32>(y, (size_t)row * dim + d, a);
-        load8<F32>(dy, (size_t)row * dim + d, b);
+    if (row0 >= n) return;
+    Pk8<F32> a[RPW][CH], b[RPW][CH];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) dot = fmaf(a[e], b[e], dot);
+    for (int r = 0; r < RPW; ++r) {
+        const bool live = row0 + r < n;
+        const size_t base = (size_t)(row0 + r) * dim;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int d = c * 256 + lane * 8;
+            const bool ok = live && d < dim;
+            a[r][c] = ok ? pk_load<F32>(y, base + d) : pk_zero<F32>();
+            b[r][c] = ok ? pk_load<F32>(dy, base + d) : pk_zero<F32>();
+        }
     }
-    dot = warp_sum(dot);
-    const float inv = inv_norm[row];
-    for (int d = lane * 8; d < dim; d += 256) {
-        float a[8], b[8], o[8];
-        load8<F32>(y, (size_t)row * dim + d, a);
-        load8<F32>(dy, (size_t)row * dim + d, b);
+    float dot[RPW];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (b[e] - a[e] * dot) * inv;
-        store8<F32>(dx, (size_t)row * dim + d, o);
+    for (int r = 0; r < RPW; ++r) {
+        dot[r] = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            float p[8], q[8];
+            pk_unpack(a[r][c], p);
+            pk_unpack(b[r][c], q);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dot[r] = fmaf(p[e], q[e], dot[r]);
+        }
+        if (row0 + r < n)
+            for (int d = CH * 256 + lane * 8; d < dim; d += 256) {
+                float p[8], q[8];
+                load8<F32>(y, (size_t)(row0 + r) * dim + d, p);
+                load8<F32>(dy, (size_t)(row0 + r) * dim + d, q);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dot[r] = fmaf(p[e], q[e], dot[r]);
+            }
+        dot[r] = warp_sum(dot[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        if (row0 + r >= n) break;
+        const size_t base = (size_t)(row0 + r) * dim;
+        const float inv = inv_norm[row0 + r];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int d = c * 256 + lane * 8;
+            if (d < dim) {
+                float p[8], q[8], o[8];
+                pk_unpack(a[r][c], p);
+                pk_unpack(b[r][c], q);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = (q[e] - p[e] * dot[r]) * inv;
+                store8<F32>(dx, base + d, o);
+            }
+        }
+        for (int d = CH * 256 + lane * 8; d < dim; d += 256) {
+            float p[8], q[8], o[8];
+            load8<F32>(y, base + d, p);
+            load8<F32>(dy, base + d, q);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (q[e] - p[e] * dot[r]) * inv;
+            store8<F32>(dx, base + d, o);
+        }
     }
 }
+
+template <bool F32, int CH, int RPW>
+static void l2norm_launch_fwd(const void* x, int n, int dim, void* y, float* inv_norm, cudaStream_t st) {
+    const int rows_per_block = 8 * RPW;
+    k_l2norm_fwd<F32, CH, RPW><<<(n + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(x, n, dim, y, inv_norm);
+}
+template <bool F32, int CH, int RPW>
+static void l2norm_launch_bwd(const void* y, const void* dy, const float* inv_norm, int n, int dim, void* dx,
+                              cudaStream_t st) {
+    const int rows_per_block = 8 * RPW;
+    k_l2norm_bwd<F32, CH, RPW><<<(n + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(y, dy, inv_norm, n, dim, dx);
+}
+
+// rows per warp: fp32 2 / 2 / 1 / 1, bf16 4 / 2 / 2 / 2 for CH = 1 / 2 / 3 / 4 (measured: more rows per warp cost
+// occupancy through registers and lose bandwidth)
+void launch_l2norm_fwd(const void* x, int n, int dim, int dtype, void* y, float* inv_norm, cudaStream_t st) {
+    if (n <= 0) return;
+    const int ch = (dim + 255) / 256;
+    if (dtype == 1) {
+        if (ch <= 1) l2norm_launch_fwd<true, 1, 2>(x, n, dim, y, inv_norm, st);
+        else if (ch == 2) l2norm_launch_fwd<true, 2, 2>(x, n, dim, y, inv_norm, st);
+        else if (ch == 3) l2norm_launch_fwd<true, 3, 1>(x, n, dim, y, inv_norm, st);
+        else l2norm_launch_fwd<true, 4, 1>(x, n, dim, y, inv_norm, st);
+    } else {
+        if (ch <= 1) l2norm_launch_fwd<false, 1, 4>(x, n, dim, y, inv_norm, st);
+        else if (ch == 2) l2norm_launch_fwd<false, 2, 2>(x, n, dim, y, inv_norm, st);
+        else if (ch == 3) l2norm_launch_fwd<false, 3, 2>(x, n, dim, y, inv_norm, st);
+        else l2norm_launch_fwd<false, 4, 2>(x, n, dim, y, inv_norm, st);
+    }
+}
+
 void launch_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n, int dim, int dtype, void* dx,
                        cudaStream_t st) {
     if (n <= 0) return;
-    const int wpb = 8;
-    dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
-    if (dtype == 1) k_l2norm_bwd<true><<<grid, block, 0, st>>>(y, dy, inv_norm, n, dim, dx);
-    else k_l2norm_bwd<false><<<grid, block, 0, st>>>(y, dy, inv_norm, n, dim, dx);
+    const int ch = (dim + 255) / 256;
+    if (dtype == 1) {
+        if (ch <= 1) l2norm_launch_bwd<true, 1, 2>(y, dy, inv_norm, n, dim, dx, st);
+        else if (ch == 2) l2norm_launch_bwd<true, 2, 2>(y, dy, inv_norm, n, dim, dx, st);
+        else if (ch == 3) l2norm_launch_bwd<true, 3, 1>(y, dy, inv_norm, n, dim, dx, st);
+        else l2norm_launch_bwd<true, 4, 1>(y, dy, inv_norm, n, dim, dx, st);
+    } else {
+        if (ch <= 1) l2norm_launch_bwd<false, 1, 4>(y, dy, inv_norm, n, dim, dx, st);
+        else if (ch == 2) l2norm_launch_bwd<false, 2, 2>(y, dy, inv_norm, n, dim, dx, st);
+        else if (ch == 3) l2norm_launch_bwd<false, 3, 2>(y, dy, inv_norm, n, dim, dx, st);
+        else l2norm_launch_bwd<false, 4, 2>(y, dy, inv_norm, n, dim, dx, st);
+    }
 }
 
 }  // namespace flyp
