@@ -439,11 +439,8 @@ __global__ void k_reduce_parts(const float* __restrict__ part, int v_tiles, int 
     const int first = (v_tiles / pairs) * pairs;
     const int tb = blockIdx.y, vb = first + tb;
     const int mb = vb / n_dh, dh = vb - mb * n_dh;
-    const long long S = (long long)(v_tiles - first) * NJ, lo = (long long)tb * NJ, hi = lo + NJ;
-    int q = (int)(lo * pairs / S);
-    while (q + 1 < pairs && flat_start(q + 1, S, pairs) <= lo) ++q;
-    while (q > 0 && flat_start(q, S, pairs) > lo) --q;
-    if (flat_start(q, S, pairs) <= lo && flat_start(q + 1, S, pairs) >= hi) return;      // swept whole
+    TailParts parts;
+    if (!parts.init(v_tiles, NJ, pairs, tb)) return;                                    // swept whole
     const int d4 = d_half / 4;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 128 * d4) return;
@@ -451,8 +448,7 @@ __global__ void k_reduce_parts(const float* __restrict__ part, int v_tiles, int 
     const int m = mb * 128 + r;
     if (m >= n_m || d >= d_out) return;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (; q < pairs && flat_start(q, S, pairs) < hi; ++q) {
-        const int slot = 2 * q + (flat_start(q, S, pairs) >= lo ? 0 : 1);
+    for (int slot = parts.next(); slot >= 0; slot = parts.next()) {
         const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)slot * 128 + r) * d_half + dl);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }

@@ -25,6 +25,7 @@
 #include "clip_kernels.cuh"
 #include "sm100.cuh"
 #include "bwd_common.cuh"
+#include "sched.h"
 #include <cstdlib>
 
 namespace flyp {
@@ -50,42 +51,6 @@ DEVI uint8_t* align1024p(uint8_t* p) {
 }
 DEVI void epi_bar_sync2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-struct ItemInfo { int mb, dh, t0, t1, part; };
-// Work items of one CTA pair under the flat schedule: its contiguous range of (row block, column step) units, cut at
-// row-block boundaries.  part = -1: the item covers its whole row block and writes the output directly; otherwise the
-// index of the fp32 partial slot it accumulates into.
-struct ItemIter {
-    long long pos, end;
-    int NJ, pair, ord, round, full_rounds, P, n_dh;
-    DEVI ItemIter(const BwdParams& p, int pair_, int NJ_) {
-        P = p.sched_pairs; NJ = NJ_; pair = pair_; ord = 0; round = 0;
-        n_dh = p.n_dh;
-        const int vtiles = p.m_tiles * n_dh;                 // virtual row blocks: (row block, d-half), d-half fastest
-        full_rounds = vtiles / P;                            // whole blocks, one per pair and round, in lockstep
-        const long long S = (long long)(vtiles - full_rounds * P) * NJ;      // units of the flat tail
-        pos = flat_start(pair_, S, P);
-        end = flat_start(pair_ + 1, S, P);
-    }
-    DEVI bool next(ItemInfo& r) {
-        if (round < full_rounds) {
-            const int vb = round * P + pair;
-            r.mb = vb / n_dh; r.dh = vb - r.mb * n_dh; r.t0 = 0; r.t1 = NJ; r.part = -1;
-            ++round;
-            return true;
-        }
-        if (pos >= end) return false;
-        const int tb = (int)(pos / NJ);
-        const int vb = full_rounds * P + tb;
-        r.mb = vb / n_dh; r.dh = vb - r.mb * n_dh;
-        r.t0 = (int)(pos - (long long)tb * NJ);
-        const long long room = NJ - r.t0, len = end - pos;
-        r.t1 = r.t0 + (int)(len < room ? len : room);
-        r.part = (r.t0 == 0 && r.t1 == NJ) ? -1 : 2 * pair + (ord == 0 ? 0 : 1);
-        pos += r.t1 - r.t0;
-        ++ord;
-        return true;
-    }
-};
 }  // namespace
 
 // Schedule of a sweep over m_tiles row blocks on P CTA pairs: floor(m_tiles / P) rounds of whole row blocks (all pairs
@@ -198,7 +163,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             };
             peer_wait_all(p.wait_b);      // multi-GPU: the N-side rows (and their fp16 copy) of every rank have arrived
             peer_wait_all(p.wait_bd);
-            ItemIter iter(p, pair, NJ);
+            SweepItems iter(p.m_tiles, p.n_dh, p.sched_pairs, NJ, pair);
             ItemInfo ii;
             for (; iter.next(ii); ++it) {
                 mbar_wait(IFREE, (it & 1) ^ 1);
@@ -292,7 +257,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 umma_commit_cg2(DSEMPTY);
                 ++gd;
             };
-            ItemIter iter(p, pair, NJ);
+            SweepItems iter(p.m_tiles, p.n_dh, p.sched_pairs, NJ, pair);
             ItemInfo ii;
             for (; iter.next(ii); ++it) {
                 const int nj = ii.t1 - ii.t0;
@@ -330,7 +295,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
         const long long t_begin = clock64();
         const bool want_ds = p.dscale_part != nullptr;
         float dsum = 0.f;                           // d(scale) share of this thread over all items of the pair
-        ItemIter iter(p, pair, NJ);
+        SweepItems iter(p.m_tiles, p.n_dh, p.sched_pairs, NJ, pair);
         ItemInfo ii;
         for (; iter.next(ii); ++it) {
             const int m = ii.mb * TILE + (int)cta * 64 + rloc;

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "peer.cuh"
+#include "sched.h"
 
 namespace flyp {
 
@@ -131,8 +132,7 @@ size_t bwd_pair_smem_bytes();
 // number of CTA pairs the schedule of launch_bwd_pair uses (<= num_sms / 2); m_tiles counts VIRTUAL row blocks
 int bwd_pair_sched_pairs(int m_tiles, int n_cols, int num_sms);
 constexpr int PAIR_NSTEP = 256;      // columns per step of the pair kernel
-// first flat unit of pair q
-__host__ __device__ inline long long flat_start(int q, long long S, int pairs) { return (long long)q * S / pairs; }
+
 size_t fwd_smem_bytes(bool stationary);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is needed once per kernel and device, not once per launch
 template <typename K>

@@ -1,0 +1,71 @@
+// Host-side property check of flyp_b200/csrc/sched.h (compiled with g++ by tests/test_sched_host.py).
+// For many (m_tiles, n_dh, NJ, P): every (virtual row block, column step) unit is covered by exactly one item; whole items
+// are the only ones with part = -1; partial slots are unique, below 2 * P; and TailParts (what the reduction kernel uses)
+// enumerates, for every tail block, exactly the slots of the partial items that cover it, in pair order - or reports the
+// block as swept whole exactly when a single whole item covers it.
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <set>
+#include <vector>
+
+#include "sched.h"
+
+using namespace flyp;
+
+static int check(int m_tiles, int n_dh, int NJ, int npairs) {
+    const int v_tiles = m_tiles * n_dh;
+    const long long S_total = (long long)v_tiles * NJ;
+    const int P = (int)(S_total < npairs ? S_total : npairs);           // bwd_pair_sched_pairs
+    std::vector<int> cover((size_t)v_tiles * NJ, 0);
+    std::map<int, std::vector<int>> slots_of_block;                     // virtual block -> partial slots, in pair order
+    std::set<int> used_slots, whole_blocks;
+    for (int pair = 0; pair < P; ++pair) {
+        SweepItems it(m_tiles, n_dh, P, NJ, pair);
+        ItemInfo ii;
+        int n_items = 0;
+        while (it.next(ii)) {
+            ++n_items;
+            if (ii.mb < 0 || ii.mb >= m_tiles || ii.dh < 0 || ii.dh >= n_dh || ii.t0 < 0 || ii.t1 > NJ || ii.t0 >= ii.t1) return 1;
+            const int vb = ii.mb * n_dh + ii.dh;
+            for (int t = ii.t0; t < ii.t1; ++t) cover[(size_t)vb * NJ + t]++;
+            const bool whole = ii.t0 == 0 && ii.t1 == NJ;
+            if (whole != (ii.part == -1)) return 2;
+            if (whole) { if (!whole_blocks.insert(vb).second) return 3; }
+            else {
+                if (ii.part < 0 || ii.part >= 2 * P) return 4;
+                if (!used_slots.insert(ii.part).second) return 5;
+                slots_of_block[vb].push_back(ii.part);
+            }
+        }
+        if (n_items == 0) return 6;                                     // every scheduled pair has work
+    }
+    for (int c : cover) if (c != 1) return 7;
+    const int first = (v_tiles / P) * P;
+    for (int vb = 0; vb < v_tiles; ++vb) {
+        if (vb < first) { if (!whole_blocks.count(vb) || slots_of_block.count(vb)) return 8; continue; }
+        TailParts parts;
+        const bool split = parts.init(v_tiles, NJ, P, vb - first);
+        if (split == (whole_blocks.count(vb) != 0)) return 9;
+        if (!split) continue;
+        std::vector<int> got;
+        for (int s = parts.next(); s >= 0; s = parts.next()) got.push_back(s);
+        if (got != slots_of_block[vb]) return 10;
+    }
+    return 0;
+}
+
+int main() {
+    long long n = 0;
+    const int npairs_list[] = {1, 2, 3, 7, 64, 66, 70, 74};
+    for (int npairs : npairs_list)
+        for (int n_dh = 1; n_dh <= 2; ++n_dh)
+            for (int m_tiles = 1; m_tiles <= 300; m_tiles += (m_tiles < 80 ? 1 : 37))
+                for (int NJ : {1, 2, 3, 5, 16, 31, 128, 256}) {
+                    const int rc = check(m_tiles, n_dh, NJ, npairs);
+                    if (rc) { printf("FAIL rc=%d m_tiles=%d n_dh=%d NJ=%d npairs=%d\n", rc, m_tiles, n_dh, NJ, npairs); return 1; }
+                    ++n;
+                }
+    printf("OK %lld schedules\n", n);
+    return 0;
+}
