@@ -70,7 +70,9 @@ int bwd_pair_sched_pairs(int m_tiles, int n_cols, int num_sms) {
 
 size_t bwd_pair_smem_bytes() { return PairCfg::SMEM_BYTES; }
 
-template <bool ROW_TERM, bool COL_TERM>
+// WIDE: feature dim > 512 (streamed A chunks, two passes over the output columns); the narrow instantiation compiles
+// that logic away.
+template <bool ROW_TERM, bool COL_TERM, bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS2, 1)
 bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmBd, const BwdParams p) {
@@ -98,11 +100,11 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
     const int pair = blockIdx.x >> 1;
     const int NJ = (p.n_n + Cfg::NSTEP - 1) / Cfg::NSTEP;
     const int KC = p.kc;                         // 64-wide K chunks of the S contraction (even, <= 16)
-    const int KCS = KC < 8 ? KC : 8;             // ... of which the first KCS are stationary, the others streamed
+    const int KCS = WIDE ? (KC < 8 ? KC : 8) : KC;   // ... of which the first KCS are stationary, the others streamed
     const int ND = (p.d_half + 255) / 256;       // pair MMAs of the dA^T product (256 feature columns each) per pass
     // the dA^T operand boxes are consumed as ADJACENT slot pairs (even, odd): when the streamed A chunks take an odd
     // number of slots per step (dim = 640, 896) an empty bubble slot restores the alignment
-    const bool pad_slot = (((KC - KCS) / 2) & 1) != 0;
+    const bool pad_slot = WIDE && (((KC - KCS) / 2) & 1) != 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLOT; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
@@ -146,7 +148,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             };
             auto load_s = [&](int t, int mb) {
                 for (int c = 0; c < KC; ++c) {
-                    if (c >= KCS && (c & 1) == 0) put_a2(c, mb);
+                    if (WIDE && c >= KCS && (c & 1) == 0) put_a2(c, mb);
                     put(&tmB, c * KCHUNK, t * Cfg::NSTEP + (int)cta * 128);
                 }
                 if (pad_slot) {                                // bubble: no data, the slot just changes hands
@@ -200,7 +202,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 int a_slot = 0;
                 for (int c = 0; c < KC; ++c) {
                     uint32_t a_addr;
-                    if (c < KCS) {
+                    if (!WIDE || c < KCS) {
                         a_addr = smem_u32(ist + c * 8192);
                     } else {
                         if ((c & 1) == 0) {                    // the slot holding the streamed A chunks c and c + 1
@@ -218,7 +220,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                         umma_f16_cg2(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
                                      umma_desc_sw128(b_addr + k * 32, 16, 1024), IDESC_S, (c | k) != 0);
                     umma_commit_cg2(EMPTY(slot));
-                    if (c >= KCS && (c & 1) == 1) umma_commit_cg2(EMPTY(a_slot));
+                    if (WIDE && c >= KCS && (c & 1) == 1) umma_commit_cg2(EMPTY(a_slot));
                     adv();
                 }
                 if (pad_slot) {
@@ -383,15 +385,22 @@ void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUt
     const int grid = p.sched_pairs * 2;
     const size_t smem = bwd_pair_smem_bytes();
     const bool row_term = p.wr != nullptr, col_term = p.wc != nullptr;
-#define FLYP_LAUNCH_BWD2(R, C)                                                                                 \
+#define FLYP_LAUNCH_BWD2(R, C, W)                                                                              \
     do {                                                                                                       \
         static bool attr_done[64] = {false};                                                                  \
-        ensure_smem_attr(bwd_pair_kernel<R, C>, smem, attr_done);                                              \
-        bwd_pair_kernel<R, C><<<grid, NTHREADS2, smem, st>>>(tmA64, tmB, tmBd, p);                             \
+        ensure_smem_attr(bwd_pair_kernel<R, C, W>, smem, attr_done);                                           \
+        bwd_pair_kernel<R, C, W><<<grid, NTHREADS2, smem, st>>>(tmA64, tmB, tmBd, p);                          \
     } while (0)
-    if (row_term && col_term) FLYP_LAUNCH_BWD2(true, true);
-    else if (row_term) FLYP_LAUNCH_BWD2(true, false);
-    else FLYP_LAUNCH_BWD2(false, true);
+    const bool wide = p.kc > 8 || p.n_dh > 1;
+    if (wide) {
+        if (row_term && col_term) FLYP_LAUNCH_BWD2(true, true, true);
+        else if (row_term) FLYP_LAUNCH_BWD2(true, false, true);
+        else FLYP_LAUNCH_BWD2(false, true, true);
+    } else {
+        if (row_term && col_term) FLYP_LAUNCH_BWD2(true, true, false);
+        else if (row_term) FLYP_LAUNCH_BWD2(true, false, false);
+        else FLYP_LAUNCH_BWD2(false, true, false);
+    }
 #undef FLYP_LAUNCH_BWD2
 }
 
