@@ -55,3 +55,18 @@ def test_unsupported_variants_raise():
 def test_clip_namespace_mirrors_reference_import_path():
     from flyp_b200.clip.loss import ClipLoss as C2, gather_features as g2
     assert C2 is ClipLoss and g2 is gather_features
+
+
+def test_comm_keyword_is_validated_and_defaults_to_auto():
+    import pytest
+    import torch
+    from flyp_b200 import ClipLoss
+    assert ClipLoss().comm == "auto"
+    with pytest.raises(ValueError):
+        ClipLoss(comm="horovod")
+    # the peer-memory exchange carries bf16 features only; everything else (and comm='nccl') takes the NCCL path,
+    # decided without touching a device
+    fn = ClipLoss(world_size=2, rank=0, comm="nccl")
+    assert fn._peer_comm(torch.zeros(4, 8, dtype=torch.bfloat16)) is None
+    fn = ClipLoss(world_size=2, rank=0, comm="auto")
+    assert fn._peer_comm(torch.zeros(4, 8, dtype=torch.float32)) is None
