@@ -25,7 +25,7 @@ COMM_MAX_WORLD = 16
 class Ready(Structure):
     """flyp_ready_t: device flag words that say which ranks' rows have arrived."""
     _fields_ = [("flags", c_void_p), ("seq", c_uint32), ("n_flags", c_int), ("rows_per_flag", c_int), ("sub", c_int),
-                ("stride", c_int), ("reserved_sms", c_int), ("err", c_void_p)]
+                ("stride", c_int), ("timeout_ms", c_uint32), ("err", c_void_p)]
 
 
 class Gathered(Structure):
@@ -70,8 +70,8 @@ SIGNATURES = {
                                       c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(Ready),
                                       POINTER(Ready), POINTER(Ready), POINTER(Ready), c_void_p]),
     "flyp_clip_fwd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
-                                   POINTER(Step), c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, POINTER(Step), c_void_p]),
     "flyp_clip_bwd_step": (c_int, [c_void_p, POINTER(Step), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -84,6 +84,8 @@ SIGNATURES = {
     "flyp_comm_connect_ipc": (c_int, [c_void_p, c_void_p]),
     "flyp_comm_connect_local": (c_int, [c_void_p, POINTER(c_void_p)]),
     "flyp_comm_error": (c_int, [c_void_p]),
+    "flyp_comm_reset_error": (c_int, [c_void_p]),
+    "flyp_comm_set_timeout_ms": (c_int, [c_void_p, c_uint32]),
     "flyp_comm_destroy": (c_int, [c_void_p]),
     "flyp_comm_gather_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(Gathered),
                                           c_void_p]),
@@ -96,11 +98,17 @@ SIGNATURES = {
                             c_void_p, c_void_p, c_size_t, c_void_p]),
     "flyp_ce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "flyp_ce_fwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                               c_void_p, c_void_p, c_size_t, POINTER(Ready), c_void_p]),
+    "flyp_ce_bwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                               c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p,
+                               POINTER(Ready), POINTER(Ready), c_void_p]),
     "flyp_l2norm_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "flyp_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "flyp_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                             c_void_p]),
     "flyp_debug_profile": (c_int, [c_void_p]),
+    "flyp_debug_kernel_events": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "flyp_debug_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                   c_void_p]),
 }

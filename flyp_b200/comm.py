@@ -153,11 +153,22 @@ class PeerComm:
     def check_error(self) -> None:
         e = _lib.load().flyp_comm_error(self._h)
         if e:
-            raise FlypError(f"a kernel timed out waiting for the rows of rank {e - 1} (peer-memory exchange)")
+            raise FlypError(f"a kernel gave up waiting for the rows of rank {e - 1} (peer-memory exchange) and trapped; "
+                            "the CUDA context of this process is lost")
 
     def alive(self, seq: int) -> bool:
-        """The buffers of gather ``seq`` stay intact until gather ``seq + 2`` is issued (double buffering)."""
-        return self.seq < seq + 2
+        """A step's gathered buffers may be consumed until the next gather is issued.  (The segments are double
+        buffered by step parity so that a FAST rank's next push cannot overwrite what a slow rank still reads: a rank
+        receives the rows of step s + 1 only after their owner has finished - in stream order - everything it issued for
+        step s.  That argument needs every rank to issue the backward of step s before its forward of step s + 1, so an
+        older step is refused rather than raced with.)"""
+        return self.seq == seq
+
+    def reset_error(self) -> None:
+        _lib.load().flyp_comm_reset_error(self._h)
+
+    def set_timeout_ms(self, ms: int) -> None:
+        _lib.check(_lib.load().flyp_comm_set_timeout_ms(self._h, int(ms)))
 
     def gather(self, img: torch.Tensor, txt: torch.Tensor) -> Gathered:
         n, d = img.shape
@@ -256,8 +267,8 @@ def bwd_local(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_i
               need_scale: bool):
     """Returns (d_img, d_txt, d_scale_partial): complete gradients of the local rows, this rank's share of d(scale)."""
     if not st.comm.alive(st.g.seq):
-        raise FlypError("the gathered features of this step were overwritten: with the peer-memory path at most one "
-                        "later forward may run before a step's backward (use ClipLoss(comm='nccl') otherwise)")
+        raise FlypError("the gathered features of this step were overwritten by a later forward: with the peer-memory "
+                        "exchange a step's backward must be issued before the next forward")
     dev = st.img.device
     lib = _lib.load()
     gdt = st.img.dtype if grad_dtype is None else grad_dtype
@@ -282,65 +293,5 @@ def bwd_local(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_i
 
 
 # ---------------------------------------------------------------------------------------------------- whole steps
-# What the drop-in module calls: one C call per direction (flyp_clip_fwd_step / flyp_clip_bwd_step).
-
-class FusedStep:
-    """State of one forward through flyp_clip_fwd_step (kept for the backward)."""
-    __slots__ = ("comm", "step", "img", "txt", "s", "b", "B", "D", "buf", "col_lse", "col_nll", "ws", "seq")
-
-
-def step_forward(comm: PeerComm, img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor, loss_dtype):
-    """Returns (loss[B] in loss_dtype, FusedStep)."""
-    from . import ops
-    ops._check_features(img, txt)
-    if img.dtype != torch.bfloat16:
-        raise FlypError("the peer-memory path carries bf16 features")
-    dev = img.device
-    st = FusedStep()
-    st.comm, st.img, st.txt, st.s = comm, img.contiguous(), txt.contiguous(), scale
-    b, D = img.shape
-    B = b * comm.world
-    st.b, st.B, st.D = b, B, D
-    st.step = Step()
-    code = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[loss_dtype]
-    with _lib.device_guard(dev):
-        st.ws = _workspace(b, B, D, dev)
-        bp, Bp = (b + 3) & ~3, (B + 3) & ~3
-        st.buf = buf = torch.empty(2 * bp + 5 * Bp, dtype=torch.float32, device=dev)
-        loss = torch.empty(B, dtype=loss_dtype, device=dev)
-        base, f4 = buf.data_ptr(), 4
-        o = 2 * bp
-        st.col_lse, st.col_nll = base + (o + 3 * Bp) * f4, base + (o + 4 * Bp) * f4
-        _lib.check(_lib.load().flyp_clip_fwd_step(
-            comm._h, st.img.data_ptr(), st.txt.data_ptr(), scale.data_ptr(), b, D, _lib.FLYP_BF16, comm.rank, comm.world,
-            base, base + bp * f4, base + o * f4, st.col_lse, st.col_nll, loss.data_ptr(), code, st.ws.data_ptr(),
-            st.ws.numel(), ctypes.byref(st.step), _lib.stream_ptr(dev)))
-    st.seq = comm.seq = int(st.step.gathered.seq)
-    return loss, st
-
-
-def step_backward(st: FusedStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_img: bool, need_txt: bool,
-                  need_scale: bool):
-    """Returns (d_img, d_txt, d_scale): complete gradients of the local rows and the all-reduced d(logit_scale)."""
-    comm = st.comm
-    if not comm.alive(st.seq):
-        raise FlypError("the gathered features of this step were overwritten: with the peer-memory path at most one "
-                        "later forward may run before a step's backward (use ClipLoss(comm='nccl') otherwise)")
-    dev = st.img.device
-    gdt = st.img.dtype if grad_dtype is None else grad_dtype
-    gcode = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[gdt]
-    if g.dtype not in (torch.float32, torch.bfloat16):
-        g = g.to(torch.float32)
-    g = g.contiguous()
-    g_code = _lib.FLYP_BF16 if g.dtype == torch.bfloat16 else _lib.FLYP_F32
-    need_img = need_img or need_scale
-    with _lib.device_guard(dev):
-        d_img = torch.empty(st.b, st.D, dtype=gdt, device=dev) if need_img else None
-        d_txt = torch.empty(st.b, st.D, dtype=gdt, device=dev) if need_txt else None
-        ds = torch.empty(2, dtype=torch.float32, device=dev) if need_scale else None      # [total, partial]
-        _lib.check(_lib.load().flyp_clip_bwd_step(
-            comm._h, ctypes.byref(st.step), st.img.data_ptr(), st.txt.data_ptr(), st.s.data_ptr(), st.b, st.D,
-            _lib.FLYP_BF16, comm.rank, comm.world, st.col_lse, st.col_nll, g.data_ptr(), g_code, float(grad_mul), gcode,
-            _lib.ptr(d_img), _lib.ptr(d_txt), (ds.data_ptr() + 4) if need_scale else None,
-            ds.data_ptr() if need_scale else None, st.ws.data_ptr(), st.ws.numel(), _lib.stream_ptr(dev)))
-    return d_img, d_txt, (ds[:1] if need_scale else None)
+# What the drop-in module calls: one C call per direction (flyp_b200/step.py), shared with the single-GPU loss.
+from .step import FusedStep, step_backward, step_forward  # noqa: E402,F401

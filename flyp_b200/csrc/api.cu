@@ -3,6 +3,7 @@
 #include "../../include/flyp_clip.h"
 #include "aux_kernels.cuh"
 #include "clip_kernels.cuh"
+#include "comm_internal.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -29,9 +30,19 @@ flyp::PeerWait to_wait(const flyp_ready_t* r) {
     if (r != nullptr && r->flags != nullptr) {
         w.flags = r->flags; w.seq = r->seq; w.n_flags = r->n_flags; w.rows_per_flag = r->rows_per_flag > 0 ? r->rows_per_flag : 1;
         w.sub = r->sub > 0 ? r->sub : 1; w.stride = r->stride > 0 ? r->stride : w.sub; w.err = r->err;
+        w.timeout_ms = r->timeout_ms;
     }
     return w;
 }
+
+// measurement switches: read from the environment ONCE per process (never on the hot path)
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+int env_bwd_impl() { static const int v = env_int("FLYP_BWD_IMPL", 0); return v; }   // 1: never the pair sweep, 2: whenever possible
+int env_fwd_mc() { static const int v = env_int("FLYP_FWD_MC", 1); return v; }
+int env_dbg() { static const int v = env_int("FLYP_DBG", 0); return v; }
 
 #define CUDA_OK(expr)                                                                                   \
     do {                                                                                                \
@@ -74,16 +85,10 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, bool
 }
 
 unsigned long long* g_prof_buf = nullptr;   // debug only (flyp_debug_profile)
-
-// SMs left to a concurrently running push kernel (comm.cu) by the kernels this thread is about to launch
-thread_local int g_reserved_sms = 0;
-struct ReserveSms {
-    int saved;
-    explicit ReserveSms(const flyp_ready_t* r) : saved(g_reserved_sms) {
-        if (r != nullptr && r->flags != nullptr && r->reserved_sms > g_reserved_sms) g_reserved_sms = r->reserved_sms;
-    }
-    ~ReserveSms() { g_reserved_sms = saved; }
-};
+// measurement only (flyp_debug_kernel_events): events recorded right before / after the forward sweep kernel and the
+// backward sweep kernel of the selected sweep, on the launching stream
+cudaEvent_t g_ev_fwd[2] = {nullptr, nullptr}, g_ev_sweep[2] = {nullptr, nullptr};
+int g_ev_sweep_idx = 0;
 
 int num_sms() {
     static int cached[64] = {0};
@@ -95,8 +100,7 @@ int num_sms() {
         cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
         cached[dev] = v > 0 ? v : 148;
     }
-    const int avail = cached[dev] - g_reserved_sms;
-    return avail >= 4 ? avail : 4;
+    return cached[dev];
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -104,8 +108,7 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // The CTA-pair backward sweep handles feature dims that are multiples of 128 up to 1024; FLYP_BWD_IMPL=1 forces the
 // single-CTA kernel (kept for other dims and for A/B measurements).
 bool use_pair_kernel(int dim, int dtype, int n_m, int n_n) {
-    const char* e = getenv("FLYP_BWD_IMPL");                              // A/B switch, read on every call
-    const int forced = (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;   // 1: never, 2: whenever the shape allows
+    const int forced = env_bwd_impl();                                    // A/B switch: 1 never, 2 whenever the shape allows
     if (forced == 1 || dtype != FLYP_BF16 || dim % 128 != 0 || dim > 1024) return false;
     if (dim <= 512 || forced == 2) return true;
     // two passes over the column halves: pays off once the sweep is long enough to amortise the extra pipeline fills and
@@ -132,21 +135,6 @@ constexpr int VEC_PAD = 256;   // per-row / per-column vectors are padded to thi
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int plane_cols(int dim) { return ceil_div(dim, 64) * 64; }
 
-// Number of M splits per N block for the forward sweep: minimise the makespan in tile units (a work item costs its
-// tiles plus ~2 tile-times to refill the stationary operand).
-int pick_m_split(int m_tiles, int n_tiles, int sms) {
-    int best = 1;
-    double best_cost = 1e30;
-    const int max_split = m_tiles < 64 ? m_tiles : 64;
-    for (int sp = 1; sp <= max_split; ++sp) {
-        const int items = n_tiles * sp;
-        const int rounds = ceil_div(items, sms);
-        const double cost = (double)rounds * (ceil_div(m_tiles, sp) + 2.0);
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
-    }
-    return best;
-}
-
 float shift_slack(int n_m, int n_n) {
     int n = n_m > n_n ? n_m : n_n;
     int lg = 0;
@@ -169,31 +157,41 @@ struct Carver {
 
 // ---- workspace of one forward statistics pass over S = A . B^T ([n_m] x [n_n]) ------------------------------------
 struct StatsWs {
-    int m_tiles, n_tiles, m_split, ld_rows, ld_cols;
+    int m_tiles, n_tiles, ld_rows, ld_cols;
     bool use_mc;                         // multicast (2-CTA cluster) forward kernel
+    int workers, n_slots;                // flat schedule of the fast forward (sched.h)
     float *rowpart, *rowmax, *colpart;   // fast pass + robust row pass
     float *rowpart2, *rowmax2;           // robust column pass (roles swapped): [m_tiles*2][ld_cols]
     float* t2;                           // [ld_rows] positive logit of each row, log2 units
-    int* pos;                            // [ld_rows] positive column of each row, -1 = none
-    int* pos_t;                          // [ld_cols] robust column pass: positive row of each column
-    float* t2_t;                         // [ld_cols] scratch (unused values) for the column pass
-    int* flag;
+    int* pos;                            // [ld_rows] positive column of each row, -1 = none, -2 = ignored row
+    int* flag;                           // [4] control words; [0]: the fixed-shift fast path was inadequate
     uint16_t *planes_a, *planes_b;       // fp32 features: three bf16 planes each ([n][3 * plane_cols])
 };
 void carve_stats(Carver& c, int n_m, int n_n, int dim, int dtype, bool want_cols, StatsWs& w) {
     w.m_tiles = ceil_div(n_m, flyp::TILE);
     w.n_tiles = ceil_div(n_n, flyp::TILE);
-    {
-        const char* e = getenv("FLYP_FWD_MC");
-        w.use_mc = dtype == FLYP_BF16 && dim <= 512 && w.n_tiles >= 2 && !(e && e[0] == '0');
-    }
+    w.use_mc = dtype == FLYP_BF16 && dim <= 512 && w.n_tiles >= 2 && env_fwd_mc() != 0;
     const int sms = num_sms();
-    w.m_split = w.use_mc ? pick_m_split(w.m_tiles, (w.n_tiles + 1) / 2, sms / 2) : pick_m_split(w.m_tiles, w.n_tiles, sms);
+    w.workers = flyp::fwd_workers(w.m_tiles, w.n_tiles, w.use_mc, sms);
+    // partial column-sum slots: the worst case over the phase splits run_stats may choose (none; the rank's own rows
+    // first) and over both kernels (the debug-logits pass always uses the plain one)
+    w.n_slots = 1;
+    for (int mc = 0; mc < 2; ++mc) {
+        if (mc && !w.use_mc) continue;
+        const int units = mc ? (w.n_tiles + 1) / 2 : w.n_tiles;
+        const int wk = flyp::fwd_workers(w.m_tiles, w.n_tiles, mc != 0, sms);
+        const int loc = n_m / (flyp::TILE * (mc ? 2 : 1));
+        const int cand[2] = {0, loc < units ? loc : 0};
+        for (int k = 0; k < 2; ++k) {
+            const int s2 = flyp::fwd_sched_slots(w.m_tiles, units, cand[k], wk);
+            if (s2 > w.n_slots) w.n_slots = s2;
+        }
+    }
     w.ld_rows = w.m_tiles * flyp::TILE;
     w.ld_cols = w.n_tiles * flyp::TILE;
     w.rowpart = c.take<float>((size_t)w.n_tiles * 2 * w.ld_rows);
     w.rowmax = c.take<float>((size_t)w.n_tiles * 2 * w.ld_rows);
-    w.colpart = c.take<float>((size_t)w.m_split * w.ld_cols);
+    w.colpart = c.take<float>((size_t)w.n_slots * (w.ld_cols + flyp::TILE));
     if (want_cols) {
         w.rowpart2 = c.take<float>((size_t)w.m_tiles * 2 * w.ld_cols);
         w.rowmax2 = c.take<float>((size_t)w.m_tiles * 2 * w.ld_cols);
@@ -202,9 +200,7 @@ void carve_stats(Carver& c, int n_m, int n_n, int dim, int dtype, bool want_cols
     }
     w.t2 = c.take<float>(w.ld_rows);
     w.pos = c.take<int>(w.ld_rows);
-    w.pos_t = want_cols ? c.take<int>(w.ld_cols) : nullptr;
-    w.t2_t = want_cols ? c.take<float>(w.ld_cols) : nullptr;
-    w.flag = c.take<int>(1);
+    w.flag = c.take<int>(4);
     if (dtype == FLYP_F32) {
         w.planes_a = c.take<uint16_t>((size_t)n_m * 3 * plane_cols(dim));
         w.planes_b = c.take<uint16_t>((size_t)n_n * 3 * plane_cols(dim));
@@ -213,84 +209,118 @@ void carve_stats(Carver& c, int n_m, int n_n, int dim, int dtype, bool want_cols
     }
 }
 
+// One forward statistics pass.
+struct StatsIO {
+    const void *A, *B;
+    const float* scale;
+    int n_m, n_n, dim, dtype;
+    const int64_t* labels;               // integer targets, or null: the positive of row i is column pos_offset + i
+    int pos_offset;
+    float *row_lse, *row_nll, *col_stat; // col_stat null: row direction only (ce head)
+    int* status;                         // optional device int: 1 when the robust path ran
+    float* dbg_logits;                   // debug: raw dot products instead of statistics
+    const flyp_ready_t* b_ready;         // multi-GPU: arrival flags of the rows of B
+    void *a16, *b16;                     // optional (bf16 features): fp16 copies of A / B to produce on the way
+    bool pre_done;                       // t2 / pos / control words were already prepared (pack kernel of the gather)
+    flyp::FwdFinish fin;                 // single-rank symmetric loss: finish col_lse / col_nll / loss in the same pass
+};
+
 // Statistics of S = scale * A . B^T with one positive per row (labels, or column pos_offset + i):
 //   row_lse[n_m] natural-log logsumexp, row_nll[n_m] = row_lse - positive logit, and (col_stat != null) the column
 //   triples (m_j, sum_j, t_j), see k_fwd_finalize.  The positives are excluded from the tensor-core sums and added back
 //   exactly, so a loss much smaller than the logits keeps full relative accuracy.
-int run_stats(const void* A, const void* B, const float* scale, int n_m, int n_n, int dim, int dtype,
-              const int64_t* labels, int pos_offset, const StatsWs& w, float* row_lse, float* row_nll,
-              float* col_stat, int* status, float* dbg_logits, cudaStream_t st, const flyp_ready_t* b_ready = nullptr) {
+// Launches: preparation (pair logits, fp16 copies, control words), the tcgen05 sweep, finalize, and the robust
+// recomputation + its finalize, both gated on a device flag (they return at once when the fast path was adequate).
+int run_stats(const StatsIO& io, const StatsWs& w, cudaStream_t st) {
     CUtensorMap tmA, tmB;
     int rc;
+    const int n_m = io.n_m, n_n = io.n_n, dim = io.dim, dtype = io.dtype;
     flyp::KPlan kplan = flyp::kplan_bf16();
+    const bool dbg = io.dbg_logits != nullptr;
     if (dtype == FLYP_F32) {
         const int dp = plane_cols(dim);
-        flyp::launch_split_planes_bf16x3(static_cast<const float*>(A), n_m, dim, dp, w.planes_a, st);
-        flyp::launch_split_planes_bf16x3(static_cast<const float*>(B), n_n, dim, dp, w.planes_b, st);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(io.A), n_m, dim, dp, w.planes_a, st);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(io.B), n_n, dim, dp, w.planes_b, st);
         CUDA_OK(cudaGetLastError());
         if ((rc = make_tmap(&tmA, w.planes_a, n_m, 3 * dp, 3 * dp)) != 0) return rc;
         if ((rc = make_tmap(&tmB, w.planes_b, n_n, 3 * dp, 3 * dp)) != 0) return rc;
         kplan = flyp::kplan_f32(dp);
     } else {
-        if ((rc = make_tmap(&tmA, A, n_m, dim, dim)) != 0) return rc;
-        if ((rc = make_tmap(&tmB, B, n_n, dim, dim)) != 0) return rc;
+        if ((rc = make_tmap(&tmA, io.A, n_m, dim, dim)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, io.B, n_n, dim, dim)) != 0) return rc;
     }
     const int sms = num_sms();
     const float slack = shift_slack(n_m, n_n);
-    CUDA_OK(cudaMemsetAsync(w.flag, 0, sizeof(int), st));
+    const bool mc = w.use_mc && !dbg;
 
     flyp::FwdParams p;
     memset(&p, 0, sizeof(p));
     p.n_m = n_m; p.n_n = n_n; p.kc = ceil_div(dim, flyp::KCHUNK); p.kplan = kplan;
-    p.m_tiles = w.m_tiles; p.n_tiles = w.n_tiles; p.m_split = w.m_split;
+    p.m_tiles = w.m_tiles; p.n_tiles = w.n_tiles; p.n_slots = w.n_slots;
     p.ld_rows = w.ld_rows; p.ld_cols = w.ld_cols;
-    p.scale = scale; p.shift_slack = slack;
+    p.scale = io.scale; p.shift_slack = slack;
     p.rowpart = w.rowpart; p.colpart = w.colpart; p.rowmax = w.rowmax; p.colmax = nullptr;
-    p.dbg_logits = dbg_logits;
-    if (dbg_logits == nullptr) {
-        flyp::launch_pair_dot(A, B, dtype, scale, n_m, w.ld_rows, n_n, dim, labels, pos_offset, w.t2, w.pos, nullptr, st);
-        CUDA_OK(cudaGetLastError());
+    p.dbg_logits = io.dbg_logits;
+    if (!dbg) {
+        if (!io.pre_done) {
+            flyp::launch_pair_dot(io.A, io.B, dtype, io.scale, n_m, w.ld_rows, n_n, dim, io.labels, io.pos_offset, w.t2,
+                                  w.pos, nullptr, w.flag, 4, io.a16, io.b16, st);
+            CUDA_OK(cudaGetLastError());
+        }
         p.pos = w.pos;
     }
+    flyp::FwdColSched cs;
     {
         // multi-GPU: rows of B owned by other ranks are still arriving; start at this rank's own column block
         flyp::FwdParams pf = p;
-        const bool mc = w.use_mc && dbg_logits == nullptr;
-        pf.wait_b = to_wait(b_ready);
-        if (pf.wait_b.flags != nullptr) pf.nb_rot = mc ? pos_offset / (2 * flyp::TILE) : pos_offset / flyp::TILE;
+        pf.wait_b = to_wait(io.b_ready);
+        const int unit_cols = flyp::TILE * (mc ? 2 : 1);
+        cs.n_units = mc ? (w.n_tiles + 1) / 2 : w.n_tiles;
+        if (pf.wait_b.flags != nullptr) {
+            // the schedule starts at this rank's own rows and follows the ring order of the pushes.  When the own rows
+            // are a large share of the work (<= 4 ranks) every worker first takes its part of them (phase A) so that
+            // nobody waits for the gather; with more ranks the local part is too short to hide the transfer and the
+            // extra work items (each reloads a 128 KB stationary operand) cost more than the overlap gains.
+            pf.nb_rot = io.pos_offset / unit_cols;
+            const int loc = n_m / unit_cols;
+            pf.n_local = (loc < cs.n_units && 4 * loc >= cs.n_units) ? loc : 0;
+        }
+        cs.m_tiles = w.m_tiles; cs.rot = pf.nb_rot; cs.n_local = pf.n_local; cs.mc = mc ? 1 : 0;
+        cs.workers = flyp::fwd_workers(w.m_tiles, w.n_tiles, mc, sms);
+        if (g_ev_fwd[0] != nullptr && !dbg) cudaEventRecord(g_ev_fwd[0], st);
         if (mc) {
             CUtensorMap tmA64;
-            if ((rc = make_tmap(&tmA64, A, n_m, dim, dim, false, 64)) != 0) return rc;
+            if ((rc = make_tmap(&tmA64, io.A, n_m, dim, dim, false, 64)) != 0) return rc;
             flyp::launch_fwd_mc(tmA64, tmB, pf, sms, st);
         } else {
             flyp::launch_fwd(tmA, tmB, pf, /*robust=*/false, nullptr, sms, st);
         }
+        if (g_ev_fwd[1] != nullptr && !dbg) cudaEventRecord(g_ev_fwd[1], st);
     }
     CUDA_OK(cudaGetLastError());
-    if (dbg_logits != nullptr) return 0;
-    flyp::launch_fwd_finalize(w.rowpart, w.n_tiles * 2, w.ld_rows, n_m, w.colpart, w.m_split, w.ld_cols, n_n, scale,
-                              slack, w.t2, w.pos, pos_offset, row_lse, row_nll, col_stat, w.flag, st);
+    if (dbg) return 0;
+    flyp::launch_fwd_finalize(w.rowpart, w.n_tiles * 2, w.ld_rows, n_m, w.colpart, cs, w.ld_cols, n_n, io.scale, slack,
+                              w.t2, w.pos, io.pos_offset, io.row_lse, io.row_nll, io.col_stat, w.flag, io.fin, st);
     CUDA_OK(cudaGetLastError());
 
     // Robust recomputation, gated on the device flag (the kernels return immediately when the fast path was adequate).
-    flyp::launch_fwd(tmA, tmB, p, /*robust=*/true, w.flag, sms, st);
-    CUDA_OK(cudaGetLastError());
-    if (col_stat != nullptr) {
-        // roles swapped: rows of S^T are the columns of S; the positive of column j is local row j - pos_offset
-        flyp::launch_pair_dot(B, A, dtype, scale, n_n, w.ld_cols, n_m, dim, nullptr, -pos_offset, w.t2_t, w.pos_t, w.flag,
-                              st);
-        CUDA_OK(cudaGetLastError());
+    if (io.col_stat != nullptr) {
+        // second pass with the roles swapped: rows of S^T are the columns of S; the positive of column j is local row
+        // j - pos_offset (explicit labels never come with a column direction)
         flyp::FwdParams pt = p;
         pt.n_m = n_n; pt.n_n = n_m; pt.m_tiles = w.n_tiles; pt.n_tiles = w.m_tiles;
-        pt.m_split = 1; pt.ld_rows = w.ld_cols; pt.ld_cols = w.ld_rows;
-        pt.rowpart = w.rowpart2; pt.rowmax = w.rowmax2; pt.colpart = nullptr; pt.pos = w.pos_t;
-        flyp::launch_fwd(tmB, tmA, pt, /*robust=*/true, w.flag, sms, st);
-        CUDA_OK(cudaGetLastError());
+        pt.ld_rows = w.ld_cols; pt.ld_cols = w.ld_rows;
+        pt.rowpart = w.rowpart2; pt.rowmax = w.rowmax2; pt.colpart = nullptr;
+        pt.pos = nullptr; pt.pos_arith = 1; pt.pos_off = -io.pos_offset;
+        flyp::launch_fwd_robust2(tmA, tmB, p, pt, w.flag, sms, st);
+    } else {
+        flyp::launch_fwd(tmA, tmB, p, /*robust=*/true, w.flag, sms, st);
     }
-    flyp::launch_fwd_finalize_robust(w.rowpart, w.rowmax, w.n_tiles * 2, w.ld_rows, n_m, w.rowpart2, w.rowmax2,
-                                     w.m_tiles * 2, w.ld_cols, n_n, w.t2, row_lse, row_nll, col_stat, w.flag, st);
     CUDA_OK(cudaGetLastError());
-    if (status != nullptr) CUDA_OK(cudaMemcpyAsync(status, w.flag, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    flyp::launch_fwd_finalize_robust(w.rowpart, w.rowmax, w.n_tiles * 2, w.ld_rows, n_m, w.rowpart2, w.rowmax2,
+                                     w.m_tiles * 2, w.ld_cols, n_n, w.t2, w.pos, io.row_lse, io.row_nll, io.col_stat,
+                                     w.flag, io.status, io.fin, st);
+    CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -301,6 +331,15 @@ void carve_vecs(Carver& c, int n_pad, VecSet& v) {
     v.lab = c.take<int>(n_pad);
 }
 
+// Control words of one backward call, cleared by ONE memset at its start:
+//   [0..3]  {bits(max|g|), key(max lse2), ~key(min lse2), -} accumulated by the prep kernels
+//   [4 + s] arrival counter of the end-of-sweep grid barrier of sweep s (0, 1)
+constexpr int CTRL_WORDS = 8;
+struct BwdCtrl {
+    uint32_t* words;
+    int* grid_cnt(int sweep) const { return reinterpret_cast<int*>(words) + 4 + sweep; }
+};
+
 int check_common(int n_m, int n_n, int dim, int dtype) {
     if (n_m <= 0 || n_n <= 0) return fail(FLYP_ERR_ARG, "empty operand (%d x %d)", n_m, n_n);
     if (dim <= 0 || dim % 8 != 0) return fail(FLYP_ERR_ARG, "dim=%d must be a positive multiple of 8", dim);
@@ -308,29 +347,44 @@ int check_common(int n_m, int n_n, int dim, int dtype) {
     return 0;
 }
 
-// One backward sweep: gradient w.r.t. the rows of A.  bf16: A / B are the features, B_f16 the fp16 copy of B.
-// fp32: A_planes / B_planes are the 3-plane bf16 splits, B_f16 the 2-plane fp16 split of B; output is fp32.
-int run_sweep(const void* A, const void* B, const void* B_f16, int dtype, const void* A_planes, const void* B_planes,
-              const float* scale, int n_m, int n_n, int dim, const float* wr,
-              const float* lr, const float* wc, const float* lc, const int* labr, const float* dr, const int* labc,
-              const float* dc, const float* fa, const float* fb, const float* fast_info, const void* a_rows_for_dscale,
-              void* out, int out_fp32, float out_mul, float* dscale_part, float* part_scratch, const uint32_t* gmax_bits,
-              cudaStream_t st, const flyp_ready_t* b_ready = nullptr, const flyp_ready_t* b16_ready = nullptr) {
+// One backward sweep: gradient w.r.t. the rows of A.
+struct SweepIO {
+    const void *A, *B, *B_f16;           // bf16: the features and the fp16 copy of B.  fp32: A_planes / B_planes are the
+    const void *A_planes, *B_planes;     // 3-plane bf16 splits, B_f16 the 2-plane fp16 split of B; output is fp32
+    int dtype;
+    const float* scale;
+    int n_m, n_n, dim;
+    const float *wr, *lr, *wc, *lc;      // row / column softmax terms (null: term absent)
+    const int* labr; const float* dr;    // exact dS at the positive of each row
+    const int* labc; const float* dc;    // ... of each column
+    const float *fa, *fb, *fast_info;
+    void* out; int out_fp32; float out_mul;
+    float* dscale_part;                  // null: no d(scale)
+    float* dscale_out;                   // the sweep's total (summed in-kernel by the pair sweep, by k_sum_parts otherwise)
+    size_t n_dscale;
+    float* part_scratch;
+    const BwdCtrl* ctrl; int sweep;      // control words and which counter set this sweep uses
+    const flyp::PeerPush* ds_push;       // multi-GPU: where the total is published (may be null)
+    const flyp_ready_t *b_ready, *b16_ready;
+};
+
+int run_sweep(const SweepIO& io, cudaStream_t st) {
     CUtensorMap tmA, tmB, tmBd;
     int rc;
+    const int n_m = io.n_m, n_n = io.n_n, dim = io.dim, dtype = io.dtype;
     const bool f32 = dtype == FLYP_F32;
     const int dp = plane_cols(dim);
     flyp::KPlan kplan = flyp::kplan_bf16();
     if (f32) {
-        if ((rc = make_tmap(&tmA, A_planes, n_m, 3 * dp, 3 * dp)) != 0) return rc;
-        if ((rc = make_tmap(&tmB, B_planes, n_n, 3 * dp, 3 * dp)) != 0) return rc;
-        if ((rc = make_tmap(&tmBd, B_f16, n_n, 2 * dp, 2 * dp, true)) != 0) return rc;
+        if (!io.out_fp32) return fail(FLYP_ERR_ARG, "fp32 features need fp32 gradients");
+        if ((rc = make_tmap(&tmA, io.A_planes, n_m, 3 * dp, 3 * dp)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, io.B_planes, n_n, 3 * dp, 3 * dp)) != 0) return rc;
+        if ((rc = make_tmap(&tmBd, io.B_f16, n_n, 2 * dp, 2 * dp, true)) != 0) return rc;
         kplan = flyp::kplan_f32(dp);
-        if (!out_fp32) return fail(FLYP_ERR_ARG, "fp32 features need fp32 gradients");
     } else {
-        if ((rc = make_tmap(&tmA, A, n_m, dim, dim)) != 0) return rc;
-        if ((rc = make_tmap(&tmB, B, n_n, dim, dim)) != 0) return rc;
-        if ((rc = make_tmap(&tmBd, B_f16, n_n, dim, dim, true)) != 0) return rc;
+        if ((rc = make_tmap(&tmA, io.A, n_m, dim, dim)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, io.B, n_n, dim, dim)) != 0) return rc;
+        if ((rc = make_tmap(&tmBd, io.B_f16, n_n, dim, dim, true)) != 0) return rc;
     }
     flyp::BwdParams p;
     memset(&p, 0, sizeof(p));
@@ -338,30 +392,42 @@ int run_sweep(const void* A, const void* B, const void* B_f16, int dtype, const 
     p.f32_mode = f32 ? 1 : 0; p.bd_plane_cols = dp;
     p.m_tiles = ceil_div(n_m, flyp::TILE); p.n_tiles = ceil_div(n_n, flyp::TILE);
     p.d_out = dim; p.d_parts = ceil_div(dim, 256);
-    p.scale = scale; p.wr = wr; p.lr = lr; p.wc = wc; p.lc = lc;
-    p.labr = labr; p.dr = dr; p.labc = labc; p.dc = dc;
-    p.fa = fa; p.fb = fb; p.fast_info = fast_info;
-    p.a_rows = a_rows_for_dscale; p.lda = dim;
-    p.out = out; p.ld_out = dim; p.out_fp32 = out_fp32; p.out_mul = out_mul; p.gmax_bits = gmax_bits;
-    p.dscale_part = dscale_part;
-    p.wait_b = to_wait(b_ready); p.wait_bd = to_wait(b16_ready);
+    p.scale = io.scale; p.wr = io.wr; p.lr = io.lr; p.wc = io.wc; p.lc = io.lc;
+    p.labr = io.labr; p.dr = io.dr; p.labc = io.labc; p.dc = io.dc;
+    p.fa = io.fa; p.fb = io.fb; p.fast_info = io.fast_info;
+    p.a_rows = io.dscale_part ? io.A : nullptr; p.lda = dim;
+    p.out = io.out; p.ld_out = dim; p.out_fp32 = io.out_fp32; p.out_mul = io.out_mul; p.gmax_bits = io.ctrl->words;
+    p.dscale_part = io.dscale_part;
+    p.wait_b = to_wait(io.b_ready); p.wait_bd = to_wait(io.b16_ready);
     p.prof = g_prof_buf;
-    { const char* e = getenv("FLYP_DBG"); p.dbg = e ? atoi(e) : 0; }
+    p.dbg = env_dbg();
+    const bool push = io.dscale_part != nullptr && io.ds_push != nullptr && io.ds_push->n_dst > 0;
+    const bool timed = g_ev_sweep[0] != nullptr && g_ev_sweep_idx == io.sweep;
+    if (timed) cudaEventRecord(g_ev_sweep[0], st);
     if (use_pair_kernel(dim, dtype, n_m, n_n)) {
         CUtensorMap tmA64;
-        if ((rc = make_tmap(&tmA64, A, n_m, dim, dim, false, 64)) != 0) return rc;
-        if (part_scratch == nullptr) return fail(FLYP_ERR_ARG, "the pair sweep needs its partial-sum scratch");
+        if ((rc = make_tmap(&tmA64, io.A, n_m, dim, dim, false, 64)) != 0) return rc;
+        if (io.part_scratch == nullptr) return fail(FLYP_ERR_ARG, "the pair sweep needs its partial-sum scratch");
         p.n_dh = pair_n_dh(dim); p.d_half = pair_d_half(dim);
         p.sched_pairs = flyp::bwd_pair_sched_pairs(p.m_tiles * p.n_dh, n_n, num_sms());
-        p.part_out = part_scratch;
+        p.part_out = io.part_scratch;
+        p.grid_cnt = (env_dbg() & 2) ? nullptr : io.ctrl->grid_cnt(io.sweep);   // (debug bit 1: partials left unreduced)
+        if (io.dscale_part != nullptr) {
+            p.dscale_out = io.dscale_out;
+            if (push) p.ds_push = *io.ds_push;
+        }
         flyp::launch_bwd_pair(tmA64, tmB, tmBd, p, num_sms(), st);
+        if (timed) cudaEventRecord(g_ev_sweep[1], st);
         CUDA_OK(cudaGetLastError());
-        flyp::launch_reduce_parts(part_scratch, p.m_tiles * p.n_dh, ceil_div(n_n, flyp::PAIR_NSTEP), p.sched_pairs, p.n_dh,
-                                  p.d_half, n_m, dim, out, dim, out_fp32, st);
     } else {
         flyp::launch_bwd(tmA, tmB, tmBd, p, num_sms(), st);
+        if (timed) cudaEventRecord(g_ev_sweep[1], st);
+        CUDA_OK(cudaGetLastError());
+        if (io.dscale_part != nullptr) {
+            flyp::launch_sum_parts(io.dscale_part, (int)io.n_dscale, io.dscale_out, push ? io.ds_push : nullptr, st);
+            CUDA_OK(cudaGetLastError());
+        }
     }
-    CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -390,9 +456,10 @@ struct ClipWs {
     float* dscale_part;
     size_t n_dscale;
     float* part_scratch;      // fp32 partial outputs of split tail blocks (pair kernel)
-    uint32_t* gmax_bits;      // {bits(max|g|), key(max lse2), key(min lse2)}
+    BwdCtrl ctrl;
     float* fast_info;         // {c0, valid}
-    uint16_t *img16, *txt16;  // fp16 staging copies of the features (backward only)
+    float* col_stat;          // [3 * n_cols] scratch for the column triples when the caller does not want them
+    uint16_t *img16, *txt16;  // fp16 staging copies of the features when the caller keeps none (backward only)
     size_t bytes;
 };
 static void carve_clip(void* base, int n_rows, int n_cols, int dim, int dtype, ClipWs& w) {
@@ -408,8 +475,9 @@ static void carve_clip(void* base, int n_rows, int n_cols, int dim, int dtype, C
         const size_t n = a > b ? a : b;
         w.part_scratch = n ? c.take<float>(n) : nullptr;
     }
-    w.gmax_bits = c.take<uint32_t>(4);
+    w.ctrl.words = c.take<uint32_t>(CTRL_WORDS);
     w.fast_info = c.take<float>(2);
+    w.col_stat = c.take<float>((size_t)3 * n_cols);
     // fp16 staging copy (bf16 features) or two fp16 planes (fp32 features)
     const size_t w16 = dtype == FLYP_F32 ? (size_t)2 * plane_cols(dim) : (size_t)dim;
     w.img16 = c.take<uint16_t>((size_t)n_rows * w16);
@@ -437,7 +505,6 @@ int flyp_clip_fwd_local(const void* img, const void* txt, const float* scale, in
 int flyp_clip_fwd_local_ex(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
                            int dtype, int row_offset, float* row_lse, float* row_nll, float* col_stat, int* status,
                            void* workspace, size_t workspace_bytes, const flyp_ready_t* txt_ready, void* stream) {
-    ReserveSms reserve(txt_ready);
     int rc = check_common(n_rows, n_cols, dim, dtype);
     if (rc) return rc;
     if (!img || !txt || !scale || !row_lse || !row_nll || !col_stat || !workspace)
@@ -447,9 +514,12 @@ int flyp_clip_fwd_local_ex(const void* img, const void* txt, const float* scale,
     ClipWs w;
     carve_clip(workspace, n_rows, n_cols, dim, dtype, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return run_stats(img, txt, scale, n_rows, n_cols, dim, dtype, nullptr, row_offset, w.stats, row_lse, row_nll,
-                     col_stat, status, nullptr, st, txt_ready);
+    StatsIO io;
+    memset(&io, 0, sizeof(io));
+    io.A = img; io.B = txt; io.scale = scale; io.n_m = n_rows; io.n_n = n_cols; io.dim = dim; io.dtype = dtype;
+    io.pos_offset = row_offset; io.row_lse = row_lse; io.row_nll = row_nll; io.col_stat = col_stat; io.status = status;
+    io.b_ready = txt_ready;
+    return run_stats(io, w.stats, static_cast<cudaStream_t>(stream));
 }
 
 int flyp_clip_fwd_finish(const float* col_stat_all, int world, const float* row_nll, int n_rows, int n_cols,
@@ -480,13 +550,22 @@ int flyp_clip_bwd_local(const void* img, const void* txt, const float* scale, in
                                   workspace_bytes, nullptr, nullptr, nullptr, stream);
 }
 
+// common fields of the two sweeps of a backward call
+static SweepIO sweep_base(const float* scale, int dtype, int dim, const ClipWs& w, int grad_dtype, float grad_mul) {
+    SweepIO io;
+    memset(&io, 0, sizeof(io));
+    io.scale = scale; io.dtype = dtype; io.dim = dim; io.fast_info = w.fast_info;
+    io.out_fp32 = grad_dtype; io.out_mul = grad_mul;
+    io.part_scratch = w.part_scratch; io.ctrl = &w.ctrl; io.n_dscale = w.n_dscale;
+    return io;
+}
+
 int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
                            int dtype, int row_offset, const float* row_lse, const float* row_nll, const float* col_lse,
                            const float* col_nll, const float* g_row, const float* g_col, float grad_mul, int grad_dtype,
                            void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
                            const void* txt16, const flyp_ready_t* txt_ready, const flyp_ready_t* txt16_ready,
                            void* stream) {
-    ReserveSms reserve(txt_ready);
     int rc = check_common(n_rows, n_cols, dim, dtype);
     if (rc) return rc;
     if (!img || !txt || !scale || !row_lse || !row_nll || !col_lse || !col_nll || !g_row || !g_col || !workspace)
@@ -494,31 +573,31 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
     if (grad_dtype != FLYP_BF16 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad grad_dtype %d", grad_dtype);
     if (row_offset < 0 || row_offset + n_rows > n_cols)
         return fail(FLYP_ERR_ARG, "row_offset %d + n_rows %d exceeds n_cols %d", row_offset, n_rows, n_cols);
+    const bool f32 = dtype == FLYP_F32;
+    if (f32 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "fp32 features need grad_dtype = FLYP_F32");
+    if (txt16 != nullptr && f32) return fail(FLYP_ERR_ARG, "a precomputed fp16 copy is only accepted for bf16 features");
+    if (d_scale && !d_img) return fail(FLYP_ERR_ARG, "d_scale requires d_img");
     ClipWs w;
     carve_clip(workspace, n_rows, n_cols, dim, dtype, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int rp = ceil_div(n_rows, VEC_PAD) * VEC_PAD, cp = ceil_div(n_cols, VEC_PAD) * VEC_PAD;
-    CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, 2 * sizeof(uint32_t), st));
-    CUDA_OK(cudaMemsetAsync(w.gmax_bits + 2, 0xff, sizeof(uint32_t), st));
+    CUDA_OK(cudaMemsetAsync(w.ctrl.words, 0, CTRL_WORDS * sizeof(uint32_t), st));
     // rows: w = g_row/2, positive column row_offset + i, exact dS there from the saved cross-entropies
     flyp::launch_bwd_prep(n_rows, rp, g_row, 0.5f, row_lse, row_nll, nullptr, row_offset, n_cols, g_col, col_nll, 0.5f,
-                          w.rows.w, w.rows.l2, w.rows.lab, w.rows.d, w.gmax_bits, st);
+                          w.rows.w, w.rows.l2, w.rows.lab, w.rows.d, w.ctrl.words, st);
     // columns: w = g_col/2, positive local row j - row_offset
     flyp::launch_bwd_prep(n_cols, cp, g_col, 0.5f, col_lse, col_nll, nullptr, -row_offset, n_rows, g_row, row_nll, 0.5f,
-                          w.cols.w, w.cols.l2, w.cols.lab, w.cols.d, w.gmax_bits, st);
-    flyp::launch_bwd_fast_vectors(w.gmax_bits, rp, w.rows.w, w.rows.l2, w.rows.f, cp, w.cols.w, w.cols.l2, w.cols.f,
+                          w.cols.w, w.cols.l2, w.cols.lab, w.cols.d, w.ctrl.words, st);
+    flyp::launch_bwd_fast_vectors(w.ctrl.words, rp, w.rows.w, w.rows.l2, w.rows.f, cp, w.cols.w, w.cols.l2, w.cols.f,
                                   w.fast_info, st);
     CUDA_OK(cudaGetLastError());
-    const bool f32 = dtype == FLYP_F32;
-    if (f32 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "fp32 features need grad_dtype = FLYP_F32");
     const int dp = plane_cols(dim);
     if (f32) {
         flyp::launch_split_planes_bf16x3(static_cast<const float*>(img), n_rows, dim, dp, w.stats.planes_a, st);
         flyp::launch_split_planes_bf16x3(static_cast<const float*>(txt), n_cols, dim, dp, w.stats.planes_b, st);
         CUDA_OK(cudaGetLastError());
     }
-    if (txt16 != nullptr && f32) return fail(FLYP_ERR_ARG, "a precomputed fp16 copy is only accepted for bf16 features");
     if (d_img) {
         const void* t16 = txt16;
         if (t16 == nullptr) {
@@ -527,31 +606,34 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
             CUDA_OK(cudaGetLastError());
             t16 = w.txt16;
         }
-        rc = run_sweep(img, txt, t16, dtype, w.stats.planes_a, w.stats.planes_b, scale, n_rows, n_cols, dim,
-                       w.rows.w, w.rows.l2, w.cols.w, w.cols.l2, w.rows.lab, w.rows.d, nullptr, nullptr, w.rows.f,
-                       w.cols.f, w.fast_info, d_scale ? img : nullptr, d_img, grad_dtype, grad_mul,
-                       d_scale ? w.dscale_part : nullptr, w.part_scratch, w.gmax_bits, st, txt_ready, txt16_ready);
-        if (rc) return rc;
-        if (d_scale) {
-            flyp::launch_sum_parts(w.dscale_part, (int)w.n_dscale, d_scale, st);
-            CUDA_OK(cudaGetLastError());
-        }
-    } else if (d_scale) {
-        return fail(FLYP_ERR_ARG, "d_scale requires d_img");
+        SweepIO io = sweep_base(scale, dtype, dim, w, grad_dtype, grad_mul);
+        io.A = img; io.B = txt; io.B_f16 = t16; io.A_planes = w.stats.planes_a; io.B_planes = w.stats.planes_b;
+        io.n_m = n_rows; io.n_n = n_cols;
+        io.wr = w.rows.w; io.lr = w.rows.l2; io.wc = w.cols.w; io.lc = w.cols.l2; io.labr = w.rows.lab; io.dr = w.rows.d;
+        io.fa = w.rows.f; io.fb = w.cols.f;
+        io.out = d_img; io.sweep = 0;
+        if (d_scale) { io.dscale_part = w.dscale_part; io.dscale_out = d_scale; }
+        io.b_ready = txt_ready; io.b16_ready = txt16_ready;
+        if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     if (d_txt) {
         if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(img), n_rows, dim, dp, w.img16, st);
         else flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
         CUDA_OK(cudaGetLastError());
-        rc = run_sweep(txt, img, w.img16, dtype, w.stats.planes_b, w.stats.planes_a, scale, n_cols, n_rows, dim,
-                       w.cols.w, w.cols.l2, w.rows.w, w.rows.l2, w.cols.lab, w.cols.d, nullptr, nullptr, w.cols.f,
-                       w.rows.f, w.fast_info, nullptr, d_txt, grad_dtype, grad_mul, nullptr, w.part_scratch, w.gmax_bits,
-                       st);
-        if (rc) return rc;
+        SweepIO io = sweep_base(scale, dtype, dim, w, grad_dtype, grad_mul);
+        io.A = txt; io.B = img; io.B_f16 = w.img16; io.A_planes = w.stats.planes_b; io.B_planes = w.stats.planes_a;
+        io.n_m = n_cols; io.n_n = n_rows;
+        io.wr = w.cols.w; io.lr = w.cols.l2; io.wc = w.rows.w; io.lc = w.rows.l2; io.labr = w.cols.lab; io.dr = w.cols.d;
+        io.fa = w.cols.f; io.fb = w.rows.f;
+        io.out = d_txt; io.sweep = 1;
+        if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     return 0;
 }
 
+// Both sweeps of a rank of the row-sharded symmetric loss (world == 1: the whole loss).  comm (may be null): the
+// d(scale) partial is published to the other ranks by the first sweep's last CTA and the W partials are summed after
+// the second sweep.
 static int bwd_sharded_impl(const void* img, const void* txt, const void* img_all, const void* txt_all,
                             const void* img16_all, const void* txt16_all, const float* scale, int n_rows, int n_cols,
                             int dim, int dtype, int row_offset, const float* row_lse_all, const float* row_nll_all,
@@ -560,15 +642,14 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
                             size_t workspace_bytes, const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready,
                             const flyp_ready_t* img16_ready, const flyp_ready_t* txt16_ready, void* stream,
                             flyp_comm* comm, uint32_t seq, float* d_scale_total) {
-    ReserveSms reserve(txt_ready ? txt_ready : img_ready);
     int rc = check_common(n_rows, n_cols, dim, dtype);
-    if (g_dtype != FLYP_BF16 && g_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad g_dtype %d", g_dtype);
     if (rc) return rc;
+    if (g_dtype != FLYP_BF16 && g_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad g_dtype %d", g_dtype);
     if (dtype != FLYP_BF16) return fail(FLYP_ERR_ARG, "the sharded backward takes bf16 features");
     if (!img || !txt || !scale || !row_lse_all || !row_nll_all || !col_lse || !col_nll || !g || !workspace)
         return fail(FLYP_ERR_ARG, "null pointer argument");
-    if ((d_img || d_scale) && (!txt_all || !txt16_all)) return fail(FLYP_ERR_ARG, "d_img needs the gathered text features");
-    if (d_txt && (!img_all || !img16_all)) return fail(FLYP_ERR_ARG, "d_txt needs the gathered image features");
+    if ((d_img || d_scale) && !txt_all) return fail(FLYP_ERR_ARG, "d_img needs the gathered text features");
+    if (d_txt && !img_all) return fail(FLYP_ERR_ARG, "d_txt needs the gathered image features");
     if (d_scale && !d_img) return fail(FLYP_ERR_ARG, "d_scale requires d_img");
     if (grad_dtype != FLYP_BF16 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad grad_dtype %d", grad_dtype);
     if (row_offset < 0 || row_offset + n_rows > n_cols)
@@ -580,33 +661,47 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
     const int cp = ceil_div(n_cols, VEC_PAD) * VEC_PAD;
     // global vectors live in the column set (its d / lab arrays hold the row-statistics l2 / f), local ones in the row set
     float *wg = w.cols.w, *l2c = w.cols.l2, *fc = w.cols.f, *l2r = w.cols.d, *fr = reinterpret_cast<float*>(w.cols.lab);
-    CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, 2 * sizeof(uint32_t), st));
-    CUDA_OK(cudaMemsetAsync(w.gmax_bits + 2, 0xff, sizeof(uint32_t), st));
+    CUDA_OK(cudaMemsetAsync(w.ctrl.words, 0, CTRL_WORDS * sizeof(uint32_t), st));
     flyp::launch_bwd_prep_sharded(n_cols, cp, row_offset, n_rows, g, g_dtype == FLYP_BF16, row_lse_all, row_nll_all, col_lse, col_nll, wg, l2c,
-                                  l2r, w.rows.lab, w.rows.d, w.gmax_bits, st);
-    flyp::launch_bwd_fast_vectors(w.gmax_bits, cp, wg, l2c, fc, cp, wg, l2r, fr, w.fast_info, st);
+                                  l2r, w.rows.lab, w.rows.d, w.ctrl.words, st);
+    flyp::launch_bwd_fast_vectors(w.ctrl.words, cp, wg, l2c, fc, cp, wg, l2r, fr, w.fast_info, st);
     CUDA_OK(cudaGetLastError());
     const int off = row_offset;
+    flyp::PeerPush push;
+    memset(&push, 0, sizeof(push));
+    if (comm != nullptr && d_scale != nullptr && (rc = flyp::comm_scalar_push_target(comm, seq, &push)) != 0) return rc;
     if (d_img) {
         // image rows of this rank against all texts: complete d_img and this row block's share of d(scale)
-        rc = run_sweep(img, txt_all, txt16_all, dtype, nullptr, nullptr, scale, n_rows, n_cols, dim, wg + off, l2r + off, wg,
-                       l2c, w.rows.lab, w.rows.d, nullptr, nullptr, fr + off, fc, w.fast_info, d_scale ? img : nullptr,
-                       d_img, grad_dtype, grad_mul, d_scale ? w.dscale_part : nullptr, w.part_scratch, w.gmax_bits, st,
-                       txt_ready, txt16_ready);
-        if (rc) return rc;
-        if (d_scale) {
-            flyp::launch_sum_parts(w.dscale_part, (int)w.n_dscale, d_scale, st);
+        const void* t16 = txt16_all;
+        if (t16 == nullptr) {                    // the caller kept no fp16 copy: make one
+            flyp::launch_to_f16(txt_all, dtype, (size_t)n_cols * dim, w.txt16, st);
             CUDA_OK(cudaGetLastError());
-            // the partial goes out now; the other ranks' partials arrive while the second sweep runs
-            if (comm != nullptr && (rc = flyp_comm_push_scalar(comm, seq, d_scale, stream)) != 0) return rc;
+            t16 = w.txt16;
         }
+        SweepIO io = sweep_base(scale, dtype, dim, w, grad_dtype, grad_mul);
+        io.A = img; io.B = txt_all; io.B_f16 = t16; io.n_m = n_rows; io.n_n = n_cols;
+        io.wr = wg + off; io.lr = l2r + off; io.wc = wg; io.lc = l2c; io.labr = w.rows.lab; io.dr = w.rows.d;
+        io.fa = fr + off; io.fb = fc;
+        io.out = d_img; io.sweep = 0;
+        if (d_scale) { io.dscale_part = w.dscale_part; io.dscale_out = d_scale; io.ds_push = &push; }
+        io.b_ready = txt_ready; io.b16_ready = txt16_all ? txt16_ready : nullptr;
+        if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     if (d_txt) {
         // the transposed problem: text rows of this rank against all images (no B x D reduce-scatter)
-        rc = run_sweep(txt, img_all, img16_all, dtype, nullptr, nullptr, scale, n_rows, n_cols, dim, wg + off, l2c + off, wg,
-                       l2r, w.rows.lab, w.rows.d, nullptr, nullptr, fc + off, fr, w.fast_info, nullptr, d_txt, grad_dtype,
-                       grad_mul, nullptr, w.part_scratch, w.gmax_bits, st, img_ready, img16_ready);
-        if (rc) return rc;
+        const void* i16 = img16_all;
+        if (i16 == nullptr) {                    // (the first sweep is done with the staging buffer: stream order)
+            flyp::launch_to_f16(img_all, dtype, (size_t)n_cols * dim, w.txt16, st);
+            CUDA_OK(cudaGetLastError());
+            i16 = w.txt16;
+        }
+        SweepIO io = sweep_base(scale, dtype, dim, w, grad_dtype, grad_mul);
+        io.A = txt; io.B = img_all; io.B_f16 = i16; io.n_m = n_rows; io.n_n = n_cols;
+        io.wr = wg + off; io.lr = l2c + off; io.wc = wg; io.lc = l2r; io.labr = w.rows.lab; io.dr = w.rows.d;
+        io.fa = fc + off; io.fb = fr;
+        io.out = d_txt; io.sweep = 1;
+        io.b_ready = img_ready; io.b16_ready = img16_all ? img16_ready : nullptr;
+        if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     if (comm != nullptr && d_scale != nullptr && d_scale_total != nullptr)
         return flyp_comm_sum_scalar(comm, seq, d_scale_total, stream);
@@ -626,20 +721,51 @@ int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all,
                             txt16_ready, stream, nullptr, 0, nullptr);
 }
 
-// ---- whole-step entry points over a communicator: what ClipLoss.forward / backward of a rank call -------------------
+// ---- whole-step entry points: what ClipLoss.forward / backward of a rank call ---------------------------------------
 int flyp_clip_fwd_step(flyp_comm* comm, const void* img, const void* txt, const float* scale, int n_rows, int dim,
                        int dtype, int rank, int world, float* row_lse, float* row_nll, float* col_stat, float* col_lse,
-                       float* col_nll, void* loss, int loss_dtype, void* workspace, size_t workspace_bytes,
-                       flyp_step_t* step, void* stream) {
-    if (!comm || !step) return fail(FLYP_ERR_ARG, "null pointer argument");
+                       float* col_nll, void* loss, int loss_dtype, void* feat16, int* status, void* workspace,
+                       size_t workspace_bytes, flyp_step_t* step, void* stream) {
+    if (!step) return fail(FLYP_ERR_ARG, "null pointer argument");
     if (world < 1 || rank < 0 || rank >= world) return fail(FLYP_ERR_ARG, "bad rank %d / world %d", rank, world);
+    if (!comm && world != 1) return fail(FLYP_ERR_ARG, "world %d needs a communicator", world);
+    if (loss_dtype != FLYP_BF16 && loss_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad loss_dtype %d", loss_dtype);
     const int n_cols = n_rows * world, off = rank * n_rows;
-    int rc = flyp_comm_gather_features(comm, img, txt, n_rows, dim, dtype, &step->gathered, stream);
+    int rc = check_common(n_rows, n_cols, dim, dtype);
     if (rc) return rc;
-    rc = flyp_clip_fwd_local_ex(img, step->gathered.txt_all, scale, n_rows, n_cols, dim, dtype, off, row_lse, row_nll,
-                                col_stat, nullptr, workspace, workspace_bytes, &step->gathered.txt_ready, stream);
+    if (!img || !txt || !scale || !row_lse || !row_nll || !col_lse || !col_nll || !loss || !workspace)
+        return fail(FLYP_ERR_ARG, "null pointer argument");
+    ClipWs w;
+    carve_clip(workspace, n_rows, n_cols, dim, dtype, w);
+    if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StatsIO io;
+    memset(&io, 0, sizeof(io));
+    io.A = img; io.scale = scale; io.n_m = n_rows; io.n_n = n_cols; io.dim = dim; io.dtype = dtype;
+    io.pos_offset = off; io.row_lse = row_lse; io.row_nll = row_nll; io.status = status;
+    io.col_stat = col_stat ? col_stat : w.col_stat;
+    if (comm == nullptr) {
+        // single rank: no exchange; the finalize kernels finish the loss themselves
+        memset(step, 0, sizeof(*step));
+        step->gathered.img_all = img; step->gathered.txt_all = txt;
+        if (feat16 != nullptr && dtype == FLYP_BF16) {
+            io.a16 = feat16;
+            io.b16 = static_cast<uint16_t*>(feat16) + (size_t)n_rows * dim;
+            step->gathered.img16_all = io.a16; step->gathered.txt16_all = io.b16;
+        }
+        step->stats.col_stat_all = io.col_stat; step->stats.row_lse_all = row_lse; step->stats.row_nll_all = row_nll;
+        io.B = txt;
+        io.fin.col_lse = col_lse; io.fin.col_nll = col_nll; io.fin.loss = loss; io.fin.loss_bf16 = loss_dtype == FLYP_BF16;
+        return run_stats(io, w.stats, st);
+    }
+    flyp::PackExtra ex;
+    ex.scale = scale; ex.t2 = w.stats.t2; ex.pos = w.stats.pos; ex.n_pad = w.stats.ld_rows; ex.row_offset = off;
+    ex.zero_words = w.stats.flag; ex.n_zero = 4;
+    rc = flyp::comm_gather(comm, img, txt, n_rows, dim, dtype, &ex, &step->gathered, stream);
     if (rc) return rc;
-    rc = flyp_comm_push_stats(comm, step->gathered.seq, col_stat, row_lse, row_nll, n_rows, n_cols, &step->stats, stream);
+    io.B = step->gathered.txt_all; io.b_ready = &step->gathered.txt_ready; io.pre_done = true;
+    if ((rc = run_stats(io, w.stats, st)) != 0) return rc;
+    rc = flyp_comm_push_stats(comm, step->gathered.seq, io.col_stat, row_lse, row_nll, n_rows, n_cols, &step->stats, stream);
     if (rc) return rc;
     return flyp_clip_fwd_finish_ex(step->stats.col_stat_all, world, step->stats.row_nll_all, n_cols, n_cols, 0, col_lse,
                                    col_nll, loss, loss_dtype, &step->stats.ready, stream);
@@ -649,11 +775,27 @@ int flyp_clip_bwd_step(flyp_comm* comm, const flyp_step_t* step, const void* img
                        int n_rows, int dim, int dtype, int rank, int world, const float* col_lse, const float* col_nll,
                        const void* g, int g_dtype, float grad_mul, int grad_dtype, void* d_img, void* d_txt,
                        float* d_scale_partial, float* d_scale, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!comm || !step) return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (!step) return fail(FLYP_ERR_ARG, "null pointer argument");
     if (world < 1 || rank < 0 || rank >= world) return fail(FLYP_ERR_ARG, "bad rank %d / world %d", rank, world);
+    if (!comm && world != 1) return fail(FLYP_ERR_ARG, "world %d needs a communicator", world);
+    const flyp_gathered_t& gg = step->gathered;
+    if (comm == nullptr && dtype == FLYP_F32) {
+        // fp32 features (split-plane products): the two-operand entry point with g on both sides
+        if (g_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "fp32 features need an fp32 upstream gradient");
+        return flyp_clip_bwd_local_ex(img, txt, scale, n_rows, n_rows, dim, dtype, 0, step->stats.row_lse_all,
+                                      step->stats.row_nll_all, col_lse, col_nll, static_cast<const float*>(g),
+                                      static_cast<const float*>(g), grad_mul, grad_dtype, d_img, d_txt, d_scale, workspace,
+                                      workspace_bytes, nullptr, nullptr, nullptr, stream);
+    }
+    if (comm == nullptr) {
+        // single rank: the row block's share of d(scale) is the whole gradient
+        return bwd_sharded_impl(img, txt, gg.img_all, gg.txt_all, gg.img16_all, gg.txt16_all, scale, n_rows, n_rows, dim,
+                                dtype, 0, step->stats.row_lse_all, step->stats.row_nll_all, col_lse, col_nll, g, g_dtype,
+                                grad_mul, grad_dtype, d_img, d_txt, d_scale, workspace, workspace_bytes, nullptr, nullptr,
+                                nullptr, nullptr, stream, nullptr, 0, nullptr);
+    }
     if ((d_scale != nullptr) != (d_scale_partial != nullptr))
         return fail(FLYP_ERR_ARG, "d_scale and d_scale_partial go together");
-    const flyp_gathered_t& gg = step->gathered;
     return bwd_sharded_impl(img, txt, gg.img_all, gg.txt_all, gg.img16_all, gg.txt16_all, scale, n_rows, n_rows * world,
                             dim, dtype, rank * n_rows, step->stats.row_lse_all, step->stats.row_nll_all, col_lse, col_nll,
                             g, g_dtype, grad_mul, grad_dtype, d_img, d_txt, d_scale_partial, workspace, workspace_bytes,
@@ -668,7 +810,7 @@ struct CeWs {
     float* dscale_part;
     size_t n_dscale;
     float* part_scratch;
-    uint32_t* gmax_bits;
+    BwdCtrl ctrl;
     float* fast_info;
     uint16_t *a16, *b16;
     size_t bytes;
@@ -685,7 +827,7 @@ static void carve_ce(void* base, int n, int n_classes, int dim, int dtype, CeWs&
         const size_t nn = a > b ? a : b;
         w.part_scratch = nn ? c.take<float>(nn) : nullptr;
     }
-    w.gmax_bits = c.take<uint32_t>(4);
+    w.ctrl.words = c.take<uint32_t>(CTRL_WORDS);
     w.fast_info = c.take<float>(2);
     const size_t w16 = dtype == FLYP_F32 ? (size_t)2 * plane_cols(dim) : (size_t)dim;
     w.a16 = c.take<uint16_t>((size_t)n * w16);
@@ -706,69 +848,97 @@ int flyp_ce_workspace_bytes(int n, int n_classes, int dim, int dtype, size_t* by
 int flyp_ce_fwd(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
                 const int64_t* labels, int label_offset, float* loss, float* lse, void* workspace,
                 size_t workspace_bytes, void* stream) {
+    return flyp_ce_fwd_ex(a, b, scale, n, n_classes, dim, dtype, labels, label_offset, loss, lse, workspace,
+                          workspace_bytes, nullptr, stream);
+}
+
+int flyp_ce_fwd_ex(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
+                   const int64_t* labels, int label_offset, float* loss, float* lse, void* workspace,
+                   size_t workspace_bytes, const flyp_ready_t* b_ready, void* stream) {
     int rc = check_common(n, n_classes, dim, dtype);
     if (rc) return rc;
     if (!a || !b || !scale || !loss || !lse || !workspace) return fail(FLYP_ERR_ARG, "null pointer argument");
     CeWs w;
     carve_ce(workspace, n, n_classes, dim, dtype, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
-    return run_stats(a, b, scale, n, n_classes, dim, dtype, labels, label_offset, w.stats, lse, loss, nullptr,
-                     nullptr, nullptr, static_cast<cudaStream_t>(stream));
+    StatsIO io;
+    memset(&io, 0, sizeof(io));
+    io.A = a; io.B = b; io.scale = scale; io.n_m = n; io.n_n = n_classes; io.dim = dim; io.dtype = dtype;
+    io.labels = labels; io.pos_offset = label_offset; io.row_lse = lse; io.row_nll = loss; io.b_ready = b_ready;
+    return run_stats(io, w.stats, static_cast<cudaStream_t>(stream));
 }
 
 int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
                 const int64_t* labels, int label_offset, const float* lse, const float* loss, const float* g,
                 int grad_dtype, void* d_a, void* d_b, float* d_scale, void* workspace, size_t workspace_bytes,
                 void* stream) {
+    return flyp_ce_bwd_ex(a, b, scale, n, n_classes, dim, dtype, labels, label_offset, lse, loss, g, grad_dtype, d_a, d_b,
+                          d_scale, workspace, workspace_bytes, nullptr, nullptr, nullptr, stream);
+}
+
+int flyp_ce_bwd_ex(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
+                   const int64_t* labels, int label_offset, const float* lse, const float* loss, const float* g,
+                   int grad_dtype, void* d_a, void* d_b, float* d_scale, void* workspace, size_t workspace_bytes,
+                   const void* b16, const flyp_ready_t* b_ready, const flyp_ready_t* b16_ready, void* stream) {
     int rc = check_common(n, n_classes, dim, dtype);
     if (rc) return rc;
     if (!a || !b || !scale || !lse || !loss || !g || !workspace) return fail(FLYP_ERR_ARG, "null pointer argument");
     if (grad_dtype != FLYP_BF16 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad grad_dtype %d", grad_dtype);
+    const bool f32 = dtype == FLYP_F32;
+    if (f32 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "fp32 features need grad_dtype = FLYP_F32");
+    if (f32 && b16 != nullptr) return fail(FLYP_ERR_ARG, "a precomputed fp16 copy is only accepted for bf16 features");
+    if (d_scale && !d_a) return fail(FLYP_ERR_ARG, "d_scale requires d_a");
     CeWs w;
     carve_ce(workspace, n, n_classes, dim, dtype, w);
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int np = ceil_div(n, VEC_PAD) * VEC_PAD;
-    CUDA_OK(cudaMemsetAsync(w.gmax_bits, 0, 2 * sizeof(uint32_t), st));
-    CUDA_OK(cudaMemsetAsync(w.gmax_bits + 2, 0xff, sizeof(uint32_t), st));
+    CUDA_OK(cudaMemsetAsync(w.ctrl.words, 0, CTRL_WORDS * sizeof(uint32_t), st));
     // w = g, positive = label, dS there = g * expm1(-loss)
     flyp::launch_bwd_prep(n, np, g, 1.0f, lse, loss, labels, label_offset, n_classes, nullptr, nullptr, 1.0f, w.v.w,
-                          w.v.l2, w.v.lab, w.v.d, w.gmax_bits, st);
-    flyp::launch_bwd_fast_vectors(w.gmax_bits, np, w.v.w, w.v.l2, w.v.f, 0, nullptr, nullptr, nullptr, w.fast_info, st);
+                          w.v.l2, w.v.lab, w.v.d, w.ctrl.words, st);
+    flyp::launch_bwd_fast_vectors(w.ctrl.words, np, w.v.w, w.v.l2, w.v.f, 0, nullptr, nullptr, nullptr, w.fast_info, st);
     CUDA_OK(cudaGetLastError());
-    const bool f32 = dtype == FLYP_F32;
-    if (f32 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "fp32 features need grad_dtype = FLYP_F32");
     const int dp = plane_cols(dim);
     if (f32) {
         flyp::launch_split_planes_bf16x3(static_cast<const float*>(a), n, dim, dp, w.stats.planes_a, st);
         flyp::launch_split_planes_bf16x3(static_cast<const float*>(b), n_classes, dim, dp, w.stats.planes_b, st);
         CUDA_OK(cudaGetLastError());
     }
+    SweepIO base;
+    memset(&base, 0, sizeof(base));
+    base.scale = scale; base.dtype = dtype; base.dim = dim; base.fast_info = w.fast_info;
+    base.out_fp32 = grad_dtype; base.out_mul = 1.0f;
+    base.part_scratch = w.part_scratch; base.ctrl = &w.ctrl; base.n_dscale = w.n_dscale;
     if (d_a) {
-        if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(b), n_classes, dim, dp, w.b16, st);
-        else flyp::launch_to_f16(b, dtype, (size_t)n_classes * dim, w.b16, st);
-        CUDA_OK(cudaGetLastError());
-        rc = run_sweep(a, b, w.b16, dtype, w.stats.planes_a, w.stats.planes_b, scale, n, n_classes, dim, w.v.w, w.v.l2,
-                       nullptr, nullptr, w.v.lab, w.v.d, nullptr, nullptr, w.v.f, nullptr, w.fast_info,
-                       d_scale ? a : nullptr, d_a, grad_dtype, 1.0f, d_scale ? w.dscale_part : nullptr, w.part_scratch,
-                       w.gmax_bits, st);
-        if (rc) return rc;
-        if (d_scale) {
-            flyp::launch_sum_parts(w.dscale_part, (int)w.n_dscale, d_scale, st);
+        const void* bb16 = b16;
+        if (bb16 == nullptr) {
+            if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(b), n_classes, dim, dp, w.b16, st);
+            else flyp::launch_to_f16(b, dtype, (size_t)n_classes * dim, w.b16, st);
             CUDA_OK(cudaGetLastError());
+            bb16 = w.b16;
         }
-    } else if (d_scale) {
-        return fail(FLYP_ERR_ARG, "d_scale requires d_a");
+        SweepIO io = base;
+        io.A = a; io.B = b; io.B_f16 = bb16; io.A_planes = w.stats.planes_a; io.B_planes = w.stats.planes_b;
+        io.n_m = n; io.n_n = n_classes;
+        io.wr = w.v.w; io.lr = w.v.l2; io.labr = w.v.lab; io.dr = w.v.d; io.fa = w.v.f;
+        io.out = d_a; io.sweep = 0;
+        if (d_scale) { io.dscale_part = w.dscale_part; io.dscale_out = d_scale; }
+        io.b_ready = b_ready; io.b16_ready = b16 ? b16_ready : nullptr;
+        if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     if (d_b) {
         // rows = classes, columns = samples: only the column (sample) softmax term exists
         if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(a), n, dim, dp, w.a16, st);
         else flyp::launch_to_f16(a, dtype, (size_t)n * dim, w.a16, st);
         CUDA_OK(cudaGetLastError());
-        rc = run_sweep(b, a, w.a16, dtype, w.stats.planes_b, w.stats.planes_a, scale, n_classes, n, dim, nullptr,
-                       nullptr, w.v.w, w.v.l2, nullptr, nullptr, w.v.lab, w.v.d, nullptr, w.v.f, w.fast_info, nullptr,
-                       d_b, grad_dtype, 1.0f, nullptr, w.part_scratch, w.gmax_bits, st);
-        if (rc) return rc;
+        SweepIO io = base;
+        io.A = b; io.B = a; io.B_f16 = w.a16; io.A_planes = w.stats.planes_b; io.B_planes = w.stats.planes_a;
+        io.n_m = n_classes; io.n_n = n;
+        io.wc = w.v.w; io.lc = w.v.l2; io.labc = w.v.lab; io.dc = w.v.d; io.fb = w.v.f;
+        io.out = d_b; io.sweep = 1;
+        // (rows of b that other ranks wrote were all consumed - and waited for - by the forward of the same step)
+        if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     return 0;
 }
@@ -798,6 +968,15 @@ int flyp_debug_profile(void* device_buffer_16_u64) {
     return 0;
 }
 
+int flyp_debug_kernel_events(void* fwd_start, void* fwd_stop, void* sweep_start, void* sweep_stop, int sweep) {
+    if ((fwd_start == nullptr) != (fwd_stop == nullptr) || (sweep_start == nullptr) != (sweep_stop == nullptr))
+        return fail(FLYP_ERR_ARG, "events come in pairs");
+    g_ev_fwd[0] = static_cast<cudaEvent_t>(fwd_start); g_ev_fwd[1] = static_cast<cudaEvent_t>(fwd_stop);
+    g_ev_sweep[0] = static_cast<cudaEvent_t>(sweep_start); g_ev_sweep[1] = static_cast<cudaEvent_t>(sweep_stop);
+    g_ev_sweep_idx = sweep;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ fused argmax
 int flyp_argmax(const void* a, const void* b, int n_m, int n_n, int dim, int dtype, int64_t* out_index, float* out_max,
                 void* workspace, size_t workspace_bytes, void* stream) {
@@ -809,8 +988,8 @@ int flyp_argmax(const void* a, const void* b, int n_m, int n_n, int dim, int dty
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* one = w.dscale_part;                       // the kernel multiplies by scale * log2(e) > 0: order-preserving
-    static const float h_one = 1.0f;
-    CUDA_OK(cudaMemcpyAsync(one, &h_one, sizeof(float), cudaMemcpyHostToDevice, st));
+    flyp::launch_fill_float(one, 1.0f, st);           // (a kernel, not a staged pageable H2D copy: graph-capturable)
+    CUDA_OK(cudaGetLastError());
     CUtensorMap tmA, tmB;
     flyp::KPlan kplan = flyp::kplan_bf16();
     if (dtype == FLYP_F32) {
@@ -829,7 +1008,7 @@ int flyp_argmax(const void* a, const void* b, int n_m, int n_n, int dim, int dty
     memset(&p, 0, sizeof(p));
     const StatsWs& s = w.stats;
     p.n_m = n_m; p.n_n = n_n; p.kc = ceil_div(dim, flyp::KCHUNK); p.kplan = kplan;
-    p.m_tiles = s.m_tiles; p.n_tiles = s.n_tiles; p.m_split = s.m_split; p.ld_rows = s.ld_rows; p.ld_cols = s.ld_cols;
+    p.m_tiles = s.m_tiles; p.n_tiles = s.n_tiles; p.n_slots = s.n_slots; p.ld_rows = s.ld_rows; p.ld_cols = s.ld_cols;
     p.scale = one; p.shift_slack = shift_slack(n_m, n_n);
     p.rowpart = s.rowpart; p.rowmax = s.rowmax; p.colpart = nullptr; p.colmax = nullptr; p.pos = nullptr;
     p.argidx = reinterpret_cast<int*>(s.rowpart);     // the sums are not needed: their buffer carries the columns
@@ -852,10 +1031,13 @@ int flyp_debug_logits(const void* a, const void* b, int n_m, int n_n, int dim, i
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     // scale is irrelevant for raw dot products but the kernel reads it: park a 1.0f in the (unused) d(scale) scratch
     float* one = w.dscale_part;
-    static const float h_one = 1.0f;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUDA_OK(cudaMemcpyAsync(one, &h_one, sizeof(float), cudaMemcpyHostToDevice, st));
-    return run_stats(a, b, one, n_m, n_n, dim, dtype, nullptr, 0, w.stats, nullptr, nullptr, nullptr, nullptr, out, st);
+    flyp::launch_fill_float(one, 1.0f, st);
+    CUDA_OK(cudaGetLastError());
+    StatsIO io;
+    memset(&io, 0, sizeof(io));
+    io.A = a; io.B = b; io.scale = one; io.n_m = n_m; io.n_n = n_n; io.dim = dim; io.dtype = dtype; io.dbg_logits = out;
+    return run_stats(io, w.stats, st);
 }
 
 }  // extern "C"

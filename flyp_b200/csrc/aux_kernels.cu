@@ -1,6 +1,7 @@
 // aux_kernels.cu — the HBM-bound helper kernels of the ClipLoss path (see aux_kernels.cuh).
 #include "aux_kernels.cuh"
 #include "clip_kernels.cuh"
+#include "sched.h"
 #include <cstring>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -51,21 +52,74 @@ __device__ __forceinline__ void store8(void* base, size_t elem, const float (&v)
 }
 
 // ------------------------------------------------------------------------------------------------ pair logits
-// t2[i] = scale * log2(e) * <A[i,:], B[idx(i),:]> (-inf when row i has no valid positive), pos[i] = idx(i) or -1.
-// Rows [n, n_pad) are padding: pos = -1, t2 = -inf.
+__device__ __forceinline__ uint4 bf16x8_to_f16x8(uint4 v) {
+    uint4 u;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float lo = __uint_as_float(s[e] << 16), hi = __uint_as_float(s[e] & 0xffff0000u);
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        d[e] = r;
+    }
+    return u;
+}
+
+// The forward's preparation pass, one warp per row index r:
+//   r < n_pad: t2[r] = scale * log2(e) * <A[r,:], B[idx(r),:]> (-inf when row r has no valid positive), pos[r] = idx(r)
+//              or -1; rows [n, n_pad) are padding (pos = -1, t2 = -inf);
+//   bf16 features, a16 / b16 given: the fp16 copies of A (rows < n) and B (rows < n_b) that the backward's second GEMM
+//              multiplies (tcgen05 kind::f16 needs both operands in one 16-bit format) - written here so that the
+//              features cross HBM once for both purposes;
+//   zero_words (n_zero ints): control words of the step (fast-path flag) cleared by the first thread.
 template <bool F32>
 __global__ void k_pair_dot(const void* __restrict__ A, const void* __restrict__ B, const float* __restrict__ scale,
                            int n, int n_pad, int n_b, int dim, const int64_t* __restrict__ labels, int offset,
-                           float* __restrict__ t2, int* __restrict__ pos, const int* __restrict__ gate) {
+                           float* __restrict__ t2, int* __restrict__ pos, const int* __restrict__ gate,
+                           int* __restrict__ zero_words, int n_zero, uint4* __restrict__ a16, uint4* __restrict__ b16) {
     if (gate != nullptr && *gate == 0) return;      // helper of the robust path: nothing to do
+    if (zero_words != nullptr && blockIdx.x == 0 && (int)threadIdx.x < n_zero) zero_words[threadIdx.x] = 0;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    if (!F32 && b16 != nullptr && row < n_b) {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(B) + (size_t)row * dim);
+        uint4* dst = b16 + (size_t)row * (dim / 8);
+        for (int c = lane; c < dim / 8; c += 32) dst[c] = bf16x8_to_f16x8(__ldg(src + c));
+    }
     if (row >= n_pad) return;
     long long idx = -1;
-    if (row < n) idx = labels ? labels[row] : (long long)offset + row;
+    bool ignored = false;
+    if (row < n) {
+        idx = labels ? labels[row] : (long long)offset + row;
+        if (labels != nullptr) {
+            // F.cross_entropy semantics (src/models/ce_ablation.py:123): ignore_index = -100 gives loss 0 / gradient 0,
+            // any other target outside [0, n_classes) is a device-side assertion failure
+            if (idx == -100) ignored = true;
+            else if (idx < 0 || idx >= n_b) __trap();
+        }
+    }
     const bool ok = idx >= 0 && idx < n_b;
     float acc = 0.f;
-    if (ok) {
+    if (!F32 && a16 != nullptr && row < n) {
+        // bf16 rows: one pass serves the conversion and the dot product
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(A) + (size_t)row * dim);
+        uint4* dst = a16 + (size_t)row * (dim / 8);
+        for (int c = lane; c < dim / 8; c += 32) {
+            const uint4 v = __ldg(src + c);
+            dst[c] = bf16x8_to_f16x8(v);
+            if (ok) {
+                float b[8];
+                load8<F32>(B, (size_t)idx * dim + c * 8, b);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    acc = fmaf(__uint_as_float(w[e] << 16), b[2 * e], acc);
+                    acc = fmaf(__uint_as_float(w[e] & 0xffff0000u), b[2 * e + 1], acc);
+                }
+            }
+        }
+    } else if (ok) {
         for (int d = lane * 8; d < dim; d += 256) {
             float a[8], b[8];
             load8<F32>(A, (size_t)row * dim + d, a);
@@ -77,19 +131,24 @@ __global__ void k_pair_dot(const void* __restrict__ A, const void* __restrict__ 
     acc = warp_sum(acc);
     if (lane == 0) {
         t2[row] = ok ? acc * scale[0] * LOG2E_F : -INFINITY;
-        pos[row] = ok ? (int)idx : -1;
+        pos[row] = ok ? (int)idx : (ignored ? -2 : -1);
     }
 }
 
 void launch_pair_dot(const void* A, const void* B, int dtype, const float* scale, int n, int n_pad, int n_b, int dim,
-                     const int64_t* labels, int offset, float* t2, int* pos, const int* gate, cudaStream_t st) {
-    if (n_pad <= 0) return;
+                     const int64_t* labels, int offset, float* t2, int* pos, const int* gate, int* zero_words,
+                     int n_zero, void* a16, void* b16, cudaStream_t st) {
+    int rows = n_pad;
+    if (dtype != 1 && b16 != nullptr && n_b > rows) rows = n_b;
+    if (rows <= 0) return;
     const int wpb = 8;
-    dim3 grid((n_pad + wpb - 1) / wpb), block(wpb * 32);
+    dim3 grid((rows + wpb - 1) / wpb), block(wpb * 32);
     if (dtype == 1)
-        k_pair_dot<true><<<grid, block, 0, st>>>(A, B, scale, n, n_pad, n_b, dim, labels, offset, t2, pos, gate);
+        k_pair_dot<true><<<grid, block, 0, st>>>(A, B, scale, n, n_pad, n_b, dim, labels, offset, t2, pos, gate, zero_words,
+                                                n_zero, nullptr, nullptr);
     else
-        k_pair_dot<false><<<grid, block, 0, st>>>(A, B, scale, n, n_pad, n_b, dim, labels, offset, t2, pos, gate);
+        k_pair_dot<false><<<grid, block, 0, st>>>(A, B, scale, n, n_pad, n_b, dim, labels, offset, t2, pos, gate,
+                                                 zero_words, n_zero, static_cast<uint4*>(a16), static_cast<uint4*>(b16));
 }
 
 // log2-domain logaddexp of a (off-positive mass) and t (positive logit): returns lse2 and nll = ln2 * (lse2 - t)
@@ -112,11 +171,24 @@ __device__ __forceinline__ void lse_with_positive(float a, float t, float& lse2,
 //                              t_j log2 positive logit of column j if its row is local else -inf)
 // Block = 8 warps x 32 lanes: lane = row / column within a group of 32, the warps split the partials 8 ways
 // (coalesced 128-byte reads, 8x more loads in flight than one thread per row), then one smem reduction.
+// fin (single-rank symmetric loss, n_m == n_n, positives on the diagonal): the column triples need no merge across
+// ranks, so col_lse / col_nll and loss[i] = (row_nll[i] + col_nll[i]) / 2 (clip/loss.py:208-209) are finished here.
+__device__ __forceinline__ void finish_item(const FwdFinish& fin, int i, float col_a, float col_t, float row_nll_i) {
+    float lse2, nll;
+    lse_with_positive(col_a, col_t, lse2, nll);
+    fin.col_lse[i] = lse2 * LN2_F;
+    fin.col_nll[i] = nll;
+    const float v = 0.5f * (row_nll_i + nll);
+    if (fin.loss_bf16) reinterpret_cast<__nv_bfloat16*>(fin.loss)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(fin.loss)[i] = v;
+}
+
 __global__ void k_fwd_finalize(const float* __restrict__ rowpart, int n_rowparts, int ld_rows, int n_m,
-                               const float* __restrict__ colpart, int n_colparts, int ld_cols, int n_n,
+                               const float* __restrict__ colpart, FwdColSched cs, int ld_cols, int n_n,
                                const float* __restrict__ scale, float slack, const float* __restrict__ t2,
                                const int* __restrict__ pos, int col_pos_offset, float* __restrict__ row_lse,
-                               float* __restrict__ row_nll, float* __restrict__ col_stat, int* __restrict__ flag) {
+                               float* __restrict__ row_nll, float* __restrict__ col_stat, int* __restrict__ flag,
+                               FwdFinish fin) {
     __shared__ float sm_r[8][32], sm_c[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lane;
@@ -128,22 +200,30 @@ __global__ void k_fwd_finalize(const float* __restrict__ rowpart, int n_rowparts
     float pr = 0.f, pc = 0.f;
     if (i < n_m)
         for (int p = w; p < n_rowparts; p += 8) pr += rowpart[(size_t)p * ld_rows + i];
-    if (i < n_n && col_stat != nullptr)
+    if (i < n_n && col_stat != nullptr) {
+        // the slots the flat schedule wrote for this column's block (sched.h)
+        const int nb = i >> 7, u = cs.mc ? nb >> 1 : nb;
+        int ub = u - cs.rot;
+        if (ub < 0) ub += cs.n_units;
+        const int n_colparts = fwd_unit_slots(ub, cs.m_tiles, cs.n_units, cs.n_local, cs.workers);
         for (int p = w; p < n_colparts; p += 8) pc += colpart[(size_t)p * ld_cols + i];
+    }
     sm_r[w][lane] = pr; sm_c[w][lane] = pc;
     __syncthreads();
     if (w != 0) return;
     bool bad = false;
+    float nll_row = 0.f;
     if (i < n_m) {
         float sum = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) sum += sm_r[k][lane];
         const float t = t2 ? t2[i] : -INFINITY;
         const float a = sum > 0.f ? log2f(sum) + c0 : -INFINITY;
-        float lse2, nll;
-        lse_with_positive(a, t, lse2, nll);
+        float lse2;
+        lse_with_positive(a, t, lse2, nll_row);
+        if (pos != nullptr && pos[i] == -2) nll_row = 0.f;       // ignored target (F.cross_entropy ignore_index)
         row_lse[i] = lse2 * LN2_F;
-        if (row_nll) row_nll[i] = nll;
+        if (row_nll) row_nll[i] = nll_row;
         const bool ok = !isinf(sum) && (sum >= exp2f(lg_r - 101.f) || t >= c0 - 101.f + lg_r);
         bad |= !ok;
     }
@@ -158,18 +238,18 @@ __global__ void k_fwd_finalize(const float* __restrict__ rowpart, int n_rowparts
         col_stat[2 * n_n + i] = t;
         const bool ok = !isinf(sum) && (sum >= exp2f(lg_c - 101.f) || t >= c0 - 101.f + lg_c);
         bad |= !ok;
+        if (fin.col_lse != nullptr && i < n_m) finish_item(fin, i, sum > 0.f ? log2f(sum) + c0 : -INFINITY, t, nll_row);
     }
     if (bad) atomicOr(flag, 1);
 }
 
 void launch_fwd_finalize(const float* rowpart, int n_rowparts, int ld_rows, int n_m, const float* colpart,
-                         int n_colparts, int ld_cols, int n_n, const float* scale, float slack, const float* t2,
+                         const FwdColSched& cs, int ld_cols, int n_n, const float* scale, float slack, const float* t2,
                          const int* pos, int col_pos_offset, float* row_lse, float* row_nll, float* col_stat,
-                         int* flag, cudaStream_t st) {
+                         int* flag, const FwdFinish& fin, cudaStream_t st) {
     const int n = n_m > n_n ? n_m : n_n;
-    k_fwd_finalize<<<(n + 31) / 32, 256, 0, st>>>(rowpart, n_rowparts, ld_rows, n_m, colpart, n_colparts, ld_cols,
-                                                    n_n, scale, slack, t2, pos, col_pos_offset, row_lse, row_nll,
-                                                    col_stat, flag);
+    k_fwd_finalize<<<(n + 31) / 32, 256, 0, st>>>(rowpart, n_rowparts, ld_rows, n_m, colpart, cs, ld_cols, n_n, scale,
+                                                    slack, t2, pos, col_pos_offset, row_lse, row_nll, col_stat, flag, fin);
 }
 
 // ------------------------------------------------------------------------------------------------ finalize (robust)
@@ -191,36 +271,42 @@ __device__ __forceinline__ void merge_pairs(const float* __restrict__ part, cons
 __global__ void k_fwd_finalize_robust(const float* __restrict__ rowpart, const float* __restrict__ rowmax,
                                       int n_rowparts, int ld_rows, int n_m, const float* __restrict__ colpart,
                                       const float* __restrict__ colmax, int n_colparts, int ld_cols, int n_n,
-                                      const float* __restrict__ t2, float* __restrict__ row_lse,
-                                      float* __restrict__ row_nll, float* __restrict__ col_stat,
-                                      const int* __restrict__ flag) {
-    if (*flag == 0) return;
+                                      const float* __restrict__ t2, const int* __restrict__ pos,
+                                      float* __restrict__ row_lse, float* __restrict__ row_nll,
+                                      float* __restrict__ col_stat, const int* __restrict__ flag,
+                                      int* __restrict__ status, FwdFinish fin) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && status != nullptr) status[0] = *flag;
+    if (*flag == 0) return;
+    float nll_row = 0.f;
     if (i < n_m) {
         float m, s;
         merge_pairs(rowpart, rowmax, n_rowparts, ld_rows, i, m, s);
         const float a = s > 0.f ? log2f(s) + m : -INFINITY;
-        float lse2, nll;
-        lse_with_positive(a, t2 ? t2[i] : -INFINITY, lse2, nll);
+        float lse2;
+        lse_with_positive(a, t2 ? t2[i] : -INFINITY, lse2, nll_row);
+        if (pos != nullptr && pos[i] == -2) nll_row = 0.f;
         row_lse[i] = lse2 * LN2_F;
-        if (row_nll) row_nll[i] = nll;
+        if (row_nll) row_nll[i] = nll_row;
     }
     if (i < n_n && col_stat != nullptr) {
         float m, s;
         merge_pairs(colpart, colmax, n_colparts, ld_cols, i, m, s);
         col_stat[i] = m;          // the positive-logit row (col_stat[2 n_n + i]) was already written by the fast finalize
         col_stat[n_n + i] = s;
+        if (fin.col_lse != nullptr && i < n_m)
+            finish_item(fin, i, s > 0.f ? log2f(s) + m : -INFINITY, col_stat[2 * n_n + i], nll_row);
     }
 }
 
 void launch_fwd_finalize_robust(const float* rowpart, const float* rowmax, int n_rowparts, int ld_rows, int n_m,
                                 const float* colpart, const float* colmax, int n_colparts, int ld_cols, int n_n,
-                                const float* t2, float* row_lse, float* row_nll, float* col_stat, const int* flag,
-                                cudaStream_t st) {
+                                const float* t2, const int* pos, float* row_lse, float* row_nll, float* col_stat,
+                                const int* flag, int* status, const FwdFinish& fin, cudaStream_t st) {
     const int n = n_m > n_n ? n_m : n_n;
     k_fwd_finalize_robust<<<(n + 255) / 256, 256, 0, st>>>(rowpart, rowmax, n_rowparts, ld_rows, n_m, colpart, colmax,
-                                                           n_colparts, ld_cols, n_n, t2, row_lse, row_nll, col_stat,
-                                                           flag);
+                                                           n_colparts, ld_cols, n_n, t2, pos, row_lse, row_nll,
+                                                           col_stat, flag, status, fin);
 }
 
 // ------------------------------------------------------------------------------------------------ argmax finalize
@@ -296,7 +382,8 @@ __global__ void k_bwd_prep(int n, int n_pad, const float* __restrict__ g, float 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float wi = 0.f, li = 0.f, di = 0.f;
     int lb = -1;
-    // words: [0] bits of max|g|, [1] / [2] order-preserving keys of max / min of lse (log2 units) over live entries
+    // words (all zero before the first prep kernel of a backward): [0] bits of max|g|, [1] order-preserving key of the
+    // max of lse (log2 units) over live entries, [2] COMPLEMENT of the key of their min (so that zero is neutral)
     uint32_t gb = 0u, khi = 0u, klo = 0xffffffffu;
     if (i < n) {
         gb = __float_as_uint(fabsf(g[i]));
@@ -311,7 +398,7 @@ __global__ void k_bwd_prep(int n, int n_pad, const float* __restrict__ g, float 
     if ((threadIdx.x & 31) == 0 && gmax_bits) {
         if (gb != 0u) atomicMax(gmax_bits, gb);
         if (khi != 0u) atomicMax(gmax_bits + 1, khi);
-        if (klo != 0xffffffffu) atomicMin(gmax_bits + 2, klo);
+        if (klo != 0xffffffffu) atomicMax(gmax_bits + 2, ~klo);
     }
     if (i >= n_pad) return;
     if (i < n) {
@@ -319,6 +406,7 @@ __global__ void k_bwd_prep(int n, int n_pad, const float* __restrict__ g, float 
         wi = wmul * gi;
         li = lse[i] * LOG2E_F;
         long long t = labels ? labels[i] : (long long)i + lab_offset;
+        if (labels != nullptr && t == -100) wi = 0.f;            // ignored target: no gradient from this row
         if (t >= 0 && t < lab_range) {
             lb = (int)t;
             // softmax - 1 at the positive = expm1(-nll), free of cancellation
@@ -374,7 +462,7 @@ __global__ void k_bwd_prep_sharded(int n, int n_pad, int off, int n_loc, const v
     if ((threadIdx.x & 31) == 0) {
         if (gb != 0u) atomicMax(words, gb);
         if (khi != 0u) atomicMax(words + 1, khi);
-        if (klo != 0xffffffffu) atomicMin(words + 2, klo);
+        if (klo != 0xffffffffu) atomicMax(words + 2, ~klo);
     }
     if (i < n_pad) { w[i] = wi; l2c[i] = lc; l2r[i] = lr; }
 }
@@ -395,7 +483,7 @@ __global__ void k_bwd_fast_vectors(const uint32_t* __restrict__ words, int n_a, 
                                    const float* __restrict__ w_b, const float* __restrict__ l_b,
                                    float* __restrict__ f_b, float* __restrict__ info) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t khi = words[1], klo = words[2];
+    const uint32_t khi = words[1], klo = ~words[2];
     float c0 = 0.f, valid = 1.f;
     if (khi != 0u && klo != 0xffffffffu) {
         const float hi = key_to_float(khi), lo = key_to_float(klo);
@@ -412,7 +500,7 @@ void launch_bwd_fast_vectors(const uint32_t* words, int n_a, const float* w_a, c
     k_bwd_fast_vectors<<<(n + 255) / 256, 256, 0, st>>>(words, n_a, w_a, l_a, f_a, n_b, w_b, l_b, f_b, info);
 }
 
-__global__ void k_sum_parts(const float* __restrict__ parts, int n, float* __restrict__ out) {
+__global__ void k_sum_parts(const float* __restrict__ parts, int n, float* __restrict__ out, PeerPush push) {
     __shared__ float sm[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) acc += parts[i];
@@ -422,54 +510,20 @@ __global__ void k_sum_parts(const float* __restrict__ parts, int n, float* __res
     if (threadIdx.x < 32) {
         float v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
         v = warp_sum(v);
-        if (threadIdx.x == 0) out[0] = v;
+        if (threadIdx.x == 0) {
+            out[0] = v;
+            peer_push_value(push, v);
+        }
     }
 }
-void launch_sum_parts(const float* parts, int n, float* out, cudaStream_t st) {
-    k_sum_parts<<<1, 256, 0, st>>>(parts, n, out);
+void launch_sum_parts(const float* parts, int n, float* out, const PeerPush* push, cudaStream_t st) {
+    PeerPush p;
+    if (push != nullptr) p = *push; else memset(&p, 0, sizeof(p));
+    k_sum_parts<<<1, 256, 0, st>>>(parts, n, out, p);
 }
 
-// ------------------------------------------------------------------------------------------------ flat-schedule partials
-// Sums, for every row block that the flat schedule of the pair backward sweep cut into several ranges, the fp32 partial
-// accumulators of those ranges (in pair order: deterministic) into `out`.  Blocks swept by one item were written directly.
-template <bool F32OUT>
-__global__ void k_reduce_parts(const float* __restrict__ part, int v_tiles, int NJ, int pairs, int n_dh, int d_half,
-                               int n_m, int d_out, void* __restrict__ out, int ld_out) {
-    // only the flat tail (virtual row blocks beyond the whole-block rounds) can be split
-    const int first = (v_tiles / pairs) * pairs;
-    const int tb = blockIdx.y, vb = first + tb;
-    const int mb = vb / n_dh, dh = vb - mb * n_dh;
-    TailParts parts;
-    if (!parts.init(v_tiles, NJ, pairs, tb)) return;                                    // swept whole
-    const int d4 = d_half / 4;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 128 * d4) return;
-    const int r = i / d4, dl = (i - r * d4) * 4, d = dh * d_half + dl;
-    const int m = mb * 128 + r;
-    if (m >= n_m || d >= d_out) return;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int slot = parts.next(); slot >= 0; slot = parts.next()) {
-        const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)slot * 128 + r) * d_half + dl);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    if (F32OUT) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)m * ld_out + d) = acc;
-    } else {
-        __nv_bfloat162 lo2 = __floats2bfloat162_rn(acc.x, acc.y), hi2 = __floats2bfloat162_rn(acc.z, acc.w);
-        uint2 u;
-        u.x = *reinterpret_cast<uint32_t*>(&lo2); u.y = *reinterpret_cast<uint32_t*>(&hi2);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)m * ld_out + d) = u;
-    }
-}
-void launch_reduce_parts(const float* part, int v_tiles, int NJ, int pairs, int n_dh, int d_half, int n_m, int d_out,
-                         void* out, int ld_out, int out_fp32, cudaStream_t st) {
-    if (v_tiles <= 0 || pairs <= 0) return;
-    const int tail = v_tiles - (v_tiles / pairs) * pairs;
-    if (tail == 0) return;
-    const dim3 grid((unsigned)((128 * (d_half / 4) + 255) / 256), (unsigned)tail);
-    if (out_fp32) k_reduce_parts<true><<<grid, 256, 0, st>>>(part, v_tiles, NJ, pairs, n_dh, d_half, n_m, d_out, out, ld_out);
-    else k_reduce_parts<false><<<grid, 256, 0, st>>>(part, v_tiles, NJ, pairs, n_dh, d_half, n_m, d_out, out, ld_out);
-}
+__global__ void k_fill_float(float* p, float v) { p[0] = v; }
+void launch_fill_float(float* p, float v, cudaStream_t st) { k_fill_float<<<1, 1, 0, st>>>(p, v); }
 
 // ------------------------------------------------------------------------------------------------ fp16 staging copy
 // The dA MMA multiplies the fp16-staged dS tile with the features, and tcgen05 kind::f16 needs both operands in the

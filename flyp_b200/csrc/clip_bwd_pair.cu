@@ -27,6 +27,7 @@
 #include "bwd_common.cuh"
 #include "sched.h"
 #include <cstdlib>
+#include <cstring>
 
 namespace flyp {
 using namespace sm100;
@@ -41,8 +42,9 @@ struct PairCfg {
     static constexpr int NSLOT = 8;
     static constexpr int IST_BYTES = 65536;            // 8 chunks [64 rows][64] bf16
     static constexpr int DS_BYTES = 32768;             // 4 chunks [64 rows][64] fp16
-    static constexpr int RED_BYTES = 64;
+    static constexpr int RED_BYTES = 512;              // 8 d(scale) partials, a flag, the slot list of a split block
     static constexpr int SMEM_BYTES = IST_BYTES + NSLOT * SLOT + DS_BYTES + RED_BYTES + 256 + 1024;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
     static constexpr int NSTEP = 256;                  // N columns per step
 };
 
@@ -70,12 +72,97 @@ int bwd_pair_sched_pairs(int m_tiles, int n_cols, int num_sms) {
 
 size_t bwd_pair_smem_bytes() { return PairCfg::SMEM_BYTES; }
 
+// ---- end-of-sweep reductions, by the whole grid ----------------------------------------------------------------------
+// The flat tail of the schedule leaves fp32 partial accumulators of the split row blocks in part_out, and every CTA a
+// partial of d(scale).  Rather than a second kernel (launch gap) or the last arriver of each block (one CTA per block,
+// latency-bound: measured +35 us per sweep at 32 blocks), ALL CTAs meet at a grid barrier - the launch is cooperative, so
+// every CTA of the grid is resident - and then share the work: one [128 rows x 128 columns] output chunk of a split
+// block at a time, its partial slots summed in pair order (deterministic), 8 independent 16-byte loads in flight per
+// thread.  Called by the 256 epilogue threads of every CTA; out of line so that it costs the main loop no registers.
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __noinline__ void sweep_tail_reduce(const BwdParams& p, const int et, const int NJ, int* red_i) {
+    // ---- grid barrier (counter zeroed by the host before the launch)
+    __threadfence();
+    epi_bar_sync2();
+    if (et == 0) {
+        atomicAdd(p.grid_cnt, 1);
+        while (ld_acquire_gpu_s32(p.grid_cnt) < (int)gridDim.x) __nanosleep(40);
+    }
+    epi_bar_sync2();
+    __threadfence();
+    const int v_tiles = p.m_tiles * p.n_dh, P = p.sched_pairs;
+    const int first = (v_tiles / P) * P, n_tail = v_tiles - first;
+    const int cpb = p.d_half / 128;                         // 128-column chunks per (virtual) row block
+    for (int c = blockIdx.x; c < n_tail * cpb; c += gridDim.x) {
+        const int tb = c / cpb, dl0 = (c - tb * cpb) * 128;
+        if (et == 0) {
+            TailParts parts;
+            int np = 0;
+            if (parts.init(v_tiles, NJ, P, tb))
+                for (int sl = parts.next(); sl >= 0; sl = parts.next()) red_i[18 + np++] = sl;
+            red_i[17] = np;                                  // 0: the block was swept whole and written directly
+        }
+        epi_bar_sync2();
+        const int np = red_i[17];
+        const int vb = first + tb, mb = vb / p.n_dh, dh = vb - mb * p.n_dh;
+        if (np > 0 && dh * p.d_half + dl0 < p.d_out) {
+#pragma unroll 1
+            for (int f0 = et; f0 < TILE * 32; f0 += 256 * 8) {
+                float4 acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < np; ++k) {
+                    const float* base = p.part_out + (size_t)red_i[18 + k] * TILE * p.d_half + dl0;
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int f = f0 + j * 256, ri = f >> 5;
+                        v[j] = (mb * TILE + ri < p.n_m)
+                                   ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)ri * p.d_half + (f & 31) * 4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { acc[j].x += v[j].x; acc[j].y += v[j].y; acc[j].z += v[j].z; acc[j].w += v[j].w; }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int f = f0 + j * 256, ri = f >> 5, mi = mb * TILE + ri;
+                    const int d = dh * p.d_half + dl0 + (f & 31) * 4;
+                    if (mi >= p.n_m) continue;
+                    if (p.out_fp32) {
+                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)mi * p.ld_out + d) = acc[j];
+                    } else {
+                        uint2 u;
+                        u.x = pack_bf16x2(acc[j].x, acc[j].y); u.y = pack_bf16x2(acc[j].z, acc[j].w);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)mi * p.ld_out + d) = u;
+                    }
+                }
+            }
+        }
+        epi_bar_sync2();          // red_i is rewritten for the next chunk
+    }
+    // ---- d(scale): CTA 0 sums the partials of the whole grid in a fixed order and publishes the total
+    if (p.dscale_out != nullptr && blockIdx.x == 0 && et < 32) {
+        float acc = 0.f;
+        for (int i = et; i < (int)gridDim.x; i += 32) acc += __ldcg(p.dscale_part + i);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (et == 0) p.dscale_out[0] = acc;
+        peer_push_value_warp(p.ds_push, acc, et);
+    }
+}
+
 // WIDE: feature dim > 512 (streamed A chunks, two passes over the output columns); the narrow instantiation compiles
 // that logic away.
 template <bool ROW_TERM, bool COL_TERM, bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS2, 1)
 bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmBd, const BwdParams p) {
+                const __grid_constant__ CUtensorMap tmBd, const __grid_constant__ BwdParams p) {
     using Cfg = PairCfg;
     constexpr int NSLOT = Cfg::NSLOT;
     extern __shared__ uint8_t smem_raw[];
@@ -294,7 +381,12 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
         uint32_t gs = 0, it = 0;
         const bool prof = p.prof != nullptr && pair == 0 && cta == 0 && threadIdx.x == 128;
         long long w_sfull = 0, w_dsempty = 0, w_accfull = 0;
-        const long long t_begin = clock64();
+        const long long t_begin = prof ? clock64() : 0;
+        auto ewait = [&](uint32_t bar, uint32_t parity, long long& acc) {
+            if (prof) { const long long t0 = clock64(); mbar_wait(bar, parity); acc += clock64() - t0; }
+            else mbar_wait(bar, parity);
+        };
+        int* const red_i = reinterpret_cast<int*>(red);    // [16] last-arriver flag, [17] slot count, [18 ..] slot list
         const bool want_ds = p.dscale_part != nullptr;
         float dsum = 0.f;                           // d(scale) share of this thread over all items of the pair
         SweepItems iter(p.m_tiles, p.n_dh, p.sched_pairs, NJ, pair);
@@ -304,7 +396,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             const RowCtx rc = load_row_ctx<ROW_TERM>(p, m, fast, G);
             for (int t = ii.t0; t < ii.t1; ++t, ++gs) {
                 const int sb = gs & 1;
-                { const long long t0 = clock64(); mbar_wait(SFULL(sb), (gs >> 1) & 1); w_sfull += clock64() - t0; }
+                ewait(SFULL(sb), (gs >> 1) & 1, w_sfull);
                 tc_fence_after();
                 const uint32_t taddr = TM_S + ((uint32_t)(q * 32) << 16) + sb * 128 + h * 64;
                 uint32_t r0[32], r1[32];
@@ -318,13 +410,13 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 ds_tile<ROW_TERM, COL_TERM>(r0, r1, p, rc, n0, c1, fast, c0, G, v, want_ds && ii.dh == 0, dsum);
                 uint32_t pk[32];
                 pack_ds(v, pk);
-                { const long long t0 = clock64(); mbar_wait(DSEMPTY, (gs & 1) ^ 1); w_dsempty += clock64() - t0; }
+                ewait(DSEMPTY, (gs & 1) ^ 1, w_dsempty);
                 store_ds_row(ds + (jq * 2 + h) * 8192 + rloc * 128, rloc, pk);
                 fence_proxy_async_smem();
                 mbar_arrive_cluster(R_DSFULL);
             }
             // -------- row block done: drain dA^T (lanes = feature columns, TMEM columns = the 128 rows of the block)
-            { const long long t0 = clock64(); mbar_wait(ACCFULL, it & 1); w_accfull += clock64() - t0; }
+            ewait(ACCFULL, it & 1, w_accfull);
             tc_fence_after();
             const float omul = s * p.out_mul * invG;
             for (int dblk = 0; dblk < ND; ++dblk) {
@@ -363,12 +455,14 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
             if (lane == 0) red[warp - 4] = dsum;
             epi_bar_sync2();
-            if (et == 0) {
-                float tot = 0.f;
-                for (int w = 0; w < 8; ++w) tot += red[w];
-                p.dscale_part[pair * 2 + (int)cta] = tot * invG;
+            if (warp == 4) {
+                float tot = lane < 8 ? red[lane] : 0.f;
+#pragma unroll
+                for (int off = 4; off >= 1; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+                if (lane == 0) p.dscale_part[pair * 2 + (int)cta] = tot * invG;
             }
         }
+        if (p.grid_cnt != nullptr) sweep_tail_reduce(p, et, NJ, red_i);
         if (prof) {
             p.prof[12] = (unsigned long long)(clock64() - t_begin);
             p.prof[13] = w_sfull; p.prof[14] = w_dsempty; p.prof[15] = w_accfull;
@@ -385,11 +479,19 @@ void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUt
     const int grid = p.sched_pairs * 2;
     const size_t smem = bwd_pair_smem_bytes();
     const bool row_term = p.wr != nullptr, col_term = p.wc != nullptr;
+    // cooperative: the end-of-sweep grid barrier needs every CTA resident (the launch fails instead of hanging otherwise)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NTHREADS2); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = p.grid_cnt != nullptr ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
 #define FLYP_LAUNCH_BWD2(R, C, W)                                                                              \
     do {                                                                                                       \
         static bool attr_done[64] = {false};                                                                  \
         ensure_smem_attr(bwd_pair_kernel<R, C, W>, smem, attr_done);                                           \
-        bwd_pair_kernel<R, C, W><<<grid, NTHREADS2, smem, st>>>(tmA64, tmB, tmBd, p);                          \
+        cudaLaunchKernelEx(&cfg, bwd_pair_kernel<R, C, W>, tmA64, tmB, tmBd, p);                               \
     } while (0)
     const bool wide = p.kc > 8 || p.n_dh > 1;
     if (wide) {

@@ -43,25 +43,17 @@ size_t fwd_smem_bytes(bool stationary) {
     return stationary ? FwdCfg<true>::SMEM_BYTES : FwdCfg<false>::SMEM_BYTES;
 }
 
-// Column block of a work item.  The schedule starts at block / block pair p.nb_rot and wraps around (multi-GPU: own rows
-// first, then the other ranks' rows in the order in which they arrive).
-template <bool MC>
-__device__ __forceinline__ int fwd_block(const FwdParams& p, int item, int cta) {
-    const int units = MC ? (p.n_tiles + 1) / 2 : p.n_tiles;
-    int u = item / p.m_split + p.nb_rot;
-    if (u >= units) u -= units;
-    return MC ? 2 * u + cta : u;
-}
-
+// Work items come from the flat schedule of sched.h (FwdItems): worker `worker` of `nworkers` walks its contiguous range
+// of (column unit, row tile) units; a column unit is one block of 128 columns, or for MC a pair of adjacent blocks.
+//
 // MC: clusters of two CTAs sweep two adjacent column blocks over the SAME stream of A tiles; each CTA fetches half of
 // every A chunk and multicasts it to both (halves the L2 -> SM traffic, the measured limiter of the 1-CTA kernel).
 template <bool STAT, bool ROBUST, bool MC>
 __device__ __forceinline__ void
-fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, const int* __restrict__ gate) {
+fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, const int worker, const int nworkers) {
     using Cfg = FwdCfg<STAT>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int ACC_STAGES = Cfg::ACC_STAGES;
-    if (ROBUST && gate != nullptr && *gate == 0) return;  // fast path was adequate: nothing to do (grid-uniform)
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
@@ -80,10 +72,8 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = MC ? (int)cluster_ctarank() : 0;
-    const int worker = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int nworkers = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    // MC: a work item covers the column blocks (2 * nbp, 2 * nbp + 1); the second may lie beyond n_tiles (all-zero B)
-    const int n_items = (MC ? (p.n_tiles + 1) / 2 : p.n_tiles) * p.m_split;
+    // MC: a column unit covers the blocks (2 u, 2 u + 1); the second may lie beyond n_tiles (all-zero B)
+    const int n_units = MC ? (p.n_tiles + 1) / 2 : p.n_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), MC ? 2 : 1); }
@@ -102,10 +92,11 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
         // ------------------------------------------------------------------ TMA producer
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0; uint32_t it = 0;
-            for (int item = worker; item < n_items; item += nworkers, ++it) {
-                const int nb = fwd_block<MC>(p, item, cta), ms = item % p.m_split;
-                const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
-                const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
+            FwdItems items(p.m_tiles, n_units, p.n_local, p.nb_rot, nworkers, worker);
+            FwdItem fi;
+            for (; items.next(fi); ++it) {
+                const int nb = MC ? 2 * fi.u + cta : fi.u;
+                const int mt0 = fi.mt0, mt1 = fi.mt1;
                 peer_wait_rows(p.wait_b, nb * TILE, min((nb + 1) * TILE, p.n_n));
                 if (STAT) {
                     mbar_wait(BFREE, (it & 1) ^ 1);
@@ -138,10 +129,10 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
         if (elect_one()) {
             constexpr uint32_t IDESC = umma_idesc_bf16(TILE, TILE, 0, 0);
             int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0; uint32_t it = 0;
-            for (int item = worker; item < n_items; item += nworkers, ++it) {
-                const int ms = item % p.m_split;
-                const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
-                const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
+            FwdItems items(p.m_tiles, n_units, p.n_local, p.nb_rot, nworkers, worker);
+            FwdItem fi;
+            for (; items.next(fi); ++it) {
+                const int mt0 = fi.mt0, mt1 = fi.mt1;
                 if (STAT) { mbar_wait(BFULL, it & 1); tc_fence_after(); }
                 for (int mt = mt0; mt < mt1; ++mt) {
                     mbar_wait(TEMPTY(as), aphase ^ 1);
@@ -175,11 +166,12 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
         const float c1 = s * LOG2E;
         const float c0 = fixed_shift(c1, p.shift_slack);
         int as = 0; uint32_t aphase = 0;
-        for (int item = worker; item < n_items; item += nworkers) {
-            const int nb = fwd_block<MC>(p, item, cta), ms = item % p.m_split;
+        FwdItems items(p.m_tiles, n_units, p.n_local, p.nb_rot, nworkers, worker);
+        FwdItem fi;
+        while (items.next(fi)) {
+            const int nb = MC ? 2 * fi.u + cta : fi.u;
             const bool nb_live = nb < p.n_tiles;           // MC: the odd block of the last pair may not exist
-            const int mt0 = (int)((long long)ms * p.m_tiles / p.m_split);
-            const int mt1 = (int)((long long)(ms + 1) * p.m_tiles / p.m_split);
+            const int mt0 = fi.mt0, mt1 = fi.mt1;
             const int col0 = nb * TILE + h * 64;
             const bool n_edge = (nb == p.n_tiles - 1) && (p.n_n % TILE != 0);
             float ca[64];
@@ -197,6 +189,10 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
                 // rel: index (within this thread's 64 columns) of the row's positive, excluded from the sums
                 int rel = -1;
                 if (p.pos != nullptr) rel = p.pos[row] - col0;
+                else if (p.pos_arith) {
+                    const int pc = row + p.pos_off;
+                    if (rowvalid && pc >= 0 && pc < p.n_n) rel = pc - col0;
+                }
                 const bool has_pos = __any_sync(0xffffffffu, rel >= 0 && rel < 64);
                 if (!ROBUST) {
 #pragma unroll
@@ -289,7 +285,7 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
                 const int et = threadIdx.x - 128;
                 if (et < TILE && nb_live) {
                     float v = (red[et] + red[TILE + et]) + (red[2 * TILE + et] + red[3 * TILE + et]);
-                    p.colpart[(size_t)ms * p.ld_cols + nb * TILE + et] = v;
+                    p.colpart[(size_t)fi.slot * p.ld_cols + nb * TILE + et] = v;
                 }
                 epi_bar_sync();
             }
@@ -304,30 +300,45 @@ template <bool STAT, bool ROBUST>
 __global__ void __launch_bounds__(NTHREADS, 1)
 fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams p,
            const int* __restrict__ gate) {
-    fwd_body<STAT, ROBUST, false>(tmA, tmB, p, gate);
+    if (ROBUST && gate != nullptr && *gate == 0) return;  // fast path was adequate: nothing to do (grid-uniform)
+    fwd_body<STAT, ROBUST, false>(tmA, tmB, p, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Both robust passes of the symmetric loss in one gated launch: CTAs [0, split) sweep the rows of S, the others the rows
+// of S^T (operand roles swapped).
+template <bool STAT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+fwd_kernel_robust2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwdParams pr,
+                   const FwdParams pc, const int* __restrict__ gate, const int split) {
+    if (gate != nullptr && *gate == 0) return;
+    if ((int)blockIdx.x < split) fwd_body<STAT, true, false>(tmA, tmB, pr, (int)blockIdx.x, split);
+    else fwd_body<STAT, true, false>(tmB, tmA, pc, (int)blockIdx.x - split, (int)gridDim.x - split);
 }
 
 // tmA64: the A operand with [64 rows][64 cols] boxes
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 fwd_kernel_mc(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
-    fwd_body<true, false, true>(tmA64, tmB, p, nullptr);
+    fwd_body<true, false, true>(tmA64, tmB, p, (int)(blockIdx.x >> 1), (int)(gridDim.x >> 1));
+}
+
+int fwd_workers(int m_tiles, int n_tiles, bool mc, int num_sms) {
+    return mc ? fwd_sched_workers(m_tiles, (n_tiles + 1) / 2, num_sms / 2) : fwd_sched_workers(m_tiles, n_tiles, num_sms);
 }
 
 void launch_fwd_mc(const CUtensorMap& tmA64, const CUtensorMap& tmB, const FwdParams& p, int num_sms, cudaStream_t st) {
-    const int n_items = ((p.n_tiles + 1) / 2) * p.m_split;
-    int workers = num_sms / 2;
-    if (n_items < workers) workers = n_items;
+    const int workers = fwd_workers(p.m_tiles, p.n_tiles, true, num_sms);
     const size_t smem = fwd_smem_bytes(true);
     static bool attr_done[64] = {false};
     ensure_smem_attr(fwd_kernel_mc, smem, attr_done);
     fwd_kernel_mc<<<workers * 2, NTHREADS, smem, st>>>(tmA64, tmB, p);
 }
 
+static bool fwd_stationary(const FwdParams& p) { return p.kplan.n_terms == 1 && p.kc <= FwdCfg<true>::KC_MAX; }
+
 void launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, bool robust, const int* gate,
                 int num_sms, cudaStream_t st) {
-    const bool stat = p.kplan.n_terms == 1 && p.kc <= FwdCfg<true>::KC_MAX;
-    const int n_items = p.n_tiles * p.m_split;
-    const int grid = n_items < num_sms ? n_items : num_sms;
+    const bool stat = fwd_stationary(p);
+    const int grid = fwd_workers(p.m_tiles, p.n_tiles, false, num_sms);
     const size_t smem = fwd_smem_bytes(stat);
 #define FLYP_LAUNCH_FWD(S, R)                                                                                  \
     do {                                                                                                       \
@@ -338,6 +349,25 @@ void launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams&
     if (stat) { if (robust) FLYP_LAUNCH_FWD(true, true); else FLYP_LAUNCH_FWD(true, false); }
     else      { if (robust) FLYP_LAUNCH_FWD(false, true); else FLYP_LAUNCH_FWD(false, false); }
 #undef FLYP_LAUNCH_FWD
+}
+
+void launch_fwd_robust2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& pr, const FwdParams& pc,
+                        const int* gate, int num_sms, cudaStream_t st) {
+    const bool stat = fwd_stationary(pr);
+    // each pass gets half of the SMs (the robust path is the rare one; simplicity over balance)
+    const int half = num_sms / 2 > 0 ? num_sms / 2 : 1;
+    const int g_r = fwd_workers(pr.m_tiles, pr.n_tiles, false, half);
+    const int g_c = fwd_workers(pc.m_tiles, pc.n_tiles, false, half);
+    const size_t smem = fwd_smem_bytes(stat);
+    if (stat) {
+        static bool attr_done[64] = {false};
+        ensure_smem_attr(fwd_kernel_robust2<true>, smem, attr_done);
+        fwd_kernel_robust2<true><<<g_r + g_c, NTHREADS, smem, st>>>(tmA, tmB, pr, pc, gate, g_r);
+    } else {
+        static bool attr_done[64] = {false};
+        ensure_smem_attr(fwd_kernel_robust2<false>, smem, attr_done);
+        fwd_kernel_robust2<false><<<g_r + g_c, NTHREADS, smem, st>>>(tmA, tmB, pr, pc, gate, g_r);
+    }
 }
 
 // ===================================================================================================================

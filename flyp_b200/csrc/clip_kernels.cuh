@@ -46,15 +46,16 @@ struct FwdParams {
     int kc;                  // number of 64-wide K chunks per plane (ceil(D / 64))
     KPlan kplan;             // total chunks of the contraction = kc * kplan.n_terms
     int m_tiles, n_tiles;    // ceil(n / 128)
-    int m_split;             // each N block is swept by m_split work items
+    int n_slots;             // partial column-sum slots per column block (flat schedule, sched.h: fwd_sched_slots)
     int ld_rows;             // leading dimension (floats) of rowpart / rowmax  (>= m_tiles * 128)
     int ld_cols;             // leading dimension (floats) of colpart / colmax  (>= n_tiles * 128)
     const float* scale;      // device scalar: logit_scale (already exp-ed)
     const int* pos;          // [ld_rows] positive column of each M row (-1: none); that element is EXCLUDED from all
-                             // sums (it is added back exactly by the finalize step); nullptr: no exclusion
+                             // sums (it is added back exactly by the finalize step); nullptr: no exclusion ...
+    int pos_arith, pos_off;  // ... unless pos_arith != 0: then the positive of row m is column m + pos_off (if it exists)
     float shift_slack;       // c0 = c1 - shift_slack (log2 units), see DESIGN.md "fixed shift"
     float* rowpart;          // [n_tiles * 2][ld_rows]  partial row sums, one per (N block, column half)
-    float* colpart;          // [m_split][ld_cols]      partial column sums, one per M split
+    float* colpart;          // [n_slots][ld_cols]      partial column sums, one per work item that touched the block
     float* rowmax;           // robust mode only: running log2-domain max paired with rowpart
     float* colmax;           // robust mode only
     float* dbg_logits;       // optional [n_m][n_n] fp32 raw dot products (debug path), may be null
@@ -63,7 +64,8 @@ struct FwdParams {
     // row-sharded multi-GPU: the N-side rows of other ranks arrive over NVLink while the kernel runs.  Column blocks are
     // visited starting at block nb_rot (this rank's own rows) so that work proceeds in arrival order, and the producer
     // polls wait_b before the first TMA read of a block.
-    int nb_rot;              // first column block (MC kernel: first column-block pair) of the static schedule
+    int nb_rot;              // first column unit (block; MC kernel: block pair) of the flat schedule
+    int n_local;             // column units (from nb_rot on) whose rows are this rank's own: phase A of the schedule
     PeerWait wait_b;
 };
 
@@ -112,14 +114,26 @@ struct BwdParams {
     unsigned long long* prof; // optional debug: per-role wait-cycle counters of cluster 0 (see tools/pair_prof.py)
     float* dscale_part;      // partial sums of dS * <a, b> (unscaled), may be null: [m_tiles * d_parts] (bwd_kernel) or
                              // [2 * sched_pairs] (pair kernel: one per CTA)
+    // pair kernel, end-of-sweep reductions by the whole grid (clip_bwd_pair.cu: sweep_tail_reduce):
+    int* grid_cnt;           // arrival counter of the grid barrier, zeroed by the host before the launch; nullptr: no
+                             // barrier, the fp32 partials of split blocks and the d(scale) partials are left as they are
+    float* dscale_out;       // the sum of all d(scale) partials (written by CTA 0 after the barrier), published to the
+                             // other ranks through ds_push
+    PeerPush ds_push;
 };
 
+// Workers (CTAs; multicast kernel: clusters) of the forward's flat schedule and its partial column-sum slots.
+int fwd_workers(int m_tiles, int n_tiles, bool mc, int num_sms);
 // robust = exact per-tile (max, sum) row statistics only; gate (device int, may be null): the robust kernel returns
-// immediately when *gate == 0.
+// immediately when *gate == 0.  The grid is fwd_workers(p.m_tiles, p.n_tiles, false, num_sms).
 void launch_fwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, bool robust, const int* gate,
                 int num_sms, cudaStream_t st);
+// Both robust passes of the symmetric loss in ONE gated launch: rows of S (tmA x tmB, pr) on the first half of the grid,
+// rows of S^T (tmB x tmA, pc) on the second.
+void launch_fwd_robust2(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& pr, const FwdParams& pc,
+                        const int* gate, int num_sms, cudaStream_t st);
 // Multicast variant of the fast forward (bf16, D <= 512, no debug logits): tmA64 has [64 rows][64 cols] boxes; the
-// m_split in p must have been chosen for (n_tiles + 1) / 2 column-block pairs on num_sms / 2 clusters.
+// schedule runs over (n_tiles + 1) / 2 column-block pairs on fwd_workers(.., true, ..) clusters.
 void launch_fwd_mc(const CUtensorMap& tmA64, const CUtensorMap& tmB, const FwdParams& p, int num_sms, cudaStream_t st);
 // tmBd: tensor map used for the N-side operand rows as the B operand of the dA MMA (box [64 d][128 n]).
 void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,

@@ -25,6 +25,7 @@
 // multicast address when there is one) and flagged the same way.  No NCCL call is on this path.
 #include "../../include/flyp_clip.h"
 #include "aux_kernels.cuh"
+#include "comm_internal.h"
 #include "peer.cuh"
 
 #include <cstdarg>
@@ -32,10 +33,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
-
-namespace flyp {
-void set_error(int code, const char* fmt, ...);   // api.cu: thread-local message returned by flyp_last_error()
-}
 
 namespace {
 
@@ -72,6 +69,7 @@ struct flyp_comm {
     uint32_t seq;
     uint32_t* err_host;
     uint32_t* err_dev;
+    uint32_t timeout_ms;        // how long a kernel waits for a peer before it traps (0: for ever)
     // byte offsets inside a segment (identical on every rank)
     size_t off_feat[2][N_ARR], off_colstat[2], off_rowstat[2], off_dscale[2], off_flags, off_seqword[2], off_counter;
 };
@@ -101,15 +99,20 @@ inline uint32_t* flag_ptr(const flyp_comm* c, int q, int set, int k) {
 }
 
 // ---- pack: local bf16 rows -> own slots (bf16 copy + fp16 conversion), sequence word, own flags ---------------------
-__global__ void k_pack(const uint4* __restrict__ img, const uint4* __restrict__ txt, size_t n8, uint4* __restrict__ img_bf,
-                       uint4* __restrict__ img_h, uint4* __restrict__ txt_bf, uint4* __restrict__ txt_h,
-                       uint32_t* seqword, uint32_t* own_flags, int rank, uint32_t seq) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        *seqword = seq;
-        for (int a = 0; a < N_ARR; ++a) own_flags[(a * MAXW + rank) * MAXG] = seq;
+// One warp per row.  With `ex` the same pass also prepares the forward that follows: the positive logit of every local
+// row (its positive is the LOCAL text row of the same index) and the control words of the step.
+__global__ void k_pack(const uint4* __restrict__ img, const uint4* __restrict__ txt, int n_rows, int dim8,
+                       uint4* __restrict__ img_bf, uint4* __restrict__ img_h, uint4* __restrict__ txt_bf,
+                       uint4* __restrict__ txt_h, uint32_t* seqword, uint32_t* own_flags, int rank, uint32_t seq,
+                       flyp::PackExtra ex) {
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            *seqword = seq;
+            for (int a = 0; a < N_ARR; ++a) own_flags[(a * MAXW + rank) * MAXG] = seq;
+        }
+        if (ex.zero_words != nullptr && (int)threadIdx.x < ex.n_zero) ex.zero_words[threadIdx.x] = 0;
     }
-    if (i >= n8) return;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     auto conv = [](uint4 v) {
         uint4 u;
         const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
@@ -123,14 +126,34 @@ __global__ void k_pack(const uint4* __restrict__ img, const uint4* __restrict__ 
         }
         return u;
     };
-    const uint4 a = img[i], b = txt[i];
-    img_bf[i] = a; txt_bf[i] = b;
-    img_h[i] = conv(a); txt_h[i] = conv(b);
+    float acc = 0.f;
+    if (row < n_rows) {
+        for (int c = lane; c < dim8; c += 32) {
+            const size_t i = (size_t)row * dim8 + c;
+            const uint4 a = img[i], b = txt[i];
+            img_bf[i] = a; txt_bf[i] = b;
+            img_h[i] = conv(a); txt_h[i] = conv(b);
+            const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc = fmaf(__uint_as_float(wa[e] << 16), __uint_as_float(wb[e] << 16), acc);
+                acc = fmaf(__uint_as_float(wa[e] & 0xffff0000u), __uint_as_float(wb[e] & 0xffff0000u), acc);
+            }
+        }
+    }
+    if (ex.t2 != nullptr && row < ex.n_pad) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) {
+            ex.t2[row] = row < n_rows ? acc * ex.scale[0] * 1.4426950408889634f : -INFINITY;
+            ex.pos[row] = row < n_rows ? ex.row_offset + row : -1;
+        }
+    }
 }
 
 // ---- statistics push: this rank's column triples and row statistics -> every rank's segment, then the flag ----------
 // ptrs.seg[0 .. n_dst): the destinations (every rank's segment, or the single multicast mapping); own_seg: this rank's
-__global__ void k_push_stats(SegPtrs ptrs, int n_dst, uint8_t* own_seg, int rank, size_t off_colstat, size_t off_rowstat, size_t off_flags,
+__global__ void k_push_stats(SegPtrs ptrs, int n_dst, SegPtrs uni, int world, uint8_t* own_seg, int rank, size_t off_colstat, size_t off_rowstat, size_t off_flags,
                              size_t off_counter, const float* __restrict__ col_stat, const float* __restrict__ row_lse,
                              const float* __restrict__ row_nll, int n_rows, int n_cols, size_t cap, uint32_t seq) {
     const int q = blockIdx.y;
@@ -152,27 +175,23 @@ __global__ void k_push_stats(SegPtrs ptrs, int n_dst, uint8_t* own_seg, int rank
     }
     __threadfence_system();
     __syncthreads();
+    __shared__ int s_last;
     if (threadIdx.x == 0) {
         uint32_t* counter = reinterpret_cast<uint32_t*>(own_seg + off_counter);
         const uint32_t total = gridDim.x * gridDim.y;
-        if (atomicInc(counter, total - 1) == total - 1) {      // last block: everything above is visible system-wide
-            __threadfence_system();
-            for (int p = 0; p < n_dst; ++p)
-                *reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint32_t*>(ptrs.seg[p] + off_flags) +
-                                                      (FLAG_STAT * MAXW + rank) * MAXG) = seq;
-        }
+        s_last = (atomicInc(counter, total - 1) == total - 1) ? 1 : 0;      // last block: all stores above are out
+        if (s_last) __threadfence_system();
     }
+    __syncthreads();
+    // the flag goes out through the UNICAST mappings with release semantics (multicast stores are only weakly ordered:
+    // a flag stored through the multicast address is not guaranteed to land behind the data), one thread per rank so
+    // that the W round trips overlap
+    if (s_last && (int)threadIdx.x < world)
+        flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(uni.seg[threadIdx.x] + off_flags) + (FLAG_STAT * MAXW + rank) * MAXG, seq);
 }
 
-__global__ void k_push_scalar(SegPtrs ptrs, int n_dst, int rank, size_t off_dscale, size_t off_flags,
-                              const float* __restrict__ value, uint32_t seq) {
-    const int q = threadIdx.x;
-    if (q < n_dst) {
-        reinterpret_cast<float*>(ptrs.seg[q] + off_dscale)[rank] = value[0];
-        __threadfence_system();
-        *reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint32_t*>(ptrs.seg[q] + off_flags) +
-                                              (FLAG_DS * MAXW + rank) * MAXG) = seq;
-    }
+__global__ void k_push_scalar(flyp::PeerPush push, const float* __restrict__ value) {
+    if (threadIdx.x == 0) flyp::peer_push_value(push, value[0]);
 }
 
 __global__ void k_sum_scalar(const float* parts, int world, flyp::PeerWait w, float* __restrict__ out) {
@@ -239,6 +258,10 @@ static int comm_new(int rank, int world, int max_rows, int dim, flyp_comm** out)
     COMM_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&c->err_host), sizeof(uint32_t), cudaHostAllocMapped));
     *c->err_host = 0;
     COMM_CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->err_dev), c->err_host, 0));
+    // Ordinary rank skew (a dataloader respawn, rank 0 evaluating or writing a checkpoint) is minutes, not seconds:
+    // the default is 10 minutes, FLYP_PEER_TIMEOUT_MS overrides it (0 = wait for ever), read once at creation.
+    c->timeout_ms = 600000u;
+    if (const char* e = getenv("FLYP_PEER_TIMEOUT_MS")) c->timeout_ms = (uint32_t)strtoul(e, nullptr, 10);
     *out = c;
     return 0;
 }
@@ -352,6 +375,19 @@ int flyp_comm_error(const flyp_comm* c) {
     return (int)*reinterpret_cast<volatile uint32_t*>(c->err_host);
 }
 
+int flyp_comm_reset_error(flyp_comm* c) {
+    if (!c) return 0;
+    *reinterpret_cast<volatile uint32_t*>(c->err_host) = 0;
+    return 0;
+}
+
+int flyp_comm_set_timeout_ms(flyp_comm* c, uint32_t timeout_ms) {
+    int rc = check_comm(c, false);
+    if (rc) return rc;
+    c->timeout_ms = timeout_ms;
+    return 0;
+}
+
 int flyp_comm_destroy(flyp_comm* c) {
     if (!c) return 0;
     cudaSetDevice(c->dev);
@@ -370,6 +406,21 @@ int flyp_comm_destroy(flyp_comm* c) {
 
 int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, int n_rows, int dim, int dtype,
                               flyp_gathered_t* out, void* stream) {
+    return flyp::comm_gather(c, img, txt, n_rows, dim, dtype, nullptr, out, stream);
+}
+
+}  // extern "C"
+
+namespace flyp {
+
+static void fill_ready(const flyp_comm* c, flyp_ready_t* r, int set, uint32_t seq, int rows_per_flag) {
+    r->flags = flag_ptr(c, c->rank, set, 0);
+    r->seq = seq; r->n_flags = c->world; r->rows_per_flag = rows_per_flag; r->err = c->err_dev;
+    r->sub = 1; r->stride = MAXG; r->timeout_ms = c->timeout_ms;
+}
+
+int comm_gather(flyp_comm* c, const void* img, const void* txt, int n_rows, int dim, int dtype, const PackExtra* extra,
+                flyp_gathered_t* out, void* stream) {
     int rc = check_comm(c, true);
     if (rc) return rc;
     if (!img || !txt || !out) { flyp::set_error(FLYP_ERR_ARG, "null pointer argument"); return FLYP_ERR_ARG; }
@@ -391,14 +442,17 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
     // the copy engines may still be reading the own slots / sequence word of the previous step
     COMM_CUDA_OK(cudaStreamWaitEvent(st, c->ev_pushed, 0));
-    const size_t n8 = (size_t)n_rows * dim / 8;
-    k_pack<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
-        static_cast<const uint4*>(img), static_cast<const uint4*>(txt), n8,
+    PackExtra ex;
+    if (extra != nullptr) ex = *extra; else memset(&ex, 0, sizeof(ex));
+    const int rows = (ex.t2 != nullptr && ex.n_pad > n_rows) ? ex.n_pad : n_rows;
+    k_pack<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
+        static_cast<const uint4*>(img), static_cast<const uint4*>(txt), n_rows, dim / 8,
         reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_IMG] + slot_off),
         reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_IMG16] + slot_off),
         reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_TXT] + slot_off),
         reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_TXT16] + slot_off),
-        reinterpret_cast<uint32_t*>(own + c->off_seqword[par]), reinterpret_cast<uint32_t*>(own + c->off_flags), c->rank, seq);
+        reinterpret_cast<uint32_t*>(own + c->off_seqword[par]), reinterpret_cast<uint32_t*>(own + c->off_flags), c->rank, seq,
+        ex);
     COMM_CUDA_OK(cudaGetLastError());
     if (c->world > 1) {
         COMM_CUDA_OK(cudaEventRecord(c->ev_packed, st));
@@ -415,14 +469,32 @@ int flyp_comm_gather_features(flyp_comm* c, const void* img, const void* txt, in
     out->img_all = own + c->off_feat[par][ARR_IMG];
     out->img16_all = own + c->off_feat[par][ARR_IMG16];
     flyp_ready_t* r[N_ARR] = {&out->txt_ready, &out->txt16_ready, &out->img_ready, &out->img16_ready};
-    for (int a = 0; a < N_ARR; ++a) {
-        r[a]->flags = flag_ptr(c, c->rank, a, 0);
-        r[a]->seq = seq; r[a]->n_flags = c->world; r[a]->rows_per_flag = n_rows; r[a]->err = c->err_dev;
-        r[a]->sub = 1; r[a]->stride = MAXG; r[a]->reserved_sms = 0;
-    }
+    for (int a = 0; a < N_ARR; ++a) fill_ready(c, r[a], a, seq, n_rows);
     out->seq = seq;
     return 0;
 }
+
+int comm_scalar_push_target(flyp_comm* c, uint32_t seq, PeerPush* out) {
+    int rc = check_comm(c, true);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    const size_t off = c->off_dscale[seq & 1u] + (size_t)c->rank * sizeof(float);
+    if (c->mc != nullptr) {
+        out->n_dst = 1;
+        out->dst[0] = reinterpret_cast<float*>(c->mc + off);
+    } else {
+        out->n_dst = c->world;
+        for (int q = 0; q < c->world; ++q) out->dst[q] = reinterpret_cast<float*>(c->seg[q] + off);
+    }
+    out->n_flag = c->world;
+    for (int q = 0; q < c->world; ++q) out->flag[q] = flag_ptr(c, q, FLAG_DS, c->rank);
+    out->seq = seq;
+    return 0;
+}
+
+}  // namespace flyp
+
+extern "C" {
 
 int flyp_comm_push_stats(flyp_comm* c, uint32_t seq, const float* col_stat, const float* row_lse, const float* row_nll,
                          int n_rows, int n_cols, flyp_stats_t* out, void* stream) {
@@ -436,24 +508,22 @@ int flyp_comm_push_stats(flyp_comm* c, uint32_t seq, const float* col_stat, cons
     }
     COMM_CUDA_OK(cudaSetDevice(c->dev));
     const int par = (int)(seq & 1u);
-    SegPtrs ptrs;
+    SegPtrs ptrs, uni;
     int n_dst = c->world;
-    for (int q = 0; q < MAXW; ++q) ptrs.seg[q] = q < c->world ? c->seg[q] : nullptr;
+    for (int q = 0; q < MAXW; ++q) uni.seg[q] = ptrs.seg[q] = q < c->world ? c->seg[q] : nullptr;
     if (c->mc != nullptr) { n_dst = 1; ptrs.seg[0] = c->mc; }      // one store stream reaches every rank
     int bx = (3 * n_cols + 1023) / 1024;
     if (bx > 16) bx = 16;
     if (bx < 1) bx = 1;
     k_push_stats<<<dim3(bx, n_dst), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        ptrs, n_dst, c->seg[c->rank], c->rank, c->off_colstat[par], c->off_rowstat[par], c->off_flags, c->off_counter, col_stat, row_lse,
+        ptrs, n_dst, uni, c->world, c->seg[c->rank], c->rank, c->off_colstat[par], c->off_rowstat[par], c->off_flags, c->off_counter, col_stat, row_lse,
         row_nll, n_rows, n_cols, cap, seq);
     COMM_CUDA_OK(cudaGetLastError());
     uint8_t* own = c->seg[c->rank];
     out->col_stat_all = reinterpret_cast<const float*>(own + c->off_colstat[par]);
     out->row_lse_all = reinterpret_cast<const float*>(own + c->off_rowstat[par]);
     out->row_nll_all = out->row_lse_all + cap;
-    out->ready.flags = flag_ptr(c, c->rank, FLAG_STAT, 0);
-    out->ready.seq = seq; out->ready.n_flags = c->world; out->ready.rows_per_flag = n_rows; out->ready.err = c->err_dev;
-    out->ready.sub = 1; out->ready.stride = MAXG; out->ready.reserved_sms = 0;
+    flyp::fill_ready(c, &out->ready, FLAG_STAT, seq, n_rows);
     return 0;
 }
 
@@ -462,12 +532,9 @@ int flyp_comm_push_scalar(flyp_comm* c, uint32_t seq, const float* value, void* 
     if (rc) return rc;
     if (!value) { flyp::set_error(FLYP_ERR_ARG, "null pointer argument"); return FLYP_ERR_ARG; }
     COMM_CUDA_OK(cudaSetDevice(c->dev));
-    SegPtrs ptrs;
-    int n_dst = c->world;
-    for (int q = 0; q < MAXW; ++q) ptrs.seg[q] = q < c->world ? c->seg[q] : nullptr;
-    if (c->mc != nullptr) { n_dst = 1; ptrs.seg[0] = c->mc; }
-    k_push_scalar<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(ptrs, n_dst, c->rank, c->off_dscale[seq & 1u],
-                                                                  c->off_flags, value, seq);
+    flyp::PeerPush push;
+    if ((rc = flyp::comm_scalar_push_target(c, seq, &push)) != 0) return rc;
+    k_push_scalar<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(push, value);
     COMM_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -479,7 +546,7 @@ int flyp_comm_sum_scalar(flyp_comm* c, uint32_t seq, float* out, void* stream) {
     COMM_CUDA_OK(cudaSetDevice(c->dev));
     flyp::PeerWait w;
     w.flags = flag_ptr(c, c->rank, FLAG_DS, 0); w.seq = seq; w.n_flags = c->world; w.rows_per_flag = 1; w.err = c->err_dev;
-    w.sub = 1; w.stride = MAXG;
+    w.sub = 1; w.stride = MAXG; w.timeout_ms = c->timeout_ms;
     k_sum_scalar<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float*>(c->seg[c->rank] + c->off_dscale[seq & 1u]), c->world, w, out);
     COMM_CUDA_OK(cudaGetLastError());

@@ -1,7 +1,7 @@
-// sched.h — integer arithmetic of the backward sweep's work schedule, shared by the pair kernel (device), the partial-sum
-// reduction kernel (device) and the host (workspace sizing; tests/test_sched_host.py compiles this header with g++ and
-// checks that every (virtual row block, column step) unit is covered exactly once and that the reduction finds exactly
-// the partial accumulators the kernel wrote).  No CUDA dependencies.
+// sched.h — integer arithmetic of the work schedules, shared by the tensor-core kernels (device), the reductions that
+// consume their partial results (device) and the host (workspace sizing).  tests/test_sched_host.py compiles this header
+// with g++ and checks that every unit of work is covered exactly once and that the consumers find exactly the partial
+// slots the producers wrote.  No CUDA dependencies.
 #pragma once
 #if defined(__CUDACC__)
 #define FLYP_HD __host__ __device__ __forceinline__
@@ -80,5 +80,87 @@ struct TailParts {
         return slot;
     }
 };
+
+// ---------------------------------------------------------------------------------------------------- forward
+// Flat schedule of the forward statistics sweep.  A unit = (column unit u, row tile mt): u is one 128-column block of
+// the N side (the multicast kernel: a pair of adjacent blocks, swept by the two CTAs of a cluster), mt one 128-row tile
+// of the M side.  Units are ordered column-unit-major, the column units in ROTATED order (ordinal ub = (u - rot) mod NU:
+// multi-GPU ranks start on their own rows and follow the order in which the other ranks' rows arrive).
+// The ordinals are split in two PHASES - [0, NA): the rank's own column units, whose operand is already in memory;
+// [NA, NU): the units of the other ranks, still arriving over NVLink (NA = 0: a single phase) - and the units of each
+// phase are cut into equal contiguous ranges, one per worker (CTA or cluster; a phase with fewer units than workers uses
+// the first workers only).  So EVERY worker starts on local data while the gather is in flight.  A worker's range is cut
+// again at column-unit boundaries: each piece is one work item (the column unit's operand stays in shared memory while
+// the row tiles stream by).  The column sums of an item go to partial slot `slot` of its column unit: the ordinal of the
+// worker among the workers that touch the unit.
+FLYP_HD int flat_worker_of(long long x, long long S, int P) { return (int)(((x + 1) * P + S - 1) / S) - 1; }
+
+struct FwdItem { int u, mt0, mt1, slot; };
+
+struct FwdPhase {
+    long long S;      // units of the phase
+    int P;            // workers that take part (each gets at least one unit)
+    int ub0;          // first column-unit ordinal
+};
+FLYP_HD FwdPhase fwd_phase(int ph, int m_tiles, int n_units, int n_local, int workers) {
+    FwdPhase f;
+    const int nu = ph == 0 ? n_local : n_units - n_local;
+    f.ub0 = ph == 0 ? 0 : n_local;
+    f.S = (long long)nu * m_tiles;
+    f.P = (int)(f.S < workers ? f.S : workers);
+    return f;
+}
+
+struct FwdItems {
+    long long pos, end;
+    FwdPhase ph;
+    int MT, NU, NA, rot, W, q, phase;
+    FLYP_HD FwdItems(int m_tiles, int n_units, int n_local, int rot_, int workers, int q_) {
+        MT = m_tiles; NU = n_units; NA = n_local; rot = rot_; W = workers; q = q_;
+        phase = -1; pos = end = 0;
+    }
+    FLYP_HD bool next(FwdItem& r) {
+        while (pos >= end) {
+            if (++phase > 1) return false;
+            ph = fwd_phase(phase, MT, NU, NA, W);
+            if (q < ph.P) { pos = flat_start(q, ph.S, ph.P); end = flat_start(q + 1, ph.S, ph.P); }
+            else pos = end = 0;
+        }
+        const int ubl = (int)(pos / MT);                       // ordinal within the phase
+        r.mt0 = (int)(pos - (long long)ubl * MT);
+        const long long room = MT - r.mt0, len = end - pos;
+        r.mt1 = r.mt0 + (int)(len < room ? len : room);
+        int u = ph.ub0 + ubl + rot;
+        if (u >= NU) u -= NU;
+        r.u = u;
+        r.slot = q - flat_worker_of((long long)ubl * MT, ph.S, ph.P);
+        pos += r.mt1 - r.mt0;
+        return true;
+    }
+};
+// workers to launch (every one of them gets at least one unit in some phase)
+FLYP_HD int fwd_sched_workers(int m_tiles, int n_units, int max_workers) {
+    const long long S = (long long)m_tiles * n_units;
+    return (int)(S < max_workers ? S : max_workers);
+}
+// upper bound on the partial column-sum slots of a column unit
+FLYP_HD int fwd_sched_slots(int m_tiles, int n_units, int n_local, int workers) {
+    int best = 1;
+    for (int p = 0; p < 2; ++p) {
+        const FwdPhase f = fwd_phase(p, m_tiles, n_units, n_local, workers);
+        if (f.S == 0) continue;
+        const long long L = f.S / f.P;                           // shortest range, >= 1
+        long long s = (m_tiles - 1 + L - 1) / L + 1;
+        if (s > m_tiles) s = m_tiles;
+        if (s > best) best = (int)s;
+    }
+    return best;
+}
+// slots actually written for the column unit with rotated ordinal ub
+FLYP_HD int fwd_unit_slots(int ub, int m_tiles, int n_units, int n_local, int workers) {
+    const FwdPhase f = fwd_phase(ub < n_local ? 0 : 1, m_tiles, n_units, n_local, workers);
+    const long long lo = (long long)(ub - f.ub0) * m_tiles;
+    return flat_worker_of(lo + m_tiles - 1, f.S, f.P) - flat_worker_of(lo, f.S, f.P) + 1;
+}
 
 }  // namespace flyp

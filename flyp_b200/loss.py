@@ -152,6 +152,9 @@ def contrastive_cross_entropy(a, b, logit_scale, labels=None, label_offset=0, re
     if reduction == "none":
         return loss
     if reduction == "mean":
+        if labels is not None:
+            # F.cross_entropy(reduction='mean') averages over the targets that are not ignore_index (-100)
+            return (loss.float().sum() / (labels != -100).sum()).to(loss.dtype)
         return loss.float().mean().to(loss.dtype)
     if reduction == "sum":
         return loss.float().sum().to(loss.dtype)
@@ -233,16 +236,19 @@ class _ClipLossFn(torch.autograd.Function):
         return (d_img if need_img else None), (d_txt if need_txt else None), gs, None, None, None, None, None
 
 
-class _ClipLossPeerFn(torch.autograd.Function):
-    """The same row-sharded symmetric loss with every exchange done over peer memory (flyp_b200/comm.py): feature
-    pushes by the copy engines (one multicast copy per matrix on NVSwitch) that overlap the forward kernel,
-    flag-polling tensor-core kernels, statistics and d(scale) by (multicast) remote stores.  One C call per direction."""
+class _ClipLossStepFn(torch.autograd.Function):
+    """The symmetric loss through the whole-step C entry points (flyp_b200/step.py): one call per direction.
+    ``comm=None``: the single-GPU loss of the FLYP loop.  With a PeerComm: the row-sharded loss with every exchange done
+    over peer memory (flyp_b200/comm.py) - feature pushes by the copy engines (one multicast copy per matrix on
+    NVSwitch) that overlap the forward kernel, flag-polling tensor-core kernels, statistics and d(scale) by (multicast)
+    remote stores."""
 
     @staticmethod
     def forward(ctx, img, txt, scale, comm, gather_with_grad, grad_dtype):
-        from . import comm as peer
+        from . import step
         s = ops._scale_tensor(scale, img.device)
-        loss, st = peer.step_forward(comm, img, txt, s, img.dtype)   # the loss is written in the feature dtype
+        need_bwd = any(ctx.needs_input_grad[:3])
+        loss, st = step.step_forward(comm, img, txt, s, img.dtype, need_backward=need_bwd)   # loss in the feature dtype
         ctx.st = st
         ctx.meta = (gather_with_grad, grad_dtype, torch.is_tensor(scale), scale.shape if torch.is_tensor(scale) else None,
                     scale.dtype if torch.is_tensor(scale) else None)
@@ -250,13 +256,13 @@ class _ClipLossPeerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        from . import comm as peer
+        from . import step
         st = ctx.st
         gwg, grad_dtype, s_is_tensor, s_shape, s_dtype = ctx.meta
         need_img, need_txt, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        mul = float(st.comm.world) if gwg else 1.0
+        mul = float(st.world) if gwg else 1.0
         # every rank differentiates the same replicated loss: d(scale) is the sum over the row blocks of all ranks
-        d_img, d_txt, tot = peer.step_backward(st, g, mul, grad_dtype, need_img, need_txt, need_s)
+        d_img, d_txt, tot = step.step_backward(st, g, mul, grad_dtype, need_img, need_txt, need_s)
         gs = None
         if need_s and s_is_tensor:
             if s_dtype == torch.float32 and len(s_shape) <= 1 and (len(s_shape) == 0 or s_shape[0] == 1):
@@ -265,7 +271,6 @@ class _ClipLossPeerFn(torch.autograd.Function):
                 gs = torch.zeros(s_shape, dtype=torch.float32, device=st.img.device).reshape(-1)
                 gs[:1] = tot
                 gs = gs.reshape(s_shape).to(s_dtype)
-        st.comm.check_error()
         return (d_img if need_img else None), (d_txt if need_txt else None), gs, None, None, None
 
 
@@ -273,8 +278,7 @@ class ClipLoss(nn.Module):
     """clip/loss.py:72-211 with the same constructor and forward signature."""
 
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
-                 use_horovod=False, normalize=False, grad_dtype: Optional[torch.dtype] = None, group=None,
-                 comm: str = "auto"):
+                 use_horovod=False, normalize=False, grad_dtype: Optional[torch.dtype] = None, group=None):
         super().__init__()
         self.local_loss = local_loss
         self.gather_with_grad = gather_with_grad
@@ -286,11 +290,10 @@ class ClipLoss(nn.Module):
         self.normalize = normalize
         self.grad_dtype = grad_dtype
         self.group = group
-        # multi-rank exchange: "peer" = NVLink peer memory (one node, bf16, the default loss), "nccl" = torch.distributed
-        # collectives, "auto" = peer when it can be set up on every rank, else nccl
-        if comm not in ("auto", "peer", "nccl"):
-            raise ValueError(f"comm must be 'auto', 'peer' or 'nccl', got {comm!r}")
-        self.comm = comm
+        # Multi-rank exchange.  Ranks of ONE node exchange over NVLink peer memory (flyp_b200/comm.py); only ranks
+        # spread over several nodes (no peer mapping possible) use torch.distributed collectives.  This is decided once,
+        # collectively, on the first forward - it is not a user-facing backend switch.  (FLYP_EXCHANGE=collective forces
+        # the multi-node path on one node: tests and A/B measurements.)
         self._peer = None          # PeerComm, or False once the set-up was tried and refused
         self._peer_shape = None
 
@@ -313,21 +316,23 @@ class ClipLoss(nn.Module):
 
     def _peer_comm(self, feats):
         """The peer-memory communicator for blocks shaped like ``feats`` (created collectively on first use; every rank
-        takes the same decision).  None -> use the NCCL path."""
-        if self.comm == "nccl" or feats.dtype != torch.bfloat16:
+        takes the same decision).  None -> the ranks do not share a node: torch.distributed collectives."""
+        import os
+        if os.environ.get("FLYP_EXCHANGE", "") == "collective" or feats.dtype != torch.bfloat16:
             return None
         shape = (feats.shape[0], feats.shape[1])
         if self._peer is not None and self._peer_shape == shape:
             return self._peer or None
         if self._peer:
+            # peers may still be copying into this rank's segment (their side streams): drain the device and meet the
+            # other ranks before the segment is unmapped
+            torch.cuda.synchronize(feats.device)
+            dist.barrier(group=self.group)
             self._peer.close()
         from .comm import PeerComm
         self._peer_shape = shape
         self._peer = PeerComm.from_process_group(self.rank, self.world_size, shape[0], shape[1], feats.device,
                                                  self.group) or False
-        if not self._peer and self.comm == "peer":
-            raise FlypError("comm='peer' was requested but the peer-memory exchange could not be set up on every rank "
-                            "(ranks on several nodes, or no CUDA IPC between the GPUs)")
         return self._peer or None
 
     def forward(self, image_features, text_features, logit_scale, ground_labels=None, ignore=False,
@@ -358,13 +363,17 @@ class ClipLoss(nn.Module):
                                            grad_dtype=self.grad_dtype)
             return (li + lt) / 2
 
-        peer = self._peer_comm(image_features) if self.world_size > 1 else None
-        if peer is not None:
-            loss = _ClipLossPeerFn.apply(image_features, text_features, logit_scale, peer, self.gather_with_grad,
+        if self.world_size == 1:
+            loss = _ClipLossStepFn.apply(image_features, text_features, logit_scale, None, self.gather_with_grad,
                                          self.grad_dtype)
         else:
-            loss = _ClipLossFn.apply(image_features, text_features, logit_scale, self.rank, self.world_size, self.group,
-                                     self.gather_with_grad, self.grad_dtype)
+            peer = self._peer_comm(image_features)
+            if peer is not None:
+                loss = _ClipLossStepFn.apply(image_features, text_features, logit_scale, peer, self.gather_with_grad,
+                                             self.grad_dtype)
+            else:
+                loss = _ClipLossFn.apply(image_features, text_features, logit_scale, self.rank, self.world_size,
+                                         self.group, self.gather_with_grad, self.grad_dtype)
         if self.cache_labels:
             self._labels(device, loss.shape[0])
         return loss

@@ -84,7 +84,9 @@ int flyp_ce_fwd(const void* a, const void* b, const float* scale, int n, int n_c
                 const int64_t* labels, int label_offset, float* loss, float* lse, void* workspace,
                 size_t workspace_bytes, void* stream);
 /* lse / loss: the saved forward outputs; g[n] upstream gradient on loss.  Out (each may be NULL): d_a[n, dim],
- * d_b[n_classes, dim] (grad_dtype), d_scale[1] fp32 (requires d_a). */
+ * d_b[n_classes, dim] (grad_dtype), d_scale[1] fp32 (requires d_a).
+ * Targets follow F.cross_entropy: label -100 (ignore_index) gives loss 0 and no gradient for that row; any other label
+ * outside [0, n_classes) traps the kernel (torch raises a device-side assertion for the same input). */
 int flyp_ce_bwd(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
                 const int64_t* labels, int label_offset, const float* lse, const float* loss, const float* g,
                 int grad_dtype, void* d_a, void* d_b, float* d_scale, void* workspace, size_t workspace_bytes,
@@ -113,8 +115,8 @@ typedef struct {
     int rows_per_flag;
     int sub;               /* flag words per producer (0 is read as 1) */
     int stride;            /* words between the flag groups of consecutive producers (0 is read as sub) */
-    int reserved_sms;      /* SMs the consuming kernels must leave free for the concurrently running push kernel */
-    uint32_t* err;         /* device-visible word set to 1 + k if waiting for flags[k] timed out (4 s); may be NULL */
+    uint32_t timeout_ms;   /* a kernel waiting longer than this for a producer traps (0: waits for ever) */
+    uint32_t* err;         /* device-visible word set to 1 + k before the trap when flags[k] timed out; may be NULL */
 } flyp_ready_t;
 
 /* The gathered matrices of one step, [world * n_rows, dim] rank-major, in this rank's exchange segment. */
@@ -150,15 +152,21 @@ int flyp_comm_ipc_handle(flyp_comm* comm, void* handle_out);
 int flyp_comm_connect_ipc(flyp_comm* comm, const void* all_handles);
 /* Same-process peers (single-process multi-GPU, or several emulated ranks on one GPU in tests). */
 int flyp_comm_connect_local(flyp_comm* comm, flyp_comm* const* peers);
-/* 0, or 1 + k if a kernel gave up waiting for rank k (host read of a mapped word; no synchronisation). */
+/* 0, or 1 + k if a kernel gave up waiting for rank k (host read of a mapped word; no synchronisation).  A kernel that
+ * gives up TRAPS right after setting the word - it never continues on rows that have not arrived - so every later CUDA
+ * call of the process fails, like after an NCCL watchdog abort. */
 int flyp_comm_error(const flyp_comm* comm);
+int flyp_comm_reset_error(flyp_comm* comm);
+/* How long a kernel waits for a peer's rows before it traps (default 600000 = 10 min, or FLYP_PEER_TIMEOUT_MS at
+ * creation; 0 = for ever). */
+int flyp_comm_set_timeout_ms(flyp_comm* comm, uint32_t timeout_ms);
 int flyp_comm_destroy(flyp_comm* comm);
 
-/* clip/loss.py:59-67 without torch.cat: pack the local rows (and their fp16 copies) into the own slots on `stream`,
- * then push them to every peer with a small persistent kernel (remote 16-byte stores over NVLink, a few SMs, on the
- * communicator's side stream): text first, peers in ring order so that every rank receives from one peer at a time,
- * each CTA flagging its slice of a block as soon as it is out.  Returns at once; `out` describes where the gathered
- * matrices will be and how many SMs the consumers must leave to the push kernel. */
+/* clip/loss.py:59-67 without torch.cat: a pack kernel on `stream` copies the local rows (and their fp16 copies) into
+ * the own slots of the gathered matrices; the copy engines then push the slots to every peer on the communicator's side
+ * stream, text first - with an NVSwitch multicast mapping ONE copy per matrix reaches all ranks, otherwise one copy per
+ * peer in ring order - each block copy followed by a 4-byte copy of the step's sequence number into the flag word the
+ * consumers poll.  Returns at once; `out` says where the gathered matrices will be and which flags announce them. */
 int flyp_comm_gather_features(flyp_comm* comm, const void* img, const void* txt, int n_rows, int dim, int dtype,
                               flyp_gathered_t* out, void* stream);
 /* Push this rank's column triples / row statistics (outputs of flyp_clip_fwd_local) into every rank's segment. */
@@ -187,6 +195,16 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
                            void* d_img, void* d_txt, float* d_scale, void* workspace, size_t workspace_bytes,
                            const void* txt16, const flyp_ready_t* txt_ready, const flyp_ready_t* txt16_ready,
                            void* stream);
+/* The one-directional cross-entropy on a class matrix `b` that other ranks are still writing (the local_loss blocks of
+ * clip/loss.py:109-111 over the gathered features): b_ready as above; b16 (may be NULL -> converted here) the fp16 copy
+ * of b and its readiness. */
+int flyp_ce_fwd_ex(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
+                   const int64_t* labels, int label_offset, float* loss, float* lse, void* workspace,
+                   size_t workspace_bytes, const flyp_ready_t* b_ready, void* stream);
+int flyp_ce_bwd_ex(const void* a, const void* b, const float* scale, int n, int n_classes, int dim, int dtype,
+                   const int64_t* labels, int label_offset, const float* lse, const float* loss, const float* g,
+                   int grad_dtype, void* d_a, void* d_b, float* d_scale, void* workspace, size_t workspace_bytes,
+                   const void* b16, const flyp_ready_t* b_ready, const flyp_ready_t* b16_ready, void* stream);
 
 /* Both backward sweeps of a rank of the row-sharded symmetric loss with one shared preparation pass: d_img from the
  * row block img . txt_all^T, d_txt from the transposed block txt . img_all^T (complete gradients of the local rows,
@@ -201,22 +219,31 @@ int flyp_clip_bwd_sharded(const void* img, const void* txt, const void* img_all,
                           size_t workspace_bytes, const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready,
                           const flyp_ready_t* img16_ready, const flyp_ready_t* txt16_ready, void* stream);
 
-/* Whole-step entry points of a rank over a communicator - what the drop-in module's forward / backward call.
- * flyp_clip_fwd_step = flyp_comm_gather_features + flyp_clip_fwd_local_ex + flyp_comm_push_stats +
- * flyp_clip_fwd_finish_ex: loss[world * n_rows] (the full per-item vector on every rank, clip/loss.py:113-114,208) and
- * the statistics the backward needs; `step` keeps where the gathered data lives (valid until the second-next
- * flyp_clip_fwd_step on this communicator).  flyp_clip_bwd_step = flyp_clip_bwd_sharded with the d(logit_scale)
- * all-reduce folded in: this rank's partial is pushed right after the first sweep and summed (fixed rank order) after
- * the second, so the exchange hides behind the second sweep.  d_scale (the global sum) and d_scale_partial (scratch,
- * 1 float) are both NULL or both given. */
+/* Whole-step entry points of a rank - what the drop-in module's forward / backward call, ONE call per direction.
+ * comm == NULL (world must be 1): the single-GPU loss of the FLYP loop (src/models/flyp_loss.py:365,496): no exchange,
+ * 5 kernel launches forward (preparation, tcgen05 sweep, finalize incl. the loss vector, two gated robust-path stubs)
+ * and 5 backward (control-word memset, 2 vector kernels, 2 tcgen05 sweeps that reduce their own partial sums).
+ * comm != NULL: flyp_clip_fwd_step = gather (the pack kernel also prepares the positive logits) + forward statistics +
+ * flyp_comm_push_stats + flyp_clip_fwd_finish_ex; flyp_clip_bwd_step = flyp_clip_bwd_sharded with the d(logit_scale)
+ * all-reduce folded in: the last CTA of the first sweep publishes this rank's partial, the W partials are summed (fixed
+ * rank order) after the second sweep.
+ * Out: loss[world * n_rows] (the full per-item vector on every rank, clip/loss.py:113-114,208) and the statistics the
+ * backward needs (row_lse, row_nll [n_rows]; col_lse, col_nll [world * n_rows]); col_stat (3 * world * n_rows floats)
+ * may be NULL (workspace scratch is used).  `step` keeps where the gathered data lives (valid until the next
+ * flyp_clip_fwd_step on this communicator: a step's backward must be issued before the next forward).
+ * feat16 (comm == NULL, bf16 features, may be NULL): 2 * n_rows * dim fp16 elements that receive the fp16 copies of img
+ * and txt for the backward (written by the forward's preparation pass; without it the backward converts again).
+ * status (may be NULL): device int, 1 when the robust recomputation ran.
+ * d_scale (the global sum) and d_scale_partial (scratch, 1 float) are both NULL or both given when comm != NULL; with
+ * comm == NULL only d_scale is used. */
 typedef struct {
     flyp_gathered_t gathered;
     flyp_stats_t stats;
 } flyp_step_t;
 int flyp_clip_fwd_step(flyp_comm* comm, const void* img, const void* txt, const float* scale, int n_rows, int dim,
                        int dtype, int rank, int world, float* row_lse, float* row_nll, float* col_stat, float* col_lse,
-                       float* col_nll, void* loss, int loss_dtype, void* workspace, size_t workspace_bytes,
-                       flyp_step_t* step, void* stream);
+                       float* col_nll, void* loss, int loss_dtype, void* feat16, int* status, void* workspace,
+                       size_t workspace_bytes, flyp_step_t* step, void* stream);
 int flyp_clip_bwd_step(flyp_comm* comm, const flyp_step_t* step, const void* img, const void* txt, const float* scale,
                        int n_rows, int dim, int dtype, int rank, int world, const float* col_lse, const float* col_nll,
                        const void* g, int g_dtype, float grad_mul, int grad_dtype, void* d_img, void* d_txt,
@@ -250,6 +277,11 @@ int flyp_debug_logits(const void* a, const void* b, int n_m, int n_n, int dim, i
 /* Debug: while set (non-NULL, 16 x uint64 device words), the backward sweep of cluster 0 records per-role wait-cycle
  * counters there (tools/pair_prof.py).  Pass NULL to switch it off.  Not thread-safe; never used by the product path. */
 int flyp_debug_profile(void* device_buffer_16_u64);
+/* Measurement: while set (cudaEvent_t handles, both of a pair or neither; NULL switches off), the library records
+ * fwd_start / fwd_stop around the launch of the forward tcgen05 sweep and sweep_start / sweep_stop around the backward
+ * sweep number `sweep` (0: d image / first operand, 1: d text) of every call, on the launching stream - kernel-only
+ * timings inside a real step (bench.py's roofline).  Not thread-safe; never used by the product path. */
+int flyp_debug_kernel_events(void* fwd_start, void* fwd_stop, void* sweep_start, void* sweep_stop, int sweep);
 
 #ifdef __cplusplus
 }

@@ -55,8 +55,60 @@ static int check(int m_tiles, int n_dh, int NJ, int npairs) {
     return 0;
 }
 
+// Forward flat schedule: every (column unit, row tile) unit covered exactly once; the slots written for a column unit are
+// exactly 0 .. fwd_unit_slots() - 1 (what the finalize kernel sums), all below fwd_sched_slots() (the workspace bound);
+// every worker has work; items of one worker do not repeat a column unit.
+static int check_fwd(int m_tiles, int n_units, int n_local, int rot, int max_workers) {
+    const int P = fwd_sched_workers(m_tiles, n_units, max_workers);
+    const int bound = fwd_sched_slots(m_tiles, n_units, n_local, P);
+    std::vector<int> cover((size_t)m_tiles * n_units, 0);
+    std::map<int, std::set<int>> slots_of_unit;
+    for (int q = 0; q < P; ++q) {
+        FwdItems it(m_tiles, n_units, n_local, rot, P, q);
+        FwdItem fi;
+        int n_items = 0;
+        std::set<int> seen;
+        bool remote_seen = false;
+        while (it.next(fi)) {
+            ++n_items;
+            if (fi.u < 0 || fi.u >= n_units || fi.mt0 < 0 || fi.mt1 > m_tiles || fi.mt0 >= fi.mt1) return 21;
+            if (fi.slot < 0 || fi.slot >= bound) return 22;
+            if (!seen.insert(fi.u).second) return 23;
+            if (!slots_of_unit[fi.u].insert(fi.slot).second) return 24;
+            for (int mt = fi.mt0; mt < fi.mt1; ++mt) cover[(size_t)fi.u * m_tiles + mt]++;
+            int ub = fi.u - rot; if (ub < 0) ub += n_units;
+            if (ub >= n_local) remote_seen = true;
+            else if (remote_seen) return 29;                   // local units always come first
+        }
+        if (n_items == 0 && n_local == 0) return 25;         // (two phases: a tiny phase may leave late workers idle)
+    }
+    for (int c : cover) if (c != 1) return 26;
+    for (int u = 0; u < n_units; ++u) {
+        int ub = u - rot; if (ub < 0) ub += n_units;
+        const int ns = fwd_unit_slots(ub, m_tiles, n_units, n_local, P);
+        const std::set<int>& got = slots_of_unit[u];
+        if ((int)got.size() != ns) return 27;
+        int k = 0;
+        for (int sl : got) if (sl != k++) return 28;
+    }
+    return 0;
+}
+
 int main() {
     long long n = 0;
+    for (int maxw : {1, 2, 5, 37, 74, 148})
+        for (int m_tiles = 1; m_tiles <= 300; m_tiles += (m_tiles < 40 ? 1 : 29))
+            for (int n_units : {1, 2, 3, 4, 8, 15, 16, 31, 32, 128, 256, 512}) {
+                const int rots[3] = {0, n_units / 3, n_units - 1};
+                const int locals[4] = {0, 1, n_units / 8, n_units / 2};
+                for (int rot : rots)
+                    for (int n_local : locals) {
+                        if (n_local > n_units) continue;
+                        const int rc = check_fwd(m_tiles, n_units, n_local, rot, maxw);
+                        if (rc) { printf("FAIL fwd rc=%d m_tiles=%d n_units=%d n_local=%d rot=%d maxw=%d\n", rc, m_tiles, n_units, n_local, rot, maxw); return 1; }
+                        ++n;
+                    }
+            }
     const int npairs_list[] = {1, 2, 3, 7, 64, 66, 70, 74};
     for (int npairs : npairs_list)
         for (int n_dh = 1; n_dh <= 2; ++n_dh)

@@ -45,8 +45,13 @@ def test_null_communicator_is_an_argument_error():
     assert lib.flyp_comm_has_multicast(None) == 0
     assert lib.flyp_comm_destroy(None) == 0
     step = _lib.Step()
+    # world 2 without a communicator; and world 1 (communicator-free single-GPU loss) with null features
     assert lib.flyp_clip_fwd_step(None, None, None, None, 128, 512, 0, 0, 2, None, None, None, None, None, None, 0, None,
-                                  0, ctypes.byref(step), None) == -1
+                                  None, None, 0, ctypes.byref(step), None) == -1
+    assert lib.flyp_clip_fwd_step(None, None, None, None, 128, 512, 0, 0, 1, None, None, None, None, None, None, 0, None,
+                                  None, None, 0, ctypes.byref(step), None) == -1
+    assert lib.flyp_comm_reset_error(None) == 0
+    assert lib.flyp_comm_set_timeout_ms(None, 5) == -1
 
 
 def test_structures_have_the_header_layout():

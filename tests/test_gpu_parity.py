@@ -27,6 +27,23 @@ def rel(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
+def rel_rows(a, b, floor=1e-3):
+    """Worst PER-ROW relative error max_j|err_rj| / max_j|want_rj| over the rows whose magnitude is at least
+    floor * max|want|: a global max-abs ratio alone would let small-magnitude gradient rows be arbitrarily wrong."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if b.ndim == 1:
+        a, b = a[:, None], b[:, None]
+    rmax = np.max(np.abs(b), axis=1)
+    live = rmax >= floor * max(np.max(np.abs(b)), 1e-300)
+    if not live.any():
+        return 0.0
+    return float(np.max(np.max(np.abs(a - b), axis=1)[live] / rmax[live]))
+
+
+ROW_TOL = 3 * TOL      # per-row bar (rows above 1e-3 of the largest): the same order as the global one
+
+
 def to_np(t):
     return t.detach().double().cpu().numpy()
 
@@ -65,6 +82,17 @@ def run_abi_fp32(I, T, s, g):
     return loss, dI, dT, ds
 
 
+def run_step_fp32(I, T, s, g):
+    """flyp_clip_fwd_step / flyp_clip_bwd_step with comm = NULL: the single-GPU loss as the module runs it."""
+    from flyp_b200 import step
+    Ic, Tc, gd = I.to(DEV), T.to(DEV), g.to(DEV)
+    sc = torch.tensor([float(s)], device=DEV)
+    loss, st = step.step_forward(None, Ic, Tc, sc, torch.float32)
+    dI, dT, ds = step.step_backward(st, gd, 1.0, torch.float32, True, True, True)
+    torch.cuda.synchronize()
+    return loss, dI, dT, ds
+
+
 BF16_EPS = 2.0 ** -8       # one round-to-nearest bf16 storage step
 
 
@@ -78,6 +106,16 @@ def check_against_oracle(I, T, s, g, tol=TOL):
     assert rel(to_np(dI), wdI) < tol, "d image_features"
     assert rel(to_np(dT), wdT) < tol, "d text_features"
     assert abs(ds.item() - wds) <= tol * max(abs(wds), 1e-30), "d logit_scale"
+    # ... and row by row: small-magnitude gradient rows and small losses are right in relative terms too
+    assert rel_rows(to_np(loss), want) < 3 * tol, "loss, element-wise"
+    assert rel_rows(to_np(dI), wdI) < 3 * tol, "d image_features, per row"
+    assert rel_rows(to_np(dT), wdT) < 3 * tol, "d text_features, per row"
+    # (1b) the whole-step entry points the module uses (one C call per direction), fp32 gradient outputs
+    loss, dI, dT, ds = run_step_fp32(I, T, s, g)
+    assert rel(to_np(loss), want) < tol and rel_rows(to_np(loss), want) < 3 * tol, "loss (step)"
+    assert rel(to_np(dI), wdI) < tol and rel_rows(to_np(dI), wdI) < 3 * tol, "d image_features (step)"
+    assert rel(to_np(dT), wdT) < tol and rel_rows(to_np(dT), wdT) < 3 * tol, "d text_features (step)"
+    assert abs(ds.item() - wds) <= tol * max(abs(wds), 1e-30), "d logit_scale (step)"
     # (2) the drop-in module: loss and feature gradients come back in the feature dtype like the reference's
     #     (autograd casts); bf16 storage costs one extra rounding
     loss, dI, dT, ds = run_module(I, T, s, g)
@@ -166,6 +204,46 @@ def test_unnormalised_inputs_take_the_robust_path():
     assert rel(to_np(col_lse), orc.logsumexp(S, 0)) < 1e-5
     assert rel(to_np(loss), orc.clip_loss(to_np(I), to_np(T), s)) < 1e-5
     check_against_oracle(I, T, s, g)
+
+
+def test_step_entry_point_reports_the_robust_path():
+    from flyp_b200 import step
+    n, d = 300, 512
+    gen = torch.Generator().manual_seed(9)
+    I = (torch.randn(n, d, generator=gen) * torch.logspace(-1.5, 0.0, n)[:, None] * 0.2).bfloat16()
+    T = (torch.randn(n, d, generator=gen) * 0.2).bfloat16()
+    sc = torch.tensor([100.0], device=DEV)
+    loss, st, status = step.step_forward(None, I.to(DEV), T.to(DEV), sc, torch.float32, want_status=True)
+    assert status.item() == 1
+    assert rel(to_np(loss), orc.clip_loss(to_np(I), to_np(T), 100.0)) < 1e-5
+    I2, T2, _ = make_inputs(n, d, seed=1)
+    loss, st, status = step.step_forward(None, I2.to(DEV), T2.to(DEV), torch.tensor([1 / 0.07], device=DEV), torch.float32,
+                                         want_status=True)
+    assert status.item() == 0
+
+
+def test_ce_head_ignore_index_like_torch():
+    """F.cross_entropy (src/models/ce_ablation.py:123) skips targets equal to ignore_index = -100: loss 0, no gradient,
+    and reduction='mean' averages over the remaining rows."""
+    n, c, d = 200, 37, 256
+    gen = torch.Generator().manual_seed(5)
+    a = torch.nn.functional.normalize(torch.randn(n, d, generator=gen), dim=-1).bfloat16()
+    b = torch.nn.functional.normalize(torch.randn(c, d, generator=gen), dim=-1).bfloat16()
+    labels = torch.randint(0, c, (n,), generator=gen)
+    labels[::7] = -100
+    s = 1 / 0.07
+    ac = a.to(DEV).requires_grad_(True); bc = b.to(DEV).requires_grad_(True)
+    loss = flyp_b200.contrastive_cross_entropy(ac, bc, torch.tensor(s, device=DEV), labels.to(DEV), reduction="mean",
+                                               grad_dtype=torch.float32)
+    loss.backward()
+    af = a.float().requires_grad_(True); bf = b.float().requires_grad_(True)
+    want = torch.nn.functional.cross_entropy(s * af @ bf.T, labels)
+    want.backward()
+    assert abs(loss.item() - want.item()) < (BF16_EPS + TOL) * abs(want.item())
+    assert rel(to_np(ac.grad), to_np(af.grad)) < BF16_EPS + TOL and rel(to_np(bc.grad), to_np(bf.grad)) < BF16_EPS + TOL
+    assert float(ac.grad[::7].abs().max()) == 0.0
+    per_item = flyp_b200.contrastive_cross_entropy(a.to(DEV), b.to(DEV), torch.tensor(s, device=DEV), labels.to(DEV))
+    assert float(per_item[::7].abs().max()) == 0.0
 
 
 def test_tiny_losses_keep_relative_accuracy():
@@ -342,42 +420,59 @@ def test_fused_argmax_equals_argmax_of_logits(n, c, d, dtype):
 
 
 # ---------------------------------------------------------------------------------------------- full size properties
-def test_full_size_properties():
-    """BASELINE config B = 32768, D = 512 bf16: size-independent checks (the oracle cannot form 32768^2 logits)."""
-    n, d, s = 32768, 512, 1 / 0.07
-    I, T, g = make_inputs(n, d, seed=0)
+def _sampled_full_size_check(n, d, s, seed, n_samples=48):
+    """Size-independent parity at full size: the float64 reference of tools/sampled_check.py (chunked logsumexp over the
+    whole matrix on the GPU, independent of the kernels) for sampled items - loss, d image_features AND d text_features
+    row by row - plus the d(scale) identities over all rows."""
+    from tools import sampled_check as sck
+    I, T, g = make_inputs(n, d, seed=seed)
     Ic, Tc, gd = I.to(DEV), T.to(DEV), g.to(DEV)
     sc = torch.tensor([s], device=DEV)
     row_lse, row_nll, col_stat, status = ops.clip_fwd_local(Ic, Tc, sc)
     col_lse, col_nll, loss = ops.clip_fwd_finish(col_stat, 1, row_nll, n)
     assert status.item() == 0
-    In, Tn = to_np(I), to_np(T)
-    idx = np.random.default_rng(0).choice(n, 48, replace=False)
-    Srows = s * (In[idx] @ Tn.T)                      # sampled rows and columns of S in float64
-    Scols = s * (In @ Tn[idx].T)
-    diag = Srows[np.arange(len(idx)), idx]
-    assert rel(to_np(row_lse)[idx], orc.logsumexp(Srows, 1)) < 1e-5
-    assert rel(to_np(col_lse)[idx], orc.logsumexp(Scols, 0)) < 1e-5
-    want = 0.5 * ((orc.logsumexp(Srows, 1) - diag) + (orc.logsumexp(Scols, 0) - diag))
-    assert rel(to_np(loss)[idx], want) < 1e-5
+    idx = torch.tensor(np.random.default_rng(0).choice(n, n_samples, replace=False), device=DEV)
+    lse64 = sck.full_lse(Ic, Tc, s)
+    want_loss, want_dI, want_dT = sck.sampled_reference(Ic, Tc, s, gd, idx, lse=lse64)
+    assert sck.row_errors(row_lse.double(), lse64[0])[0] < 1e-5
+    assert sck.row_errors(col_lse.double(), lse64[1])[0] < 1e-5
+    assert sck.row_errors(loss[idx], want_loss)[0] < 1e-5
     d_img, d_txt, d_s = ops.clip_bwd_local(Ic, Tc, sc, 0, row_lse, row_nll, col_lse, col_nll, gd, gd,
                                            grad_dtype=torch.float32)
-    # sampled gradient rows from the closed form, using the (validated) statistics vectors
-    gn = to_np(g)
-    Pr = np.exp(Srows - to_np(row_lse)[idx][:, None])
-    Pc = np.exp(Srows - to_np(col_lse)[None, :])
-    dS = 0.5 * gn[idx][:, None] * Pr + 0.5 * gn[None, :] * Pc
-    dS[np.arange(len(idx)), idx] -= gn[idx]
-    assert rel(to_np(d_img)[idx], s * (dS @ Tn)) < TOL
+    for got, want, what in ((d_img[idx], want_dI, "d image_features"), (d_txt[idx], want_dT, "d text_features")):
+        glob, per_row = sck.row_errors(got, want)
+        assert glob < TOL and per_row < ROW_TOL, (what, glob, per_row)
+    # the whole-step entry points (what the module runs) at the same size
+    from flyp_b200 import step
+    loss2, st = step.step_forward(None, Ic, Tc, sc, torch.float32)
+    dI2, dT2, ds2 = step.step_backward(st, gd, 1.0, torch.float32, True, True, True)
+    assert sck.row_errors(loss2[idx], want_loss)[0] < 1e-5
+    for got, want, what in ((dI2[idx], want_dI, "d image_features (step)"), (dT2[idx], want_dT, "d text_features (step)")):
+        glob, per_row = sck.row_errors(got, want)
+        assert glob < TOL and per_row < ROW_TOL, (what, glob, per_row)
     # d(scale) identities: sum_i <dI_i, I_i> / s = sum_j <dT_j, T_j> / s = ds
     a = (d_img.double() * Ic.double()).sum().item() / s
     b = (d_txt.double() * Tc.double()).sum().item() / s
     assert abs(a - d_s.item()) < 1e-3 * abs(a) and abs(b - d_s.item()) < 1e-3 * abs(a)
+    assert abs(ds2.item() - d_s.item()) < 1e-4 * abs(a)
+    return Ic, Tc, sc, loss
+
+
+def test_full_size_properties():
+    """BASELINE config B = 32768, D = 512 bf16 (the oracle cannot form 32768^2 logits)."""
+    n = 32768
+    Ic, Tc, sc, loss = _sampled_full_size_check(n, 512, 1 / 0.07, seed=0)
     # the loss is permutation-equivariant: permuting the pairs permutes the per-item losses
     perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).to(DEV)
     r2, n2, c2, _ = ops.clip_fwd_local(Ic[perm].contiguous(), Tc[perm].contiguous(), sc)
     _, _, loss_p = ops.clip_fwd_finish(c2, 1, n2, n)
     assert rel(to_np(loss_p), to_np(loss[perm])) < 1e-5
+
+
+@pytest.mark.parametrize("n,d", [(65536, 512), (32768, 1024), (16384, 768)])
+def test_sweep_shapes_sampled_rows(n, d):
+    """The other points of the BASELINE sweep (B up to 64k, D = 1024: the two-pass pair sweep), row by row."""
+    _sampled_full_size_check(n, d, 1 / 0.07, seed=n // 1024 + d, n_samples=32)
 
 
 # ---------------------------------------------------------------------------------------------- fp32 features

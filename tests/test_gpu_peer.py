@@ -78,6 +78,114 @@ def test_emulated_ranks_match_oracle(world, b, dim):
             c.close()
 
 
+def test_emulated_eight_ranks_at_the_benchmark_size():
+    """The BASELINE multi-GPU configuration itself - global B = 32768, D = 512, 8 ranks of 4096 rows - emulated on ONE
+    GPU (the driver's test box has one), phase by phase: gathered bits, the loss vector, and sampled rows of d image /
+    d text of EVERY rank against the float64 reference of tools/sampled_check.py; gather_with_grad=True multiplies the
+    feature gradients by the world size."""
+    from flyp_b200 import comm as peer
+    from flyp_b200.comm import PeerComm
+    from oracle import torch_port
+    from tools import sampled_check as sck
+    dev = torch.device("cuda:0")
+    world, b, dim = 8, 4096, 512
+    B = world * b
+    s = 1.0 / 0.07
+    sc = torch.tensor([s], device=dev)
+    comms = [PeerComm(r, world, b, dim, dev) for r in range(world)]
+    PeerComm.connect_local(comms)
+    try:
+        I, T = torch_port.synthetic_pairs(B, dim, seed=3, dtype=torch.bfloat16)
+        Id, Td = I.to(dev), T.to(dev)
+        g = (torch.rand(B, generator=torch.Generator().manual_seed(11)) / B).to(dev)
+        steps = [peer.fwd_gather(comms[r], Id[r * b:(r + 1) * b], Td[r * b:(r + 1) * b], sc) for r in range(world)]
+        for st in steps:
+            peer.fwd_local(st)
+        losses = [peer.fwd_finish(st) for st in steps]
+        grads = [peer.bwd_local(st, g, float(world) if r % 2 else 1.0, torch.float32, True, True, True)
+                 for r, st in enumerate(steps)]
+        seq = steps[0].g.seq
+        for r in range(world):
+            comms[r].push_scalar(seq, grads[r][2])
+        ds_tot = [torch.empty(1, device=dev) for _ in range(world)]
+        for r in range(world):
+            comms[r].sum_scalar(seq, ds_tot[r])
+        torch.cuda.synchronize()
+        for c in comms:
+            c.check_error()
+        lse64 = sck.full_lse(Id, Td, s)
+        gen = np.random.default_rng(5)
+        for r, st in enumerate(steps):
+            assert torch.equal(_view_bf16(st.g.txt_all, B, dim), Td)
+            assert torch.equal(_view_bf16(st.g.img_all, B, dim), Id)
+            assert torch.equal(losses[0], losses[r])
+            loc = torch.tensor(gen.choice(b, 32, replace=False), device=dev)
+            idx = loc + r * b
+            want_loss, want_dI, want_dT = sck.sampled_reference(Id, Td, s, g, idx, lse=lse64)
+            assert sck.row_errors(losses[r][idx], want_loss)[0] < 1e-5
+            mul = float(world) if r % 2 else 1.0
+            for got, want, what in ((grads[r][0][loc], mul * want_dI, "d image"), (grads[r][1][loc], mul * want_dT, "d text")):
+                glob, per_row = sck.row_errors(got, want)
+                assert glob < 2e-3 and per_row < 6e-3, (r, what, glob, per_row)
+        assert len({t.item() for t in ds_tot}) == 1
+        # d(scale) = sum over all rows of <dI_i, I_i> / s (ranks with the doubled gradients rescaled)
+        tot = sum((grads[r][0].double() * Id[r * b:(r + 1) * b].double()).sum().item() / (float(world) if r % 2 else 1.0)
+                  for r in range(world)) / s
+        assert abs(ds_tot[0].item() - tot) < 1e-3 * abs(tot)
+    finally:
+        for c in comms:
+            c.close()
+
+
+@pytest.mark.parametrize("gwg", [False, True])
+def test_local_loss_blocks_emulated(golden_dir, gwg):
+    """local_loss=True (clip/loss.py:109-111,200-201) for both gather_with_grad settings with two emulated ranks on one
+    GPU: the two one-directional cross-entropy blocks of every rank over the gathered matrices, the gathered-side
+    gradients reduce-scattered by hand, against the float64 oracle (which is pinned to the reference's gloo runs)."""
+    import os
+    import flyp_b200
+    from oracle import clip_oracle as orc
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(golden_dir, "clip_w2_n264_d64.npz"))
+    world = 2
+    I = torch.tensor(z["I"]).bfloat16(); T = torch.tensor(z["T"]).bfloat16()
+    n = I.shape[0]
+    b = n // world
+    s = float(z["scale"])
+    g = torch.tensor(z["g"][:b], dtype=torch.float32, device=dev)
+    I_all = I.to(dev); T_all = T.to(dev)
+    Ib = [I[r * b:(r + 1) * b].double().numpy() for r in range(world)]
+    Tb = [T[r * b:(r + 1) * b].double().numpy() for r in range(world)]
+    leaves, out = [], []
+    for r in range(world):
+        Il = I_all[r * b:(r + 1) * b].clone().requires_grad_(True)
+        Tl = T_all[r * b:(r + 1) * b].clone().requires_grad_(True)
+        # what gather_features hands the rank: the gathered matrices carry gradient only with gather_with_grad
+        Ia = I_all.clone().requires_grad_(gwg); Ta = T_all.clone().requires_grad_(gwg)
+        sc = torch.tensor(s, device=dev, requires_grad=True)
+        li = flyp_b200.contrastive_cross_entropy(Il, Ta, sc, None, r * b, grad_dtype=torch.float32)
+        lt = flyp_b200.contrastive_cross_entropy(Tl, Ia, sc, None, r * b, grad_dtype=torch.float32)
+        loss = (li + lt) / 2
+        (loss.float() * g).sum().backward()
+        leaves.append((Il, Tl, Ia, Ta, sc)); out.append(loss)
+    torch.cuda.synchronize()
+    # bf16 storage of the gradients by autograd on top of the 2e-3 bar (several bf16 terms with gather_with_grad)
+    tol = (3 if gwg else 1) * 2.0 ** -8 + 2e-3
+    for r in range(world):
+        Il, Tl, Ia, Ta, sc = leaves[r]
+        want = orc.clip_loss_distributed(Ib, Tb, s, r, True)
+        assert rel(out[r].detach().double().cpu().numpy(), want) < tol
+        wI, wT, ws = orc.clip_loss_distributed_grads(Ib, Tb, s, r, True, gwg, z["g"][:b])
+        dI = Il.grad.double(); dT = Tl.grad.double()
+        if gwg:                      # reduce-scatter (sum over ranks) of the gradients w.r.t. the gathered matrices
+            sl = slice(r * b, (r + 1) * b)
+            for q in range(world):
+                dI = dI + leaves[q][2].grad.double()[sl]
+                dT = dT + leaves[q][3].grad.double()[sl]
+        assert rel(dI.cpu().numpy(), wI) < tol and rel(dT.cpu().numpy(), wT) < tol
+        assert abs(sc.grad.item() - ws) < tol * abs(ws)
+
+
 def test_stale_step_is_refused():
     from flyp_b200 import comm as peer
     from flyp_b200.comm import PeerComm
@@ -91,8 +199,7 @@ def test_stale_step_is_refused():
     c = PeerComm(0, 1, b, dim, dev)
     try:
         first = peer.fwd_gather(c, Id, Td, sc); peer.fwd_local(first); peer.fwd_finish(first)
-        for _ in range(2):
-            st = peer.fwd_gather(c, Id, Td, sc); peer.fwd_local(st); peer.fwd_finish(st)
+        st = peer.fwd_gather(c, Id, Td, sc); peer.fwd_local(st); peer.fwd_finish(st)   # a step's backward comes first
         g = torch.ones(b, device=dev)
         with pytest.raises(FlypError):
             peer.bwd_local(first, g, 1.0, torch.float32, True, True, True)

@@ -57,16 +57,15 @@ def test_clip_namespace_mirrors_reference_import_path():
     assert C2 is ClipLoss and g2 is gather_features
 
 
-def test_comm_keyword_is_validated_and_defaults_to_auto():
-    import pytest
+def test_exchange_is_an_internal_decision(monkeypatch):
+    import inspect
     import torch
     from flyp_b200 import ClipLoss
-    assert ClipLoss().comm == "auto"
-    with pytest.raises(ValueError):
-        ClipLoss(comm="horovod")
-    # the peer-memory exchange carries bf16 features only; everything else (and comm='nccl') takes the NCCL path,
-    # decided without touching a device
-    fn = ClipLoss(world_size=2, rank=0, comm="nccl")
-    assert fn._peer_comm(torch.zeros(4, 8, dtype=torch.bfloat16)) is None
-    fn = ClipLoss(world_size=2, rank=0, comm="auto")
+    # no user-facing backend switch (north star: no multi-backend dispatch) ...
+    assert "comm" not in inspect.signature(ClipLoss.__init__).parameters
+    # ... the peer-memory exchange carries bf16 features; the multi-node path can be forced for tests, decided without
+    # touching a device
+    fn = ClipLoss(world_size=2, rank=0)
     assert fn._peer_comm(torch.zeros(4, 8, dtype=torch.float32)) is None
+    monkeypatch.setenv("FLYP_EXCHANGE", "collective")
+    assert fn._peer_comm(torch.zeros(4, 8, dtype=torch.bfloat16)) is None
