@@ -4,6 +4,7 @@
 #include "aux_kernels.cuh"
 #include "clip_kernels.cuh"
 #include "comm_internal.h"
+#include "tail_kernel.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -107,19 +108,22 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // The CTA-pair backward sweep handles feature dims that are multiples of 128 up to 1024; FLYP_BWD_IMPL=1 forces the
 // single-CTA kernel (kept for other dims and for A/B measurements).
+int num_sms();
 bool use_pair_kernel(int dim, int dtype, int n_m, int n_n) {
     const int forced = env_bwd_impl();                                    // A/B switch: 1 never, 2 whenever the shape allows
     if (forced == 1 || dtype != FLYP_BF16 || dim % 128 != 0 || dim > 1024) return false;
     if (dim <= 512 || forced == 2) return true;
     // two passes over the column halves: pays off once the sweep is long enough to amortise the extra pipeline fills and
-    // partial sums (measured: B = 8192, D = 1024 1.02 ms vs 1.35 ms; B = 4096, D = 768 0.42 ms vs 0.35 ms)
-    return (long long)ceil_div(n_m, flyp::TILE) * ceil_div(n_n, flyp::TILE) >= 2048;
+    // partial sums (measured: B = 8192, D = 1024 1.02 ms vs 1.35 ms; B = 4096, D = 768 0.42 ms vs 0.35 ms) ...
+    const int m_tiles = ceil_div(n_m, flyp::TILE);
+    if ((long long)m_tiles * ceil_div(n_n, flyp::TILE) >= 2048) return true;
+    // ... or when the single-CTA kernel, which cannot split a row block along the columns, would leave most SMs idle
+    // (a rank's share of B = 4096, D = 768 on 8 GPUs: 12 work items, 110 us however few rows the rank owns)
+    return 2 * m_tiles * ceil_div(dim, 256) < num_sms();
 }
 // passes over the output columns of the pair sweep and columns per pass (a multiple of 128, <= 512)
 inline int pair_n_dh(int dim) { return dim > 512 ? 2 : 1; }
 inline int pair_d_half(int dim) { const int n = pair_n_dh(dim); return ((dim + n - 1) / n + 127) / 128 * 128; }
-// number of d(scale) partial slots / fp32 tail-partial blocks a sweep over m_tiles row blocks may use
-int num_sms();
 // d(scale) partial slots and fp32 tail-partial floats a backward sweep over n_m rows x n_n columns may use
 size_t sweep_dscale_slots(int n_m, int n_n, int dim, int dtype) {
     const int m_tiles = ceil_div(n_m, flyp::TILE);
@@ -940,6 +944,59 @@ int flyp_ce_bwd_ex(const void* a, const void* b, const float* scale, int n, int 
         // (rows of b that other ranks wrote were all consumed - and waited for - by the forward of the same step)
         if ((rc = run_sweep(io, st)) != 0) return rc;
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ encoder tail
+int flyp_project_normalize_workspace_bytes(int n, int k, int n_out, int dtype, size_t* bytes) {
+    if (!bytes) return fail(FLYP_ERR_ARG, "bytes is null");
+    if (n <= 0 || k <= 0 || n_out <= 0) return fail(FLYP_ERR_ARG, "bad shape");
+    if (dtype != FLYP_BF16 && dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad dtype %d", dtype);
+    // fp32 inputs: three bf16 planes of x ([n][3 k]) and of W ([3][k][n_out])
+    *bytes = dtype == FLYP_F32 ? align_up((size_t)n * 3 * k * 2, 256) + align_up((size_t)3 * k * n_out * 2, 256) + 256 : 256;
+    return 0;
+}
+
+int flyp_project_normalize_fwd(const void* x, const void* w, int n, int k, int n_out, int dtype, void* y, int y_dtype,
+                               void* y16, float* inv_norm, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x || !w || !y) return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (n <= 0 || k <= 0 || k % 8 != 0) return fail(FLYP_ERR_ARG, "bad shape [%d, %d] (k %% 8 must be 0)", n, k);
+    if (n_out <= 0 || n_out % 64 != 0 || n_out > 1024)
+        return fail(FLYP_ERR_ARG, "output dim %d must be a multiple of 64, at most 1024", n_out);
+    if (dtype != FLYP_BF16 && dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad dtype %d", dtype);
+    if (y_dtype != FLYP_BF16 && y_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad y_dtype %d", y_dtype);
+    if (y16 != nullptr && y_dtype != FLYP_BF16) return fail(FLYP_ERR_ARG, "the fp16 copy goes with bf16 features");
+    if (dtype == FLYP_F32 && k % 64 != 0) return fail(FLYP_ERR_ARG, "fp32 inputs need k %% 64 == 0 (k = %d)", k);
+    size_t need = 0;
+    flyp_project_normalize_workspace_bytes(n, k, n_out, dtype, &need);
+    if (dtype == FLYP_F32 && (!workspace || workspace_bytes < need))
+        return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, need);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUtensorMap tmX, tmW;
+    int rc;
+    flyp::TailParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = n; p.n_out = n_out; p.kc = ceil_div(k, flyp::KCHUNK);
+    const int split = flyp::tail_n_split(n_out);
+    p.n_cta = ceil_div(ceil_div(n_out, split), 64) * 64;
+    p.y = y; p.y_fp32 = y_dtype == FLYP_F32; p.y16 = y16; p.inv_norm = inv_norm;
+    if (dtype == FLYP_F32) {
+        uint16_t* px = static_cast<uint16_t*>(workspace);
+        uint16_t* pw = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(workspace) + align_up((size_t)n * 3 * k * 2, 256));
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(x), n, k, k, px, st);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(w), 1, k * n_out, k * n_out, pw, st);   // [3][k][n_out]
+        CUDA_OK(cudaGetLastError());
+        if ((rc = make_tmap(&tmX, px, n, 3 * k, 3 * k)) != 0) return rc;
+        if ((rc = make_tmap(&tmW, pw, 3 * k, n_out, n_out, false, 64)) != 0) return rc;
+        p.kplan = flyp::kplan_f32(k);
+        p.w_plane_rows = k;
+    } else {
+        if ((rc = make_tmap(&tmX, x, n, k, k)) != 0) return rc;
+        if ((rc = make_tmap(&tmW, w, k, n_out, n_out, false, 64)) != 0) return rc;
+        p.kplan = flyp::kplan_bf16();
+    }
+    flyp::launch_tail(tmX, tmW, p, st);
+    CUDA_OK(cudaGetLastError());
     return 0;
 }
 

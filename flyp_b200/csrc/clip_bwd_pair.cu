@@ -62,11 +62,17 @@ DEVI void epi_bar_sync2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // B = 32768 on 8 or 4 GPUs).
 int bwd_pair_sched_pairs(int m_tiles, int n_cols, int num_sms) {
     int npairs = num_sms / 2;
-    if (const char* e = getenv("FLYP_SCHED_PAIRS")) {          // A/B switch for measurements
-        const int v = atoi(e);
-        if (v > 0 && v < npairs) npairs = v;
-    }
-    const long long S = (long long)m_tiles * ((n_cols + PairCfg::NSTEP - 1) / PairCfg::NSTEP);
+    static const int forced = [] { const char* e = getenv("FLYP_SCHED_PAIRS"); return e ? atoi(e) : 0; }();   // A/B switch
+    if (forced > 0 && forced < npairs) npairs = forced;
+    const int NJ = (n_cols + PairCfg::NSTEP - 1) / PairCfg::NSTEP;
+    const long long S = (long long)m_tiles * NJ;
+    // A range shorter than MIN_STEPS column steps does not pay for its share of the end-of-sweep reduction (fp32
+    // partials, grid barrier): small problems use fewer pairs - down to one per row block, i.e. no partials at all
+    // (B = 512: 4 pairs x 2 steps instead of 8 x 1 - measured 30 us -> 12 us per sweep).
+    constexpr int MIN_STEPS = 4;
+    long long cap = S / MIN_STEPS;
+    if (cap < m_tiles) cap = m_tiles;
+    if (cap < npairs) npairs = (int)cap;
     return (int)(S < npairs ? S : npairs);
 }
 
@@ -233,10 +239,18 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 tma_load_2d_cg2(dst + 8192, &tmA64, bar, (c + 1) * KCHUNK, mb * TILE + (int)cta * 64);
                 if (++slot == NSLOT) { slot = 0; ph ^= 1; }
             };
+            // measurement switches (FLYP_DBG bits 8 / 16): the loads of the dA^T operand / of the S operand are skipped
+            // altogether - the slot just changes hands with stale contents (wrong results, right timing)
+            auto skip_slot = [&]() {
+                mbar_wait(EMPTY(slot), ph ^ 1);
+                if (cta == 0) mbar_arrive(FULL(slot));
+                if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+            };
             auto load_s = [&](int t, int mb) {
                 for (int c = 0; c < KC; ++c) {
                     if (WIDE && c >= KCS && (c & 1) == 0) put_a2(c, mb);
-                    put(&tmB, c * KCHUNK, t * Cfg::NSTEP + (int)cta * 128);
+                    if (p.dbg & 16) skip_slot();
+                    else put(&tmB, c * KCHUNK, t * Cfg::NSTEP + (int)cta * 128);
                 }
                 if (pad_slot) {                                // bubble: no data, the slot just changes hands
                     mbar_wait(EMPTY(slot), ph ^ 1);
@@ -247,8 +261,10 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             auto load_t = [&](int t, int dcol0) {
                 for (int dblk = 0; dblk < ND; ++dblk)
                     for (int jh = 0; jh < 2; ++jh)
-                        for (int dsub = 0; dsub < 2; ++dsub)
-                            put(&tmBd, dcol0 + (dblk * 2 + (int)cta) * 128 + dsub * 64, t * Cfg::NSTEP + jh * 128);
+                        for (int dsub = 0; dsub < 2; ++dsub) {
+                            if (p.dbg & 8) skip_slot();
+                            else put(&tmBd, dcol0 + (dblk * 2 + (int)cta) * 128 + dsub * 64, t * Cfg::NSTEP + jh * 128);
+                        }
             };
             peer_wait_all(p.wait_b);      // multi-GPU: the N-side rows (and their fp16 copy) of every rank have arrived
             peer_wait_all(p.wait_bd);

@@ -259,6 +259,19 @@ int flyp_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n,
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Encoder tail, fused: the final projection of a tower followed by the L2 normalisation that feeds the loss -
+ * clip/model.py:242-243 (`x @ self.proj`), :359 (`x[eot] @ self.text_projection`), :375-376 (x / x.norm(dim=-1,
+ * keepdim=True)).  y[n, n_out] = z / ||z||_2, z = x[n, k] . w[k, n_out]: one tcgen05 GEMM whose accumulator tile stays
+ * in tensor memory, normalised in the epilogue; z is never written.  x, w: bf16, or fp32 (evaluated as 3-way bf16 split
+ * products, fp32-accurate; needs the workspace).  y: y_dtype FLYP_BF16 or FLYP_F32; y16 (bf16 y only, may be NULL): fp16
+ * copy of the rounded features, the operand format of the loss's backward; inv_norm[n] (may be NULL) = 1 / ||z|| for
+ * the backward (flyp_l2norm_bwd, then two plain GEMMs).  n_out % 64 == 0, n_out <= 1024; k % 8 == 0 (fp32: k % 64 == 0).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int flyp_project_normalize_workspace_bytes(int n, int k, int n_out, int dtype, size_t* bytes);
+int flyp_project_normalize_fwd(const void* x, const void* w, int n, int k, int n_out, int dtype, void* y, int y_dtype,
+                               void* y16, float* inv_norm, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Zero-shot prediction, src/models/eval.py:150-158 (`logits = ...; pred = logits.argmax(dim=1)`) and
  * src/models/zeroshot.py:56-81: out_index[i] = argmax_j <a_i, b_j> (ties -> lowest j, like torch.argmax), fused into the
  * forward kernel's epilogue - the [n_m, n_n] logits are never written.  out_max (optional) = the maximal dot product.

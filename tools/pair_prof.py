@@ -28,16 +28,3 @@ for name, x in zip(["sempty", "full_s", "dsfull", "full_t", "accempty", "ifull"]
     print(f"   wait {name:9s} {x:12d} clk  {100 * x / tot:5.1f}%  ({x / max(v[7],1):.0f}/step)")
 print(f"producer cta0: total {v[8]} wait_empty {v[9]} ({100*v[9]/max(v[8],1):.1f}%)   cta1: total {v[10]} wait_empty {v[11]} ({100*v[11]/max(v[10],1):.1f}%)")
 print(f"epilogue t128: total {v[12]} wait_sfull {v[13]} ({100*v[13]/max(v[12],1):.1f}%) wait_dsempty {v[14]} ({100*v[14]/max(v[12],1):.1f}%) wait_accfull {v[15]} ({100*v[15]/max(v[12],1):.1f}%)")
-import os
-for rep in range(3):
-    for split in ("0", "1"):
-        os.environ["FLYP_NO_SPLIT"] = split
-        for name, kw in (("dI+ds", dict(need_txt=False, need_scale=True)), ("dI", dict(need_txt=False, need_scale=False))):
-            ts = []
-            for _ in range(4):
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-                ops.clip_bwd_local(I, T, sc, 0, row_lse, row_nll, col_lse, col_nll, g, g, **kw)
-                e1.record(); torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            print(f"no_split={split} {name:6s}", " ".join(f"{t:.3f}" for t in ts))
