@@ -212,16 +212,14 @@ class PeerStep:
                  "col_lse", "col_nll", "loss", "ws")
 
 
-def _workspace(b: int, B: int, D: int, dev) -> torch.Tensor:
+def _workspace(b: int, B: int, D: int, dev, code: int = _lib.FLYP_BF16) -> torch.Tensor:
     from . import ops
-    return ops.cached_clip_workspace(b, B, D, _lib.FLYP_BF16, dev)
+    return ops.cached_clip_workspace(b, B, D, code, dev)
 
 
 def fwd_gather(comm: PeerComm, img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor) -> PeerStep:
     from . import ops
     ops._check_features(img, txt)
-    if img.dtype != torch.bfloat16:
-        raise FlypError("the peer-memory path carries bf16 features")
     st = PeerStep()
     st.comm, st.img, st.txt, st.s = comm, img.contiguous(), txt.contiguous(), scale
     st.b, st.D = img.shape
@@ -235,7 +233,7 @@ def fwd_local(st: PeerStep) -> None:
     lib = _lib.load()
     b, B = st.b, st.B
     with _lib.device_guard(dev):
-        st.ws = _workspace(b, B, st.D, dev)
+        st.ws = _workspace(b, B, st.D, dev, _lib.dtype_code(st.img))
         # one allocation for every fp32 vector of the step (each slice 16-byte aligned)
         bp = (b + 3) & ~3
         Bp = (B + 3) & ~3
@@ -245,7 +243,7 @@ def fwd_local(st: PeerStep) -> None:
         st.col_stat = st.buf[o:o + 3 * B]
         st.col_lse, st.col_nll = st.buf[o + 3 * Bp:o + 3 * Bp + B], st.buf[o + 4 * Bp:o + 4 * Bp + B]
         _lib.check(lib.flyp_clip_fwd_local_ex(
-            st.img.data_ptr(), st.g.txt_all, st.s.data_ptr(), b, B, st.D, _lib.FLYP_BF16, st.off,
+            st.img.data_ptr(), st.g.txt_all, st.s.data_ptr(), b, B, st.D, _lib.dtype_code(st.img), st.off,
             st.row_lse.data_ptr(), st.row_nll.data_ptr(), st.col_stat.data_ptr(), None,
             st.ws.data_ptr(), st.ws.numel(), ctypes.byref(st.g.txt_ready), _lib.stream_ptr(dev)))
     st.st = st.comm.push_stats(st.g.seq, st.col_stat, st.row_lse, st.row_nll)
@@ -285,11 +283,103 @@ def bwd_local(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_i
         gg = st.g
         _lib.check(lib.flyp_clip_bwd_sharded(
             st.img.data_ptr(), st.txt.data_ptr(), gg.img_all, gg.txt_all, gg.img16_all, gg.txt16_all, st.s.data_ptr(),
-            st.b, st.B, st.D, _lib.FLYP_BF16, st.off, st.st.row_lse_all, st.st.row_nll_all, st.col_lse.data_ptr(),
+            st.b, st.B, st.D, _lib.dtype_code(st.img), st.off, st.st.row_lse_all, st.st.row_nll_all, st.col_lse.data_ptr(),
             st.col_nll.data_ptr(), g.data_ptr(), g_code, float(grad_mul), gcode, _lib.ptr(d_img), _lib.ptr(d_txt),
             _lib.ptr(d_s), st.ws.data_ptr(), st.ws.numel(), ctypes.byref(gg.img_ready), ctypes.byref(gg.txt_ready),
             ctypes.byref(gg.img16_ready), ctypes.byref(gg.txt16_ready), _lib.stream_ptr(dev)))
     return d_img, d_txt, d_s
+
+
+# ---------------------------------------------------------------------------------------------------- local_loss
+# clip/loss.py:109-111,200-201: with local_loss=True a rank's loss is two one-directional cross-entropies of its OWN rows
+# against the gathered matrices.  The gather is the peer-memory exchange above; the class matrix of each block lives in
+# this rank's segment and the kernels wait for its rows as they arrive.
+
+class LocalStep:
+    __slots__ = ("comm", "g", "img", "txt", "s", "b", "B", "D", "off", "seq", "ws_i", "ws_t", "lse_i", "lse_t", "loss_i",
+                 "loss_t", "code")
+
+
+def _ce_ws(n, c, d, code, dev):
+    from . import ops
+    return ops.ce_workspace(n, c, d, code, dev)
+
+
+def local_fwd(comm: PeerComm, img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor):
+    """Returns (loss_image[b], loss_text[b]) in fp32 and the state for local_bwd."""
+    return local_compute(local_gather(comm, img, txt, scale))
+
+
+def local_gather(comm: PeerComm, img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor) -> "LocalStep":
+    """Phase 1 (pack + pushes).  Split from the compute phase so that several emulated ranks on ONE GPU can be stepped
+    phase by phase (a kernel must never wait for a kernel that has not been enqueued)."""
+    from . import ops
+    ops._check_features(img, txt)
+    dev = img.device
+    st = LocalStep()
+    st.comm, st.img, st.txt, st.s = comm, img.contiguous(), txt.contiguous(), scale
+    st.b, st.D = img.shape
+    st.B, st.off = st.b * comm.world, comm.rank * st.b
+    st.code = _lib.dtype_code(img)
+    st.g = comm.gather(st.img, st.txt)
+    st.seq = int(st.g.seq)
+    return st
+
+
+def local_compute(st: "LocalStep"):
+    """Phase 2: the two cross-entropy blocks over the gathered matrices (their kernels wait for the rows as they arrive)."""
+    comm, scale, dev = st.comm, st.s, st.img.device
+    lib = _lib.load()
+    with _lib.device_guard(dev):
+        st.ws_i = _ce_ws(st.b, st.B, st.D, st.code, dev)
+        st.ws_t = _ce_ws(st.b, st.B, st.D, st.code, dev)
+        buf = torch.empty(4, st.b, dtype=torch.float32, device=dev)
+        st.loss_i, st.lse_i, st.loss_t, st.lse_t = buf[0], buf[1], buf[2], buf[3]
+        stream = _lib.stream_ptr(dev)
+        _lib.check(lib.flyp_ce_fwd_ex(st.img.data_ptr(), st.g.txt_all, scale.data_ptr(), st.b, st.B, st.D, st.code, None,
+                                      st.off, st.loss_i.data_ptr(), st.lse_i.data_ptr(), st.ws_i.data_ptr(),
+                                      st.ws_i.numel(), ctypes.byref(st.g.txt_ready), stream))
+        _lib.check(lib.flyp_ce_fwd_ex(st.txt.data_ptr(), st.g.img_all, scale.data_ptr(), st.b, st.B, st.D, st.code, None,
+                                      st.off, st.loss_t.data_ptr(), st.lse_t.data_ptr(), st.ws_t.data_ptr(),
+                                      st.ws_t.numel(), ctypes.byref(st.g.img_ready), stream))
+    comm.check_error()
+    return st.loss_i, st.loss_t, st
+
+
+def local_bwd(st: LocalStep, g: torch.Tensor, grad_dtype, need_gathered: bool):
+    """g[b]: upstream gradient on (loss_image + loss_text) / 2.  Returns (d_img[b, D], d_txt[b, D], d_scale[1]) of the
+    local operands and, with need_gathered (gather_with_grad=True), the gradients w.r.t. the GATHERED matrices
+    (d_img_all[B, D], d_txt_all[B, D]) that the caller reduce-scatters."""
+    comm = st.comm
+    if not comm.alive(st.seq):
+        raise FlypError("the gathered features of this step were overwritten by a later forward: with the peer-memory "
+                        "exchange a step's backward must be issued before the next forward")
+    dev = st.img.device
+    gdt = st.img.dtype if grad_dtype is None else grad_dtype
+    gcode = _lib.FLYP_BF16 if gdt == torch.bfloat16 else _lib.FLYP_F32
+    lib = _lib.load()
+    half = (0.5 * g.to(torch.float32)).contiguous()
+    with _lib.device_guard(dev):
+        d_img = torch.empty(st.b, st.D, dtype=gdt, device=dev)
+        d_txt = torch.empty(st.b, st.D, dtype=gdt, device=dev)
+        d_txt_all = torch.empty(st.B, st.D, dtype=gdt, device=dev) if need_gathered else None
+        d_img_all = torch.empty(st.B, st.D, dtype=gdt, device=dev) if need_gathered else None
+        ds = torch.empty(2, dtype=torch.float32, device=dev)
+        stream = _lib.stream_ptr(dev)
+        gg = st.g
+        bf16 = st.code == _lib.FLYP_BF16
+        _lib.check(lib.flyp_ce_bwd_ex(st.img.data_ptr(), gg.txt_all, st.s.data_ptr(), st.b, st.B, st.D, st.code, None, st.off,
+                                      st.lse_i.data_ptr(), st.loss_i.data_ptr(), half.data_ptr(), gcode, d_img.data_ptr(),
+                                      _lib.ptr(d_txt_all), ds.data_ptr(), st.ws_i.data_ptr(), st.ws_i.numel(),
+                                      gg.txt16_all if bf16 else None, ctypes.byref(gg.txt_ready),
+                                      ctypes.byref(gg.txt16_ready), stream))
+        _lib.check(lib.flyp_ce_bwd_ex(st.txt.data_ptr(), gg.img_all, st.s.data_ptr(), st.b, st.B, st.D, st.code, None, st.off,
+                                      st.lse_t.data_ptr(), st.loss_t.data_ptr(), half.data_ptr(), gcode, d_txt.data_ptr(),
+                                      _lib.ptr(d_img_all), ds.data_ptr() + 4, st.ws_t.data_ptr(), st.ws_t.numel(),
+                                      gg.img16_all if bf16 else None, ctypes.byref(gg.img_ready),
+                                      ctypes.byref(gg.img16_ready), stream))
+    comm.check_error()
+    return d_img, d_txt, ds.sum().reshape(1), d_img_all, d_txt_all
 
 
 # ---------------------------------------------------------------------------------------------------- whole steps

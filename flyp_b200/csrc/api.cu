@@ -241,10 +241,14 @@ int run_stats(const StatsIO& io, const StatsWs& w, cudaStream_t st) {
     const int n_m = io.n_m, n_n = io.n_n, dim = io.dim, dtype = io.dtype;
     flyp::KPlan kplan = flyp::kplan_bf16();
     const bool dbg = io.dbg_logits != nullptr;
+    // fp32 features whose rows other ranks are still writing: the kernel that splits them into planes waits for the
+    // owners of its rows; the tensor-core kernels then read complete, local planes
+    const flyp_ready_t* kernel_b_ready = dtype == FLYP_F32 ? nullptr : io.b_ready;
     if (dtype == FLYP_F32) {
         const int dp = plane_cols(dim);
+        const flyp::PeerWait wb = to_wait(io.b_ready);
         flyp::launch_split_planes_bf16x3(static_cast<const float*>(io.A), n_m, dim, dp, w.planes_a, st);
-        flyp::launch_split_planes_bf16x3(static_cast<const float*>(io.B), n_n, dim, dp, w.planes_b, st);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(io.B), n_n, dim, dp, w.planes_b, st, &wb);
         CUDA_OK(cudaGetLastError());
         if ((rc = make_tmap(&tmA, w.planes_a, n_m, 3 * dp, 3 * dp)) != 0) return rc;
         if ((rc = make_tmap(&tmB, w.planes_b, n_n, 3 * dp, 3 * dp)) != 0) return rc;
@@ -277,7 +281,7 @@ int run_stats(const StatsIO& io, const StatsWs& w, cudaStream_t st) {
     {
         // multi-GPU: rows of B owned by other ranks are still arriving; start at this rank's own column block
         flyp::FwdParams pf = p;
-        pf.wait_b = to_wait(io.b_ready);
+        pf.wait_b = to_wait(kernel_b_ready);
         const int unit_cols = flyp::TILE * (mc ? 2 : 1);
         cs.n_units = mc ? (w.n_tiles + 1) / 2 : w.n_tiles;
         if (pf.wait_b.flags != nullptr) {
@@ -649,7 +653,9 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
     int rc = check_common(n_rows, n_cols, dim, dtype);
     if (rc) return rc;
     if (g_dtype != FLYP_BF16 && g_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad g_dtype %d", g_dtype);
-    if (dtype != FLYP_BF16) return fail(FLYP_ERR_ARG, "the sharded backward takes bf16 features");
+    const bool f32 = dtype == FLYP_F32;
+    if (f32 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "fp32 features need grad_dtype = FLYP_F32");
+    if (f32 && (img16_all || txt16_all)) return fail(FLYP_ERR_ARG, "fp16 copies are only accepted for bf16 features");
     if (!img || !txt || !scale || !row_lse_all || !row_nll_all || !col_lse || !col_nll || !g || !workspace)
         return fail(FLYP_ERR_ARG, "null pointer argument");
     if ((d_img || d_scale) && !txt_all) return fail(FLYP_ERR_ARG, "d_img needs the gathered text features");
@@ -671,40 +677,59 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
     flyp::launch_bwd_fast_vectors(w.ctrl.words, cp, wg, l2c, fc, cp, wg, l2r, fr, w.fast_info, st);
     CUDA_OK(cudaGetLastError());
     const int off = row_offset;
+    const int dp = plane_cols(dim);
     flyp::PeerPush push;
     memset(&push, 0, sizeof(push));
     if (comm != nullptr && d_scale != nullptr && (rc = flyp::comm_scalar_push_target(comm, seq, &push)) != 0) return rc;
     if (d_img) {
         // image rows of this rank against all texts: complete d_img and this row block's share of d(scale)
         const void* t16 = txt16_all;
-        if (t16 == nullptr) {                    // the caller kept no fp16 copy: make one
+        if (f32) {
+            // split planes of the operands of this sweep (the gathered rows have arrived once the split kernel's own
+            // wait on their flags is over: the sweep itself then needs no flags)
+            const flyp::PeerWait wt = to_wait(txt_ready);
+            flyp::launch_split_planes_bf16x3(static_cast<const float*>(img), n_rows, dim, dp, w.stats.planes_a, st);
+            flyp::launch_split_planes_bf16x3(static_cast<const float*>(txt_all), n_cols, dim, dp, w.stats.planes_b, st, &wt);
+            flyp::launch_split_planes_f16x2(static_cast<const float*>(txt_all), n_cols, dim, dp, w.txt16, st, &wt);
+            CUDA_OK(cudaGetLastError());
+            t16 = w.txt16;
+        } else if (t16 == nullptr) {             // the caller kept no fp16 copy: make one
             flyp::launch_to_f16(txt_all, dtype, (size_t)n_cols * dim, w.txt16, st);
             CUDA_OK(cudaGetLastError());
             t16 = w.txt16;
         }
         SweepIO io = sweep_base(scale, dtype, dim, w, grad_dtype, grad_mul);
         io.A = img; io.B = txt_all; io.B_f16 = t16; io.n_m = n_rows; io.n_n = n_cols;
+        io.A_planes = w.stats.planes_a; io.B_planes = w.stats.planes_b;
         io.wr = wg + off; io.lr = l2r + off; io.wc = wg; io.lc = l2c; io.labr = w.rows.lab; io.dr = w.rows.d;
         io.fa = fr + off; io.fb = fc;
         io.out = d_img; io.sweep = 0;
         if (d_scale) { io.dscale_part = w.dscale_part; io.dscale_out = d_scale; io.ds_push = &push; }
-        io.b_ready = txt_ready; io.b16_ready = txt16_all ? txt16_ready : nullptr;
+        if (!f32) { io.b_ready = txt_ready; io.b16_ready = txt16_all ? txt16_ready : nullptr; }
         if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     if (d_txt) {
         // the transposed problem: text rows of this rank against all images (no B x D reduce-scatter)
         const void* i16 = img16_all;
-        if (i16 == nullptr) {                    // (the first sweep is done with the staging buffer: stream order)
+        if (f32) {                               // (the first sweep is done with the plane buffers: stream order)
+            const flyp::PeerWait wi = to_wait(img_ready);
+            flyp::launch_split_planes_bf16x3(static_cast<const float*>(txt), n_rows, dim, dp, w.stats.planes_a, st);
+            flyp::launch_split_planes_bf16x3(static_cast<const float*>(img_all), n_cols, dim, dp, w.stats.planes_b, st, &wi);
+            flyp::launch_split_planes_f16x2(static_cast<const float*>(img_all), n_cols, dim, dp, w.txt16, st, &wi);
+            CUDA_OK(cudaGetLastError());
+            i16 = w.txt16;
+        } else if (i16 == nullptr) {
             flyp::launch_to_f16(img_all, dtype, (size_t)n_cols * dim, w.txt16, st);
             CUDA_OK(cudaGetLastError());
             i16 = w.txt16;
         }
         SweepIO io = sweep_base(scale, dtype, dim, w, grad_dtype, grad_mul);
         io.A = txt; io.B = img_all; io.B_f16 = i16; io.n_m = n_rows; io.n_n = n_cols;
+        io.A_planes = w.stats.planes_a; io.B_planes = w.stats.planes_b;
         io.wr = wg + off; io.lr = l2c + off; io.wc = wg; io.lc = l2r; io.labr = w.rows.lab; io.dr = w.rows.d;
         io.fa = fc + off; io.fb = fr;
         io.out = d_txt; io.sweep = 1;
-        io.b_ready = img_ready; io.b16_ready = img16_all ? img16_ready : nullptr;
+        if (!f32) { io.b_ready = img_ready; io.b16_ready = img16_all ? img16_ready : nullptr; }
         if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     if (comm != nullptr && d_scale != nullptr && d_scale_total != nullptr)
@@ -783,14 +808,6 @@ int flyp_clip_bwd_step(flyp_comm* comm, const flyp_step_t* step, const void* img
     if (world < 1 || rank < 0 || rank >= world) return fail(FLYP_ERR_ARG, "bad rank %d / world %d", rank, world);
     if (!comm && world != 1) return fail(FLYP_ERR_ARG, "world %d needs a communicator", world);
     const flyp_gathered_t& gg = step->gathered;
-    if (comm == nullptr && dtype == FLYP_F32) {
-        // fp32 features (split-plane products): the two-operand entry point with g on both sides
-        if (g_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "fp32 features need an fp32 upstream gradient");
-        return flyp_clip_bwd_local_ex(img, txt, scale, n_rows, n_rows, dim, dtype, 0, step->stats.row_lse_all,
-                                      step->stats.row_nll_all, col_lse, col_nll, static_cast<const float*>(g),
-                                      static_cast<const float*>(g), grad_mul, grad_dtype, d_img, d_txt, d_scale, workspace,
-                                      workspace_bytes, nullptr, nullptr, nullptr, stream);
-    }
     if (comm == nullptr) {
         // single rank: the row block's share of d(scale) is the whole gradient
         return bwd_sharded_impl(img, txt, gg.img_all, gg.txt_all, gg.img16_all, gg.txt16_all, scale, n_rows, n_rows, dim,

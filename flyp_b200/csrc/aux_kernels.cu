@@ -556,14 +556,24 @@ void launch_to_f16(const void* src, int dtype, size_t n_elems, void* dst, cudaSt
 // x (fp32 [n][dim]) -> NP planes of 16-bit floats side by side: out[n][NP * dp], plane p at columns [p*dp, p*dp+dim),
 // x = x_1 + x_2 (+ x_3) with x_1 = round(x), x_2 = round(x - x_1), ...  Columns [dim, dp) of every plane are zero.
 template <int NP, bool BF16>
-__global__ void k_split_planes(const float* __restrict__ x, int n, int dim, int dp, uint16_t* __restrict__ out) {
+__global__ void k_split_planes(const float* __restrict__ x, int n, int dim, int dp, uint16_t* __restrict__ out,
+                               PeerWait wait) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one thread per 8 columns of dp
     const int cols8 = dp / 8;
+    if (wait.flags != nullptr) {
+        // multi-GPU: the rows are being written by other ranks - wait for the owners of this block's rows (peer.cuh)
+        if (threadIdx.x == 0) {
+            const size_t i0 = (size_t)blockIdx.x * blockDim.x, i1 = i0 + blockDim.x - 1;
+            const int r0 = (int)(i0 / cols8), r1 = (int)(i1 / cols8);
+            peer_wait_rows(wait, r0, (r1 < n ? r1 : n - 1) + 1);
+        }
+        __syncthreads();
+    }
     if (i >= (size_t)n * cols8) return;
     const int row = (int)(i / cols8), c0 = (int)(i - (size_t)row * cols8) * 8;
     float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (c0 + e < dim) ? x[(size_t)row * dim + c0 + e] : 0.f;
+    for (int e = 0; e < 8; ++e) v[e] = (c0 + e < dim) ? __ldcg(x + (size_t)row * dim + c0 + e) : 0.f;
 #pragma unroll
     for (int pl = 0; pl < NP; ++pl) {
         uint4 u;
@@ -578,13 +588,20 @@ __global__ void k_split_planes(const float* __restrict__ x, int n, int dim, int 
         *reinterpret_cast<uint4*>(out + (size_t)row * NP * dp + (size_t)pl * dp + c0) = u;
     }
 }
-void launch_split_planes_bf16x3(const float* x, int n, int dim, int dp, void* out, cudaStream_t st) {
-    const size_t t = (size_t)n * (dp / 8);
-    if (t) k_split_planes<3, true><<<(unsigned)((t + 255) / 256), 256, 0, st>>>(x, n, dim, dp, static_cast<uint16_t*>(out));
+static PeerWait wait_or_none(const PeerWait* w) {
+    PeerWait r;
+    if (w != nullptr) r = *w; else memset(&r, 0, sizeof(r));
+    return r;
 }
-void launch_split_planes_f16x2(const float* x, int n, int dim, int dp, void* out, cudaStream_t st) {
+void launch_split_planes_bf16x3(const float* x, int n, int dim, int dp, void* out, cudaStream_t st, const PeerWait* wait) {
     const size_t t = (size_t)n * (dp / 8);
-    if (t) k_split_planes<2, false><<<(unsigned)((t + 255) / 256), 256, 0, st>>>(x, n, dim, dp, static_cast<uint16_t*>(out));
+    if (t) k_split_planes<3, true><<<(unsigned)((t + 255) / 256), 256, 0, st>>>(x, n, dim, dp, static_cast<uint16_t*>(out),
+                                                                                 wait_or_none(wait));
+}
+void launch_split_planes_f16x2(const float* x, int n, int dim, int dp, void* out, cudaStream_t st, const PeerWait* wait) {
+    const size_t t = (size_t)n * (dp / 8);
+    if (t) k_split_planes<2, false><<<(unsigned)((t + 255) / 256), 256, 0, st>>>(x, n, dim, dp, static_cast<uint16_t*>(out),
+                                                                                  wait_or_none(wait));
 }
 
 // ------------------------------------------------------------------------------------------------ L2 normalise

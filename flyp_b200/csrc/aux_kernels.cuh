@@ -67,8 +67,11 @@ void launch_fill_float(float* p, float v, cudaStream_t st);
 void launch_to_f16(const void* src, int dtype, size_t n_elems, void* dst, cudaStream_t st);
 
 // fp32 [n][dim] -> three bf16 planes / two fp16 planes side by side ([n][NP * dp], dp = dim rounded up to 64, zero pad)
-void launch_split_planes_bf16x3(const float* x, int n, int dim, int dp, void* out, cudaStream_t st);
-void launch_split_planes_f16x2(const float* x, int n, int dim, int dp, void* out, cudaStream_t st);
+// wait (may be null): the rows of x are written by other ranks; every block waits for the owners of its rows first
+void launch_split_planes_bf16x3(const float* x, int n, int dim, int dp, void* out, cudaStream_t st,
+                                const PeerWait* wait = nullptr);
+void launch_split_planes_f16x2(const float* x, int n, int dim, int dp, void* out, cudaStream_t st,
+                               const PeerWait* wait = nullptr);
 
 void launch_l2norm_fwd(const void* x, int n, int dim, int dtype, void* y, float* inv_norm, cudaStream_t st);
 void launch_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n, int dim, int dtype, void* dx,

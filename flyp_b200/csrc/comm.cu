@@ -81,7 +81,11 @@ void layout(flyp_comm* c) {
     size_t off = 0;
     auto take = [&](size_t bytes) { off = align_up(off, 1024); const size_t r = off; off += bytes; return r; };
     for (int par = 0; par < 2; ++par) {
-        for (int a = 0; a < N_ARR; ++a) c->off_feat[par][a] = take(cap * c->dim * 2);
+        // a matrix and its fp16 copy are adjacent: for fp32 features the pair holds ONE gathered fp32 matrix instead
+        for (int a = 0; a < N_ARR; a += 2) {
+            c->off_feat[par][a] = take(cap * c->dim * 4);
+            c->off_feat[par][a + 1] = c->off_feat[par][a] + cap * c->dim * 2;
+        }
         c->off_colstat[par] = take((size_t)c->world * 3 * cap * sizeof(float));
         c->off_rowstat[par] = take(2 * cap * sizeof(float));
         c->off_dscale[par] = take(MAXW * sizeof(float));
@@ -139,6 +143,37 @@ __global__ void k_pack(const uint4* __restrict__ img, const uint4* __restrict__ 
                 acc = fmaf(__uint_as_float(wa[e] << 16), __uint_as_float(wb[e] << 16), acc);
                 acc = fmaf(__uint_as_float(wa[e] & 0xffff0000u), __uint_as_float(wb[e] & 0xffff0000u), acc);
             }
+        }
+    }
+    if (ex.t2 != nullptr && row < ex.n_pad) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) {
+            ex.t2[row] = row < n_rows ? acc * ex.scale[0] * 1.4426950408889634f : -INFINITY;
+            ex.pos[row] = row < n_rows ? ex.row_offset + row : -1;
+        }
+    }
+}
+
+// fp32 features: the rows go out as they are (the consumers split them into bf16 / fp16 planes on arrival)
+__global__ void k_pack32(const float4* __restrict__ img, const float4* __restrict__ txt, int n_rows, int dim4,
+                         float4* __restrict__ img_o, float4* __restrict__ txt_o, uint32_t* seqword, uint32_t* own_flags,
+                         int rank, uint32_t seq, flyp::PackExtra ex) {
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            *seqword = seq;
+            for (int a = 0; a < N_ARR; ++a) own_flags[(a * MAXW + rank) * MAXG] = seq;
+        }
+        if (ex.zero_words != nullptr && (int)threadIdx.x < ex.n_zero) ex.zero_words[threadIdx.x] = 0;
+    }
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    float acc = 0.f;
+    if (row < n_rows) {
+        for (int c = lane; c < dim4; c += 32) {
+            const size_t i = (size_t)row * dim4 + c;
+            const float4 a = img[i], b = txt[i];
+            img_o[i] = a; txt_o[i] = b;
+            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
         }
     }
     if (ex.t2 != nullptr && row < ex.n_pad) {
@@ -213,22 +248,26 @@ int check_comm(const flyp_comm* c, bool need_connected) {
 // fp16 copy (second sweep).  Each block copy is followed by the 4-byte copy of the sequence number into the flag word.
 struct PushOp { void* dst; const void* src; size_t bytes; };
 constexpr int MAX_PUSH_OPS = 2 * N_ARR * MAXW;
-int build_push_ops(const flyp_comm* c, int par, int n_rows, int dim, PushOp* ops) {
+int build_push_ops(const flyp_comm* c, int par, int n_rows, int dim, bool f32, PushOp* ops) {
     int n = 0;
-    const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
+    const size_t esz = f32 ? 4 : 2;
+    const size_t slot_bytes = (size_t)n_rows * dim * esz, slot_off = (size_t)c->rank * slot_bytes;
     uint8_t* own = c->seg[c->rank];
     const void* seqword = own + c->off_seqword[par];
     const size_t flag_stride = (size_t)MAXG * sizeof(uint32_t);
     for (int a = 0; a < N_ARR; ++a) {
+        // fp32 features: arrays 1 and 3 (the fp16 copies) do not exist - only their flags are raised, together with
+        // the flags of the fp32 matrix that occupies the pair
+        const bool data = !f32 || (a & 1) == 0;
         const size_t off_data = c->off_feat[par][a] + slot_off;
         const size_t off_flag = c->off_flags + ((size_t)a * MAXW + c->rank) * flag_stride;
         if (c->mc != nullptr) {                                  // one multicast copy reaches every rank
-            ops[n++] = {c->mc + off_data, own + off_data, slot_bytes};
+            if (data) ops[n++] = {c->mc + off_data, own + off_data, slot_bytes};
             ops[n++] = {c->mc + off_flag, seqword, sizeof(uint32_t)};
         } else {
             for (int k = 1; k < c->world; ++k) {                 // ring order: one sender per receiver at a time
                 const int q = (c->rank - k + c->world) % c->world;
-                ops[n++] = {c->seg[q] + off_data, own + off_data, slot_bytes};
+                if (data) ops[n++] = {c->seg[q] + off_data, own + off_data, slot_bytes};
                 ops[n++] = {c->seg[q] + off_flag, seqword, sizeof(uint32_t)};
             }
         }
@@ -424,7 +463,8 @@ int comm_gather(flyp_comm* c, const void* img, const void* txt, int n_rows, int 
     int rc = check_comm(c, true);
     if (rc) return rc;
     if (!img || !txt || !out) { flyp::set_error(FLYP_ERR_ARG, "null pointer argument"); return FLYP_ERR_ARG; }
-    if (dtype != FLYP_BF16) { flyp::set_error(FLYP_ERR_ARG, "the peer-memory gather carries bf16 features only"); return FLYP_ERR_ARG; }
+    if (dtype != FLYP_BF16 && dtype != FLYP_F32) { flyp::set_error(FLYP_ERR_ARG, "bad dtype %d", dtype); return FLYP_ERR_ARG; }
+    const bool f32 = dtype == FLYP_F32;
     if (n_rows <= 0 || dim != c->dim || n_rows > c->max_rows) {
         flyp::set_error(FLYP_ERR_ARG, "gather shape [%d, %d] does not fit the communicator (max rows %d, dim %d)", n_rows, dim,
                         c->max_rows, c->dim);
@@ -439,35 +479,43 @@ int comm_gather(flyp_comm* c, const void* img, const void* txt, int n_rows, int 
     const uint32_t seq = ++c->seq;
     const int par = (int)(seq & 1u);
     uint8_t* own = c->seg[c->rank];
-    const size_t slot_bytes = (size_t)n_rows * dim * 2, slot_off = (size_t)c->rank * slot_bytes;
+    const size_t slot_bytes = (size_t)n_rows * dim * (f32 ? 4 : 2), slot_off = (size_t)c->rank * slot_bytes;
     // the copy engines may still be reading the own slots / sequence word of the previous step
     COMM_CUDA_OK(cudaStreamWaitEvent(st, c->ev_pushed, 0));
     PackExtra ex;
     if (extra != nullptr) ex = *extra; else memset(&ex, 0, sizeof(ex));
     const int rows = (ex.t2 != nullptr && ex.n_pad > n_rows) ? ex.n_pad : n_rows;
-    k_pack<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
-        static_cast<const uint4*>(img), static_cast<const uint4*>(txt), n_rows, dim / 8,
-        reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_IMG] + slot_off),
-        reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_IMG16] + slot_off),
-        reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_TXT] + slot_off),
-        reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_TXT16] + slot_off),
-        reinterpret_cast<uint32_t*>(own + c->off_seqword[par]), reinterpret_cast<uint32_t*>(own + c->off_flags), c->rank, seq,
-        ex);
+    if (f32)
+        k_pack32<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
+            static_cast<const float4*>(img), static_cast<const float4*>(txt), n_rows, dim / 4,
+            reinterpret_cast<float4*>(own + c->off_feat[par][ARR_IMG] + slot_off),
+            reinterpret_cast<float4*>(own + c->off_feat[par][ARR_TXT] + slot_off),
+            reinterpret_cast<uint32_t*>(own + c->off_seqword[par]), reinterpret_cast<uint32_t*>(own + c->off_flags), c->rank,
+            seq, ex);
+    else
+        k_pack<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
+            static_cast<const uint4*>(img), static_cast<const uint4*>(txt), n_rows, dim / 8,
+            reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_IMG] + slot_off),
+            reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_IMG16] + slot_off),
+            reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_TXT] + slot_off),
+            reinterpret_cast<uint4*>(own + c->off_feat[par][ARR_TXT16] + slot_off),
+            reinterpret_cast<uint32_t*>(own + c->off_seqword[par]), reinterpret_cast<uint32_t*>(own + c->off_flags), c->rank,
+            seq, ex);
     COMM_CUDA_OK(cudaGetLastError());
     if (c->world > 1) {
         COMM_CUDA_OK(cudaEventRecord(c->ev_packed, st));
         COMM_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_packed, 0));
         PushOp ops[MAX_PUSH_OPS];
-        const int n = build_push_ops(c, par, n_rows, dim, ops);
+        const int n = build_push_ops(c, par, n_rows, dim, f32, ops);
         for (int i = 0; i < n; ++i)
             COMM_CUDA_OK(cudaMemcpyAsync(ops[i].dst, ops[i].src, ops[i].bytes, cudaMemcpyDefault, c->side));
         COMM_CUDA_OK(cudaEventRecord(c->ev_pushed, c->side));
     }
     memset(out, 0, sizeof(*out));
     out->txt_all = own + c->off_feat[par][ARR_TXT];
-    out->txt16_all = own + c->off_feat[par][ARR_TXT16];
+    out->txt16_all = f32 ? nullptr : own + c->off_feat[par][ARR_TXT16];
     out->img_all = own + c->off_feat[par][ARR_IMG];
-    out->img16_all = own + c->off_feat[par][ARR_IMG16];
+    out->img16_all = f32 ? nullptr : own + c->off_feat[par][ARR_IMG16];
     flyp_ready_t* r[N_ARR] = {&out->txt_ready, &out->txt16_ready, &out->img_ready, &out->img16_ready};
     for (int a = 0; a < N_ARR; ++a) fill_ready(c, r[a], a, seq, n_rows);
     out->seq = seq;

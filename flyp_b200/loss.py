@@ -274,6 +274,42 @@ class _ClipLossStepFn(torch.autograd.Function):
         return (d_img if need_img else None), (d_txt if need_txt else None), gs, None, None, None
 
 
+class _LocalLossPeerFn(torch.autograd.Function):
+    """local_loss=True over peer memory (clip/loss.py:109-111,200-201): the loss of the LOCAL rows as two one-directional
+    cross-entropies against the gathered matrices, which arrive in this rank's exchange segment while the kernels run.
+    gather_with_grad=False: gradients flow to the local operands only (the gathered matrices carry none, :54-61);
+    True: the gradients w.r.t. the gathered matrices are reduce-scattered (sum) to their owners, like the backward of
+    torch.distributed.nn.all_gather (:48-52) - the one real B x D exchange of this mode, an NCCL collective."""
+
+    @staticmethod
+    def forward(ctx, img, txt, scale, comm, gather_with_grad, grad_dtype, group):
+        from . import comm as peer
+        s = ops._scale_tensor(scale, img.device)
+        li, lt, st = peer.local_fwd(comm, img, txt, s)
+        ctx.st = st
+        ctx.meta = (gather_with_grad, grad_dtype, group, torch.is_tensor(scale),
+                    scale.shape if torch.is_tensor(scale) else None, scale.dtype if torch.is_tensor(scale) else None)
+        return ((li + lt) * 0.5).to(img.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import comm as peer
+        st = ctx.st
+        gwg, grad_dtype, group, s_is_tensor, s_shape, s_dtype = ctx.meta
+        d_img, d_txt, d_s, d_img_all, d_txt_all = peer.local_bwd(st, g, grad_dtype, gwg)
+        if gwg:
+            for local, gathered in ((d_img, d_img_all), (d_txt, d_txt_all)):
+                part = torch.empty_like(local)
+                dist.reduce_scatter_tensor(part, gathered.contiguous(), op=dist.ReduceOp.SUM, group=group)
+                local += part
+        gs = None
+        if ctx.needs_input_grad[2] and s_is_tensor:
+            gs = torch.zeros(s_shape, dtype=torch.float32, device=st.img.device).reshape(-1)
+            gs[:1] = d_s
+            gs = gs.reshape(s_shape).to(s_dtype)
+        return d_img, d_txt, gs, None, None, None, None
+
+
 class ClipLoss(nn.Module):
     """clip/loss.py:72-211 with the same constructor and forward signature."""
 
@@ -318,7 +354,7 @@ class ClipLoss(nn.Module):
         """The peer-memory communicator for blocks shaped like ``feats`` (created collectively on first use; every rank
         takes the same decision).  None -> the ranks do not share a node: torch.distributed collectives."""
         import os
-        if os.environ.get("FLYP_EXCHANGE", "") == "collective" or feats.dtype != torch.bfloat16:
+        if os.environ.get("FLYP_EXCHANGE", "") == "collective" or feats.dtype not in (torch.bfloat16, torch.float32):
             return None
         shape = (feats.shape[0], feats.shape[1])
         if self._peer is not None and self._peer_shape == shape:
@@ -352,11 +388,16 @@ class ClipLoss(nn.Module):
 
         if self.world_size > 1 and self.local_loss:
             # clip/loss.py:109-111: two row blocks against the gathered matrices; loss for the local rows only
+            if self.cache_labels:
+                self._labels(device, image_features.shape[0])
+            peer = self._peer_comm(image_features)
+            if peer is not None:
+                return _LocalLossPeerFn.apply(image_features, text_features, logit_scale, peer, self.gather_with_grad,
+                                              self.grad_dtype, self.group)
+            # ranks on several nodes: torch.distributed collectives
             all_image, all_text = gather_features(image_features, text_features, True, self.gather_with_grad,
                                                   self.rank, self.world_size, False, self.group)
             off = self.rank * image_features.shape[0]
-            if self.cache_labels:
-                self._labels(device, image_features.shape[0])
             li = contrastive_cross_entropy(image_features, all_text, logit_scale, None, off,
                                            grad_dtype=self.grad_dtype)
             lt = contrastive_cross_entropy(text_features, all_image, logit_scale, None, off,

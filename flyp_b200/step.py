@@ -36,8 +36,6 @@ def step_forward(comm, img: torch.Tensor, txt: torch.Tensor, scale: torch.Tensor
     ops._check_features(img, txt)
     dev = img.device
     code = _lib.dtype_code(img)
-    if comm is not None and code != _lib.FLYP_BF16:
-        raise FlypError("the peer-memory path carries bf16 features")
     st = FusedStep()
     st.comm, st.img, st.txt, st.s, st.code = comm, img.contiguous(), txt.contiguous(), scale, code
     b, D = img.shape

@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# a kernel that waits for a peer's rows traps after this long (the library's default is 10 minutes): a test that got its
+# phases wrong must fail in seconds, not hold the GPU box
+os.environ.setdefault("FLYP_PEER_TIMEOUT_MS", "15000")
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 

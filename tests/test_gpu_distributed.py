@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _worker(rank, world, port, name, local_loss, gwg, ret):
+def _worker(rank, world, port, name, local_loss, gwg, ret, fdt=torch.bfloat16):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -25,7 +25,7 @@ def _worker(rank, world, port, name, local_loss, gwg, ret):
     z = np.load(os.path.join(GOLDEN, name))
     n = z["I"].shape[0]
     b = n // world
-    I = torch.tensor(z["I"]).bfloat16(); T = torch.tensor(z["T"]).bfloat16()
+    I = torch.tensor(z["I"]).to(fdt); T = torch.tensor(z["T"]).to(fdt)
     Il = I[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
     Tl = T[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
     sc = torch.tensor(float(z["scale"]), device=dev, requires_grad=True)
@@ -80,3 +80,50 @@ def test_multi_gpu_semantics(local_loss, gwg, world):
         assert rel(got["loss"], want) < tol
         assert rel(got["dI"], wI) < tol and rel(got["dT"], wT) < tol
         assert abs(got["ds"] - ws) < tol * abs(ws)
+
+
+@pytest.mark.parametrize("local_loss,gwg", [(False, False), (True, True)])
+def test_multi_gpu_fp32_features(local_loss, gwg):
+    """fp32 features (what FLYP trains in) over the peer-memory exchange on two real GPUs: 1e-5 / 1e-4."""
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from oracle import clip_oracle as orc
+    name = "clip_w2_n264_d64.npz"
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    _PORT[0] += 1
+    mp.spawn(_worker, args=(world, _PORT[0], name, local_loss, gwg, ret, torch.float32), nprocs=world, join=True)
+    z = np.load(os.path.join(GOLDEN, name))
+    n = z["I"].shape[0]
+    b = n // world
+    I = torch.tensor(z["I"]).float().double().numpy(); T = torch.tensor(z["T"]).float().double().numpy()
+    Ib, Tb = [I[r * b:(r + 1) * b] for r in range(world)], [T[r * b:(r + 1) * b] for r in range(world)]
+    for r in range(world):
+        got = ret[r]
+        want = orc.clip_loss_distributed(Ib, Tb, float(z["scale"]), r, local_loss)
+        g = z["g"][:b] if local_loss else z["g"]
+        wI, wT, ws = orc.clip_loss_distributed_grads(Ib, Tb, float(z["scale"]), r, local_loss, gwg, g)
+        assert rel(got["loss"], want) < 1e-5
+        assert rel(got["dI"], wI) < 1e-4 and rel(got["dT"], wT) < 1e-4
+        assert abs(got["ds"] - ws) < 1e-4 * abs(ws)
+
+
+def test_soak_changing_inputs_two_gpus():
+    """The copy-engine flag ordering under changing inputs (every step pushes NEW bits into the same slots): bench.py's
+    soak on two real GPUs - gathered matrices bit-exact after the consumers ran, loss = the rolled base loss."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    _PORT[0] += 1
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(_PORT[0]), os.path.join(root, "bench.py"),
+                          "--gpus", "2", "--batch", "4096", "--steps", "3", "--warmup", "3", "--soak", "2000"],
+                         capture_output=True, text=True, timeout=900, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["check"]["passed"] and line["check"]["soak"]["passed"], line["check"]
+    assert line["check"]["soak"]["steps"] == 2000 and line["check"]["soak"]["mismatching_gathered_elements"] == 0

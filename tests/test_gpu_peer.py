@@ -186,6 +186,108 @@ def test_local_loss_blocks_emulated(golden_dir, gwg):
         assert abs(sc.grad.item() - ws) < tol * abs(ws)
 
 
+def _view_f32(ptr, rows, cols):
+    class _Raw32:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(_Raw32(ptr, rows * cols), device="cuda").reshape(rows, cols)
+
+
+@pytest.mark.parametrize("world,b,dim", [(2, 132, 64), (4, 96, 256), (3, 200, 512)])
+def test_emulated_ranks_fp32_features(world, b, dim):
+    """fp32 features (what FLYP trains in) over the peer-memory exchange: the fp32 rows are pushed as they are and split
+    into bf16 / fp16 planes on arrival; 1e-5 / 1e-4 against the float64 oracle, gathered bits exact."""
+    from flyp_b200 import comm as peer
+    from flyp_b200.comm import PeerComm
+    from oracle import clip_oracle as orc
+    from oracle import torch_port
+    dev = torch.device("cuda:0")
+    B = world * b
+    s = 1.0 / 0.07
+    sc = torch.tensor([s], device=dev)
+    comms = [PeerComm(r, world, b, dim, dev) for r in range(world)]
+    PeerComm.connect_local(comms)
+    try:
+        for step in range(2):
+            I, T = torch_port.synthetic_pairs(B, dim, seed=10 + step, dtype=torch.float32)
+            Id, Td = I.to(dev), T.to(dev)
+            g = torch.rand(B, generator=torch.Generator().manual_seed(3 + step)).to(dev)
+            steps = [peer.fwd_gather(comms[r], Id[r * b:(r + 1) * b], Td[r * b:(r + 1) * b], sc) for r in range(world)]
+            for st in steps:
+                peer.fwd_local(st)
+            losses = [peer.fwd_finish(st) for st in steps]
+            grads = [peer.bwd_local(st, g, 1.0, torch.float32, True, True, True) for st in steps]
+            torch.cuda.synchronize()
+            for c in comms:
+                c.check_error()
+            In, Tn = I.double().numpy(), T.double().numpy()
+            want = orc.clip_loss(In, Tn, s)
+            wI, wT, ws = orc.clip_loss_grads(In, Tn, s, g.double().cpu().numpy())
+            ds = sum(gr[2].item() for gr in grads)
+            assert abs(ds - ws) < 1e-4 * abs(ws)
+            for r, st in enumerate(steps):
+                assert torch.equal(_view_f32(st.g.txt_all, B, dim), Td)
+                assert torch.equal(_view_f32(st.g.img_all, B, dim), Id)
+                assert rel(losses[r].double().cpu().numpy(), want) < 1e-5
+                sl = slice(r * b, (r + 1) * b)
+                assert rel(grads[r][0].double().cpu().numpy(), wI[sl]) < 1e-4 * max(1.0, np.abs(wI).max() / np.abs(wI[sl]).max())
+                assert rel(grads[r][1].double().cpu().numpy(), wT[sl]) < 1e-4 * max(1.0, np.abs(wT).max() / np.abs(wT[sl]).max())
+    finally:
+        for c in comms:
+            c.close()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_local_loss_over_peer_memory_emulated(golden_dir, dtype):
+    """local_loss=True through the peer-memory exchange (flyp_b200/comm.py local_fwd / local_bwd) with two emulated
+    ranks: loss of the local rows, gradients of the local operands (gather_with_grad=False semantics) and - summed by
+    hand over the ranks - the reduce-scattered gradients of the gathered operands (gather_with_grad=True)."""
+    import os
+    from flyp_b200 import comm as peer
+    from flyp_b200.comm import PeerComm
+    from oracle import clip_oracle as orc
+    dev = torch.device("cuda:0")
+    z = np.load(os.path.join(golden_dir, "clip_w2_n264_d64.npz"))
+    world = 2
+    I = torch.tensor(z["I"]).to(dtype); T = torch.tensor(z["T"]).to(dtype)
+    n, dim = I.shape
+    b = n // world
+    s = float(z["scale"])
+    sc = torch.tensor([s], device=dev)
+    g = torch.tensor(z["g"][:b], dtype=torch.float32, device=dev)
+    Ib = [I[r * b:(r + 1) * b].double().numpy() for r in range(world)]
+    Tb = [T[r * b:(r + 1) * b].double().numpy() for r in range(world)]
+    comms = [PeerComm(r, world, b, dim, dev) for r in range(world)]
+    PeerComm.connect_local(comms)
+    try:
+        # phase 1: every rank's gather (pack + pushes); phase 2: the cross-entropy blocks; phase 3: backward
+        Id, Td = I.to(dev), T.to(dev)
+        gathered = [peer.local_gather(comms[r], Id[r * b:(r + 1) * b].contiguous(), Td[r * b:(r + 1) * b].contiguous(), sc)
+                    for r in range(world)]
+        fwd = [peer.local_compute(st) for st in gathered]
+        bwd = [peer.local_bwd(f[2], g, torch.float32, True) for f in fwd]
+        torch.cuda.synchronize()
+        for c in comms:
+            c.check_error()
+        tol_l, tol_g = (1e-5, 1e-4) if dtype == torch.float32 else (2e-3, 2e-3)
+        for r in range(world):
+            li, lt, _ = fwd[r]
+            want = orc.clip_loss_distributed(Ib, Tb, s, r, True)
+            assert rel((0.5 * (li + lt)).double().cpu().numpy(), want) < tol_l
+            d_img, d_txt, d_s, d_img_all, d_txt_all = bwd[r]
+            wI, wT, ws = orc.clip_loss_distributed_grads(Ib, Tb, s, r, True, False, z["g"][:b])
+            assert rel(d_img.double().cpu().numpy(), wI) < tol_g and rel(d_txt.double().cpu().numpy(), wT) < tol_g
+            assert abs(d_s.item() - ws) < tol_g * abs(ws)
+            wI2, wT2, _ = orc.clip_loss_distributed_grads(Ib, Tb, s, r, True, True, z["g"][:b])
+            sl = slice(r * b, (r + 1) * b)
+            gi = d_img.double() + sum(bwd[q][3].double()[sl] for q in range(world))
+            gt = d_txt.double() + sum(bwd[q][4].double()[sl] for q in range(world))
+            assert rel(gi.cpu().numpy(), wI2) < tol_g and rel(gt.cpu().numpy(), wT2) < tol_g
+    finally:
+        for c in comms:
+            c.close()
+
+
 def test_stale_step_is_refused():
     from flyp_b200 import comm as peer
     from flyp_b200.comm import PeerComm

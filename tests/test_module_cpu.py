@@ -66,6 +66,6 @@ def test_exchange_is_an_internal_decision(monkeypatch):
     # ... the peer-memory exchange carries bf16 features; the multi-node path can be forced for tests, decided without
     # touching a device
     fn = ClipLoss(world_size=2, rank=0)
-    assert fn._peer_comm(torch.zeros(4, 8, dtype=torch.float32)) is None
+    assert fn._peer_comm(torch.zeros(4, 8, dtype=torch.float16)) is None
     monkeypatch.setenv("FLYP_EXCHANGE", "collective")
     assert fn._peer_comm(torch.zeros(4, 8, dtype=torch.bfloat16)) is None
