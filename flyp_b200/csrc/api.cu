@@ -374,6 +374,9 @@ struct SweepIO {
     const BwdCtrl* ctrl; int sweep;      // control words and which counter set this sweep uses
     const flyp::PeerPush* ds_push;       // multi-GPU: where the total is published (may be null)
     const flyp_ready_t *b_ready, *b16_ready;
+    const int *cls_m, *cls_n;            // label-aware variants (clip_kernels.cuh BwdParams): class ids, weights, mode
+    const float *mk_r, *mk_c;
+    int mask_mode;
 };
 
 int run_sweep(const SweepIO& io, cudaStream_t st) {
@@ -412,7 +415,8 @@ int run_sweep(const SweepIO& io, cudaStream_t st) {
     const bool push = io.dscale_part != nullptr && io.ds_push != nullptr && io.ds_push->n_dst > 0;
     const bool timed = g_ev_sweep[0] != nullptr && g_ev_sweep_idx == io.sweep;
     if (timed) cudaEventRecord(g_ev_sweep[0], st);
-    if (use_pair_kernel(dim, dtype, n_m, n_n)) {
+    p.cls_m = io.cls_m; p.cls_n = io.cls_n; p.mk_r = io.mk_r; p.mk_c = io.mk_c; p.mask_mode = io.mask_mode;
+    if (io.mask_mode == 0 && use_pair_kernel(dim, dtype, n_m, n_n)) {
         CUtensorMap tmA64;
         if ((rc = make_tmap(&tmA64, io.A, n_m, dim, dim, false, 64)) != 0) return rc;
         if (io.part_scratch == nullptr) return fail(FLYP_ERR_ARG, "the pair sweep needs its partial-sum scratch");
@@ -962,6 +966,109 @@ int flyp_ce_bwd_ex(const void* a, const void* b, const float* scale, int n, int 
         if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ label-aware variants
+// Building blocks of the label-aware ClipLoss variants (clip/loss.py:123-192: soft labels, `ignore`, `google_sup_loss`),
+// orchestrated by flyp_b200/labeled.py.  Square problems (n x n), positives on the diagonal, one class id per item.
+int flyp_label_stats(const void* a, const void* b, const float* scale, int n, int dim, int dtype, const int* cls_a,
+                     const int* cls_b, int mode, const float* lse_rows, float* out0, float* out1, float* out2,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(n, n, dim, dtype);
+    if (rc) return rc;
+    if (!a || !b || !scale || !cls_a || !cls_b || !out0 || !out1 || !workspace) return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (mode != 1 && mode != 2) return fail(FLYP_ERR_ARG, "mode %d (1: exclude same-class entries, 2: accumulate over them)", mode);
+    if (mode == 2 && (!lse_rows || !out2)) return fail(FLYP_ERR_ARG, "mode 2 needs lse_rows and out2");
+    ClipWs w;
+    carve_clip(workspace, n, n, dim, dtype, w);
+    if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const StatsWs& s = w.stats;
+    const int rp = ceil_div(n, VEC_PAD) * VEC_PAD;
+    CUtensorMap tmA, tmB;
+    flyp::KPlan kplan = flyp::kplan_bf16();
+    if (dtype == FLYP_F32) {
+        const int dp = plane_cols(dim);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(a), n, dim, dp, s.planes_a, st);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(b), n, dim, dp, s.planes_b, st);
+        CUDA_OK(cudaGetLastError());
+        if ((rc = make_tmap(&tmA, s.planes_a, n, 3 * dp, 3 * dp)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, s.planes_b, n, 3 * dp, 3 * dp)) != 0) return rc;
+        kplan = flyp::kplan_f32(dp);
+    } else {
+        if ((rc = make_tmap(&tmA, a, n, dim, dim)) != 0) return rc;
+        if ((rc = make_tmap(&tmB, b, n, dim, dim)) != 0) return rc;
+    }
+    // positives on the diagonal: t2 / pos; class ids padded with -1 / -2 (never equal); lse in log2 units
+    flyp::launch_pair_dot(a, b, dtype, scale, n, s.ld_rows, n, dim, nullptr, 0, s.t2, s.pos, nullptr, s.flag, 4, nullptr, nullptr, st);
+    flyp::launch_label_prep(n, rp, cls_a, cls_b, w.rows.lab, w.cols.lab, lse_rows, w.rows.l2, st);
+    CUDA_OK(cudaGetLastError());
+    flyp::FwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_m = n; p.n_n = n; p.kc = ceil_div(dim, flyp::KCHUNK); p.kplan = kplan;
+    p.m_tiles = s.m_tiles; p.n_tiles = s.n_tiles; p.n_slots = s.n_slots; p.ld_rows = s.ld_rows; p.ld_cols = s.ld_cols;
+    p.scale = scale; p.shift_slack = shift_slack(n, n);
+    p.rowpart = s.rowpart; p.rowmax = s.rowmax; p.pos = s.pos;
+    p.cls_m = w.rows.lab; p.cls_n = w.cols.lab; p.mask_mode = mode; p.acc_lse = w.rows.l2; p.acc3 = s.rowpart2;
+    flyp::launch_fwd(tmA, tmB, p, /*robust=*/true, nullptr, num_sms(), st);
+    CUDA_OK(cudaGetLastError());
+    if (mode == 1) {
+        CUDA_OK(cudaMemsetAsync(s.flag, 1, sizeof(int), st));             // non-zero: the robust finalize does its work
+        flyp::FwdFinish nofin;
+        memset(&nofin, 0, sizeof(nofin));
+        flyp::launch_fwd_finalize_robust(s.rowpart, s.rowmax, s.n_tiles * 2, s.ld_rows, n, nullptr, nullptr, 0, s.ld_cols, n,
+                                         s.t2, s.pos, out0, out1, nullptr, s.flag, nullptr, nofin, st);
+    } else {
+        flyp::launch_label_sum3(s.rowpart, s.rowmax, s.rowpart2, s.n_tiles * 2, s.ld_rows, n, out0, out1, out2, st);
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int flyp_label_sweep(const void* a, const void* b, const float* scale, int n, int dim, int dtype, const float* wr,
+                     const float* lr, const float* wc, const float* lc, const float* d_diag, const int* cls_a,
+                     const int* cls_b, const float* mk_r, const float* mk_c, int mode, const float* gmax, int grad_dtype,
+                     void* out, float* d_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(n, n, dim, dtype);
+    if (rc) return rc;
+    if (!a || !b || !scale || !wr || !lr || !wc || !lc || !gmax || !out || !workspace)
+        return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (mode < 0 || mode > 3) return fail(FLYP_ERR_ARG, "bad mode %d", mode);
+    if (mode != 0 && (!cls_a || !cls_b)) return fail(FLYP_ERR_ARG, "class ids are required for mode %d", mode);
+    if (mode >= 2 && (!mk_r || !mk_c)) return fail(FLYP_ERR_ARG, "mode %d needs the same-class weights", mode);
+    if (grad_dtype != FLYP_BF16 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad grad_dtype %d", grad_dtype);
+    const bool f32 = dtype == FLYP_F32;
+    if (f32 && grad_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "fp32 features need grad_dtype = FLYP_F32");
+    ClipWs w;
+    carve_clip(workspace, n, n, dim, dtype, w);
+    if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rp = ceil_div(n, VEC_PAD) * VEC_PAD;
+    // vectors padded into the workspace (log2 units for the logsumexps), staging scale from the caller's bound on |dS|
+    CUDA_OK(cudaMemsetAsync(w.ctrl.words, 0, CTRL_WORDS * sizeof(uint32_t), st));
+    flyp::launch_label_sweep_prep(n, rp, wr, lr, wc, lc, d_diag, mk_r, mk_c, cls_a, cls_b, gmax, w.rows.w, w.rows.l2, w.rows.d,
+                                  w.rows.f, w.rows.lab, w.cols.w, w.cols.l2, w.cols.f, w.cols.lab,
+                                  reinterpret_cast<int*>(w.cols.d), w.ctrl.words, w.fast_info, st);
+    CUDA_OK(cudaGetLastError());
+    const int dp = plane_cols(dim);
+    if (f32) {
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(a), n, dim, dp, w.stats.planes_a, st);
+        flyp::launch_split_planes_bf16x3(static_cast<const float*>(b), n, dim, dp, w.stats.planes_b, st);
+        flyp::launch_split_planes_f16x2(static_cast<const float*>(b), n, dim, dp, w.txt16, st);
+    } else {
+        flyp::launch_to_f16(b, dtype, (size_t)n * dim, w.txt16, st);
+    }
+    CUDA_OK(cudaGetLastError());
+    SweepIO io = sweep_base(scale, dtype, dim, w, grad_dtype, 1.0f);
+    io.A = a; io.B = b; io.B_f16 = w.txt16; io.A_planes = w.stats.planes_a; io.B_planes = w.stats.planes_b;
+    io.n_m = n; io.n_n = n;
+    io.wr = w.rows.w; io.lr = w.rows.l2; io.wc = w.cols.w; io.lc = w.cols.l2;
+    if (d_diag != nullptr) { io.labr = reinterpret_cast<int*>(w.cols.d); io.dr = w.rows.d; }   // positive of row i: column i
+    io.fa = nullptr; io.fb = nullptr;
+    io.out = out; io.sweep = 0;
+    if (d_scale) { io.dscale_part = w.dscale_part; io.dscale_out = d_scale; }
+    if (mode != 0) { io.cls_m = w.rows.lab; io.cls_n = w.cols.lab; io.mk_r = w.rows.f; io.mk_c = w.cols.f; io.mask_mode = mode; }
+    return run_sweep(io, st);
 }
 
 // ------------------------------------------------------------------------------------------------ encoder tail

@@ -525,6 +525,71 @@ void launch_sum_parts(const float* parts, int n, float* out, const PeerPush* pus
 __global__ void k_fill_float(float* p, float v) { p[0] = v; }
 void launch_fill_float(float* p, float v, cudaStream_t st) { k_fill_float<<<1, 1, 0, st>>>(p, v); }
 
+// ------------------------------------------------------------------------------------------------ label-aware variants
+// class ids padded to n_pad (rows with -2, columns with -1: padding never matches), lse -> log2 units
+__global__ void k_label_prep(int n, int n_pad, const int* __restrict__ cls_a, const int* __restrict__ cls_b,
+                             int* __restrict__ pa, int* __restrict__ pb, const float* __restrict__ lse,
+                             float* __restrict__ lse2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    pa[i] = i < n ? cls_a[i] : -2;
+    pb[i] = i < n ? cls_b[i] : -1;
+    if (lse != nullptr) lse2[i] = i < n ? lse[i] * LOG2E_F : 0.f;
+}
+void launch_label_prep(int n, int n_pad, const int* cls_a, const int* cls_b, int* pa, int* pb, const float* lse,
+                       float* lse2, cudaStream_t st) {
+    k_label_prep<<<(n_pad + 255) / 256, 256, 0, st>>>(n, n_pad, cls_a, cls_b, pa, pb, lse, lse2);
+}
+
+// sums of the three accumulators of the forward kernel's mask_mode 2 over the (column block, half) partials;
+// out0 = sum of the same-class logits (natural units), out1 = sum ln(1 - P), out2 = sum P / (1 - P)
+__global__ void k_label_sum3(const float* __restrict__ px, const float* __restrict__ pl, const float* __restrict__ pr,
+                             int n_parts, int ld, int n, float* __restrict__ out0, float* __restrict__ out1,
+                             float* __restrict__ out2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int p = 0; p < n_parts; ++p) {
+        a += px[(size_t)p * ld + i]; b += pl[(size_t)p * ld + i]; c += pr[(size_t)p * ld + i];
+    }
+    out0[i] = a * LN2_F; out1[i] = b * LN2_F; out2[i] = c;
+}
+void launch_label_sum3(const float* px, const float* pl, const float* pr, int n_parts, int ld, int n, float* out0,
+                       float* out1, float* out2, cudaStream_t st) {
+    k_label_sum3<<<(n + 255) / 256, 256, 0, st>>>(px, pl, pr, n_parts, ld, n, out0, out1, out2);
+}
+
+// vectors of a label-aware backward sweep, padded to n_pad; words[0] = bits(gmax[0]); fast path off
+__global__ void k_label_sweep_prep(int n, int n_pad, const float* __restrict__ wr, const float* __restrict__ lr,
+                                   const float* __restrict__ wc, const float* __restrict__ lc,
+                                   const float* __restrict__ d_diag, const float* __restrict__ mk_r,
+                                   const float* __restrict__ mk_c, const int* __restrict__ cls_a,
+                                   const int* __restrict__ cls_b, const float* __restrict__ gmax, float* __restrict__ o_wr,
+                                   float* __restrict__ o_lr, float* __restrict__ o_d, float* __restrict__ o_kr,
+                                   int* __restrict__ o_ca, float* __restrict__ o_wc, float* __restrict__ o_lc,
+                                   float* __restrict__ o_kc, int* __restrict__ o_cb, int* __restrict__ o_pos,
+                                   uint32_t* __restrict__ words, float* __restrict__ fast_info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { words[0] = __float_as_uint(fabsf(gmax[0])); fast_info[0] = 0.f; fast_info[1] = 0.f; }
+    if (i >= n_pad) return;
+    const bool live = i < n;
+    o_wr[i] = live ? wr[i] : 0.f; o_lr[i] = live ? lr[i] * LOG2E_F : 0.f;
+    o_wc[i] = live ? wc[i] : 0.f; o_lc[i] = live ? lc[i] * LOG2E_F : 0.f;
+    o_d[i] = (live && d_diag) ? d_diag[i] : 0.f;
+    o_kr[i] = (live && mk_r) ? mk_r[i] : 0.f; o_kc[i] = (live && mk_c) ? mk_c[i] : 0.f;
+    o_ca[i] = (live && cls_a) ? cls_a[i] : -2; o_cb[i] = (live && cls_b) ? cls_b[i] : -1;
+    o_pos[i] = live ? i : -1;
+}
+void launch_label_sweep_prep(int n, int n_pad, const float* wr, const float* lr, const float* wc, const float* lc,
+                             const float* d_diag, const float* mk_r, const float* mk_c, const int* cls_a, const int* cls_b,
+                             const float* gmax, float* o_wr, float* o_lr, float* o_d, float* o_kr, int* o_ca, float* o_wc,
+                             float* o_lc, float* o_kc, int* o_cb, int* o_pos, uint32_t* words, float* fast_info,
+                             cudaStream_t st) {
+    k_label_sweep_prep<<<(n_pad + 255) / 256, 256, 0, st>>>(n, n_pad, wr, lr, wc, lc, d_diag, mk_r, mk_c, cls_a, cls_b, gmax,
+                                                            o_wr, o_lr, o_d, o_kr, o_ca, o_wc, o_lc, o_kc, o_cb, o_pos,
+                                                            words, fast_info);
+}
+
 // ------------------------------------------------------------------------------------------------ fp16 staging copy
 // The dA MMA multiplies the fp16-staged dS tile with the features, and tcgen05 kind::f16 needs both operands in the
 // same 16-bit format, so the backward keeps an fp16 copy of the features (exact for bf16 inputs within fp16 range).

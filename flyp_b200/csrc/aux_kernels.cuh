@@ -73,6 +73,17 @@ void launch_split_planes_bf16x3(const float* x, int n, int dim, int dp, void* ou
 void launch_split_planes_f16x2(const float* x, int n, int dim, int dp, void* out, cudaStream_t st,
                                const PeerWait* wait = nullptr);
 
+// label-aware variants (clip/loss.py:123-192), see flyp_label_stats / flyp_label_sweep in api.cu
+void launch_label_prep(int n, int n_pad, const int* cls_a, const int* cls_b, int* pa, int* pb, const float* lse,
+                       float* lse2, cudaStream_t st);
+void launch_label_sum3(const float* px, const float* pl, const float* pr, int n_parts, int ld, int n, float* out0,
+                       float* out1, float* out2, cudaStream_t st);
+void launch_label_sweep_prep(int n, int n_pad, const float* wr, const float* lr, const float* wc, const float* lc,
+                             const float* d_diag, const float* mk_r, const float* mk_c, const int* cls_a, const int* cls_b,
+                             const float* gmax, float* o_wr, float* o_lr, float* o_d, float* o_kr, int* o_ca, float* o_wc,
+                             float* o_lc, float* o_kc, int* o_cb, int* o_pos, uint32_t* words, float* fast_info,
+                             cudaStream_t st);
+
 void launch_l2norm_fwd(const void* x, int n, int dim, int dtype, void* y, float* inv_norm, cudaStream_t st);
 void launch_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n, int dim, int dtype, void* dx,
                        cudaStream_t st);

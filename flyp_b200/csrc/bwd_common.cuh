@@ -27,13 +27,16 @@ struct RowCtx {
     float d;      // G * dr[m]: exact dS at the positive
     int lab;      // positive column or -1
     int m;        // global row
+    int cls;      // class id of the row (label-aware variants)
+    float k;      // G * mk_r[m]                       (label-aware variants)
 };
 
 template <bool ROW_TERM>
 __device__ __forceinline__ RowCtx load_row_ctx(const BwdParams& p, int m, bool fast, float G) {
     RowCtx c;
-    c.w = 0.f; c.l = 0.f; c.a = 0.f; c.d = 0.f; c.lab = -1; c.m = m;
+    c.w = 0.f; c.l = 0.f; c.a = 0.f; c.d = 0.f; c.lab = -1; c.m = m; c.cls = -2; c.k = 0.f;
     if (m < p.n_m) {
+        if (p.mask_mode != 0) { c.cls = p.cls_m[m]; c.k = p.mk_r != nullptr ? p.mk_r[m] * G : 0.f; }
         if (ROW_TERM) {
             if (fast) c.a = p.fa[m] * G;
             else { c.w = p.wr[m] * G; c.l = p.lr[m]; }
@@ -48,7 +51,7 @@ __device__ __forceinline__ RowCtx load_row_ctx(const BwdParams& p, int m, bool f
 //   fast:   dS = 2^(x - c0) * (fa[m] + fb[n]),  fa = wr 2^(c0 - lr), fb = wc 2^(c0 - lc)   (one exponential);
 //           valid when every |lse - c0| <= 100 (checked by k_bwd_fast_vectors), then neither factor over/underflows
 //           in a way that matters: a flushed 2^(x - c0) corresponds to softmax weights below 2^-26.
-template <bool ROW_TERM, bool COL_TERM>
+template <bool ROW_TERM, bool COL_TERM, bool MASK = false>
 __device__ __forceinline__ void ds_tile(const uint32_t (&r0)[32], const uint32_t (&r1)[32], const BwdParams& p,
                                         const RowCtx& rc, int n0, float c1, bool fast, float c0, float G,
                                         float (&v)[64], bool want_ds, float& dsum) {
@@ -88,6 +91,36 @@ __device__ __forceinline__ void ds_tile(const uint32_t (&r0)[32], const uint32_t
                 if (ROW_TERM) acc = rc.w * sm100::ex2f(x - rc.l);
                 if (COL_TERM) acc = fmaf(wcs[j], sm100::ex2f(x - lcs[j]), acc);
                 v[k] = acc;
+            }
+        }
+    }
+    if (MASK) {
+        // label-aware variants: the entries whose column has the row's class (the positive itself is substituted below)
+#pragma unroll
+        for (int k4 = 0; k4 < 16; ++k4) {
+            const int4 c4 = __ldg(reinterpret_cast<const int4*>(p.cls_n + n0) + k4);
+            const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+            float kcs[4] = {0.f, 0.f, 0.f, 0.f}, lcs[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.mask_mode >= 2) {
+                const float4 k4v = __ldg(reinterpret_cast<const float4*>(p.mk_c + n0) + k4);
+                kcs[0] = k4v.x * G; kcs[1] = k4v.y * G; kcs[2] = k4v.z * G; kcs[3] = k4v.w * G;
+            }
+            if (p.mask_mode == 3) {
+                const float4 l4 = __ldg(reinterpret_cast<const float4*>(p.lc + n0) + k4);
+                lcs[0] = l4.x; lcs[1] = l4.y; lcs[2] = l4.z; lcs[3] = l4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k4 * 4 + j;
+                const bool same = cc[j] == rc.cls;
+                float nv;
+                if (p.mask_mode == 1) nv = 0.f;
+                else if (p.mask_mode == 2) nv = v[k] - (rc.k + kcs[j]);
+                else {
+                    const float x = __uint_as_float(k < 32 ? r0[k & 31] : r1[k & 31]) * c1;
+                    nv = v[k] - (__fdividef(rc.k, 1.f - sm100::ex2f(x - rc.l)) + __fdividef(kcs[j], 1.f - sm100::ex2f(x - lcs[j])));
+                }
+                v[k] = same ? nv : v[k];
             }
         }
     }

@@ -243,9 +243,42 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
                         for (int k = 0; k < 64; ++k)
                             if (!rowvalid || (col0 + k) >= p.n_n || k == rel) x[k] = -INFINITY;
                     }
+                    float acc_r = 0.f;
+                    if (p.mask_mode != 0) {
+                        // label-aware variants: same-class entries (cls_n padded to ld_cols with -1, never equal)
+                        const int crow = rowvalid ? p.cls_m[row] : -2;
+                        const float lrow = (p.mask_mode == 2 && rowvalid) ? p.acc_lse[row] : 0.f;
+                        float acc_x = 0.f, acc_l = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 64; ++k) rmax = fmaxf(rmax, x[k]);
-                    if (p.argidx != nullptr) {
+                        for (int k4 = 0; k4 < 16; ++k4) {
+                            const int4 c4 = __ldg(reinterpret_cast<const int4*>(p.cls_n + col0) + k4);
+                            const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int k = k4 * 4 + j;
+                                const bool same = cc[j] == crow && x[k] != -INFINITY;      // (-inf: padding / the positive)
+                                if (p.mask_mode == 1) {
+                                    if (same) x[k] = -INFINITY;
+                                } else if (same) {
+                                    const float pr = ex2f(x[k] - lrow);
+                                    const float om = 1.f - pr;
+                                    acc_x += x[k];
+                                    acc_l += __log2f(om);
+                                    acc_r += __fdividef(pr, om);
+                                }
+                            }
+                        }
+                        if (p.mask_mode == 2) { rs = acc_x; rmax = acc_l; }
+                    }
+                    if (p.mask_mode == 2) {
+                        if (nb_live) p.acc3[(size_t)(nb * 2 + h) * p.ld_rows + row] = acc_r;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 64; ++k) rmax = fmaxf(rmax, x[k]);
+                    }
+                    if (p.mask_mode == 2) {
+                        // (sums already in rs / rmax)
+                    } else if (p.argidx != nullptr) {
                         // fused argmax: first column (lowest index) that attains the maximum of this thread's 64 columns
                         int bi = 63;
 #pragma unroll
@@ -385,7 +418,7 @@ struct BwdCfg {
 };
 size_t bwd_smem_bytes() { return BwdCfg::SMEM_BYTES; }
 
-template <bool ROW_TERM, bool COL_TERM>
+template <bool ROW_TERM, bool COL_TERM, bool MASK>
 __global__ void __launch_bounds__(NTHREADS, 1)
 bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
            const __grid_constant__ CUtensorMap tmBd, const BwdParams p) {
@@ -533,7 +566,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const float c1 = s * LOG2E;
         float G, invG;
         staging_scale(p.gmax_bits, G, invG);
-        const bool fast = p.fast_info != nullptr && p.fast_info[1] != 0.f;
+        const bool fast = !MASK && p.fast_info != nullptr && p.fast_info[1] != 0.f;    // (masks use the two-exponential form)
         const float c0 = fast ? p.fast_info[0] : 0.f;
         uint32_t gs = 0, it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -558,7 +591,7 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 mbar_arrive(SEMPTY(sb));
                 const int n0 = t * TILE + h * 64;
                 float v[64];
-                ds_tile<ROW_TERM, COL_TERM>(r0, r1, p, rc, n0, c1, fast, c0, G, v, want_ds, dsum);
+                ds_tile<ROW_TERM, COL_TERM, MASK>(r0, r1, p, rc, n0, c1, fast, c0, G, v, want_ds, dsum);
                 uint32_t pk[32];
                 pack_ds(v, pk);
                 // dS buffer is free once the dA MMA of the previous tile has completed
@@ -638,15 +671,16 @@ void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     const int grid = n_items < num_sms ? n_items : num_sms;
     const size_t smem = bwd_smem_bytes();
     const bool row_term = p.wr != nullptr, col_term = p.wc != nullptr;
-#define FLYP_LAUNCH_BWD(R, C)                                                                                  \
+#define FLYP_LAUNCH_BWD(R, C, M)                                                                               \
     do {                                                                                                       \
         static bool attr_done[64] = {false};                                                                   \
-        ensure_smem_attr(bwd_kernel<R, C>, smem, attr_done);                                                   \
-        bwd_kernel<R, C><<<grid, NTHREADS, smem, st>>>(tmA, tmB, tmBd, p);                                     \
+        ensure_smem_attr(bwd_kernel<R, C, M>, smem, attr_done);                                                \
+        bwd_kernel<R, C, M><<<grid, NTHREADS, smem, st>>>(tmA, tmB, tmBd, p);                                  \
     } while (0)
-    if (row_term && col_term) FLYP_LAUNCH_BWD(true, true);
-    else if (row_term) FLYP_LAUNCH_BWD(true, false);
-    else FLYP_LAUNCH_BWD(false, true);
+    if (p.mask_mode != 0) FLYP_LAUNCH_BWD(true, true, true);         // label-aware variants always carry both terms
+    else if (row_term && col_term) FLYP_LAUNCH_BWD(true, true, false);
+    else if (row_term) FLYP_LAUNCH_BWD(true, false, false);
+    else FLYP_LAUNCH_BWD(false, true, false);
 #undef FLYP_LAUNCH_BWD
 }
 

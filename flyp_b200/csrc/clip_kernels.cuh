@@ -64,6 +64,18 @@ struct FwdParams {
     // row-sharded multi-GPU: the N-side rows of other ranks arrive over NVLink while the kernel runs.  Column blocks are
     // visited starting at block nb_rot (this rank's own rows) so that work proceeds in arrival order, and the producer
     // polls wait_b before the first TMA read of a block.
+    // label-aware variants (clip/loss.py:123-192; robust kernel only, all nullptr / 0 otherwise): cls_m / cls_n are the
+    // class ids of the M-side rows / N-side columns.
+    //   mask_mode 1 (exclude): entries with equal class ids are dropped from the sums (the diagonal positive of such a
+    //                row is still added back exactly by the finalize step) - the `ignore` variant;
+    //   mask_mode 2 (accumulate): instead of (max, sum) the kernel accumulates, over the entries with equal class ids
+    //                EXCEPT the positive, rowpart = sum x (log2 units), rowmax = sum log2(1 - P), acc3 = sum P / (1 - P)
+    //                with P = 2^(x - acc_lse[row]) - the same-label terms of the soft-label and google_sup variants.
+    const int* cls_m;
+    const int* cls_n;
+    int mask_mode;
+    const float* acc_lse;    // [ld_rows] row logsumexp in log2 units (mask_mode 2)
+    float* acc3;             // [n_tiles * 2][ld_rows] third accumulator (mask_mode 2)
     int nb_rot;              // first column unit (block; MC kernel: block pair) of the flat schedule
     int n_local;             // column units (from nb_rot on) whose rows are this rank's own: phase A of the schedule
     PeerWait wait_b;
@@ -114,6 +126,16 @@ struct BwdParams {
     unsigned long long* prof; // optional debug: per-role wait-cycle counters of cluster 0 (see tools/pair_prof.py)
     float* dscale_part;      // partial sums of dS * <a, b> (unscaled), may be null: [m_tiles * d_parts] (bwd_kernel) or
                              // [2 * sched_pairs] (pair kernel: one per CTA)
+    // label-aware variants (single-CTA kernel only; nullptr / 0 otherwise): class ids of the M rows / N columns (cls_n
+    // padded with -1), and what happens at the entries with equal ids other than the row's positive:
+    //   mask_mode 1: dS = 0 (`ignore`);
+    //   mask_mode 2: dS -= mk_r[m] + mk_c[n]                                   (soft labels: the -E/c terms);
+    //   mask_mode 3: dS -= mk_r[m] / (1 - P_row) + mk_c[n] / (1 - P_col)       (google_sup_loss).
+    const int* cls_m;
+    const int* cls_n;
+    const float* mk_r;
+    const float* mk_c;
+    int mask_mode;
     // pair kernel, end-of-sweep reductions by the whole grid (clip_bwd_pair.cu: sweep_tail_reduce):
     int* grid_cnt;           // arrival counter of the grid barrier, zeroed by the host before the launch; nullptr: no
                              // barrier, the fp32 partials of split blocks and the d(scale) partials are left as they are

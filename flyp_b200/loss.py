@@ -8,8 +8,8 @@ O(B) statistics are exchanged in addition to the feature all-gather the referenc
 
 Differences that are deliberate and documented:
   * ``use_horovod=True`` raises (NCCL / torch.distributed only, no multi-backend dispatch);
-  * the never-called label-aware variants (``ground_labels``, ``ignore``, ``google_sup_loss``; clip/loss.py:123-192)
-    raise ``NotImplementedError``;
+  * the label-aware variants (``ground_labels``, ``ignore``, ``google_sup_loss``; clip/loss.py:123-192) are implemented
+    for world_size == 1 (flyp_b200/labeled.py) and, like the reference's, return a scalar;
   * new opt-in keyword ``normalize`` (default False) L2-normalises both inputs first with a fused kernel
     (what the callers do at clip/model.py:375-376);
   * there is no CPU path: CPU tensors raise.
@@ -374,9 +374,6 @@ class ClipLoss(nn.Module):
     def forward(self, image_features, text_features, logit_scale, ground_labels=None, ignore=False,
                 google_sup_loss=False):
         assert not (ignore and google_sup_loss), 'please specify only one'
-        if ground_labels is not None:
-            raise NotImplementedError("the label-aware ClipLoss variants (clip/loss.py:123-192) have no caller in FLYP "
-                                      "and are not implemented by flyp_b200")
         if self.use_horovod and self.world_size > 1:
             raise NotImplementedError("use_horovod=True is not supported (NCCL via torch.distributed only)")
         if not image_features.is_cuda:
@@ -385,6 +382,15 @@ class ClipLoss(nn.Module):
             image_features = l2_normalize(image_features)
             text_features = l2_normalize(text_features)
         device = image_features.device
+        if ground_labels is not None:
+            # clip/loss.py:123-192: the label-aware variants return a scalar.  In the reference they only make sense for
+            # world_size == 1 (the labels are local while the gathered logits are global: the shapes do not match).
+            if self.world_size > 1:
+                raise NotImplementedError("ground_labels with world_size > 1 is ill-defined in the reference "
+                                          "(clip/loss.py:124-127 compares local labels with gathered logits)")
+            from .labeled import labeled_clip_loss
+            return labeled_clip_loss(image_features, text_features, logit_scale, ground_labels, ignore, google_sup_loss,
+                                     self.grad_dtype)
 
         if self.world_size > 1 and self.local_loss:
             # clip/loss.py:109-111: two row blocks against the gathered matrices; loss for the local rows only

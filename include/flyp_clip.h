@@ -259,6 +259,31 @@ int flyp_l2norm_bwd(const void* y, const void* dy, const float* inv_norm, int n,
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Label-aware ClipLoss variants - clip/loss.py:123-192: soft labels over the items of equal ground label (:188-192),
+ * `ignore` (:132-159: same-label non-diagonal logits leave the softmax), `google_sup_loss` (:160-187).  The same S tiles
+ * as the default loss with a class-equality mask in the epilogues; flyp_b200/labeled.py combines the two building
+ * blocks below into the three losses and their gradients.  Square problems: a, b are [n, dim], the positive of row i is
+ * column i, cls_a / cls_b (int32 device vectors) are the class ids of the rows of a / b.
+ * Workspace: flyp_clip_workspace_bytes(n, n, dim, dtype).
+ *   flyp_label_stats, mode 1: out0[i] = log sum_j exp S_ij over the columns of a DIFFERENT class plus the diagonal,
+ *                              out1[i] = out0[i] - S_ii                             (masked cross-entropy of row i);
+ *                     mode 2: over the columns j != i of the SAME class: out0[i] = sum S_ij, out1[i] = sum ln(1 - P_ij),
+ *                              out2[i] = sum P_ij / (1 - P_ij), P_ij = exp(S_ij - lse_rows[i]).
+ *   flyp_label_sweep: out[m, :] = scale * sum_n dS[m, n] b[n, :] (grad_dtype), d_scale = sum dS[m, n] <a_m, b_n>, with
+ *       dS[m, n] = wr[m] exp(S - lr[m]) + wc[n] exp(S - lc[n]) off the same-class entries, d_diag[m] at n = m (if given),
+ *       and at the other same-class entries: mode 0 the same; 1: 0; 2: that minus (mk_r[m] + mk_c[n]);
+ *       3: that minus (mk_r[m] / (1 - exp(S - lr[m])) + mk_c[n] / (1 - exp(S - lc[n]))).  lr / lc natural-log units;
+ *       gmax[0] (device) >= max |dS| sets the fp16 staging scale.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int flyp_label_stats(const void* a, const void* b, const float* scale, int n, int dim, int dtype, const int* cls_a,
+                     const int* cls_b, int mode, const float* lse_rows, float* out0, float* out1, float* out2,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int flyp_label_sweep(const void* a, const void* b, const float* scale, int n, int dim, int dtype, const float* wr,
+                     const float* lr, const float* wc, const float* lc, const float* d_diag, const int* cls_a,
+                     const int* cls_b, const float* mk_r, const float* mk_c, int mode, const float* gmax, int grad_dtype,
+                     void* out, float* d_scale, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Encoder tail, fused: the final projection of a tower followed by the L2 normalisation that feeds the loss -
  * clip/model.py:242-243 (`x @ self.proj`), :359 (`x[eot] @ self.text_projection`), :375-376 (x / x.norm(dim=-1,
  * keepdim=True)).  y[n, n_out] = z / ||z||_2, z = x[n, k] . w[k, n_out]: one tcgen05 GEMM whose accumulator tile stays

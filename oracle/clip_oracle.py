@@ -89,6 +89,82 @@ def cross_entropy_grads(a, b, scale, labels, g):
     return s * (dS @ B), s * (dS.T @ A), float(np.sum(dS * (A @ B.T)))
 
 
+def _soft_targets(E):
+    """clip/loss.py:126-127,189-190: equal_labels is cast `.type(torch.float)`, so the soft targets E / c are float32
+    numbers whatever the feature dtype (their rows sum to 1 only to ~1e-8)."""
+    E32 = E.astype(np.float32)
+    return (E32 / E32.sum(1, keepdims=True)).astype(np.float64)
+
+
+def labeled_clip_loss(image, text, scale, labels, variant="soft"):
+    """clip/loss.py:123-192 (world_size == 1, `ground_labels` given): the scalar label-aware losses.
+    E_ij = [y_i == y_j] (:124-127), c_i = sum_j E_ij.
+      "soft"    (:188-192) (CE(S, E / c) + CE(S.T, E / c)) / 2 with probability targets (mean over rows);
+      "ignore"  (:132-159) -log(e_ii / sum_{j: E_ij = 0 or j = i} e_ij), both directions, means, / 2;
+      "google"  (:160-187) mean_i 1/c_i sum_j E_ij (-log(e_ij / (sum_k e_ik - e_ij))), both directions, / 2.
+    The reference evaluates "google" as written (exp, subtract, divide): where P_ii rounds to 1 it returns inf; this
+    restatement uses log1p(-P) and stays finite a little longer - compare only where the reference is finite."""
+    S = logits(image, text, scale)
+    y = np.asarray(labels).reshape(-1)
+    E = (y[None, :] == y[:, None]).astype(np.float64)
+    c = E.sum(1)
+    n = S.shape[0]
+    eye = np.eye(n)
+    total = 0.0
+    for L in (S, S.T):
+        if variant == "soft":
+            t = _soft_targets(E)
+            total += np.mean(t.sum(1) * logsumexp(L, 1) - (t * L).sum(1))
+        elif variant == "ignore":
+            keep = (E == 0) | (eye == 1)
+            total += np.mean(logsumexp(np.where(keep, L, -np.inf), 1) - np.diagonal(L))
+        elif variant == "google":
+            lse = logsumexp(L, 1)[:, None]
+            total += np.mean((E * (lse - L + np.log1p(-np.exp(L - lse)))).sum(1) / c)
+        else:
+            raise ValueError(variant)
+    return 0.5 * total
+
+
+def labeled_clip_loss_grads(image, text, scale, labels, variant="soft"):
+    """Closed-form gradient of labeled_clip_loss (upstream gradient 1):  dI = s dS T, dT = s dS^T I, ds = sum(dS * S) / s.
+      soft:    dS = [(P_row + P_col) - E (1/c_i + 1/c_j)] / 2n   (with the reference's float32 targets, _soft_targets)
+      ignore:  dS = [(P'_row - 1) + (P'_col - 1)] / 2n on the diagonal, (P'_row + P'_col) / 2n where E = 0, 0 elsewhere
+               (P' = softmax over the kept entries)
+      google:  dS = [(1 + R_i / c_i) P_row + (1 + R'_j / c_j) P_col - E (1 / (c_i (1 - P_row)) + 1 / (c_j (1 - P_col)))] / 2n,
+               R_i = sum_j E_ij P_row_ij / (1 - P_row_ij), R'_j the same over the column."""
+    I, T = _f64(image), _f64(text)
+    s = float(scale)
+    S = s * (I @ T.T)
+    y = np.asarray(labels).reshape(-1)
+    E = (y[None, :] == y[:, None]).astype(np.float64)
+    c = E.sum(1)
+    n = S.shape[0]
+    eye = np.eye(n)
+    w = 1.0 / (2.0 * n)
+    if variant == "ignore":
+        keep = (E == 0) | (eye == 1)
+        Sm = np.where(keep, S, -np.inf)
+        Pr = np.exp(Sm - logsumexp(Sm, 1)[:, None])
+        Pc = np.exp(Sm - logsumexp(Sm, 0)[None, :])
+        dS = w * ((Pr - eye) + (Pc - eye))
+    else:
+        Pr = np.exp(S - logsumexp(S, 1)[:, None])
+        Pc = np.exp(S - logsumexp(S, 0)[None, :])
+        if variant == "soft":
+            t = _soft_targets(E)
+            tr = t.sum(1)
+            dS = w * (tr[:, None] * Pr + tr[None, :] * Pc) - w * (t + t.T)
+        elif variant == "google":
+            R = (E * Pr / (1.0 - Pr)).sum(1)
+            Rc = (E * Pc / (1.0 - Pc)).sum(0)
+            dS = (w * (1.0 + R / c)[:, None] * Pr + w * (1.0 + Rc / c)[None, :] * Pc
+                  - w * E * (1.0 / (c[:, None] * (1.0 - Pr)) + 1.0 / (c[None, :] * (1.0 - Pc))))
+        else:
+            raise ValueError(variant)
+    return s * (dS @ T), s * (dS.T @ I), float(np.sum(dS * (I @ T.T)))
+
+
 def clip_loss_distributed(image_blocks, text_blocks, scale, rank, local_loss):
     """clip/loss.py:103-114,195-209 for world_size > 1 as seen by `rank`.
     local_loss=False: full [B] vector (identical on every rank); True: the local [b] slice with labels offset by

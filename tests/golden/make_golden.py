@@ -10,6 +10,12 @@ What is recorded (all inputs are seeded, float64 unless noted):
   ce_*.npz        the --ce_ablation head: F.cross_entropy(scale * img @ txt.T, labels) with normalised inputs
                                                                            (src/models/ce_ablation.py:115-123)
   l2norm.npz      x / x.norm(dim=-1, keepdim=True) and its autograd        (clip/model.py:375-376)
+  labeled_*.npz   ClipLoss(world_size=1)(I, T, s, ground_labels=y [, ignore=True | google_sup_loss=True]): scalar loss
+                  and autograd gradients                                   (clip/loss.py:123-192).
+                  The reference's google_sup_loss branch modifies the output of torch.exp in place (:166, :178), so its
+                  backward raises "modified by an inplace operation": for that variant only the LOSS comes from the
+                  unmodified reference; the gradients are autograd through an out-of-place restatement of the same
+                  lines (checked here to reproduce the reference's loss to the last bit).
 """
 import os
 import sys
@@ -116,6 +122,43 @@ def run_l2norm():
              dx=x.grad.numpy())
 
 
+def _google_sup_out_of_place(I, T, s, y):
+    """clip/loss.py:123-127,160-187 with `a /= b` / `a *= b` written out of place (the only change)."""
+    lpi = s * I @ T.T
+    lpt = s * T @ I.T
+    E = (y.view(1, -1).repeat(I.shape[0], 1) == y.view(-1, 1)).type(torch.float)
+    out = []
+    for L in (lpi, lpt):
+        e = torch.exp(L - torch.max(L, dim=1, keepdim=True).values)
+        tot = torch.sum(e, dim=1, keepdim=True).repeat(1, e.shape[1])
+        v = -torch.log(e / (tot - e)) * E
+        out.append(torch.mean(torch.sum(v, dim=1) / torch.sum(E, dim=1)))
+    return (out[0] + out[1]) / 2
+
+
+def run_labeled(n, d, n_cls, s, seed, name, mix=0.5):
+    sys.path.insert(0, REF)
+    from clip.loss import ClipLoss
+    gen = torch.Generator().manual_seed(seed + 1000)
+    y = torch.randint(0, n_cls, (n,), generator=gen) * 7 - 3            # arbitrary (negative, sparse) label values
+    out = dict(y=y.numpy(), scale=np.float64(s))
+    for variant, kw in (("soft", {}), ("ignore", dict(ignore=True)), ("google", dict(google_sup_loss=True))):
+        I, T, _ = make_inputs(n, d, seed, torch.float64, mix)
+        I.requires_grad_(True); T.requires_grad_(True)
+        sc = torch.tensor(float(s), dtype=torch.float64, requires_grad=True)
+        loss = ClipLoss()(I, T, sc, ground_labels=y, **kw)
+        assert loss.dim() == 0
+        if variant == "google":
+            again = _google_sup_out_of_place(I, T, sc, y)
+            assert again.item() == loss.item(), (again.item(), loss.item())
+            again.backward()
+        else:
+            loss.backward()
+        out.update({"I": I.detach().numpy(), "T": T.detach().numpy(), f"{variant}_loss": np.float64(loss.item()),
+                    f"{variant}_dI": I.grad.numpy(), f"{variant}_dT": T.grad.numpy(), f"{variant}_ds": sc.grad.numpy()})
+    np.savez(os.path.join(OUT, name), **out)
+
+
 if __name__ == "__main__":
     assert os.path.isdir(REF), "the reference is not mounted"
     run_w1(24, 16, 1 / 0.07, 1, torch.float64, "clip_w1_n24_d16_f64.npz")
@@ -128,4 +171,7 @@ if __name__ == "__main__":
     run_ce(20, 7, 16, 1 / 0.07, 8, "ce_n20_c7_d16.npz")
     run_ce(150, 182, 64, 100.0, 9, "ce_n150_c182_d64.npz")
     run_l2norm()
+    run_labeled(24, 16, 5, 1 / 0.07, 11, "labeled_n24_d16_c5.npz")
+    run_labeled(150, 64, 9, 1 / 0.07, 12, "labeled_n150_d64_c9.npz")
+    run_labeled(40, 32, 40, 30.0, 13, "labeled_n40_d32_c40_s30.npz", mix=0.3)        # most classes are singletons
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

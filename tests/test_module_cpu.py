@@ -42,7 +42,7 @@ def test_no_cpu_fallback():
 def test_unsupported_variants_raise():
     m = ClipLoss()
     x = torch.randn(8, 16)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FlypError):                       # implemented (flyp_b200/labeled.py) - but not on the CPU
         m(x, x, torch.tensor(10.0), ground_labels=torch.arange(8))
     with pytest.raises(AssertionError):
         m(x, x, torch.tensor(10.0), ignore=True, google_sup_loss=True)

@@ -86,3 +86,27 @@ def test_scale_gradient_identities():
     dI, dT, ds = orc.clip_loss_grads(I, T, 14.3, g)
     assert abs(np.sum(dI * I) / 14.3 - ds) < 1e-12
     assert abs(np.sum(dT * T) / 14.3 - ds) < 1e-12
+
+
+LABELED = ["labeled_n24_d16_c5.npz", "labeled_n150_d64_c9.npz", "labeled_n40_d32_c40_s30.npz"]
+
+
+@pytest.mark.parametrize("name", LABELED)
+@pytest.mark.parametrize("variant", ["soft", "ignore", "google"])
+def test_label_aware_variants_match_reference(golden_dir, name, variant):
+    # clip/loss.py:123-192; the google_sup gradients come from the out-of-place restatement (make_golden.py docstring)
+    z = np.load(os.path.join(golden_dir, name))
+    loss = orc.labeled_clip_loss(z["I"], z["T"], z["scale"], z["y"], variant)
+    assert abs(loss - z[f"{variant}_loss"]) < 1e-11 * abs(z[f"{variant}_loss"])
+    dI, dT, ds = orc.labeled_clip_loss_grads(z["I"], z["T"], z["scale"], z["y"], variant)
+    assert rel(dI, z[f"{variant}_dI"]) < 1e-10 and rel(dT, z[f"{variant}_dT"]) < 1e-10
+    assert rel(ds, z[f"{variant}_ds"]) < 1e-10
+
+
+def test_label_aware_variants_reduce_to_the_default_loss_for_distinct_labels():
+    rng = np.random.default_rng(3)
+    I, T = orc.l2_normalize(rng.standard_normal((21, 12))), orc.l2_normalize(rng.standard_normal((21, 12)))
+    want = orc.clip_loss(I, T, 14.3).mean()
+    y = rng.permutation(21)
+    for v in ("soft", "ignore"):
+        assert abs(orc.labeled_clip_loss(I, T, 14.3, y, v) - want) < 1e-12
