@@ -10,8 +10,10 @@ A step = one forward (per-item loss vector) + one backward of loss.mean() throug
              timed region.
 `roofline`   the dominant kernel (the tcgen05 backward sweep `bwd_pair_kernel`), timed ALONE with CUDA events that the
              library records around its launch inside real module steps (flyp_debug_kernel_events); credited with its
-             ALGORITHMIC FLOPs (3 b B D per launch: half of the one credited recompute + one output GEMM) and
-             compared with the BURST bf16 peak of MEASURED_PEAKS.json (kernel timed in isolation).
+             ALGORITHMIC FLOPs and compared with the BURST bf16 peak of MEASURED_PEAKS.json (kernel timed in isolation).
+             One GPU: the kept-dS backward runs ONE sweep (4 b B D: the recompute + dS . T, all algorithmic) and the
+             d-text product over the kept dS (`dst_gemm_kernel`, 2 b B D, reported beside it).  Several GPUs: two
+             sweeps, 3 b B D credited per launch (half of the one credited recompute + one output product).
 `step_frac`  8 B^2 D / ms_per_step / n_gpus / burst peak: the whole step against the tensor-core roofline.
 `check`      sampled rows of d image AND d text (32 per rank) and the loss against a float64 reference on the GPU
              (tools/sampled_check.py), at every world size; for n_gpus > 1 also a soak over changing inputs.
@@ -412,9 +414,21 @@ def run_ours(args):
     del Ia, Ta
 
     pk = peaks()
-    f_sweep = 3.0 * b * B * D                    # ALGORITHMIC FLOPs of one sweep launch on this rank
-    f_exec = 4.0 * b * B * D                     # executed (S recompute + one output GEMM)
-    sweep_ms = 0.5 * (sweep0_ms + sweep1_ms)
+    from flyp_b200 import _lib as _flyp_lib
+    kept = world == 1 and bool(_flyp_lib.load().flyp_clip_keeps_ds(b, B, D, _flyp_lib.FLYP_BF16 if fdt == torch.bfloat16
+                                                                     else _flyp_lib.FLYP_F32))
+    f_exec = 4.0 * b * B * D                     # executed by a sweep launch (S recompute + one output GEMM)
+    if kept:
+        # kept-dS backward: ONE sweep (S recompute + dS . T, and the dS tiles written out) and the product dS^T . I:
+        # every executed FLOP is algorithmic (8 B^2 D per step: forward S, one recompute, dI, dT)
+        f_sweep = f_exec
+        sweep_ms = sweep0_ms
+        kname = ("bwd_pair_kernel (the backward sweep: S recompute + dS . T product, dS tiles kept in HBM for the "
+                 "d-text product dst_gemm_kernel), per launch")
+    else:
+        f_sweep = 3.0 * b * B * D                # ALGORITHMIC FLOPs of one of two sweep launches on this rank
+        sweep_ms = 0.5 * (sweep0_ms + sweep1_ms)
+        kname = "bwd_pair_kernel (backward sweep: S recompute + dS.B product), per launch, mean of the d-image and d-text launches"
     ach = f_sweep / (sweep_ms * 1e-3) / 1e12
     f_step = 8.0 * B * B * D
     step_tflops = f_step / (ms_res * 1e-3) / 1e12 / world
@@ -422,7 +436,7 @@ def run_ours(args):
     try:                                         # dram bytes per launch of the same kernel from an ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
             prof = json.load(f)
-        key = "bwd_pair_kernel" if world == 1 else f"bwd_pair_kernel_w{world}"
+        key = ("bwd_pair_kernel_keep" if kept else "bwd_pair_kernel") if world == 1 else f"bwd_pair_kernel_w{world}"
         if (B, D) == (32768, 512) and fdt == torch.bfloat16 and key in prof:
             traffic = prof[key]["traffic_bytes_per_launch"]
     except Exception:
@@ -447,11 +461,14 @@ def run_ours(args):
         # backward (2 vector kernels, 2 tcgen05 sweeps); peer path 7 forward (pack, sweep, finalize, 2 gated stubs,
         # statistics push, finish) + 5 backward (2 vector kernels, 2 sweeps, d(scale) sum)
         "gpu_launches": (9 if world == 1 else 12) * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "bwd_pair_kernel (backward sweep: S recompute + dS.B product), per launch, mean of the d-image and d-text launches",
+        "roofline": {"bound": "tensor", "kernel": kname,
                      "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"],
                      "peak_kind": "burst bf16 (kernel timed alone), " + pk["source"],
                      "frac_of_sustained": ach / pk["sustained"],
                      "ms_per_launch": sweep_ms, "ms_d_image_launch": sweep0_ms, "ms_d_text_launch": sweep1_ms,
+                     "d_text_kernel": ("dst_gemm_kernel (dS^T . I over the kept dS, 2 b B D FLOPs)" if kept
+                                       else "bwd_pair_kernel (second sweep)"),
+                     "d_text_tflops": (2.0 if kept else 3.0) * b * B * D / (sweep1_ms * 1e-3) / 1e12,
                      "algorithmic_flops_per_launch": f_sweep, "executed_flops_per_launch": f_exec,
                      "executed_tflops": f_exec / (sweep_ms * 1e-3) / 1e12,
                      "how": "cudaEventRecord by the library right before / after the kernel launch, inside real module steps",
@@ -462,6 +479,7 @@ def run_ours(args):
                            "other_ms": ms_res - (fwd_ms + sweep0_ms + sweep1_ms),
                            "step_tflops_8B2D_per_gpu": step_tflops, "step_frac_of_burst": step_tflops / pk["burst"],
                            "step_frac_of_sustained": step_tflops / pk["sustained"],
+                           "executed_flops_per_step": (8.0 if kept else 10.0) * b * B * D,
                            "step_tflops_6B2D_per_gpu": step_tflops * 0.75},
     }
     if rank == 0:

@@ -127,13 +127,28 @@ inline int pair_d_half(int dim) { const int n = pair_n_dh(dim); return ((dim + n
 // d(scale) partial slots and fp32 tail-partial floats a backward sweep over n_m rows x n_n columns may use
 size_t sweep_dscale_slots(int n_m, int n_n, int dim, int dtype) {
     const int m_tiles = ceil_div(n_m, flyp::TILE);
-    if (!use_pair_kernel(dim, dtype, n_m, n_n)) return (size_t)m_tiles * ceil_div(dim, 256);
-    return (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles * pair_n_dh(dim), n_n, num_sms());
+    const size_t single = (size_t)m_tiles * ceil_div(dim, 256);      // bwd_kernel: one per (row block, 256 output columns)
+    if (!use_pair_kernel(dim, dtype, n_m, n_n)) return single;
+    // (the label-aware sweeps always run the single-CTA kernel: room for either)
+    const size_t pair = (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles * pair_n_dh(dim), n_n, num_sms());
+    return pair > single ? pair : single;
 }
 size_t sweep_part_floats(int n_m, int n_n, int dim, int dtype) {
     if (!use_pair_kernel(dim, dtype, n_m, n_n)) return 0;
     const int m_tiles = ceil_div(n_m, flyp::TILE);
     return (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles * pair_n_dh(dim), n_n, num_sms()) * flyp::TILE * pair_d_half(dim);
+}
+// Kept-dS backward (single rank, both feature gradients wanted): the first sweep also writes its staged fp16 dS tiles to
+// the workspace and the second gradient is the product dS^T . A over them (clip_dst_gemm.cu) instead of a second sweep.
+// FLYP_KEEP_DS=0 switches it off (A/B), FLYP_KEEP_DS_MAX_MB bounds the n_rows x n_cols fp16 matrix (default 24 GiB).
+int env_keep_ds() { static const int v = env_int("FLYP_KEEP_DS", 1); return v; }
+int env_keep_ds_max_mb() { static const int v = env_int("FLYP_KEEP_DS_MAX_MB", 24576); return v; }
+inline int keep_ds_ld(int n_cols) { return ceil_div(n_cols, flyp::PAIR_NSTEP) * flyp::PAIR_NSTEP; }
+bool keep_ds_eligible(int n_rows, int n_cols, int dim, int dtype) {
+    if (env_keep_ds() == 0 || n_rows != n_cols || n_rows < 1024) return false;
+    if (dtype != FLYP_BF16 || dim % 128 != 0 || dim > 1024) return false;
+    if (!use_pair_kernel(dim, dtype, n_rows, n_cols)) return false;
+    return (size_t)n_rows * keep_ds_ld(n_cols) * 2 <= (size_t)env_keep_ds_max_mb() << 20;
 }
 constexpr int VEC_PAD = 256;   // per-row / per-column vectors are padded to this many entries
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -377,6 +392,7 @@ struct SweepIO {
     const int *cls_m, *cls_n;            // label-aware variants (clip_kernels.cuh BwdParams): class ids, weights, mode
     const float *mk_r, *mk_c;
     int mask_mode;
+    uint16_t* ds_keep; int ds_ld;        // pair sweep: also write the staged dS tiles here ([n_m][ds_ld] fp16); may be null
 };
 
 int run_sweep(const SweepIO& io, cudaStream_t st) {
@@ -428,7 +444,12 @@ int run_sweep(const SweepIO& io, cudaStream_t st) {
             p.dscale_out = io.dscale_out;
             if (push) p.ds_push = *io.ds_push;
         }
-        flyp::launch_bwd_pair(tmA64, tmB, tmBd, p, num_sms(), st);
+        CUtensorMap tmDS;
+        if (io.ds_keep != nullptr) {
+            if ((rc = make_tmap(&tmDS, io.ds_keep, n_m, n_n, io.ds_ld, true, 64)) != 0) return rc;
+            p.keep_ds = 1;
+        }
+        flyp::launch_bwd_pair(tmA64, tmB, tmBd, io.ds_keep != nullptr ? &tmDS : nullptr, p, num_sms(), st);
         if (timed) cudaEventRecord(g_ev_sweep[1], st);
         CUDA_OK(cudaGetLastError());
     } else {
@@ -436,7 +457,8 @@ int run_sweep(const SweepIO& io, cudaStream_t st) {
         if (timed) cudaEventRecord(g_ev_sweep[1], st);
         CUDA_OK(cudaGetLastError());
         if (io.dscale_part != nullptr) {
-            flyp::launch_sum_parts(io.dscale_part, (int)io.n_dscale, io.dscale_out, push ? io.ds_push : nullptr, st);
+            if ((size_t)p.m_tiles * p.d_parts > io.n_dscale) return fail(FLYP_ERR_WORKSPACE, "d(scale) partial slots");
+            flyp::launch_sum_parts(io.dscale_part, p.m_tiles * p.d_parts, io.dscale_out, push ? io.ds_push : nullptr, st);
             CUDA_OK(cudaGetLastError());
         }
     }
@@ -472,6 +494,9 @@ struct ClipWs {
     float* fast_info;         // {c0, valid}
     float* col_stat;          // [3 * n_cols] scratch for the column triples when the caller does not want them
     uint16_t *img16, *txt16;  // fp16 staging copies of the features when the caller keeps none (backward only)
+    uint16_t* ds_keep;        // kept-dS backward (keep_ds_eligible): [n_rows][ds_ld] fp16, else nullptr
+    int ds_ld, gemm_pairs;
+    float* gemm_part;         // fp32 partial tiles of the dS^T . A product
     size_t bytes;
 };
 static void carve_clip(void* base, int n_rows, int n_cols, int dim, int dtype, ClipWs& w) {
@@ -494,7 +519,38 @@ static void carve_clip(void* base, int n_rows, int n_cols, int dim, int dtype, C
     const size_t w16 = dtype == FLYP_F32 ? (size_t)2 * plane_cols(dim) : (size_t)dim;
     w.img16 = c.take<uint16_t>((size_t)n_rows * w16);
     w.txt16 = c.take<uint16_t>((size_t)n_cols * w16);
+    w.ds_keep = nullptr; w.gemm_part = nullptr; w.ds_ld = 0; w.gemm_pairs = 0;
+    if (keep_ds_eligible(n_rows, n_cols, dim, dtype)) {
+        w.ds_ld = keep_ds_ld(n_cols);
+        w.gemm_pairs = flyp::dst_gemm_sched_pairs(ceil_div(n_cols, flyp::DST_TILE_ROWS) * ceil_div(dim, flyp::DST_TILE_COLS),
+                                                  ceil_div(n_rows, 128), num_sms());
+        w.gemm_part = c.take<float>(flyp::dst_gemm_part_floats(w.gemm_pairs));
+        w.ds_keep = c.take<uint16_t>((size_t)n_rows * w.ds_ld);
+    }
     w.bytes = align_up(c.off, 256);
+}
+
+// out[n, :] = scale * out_mul / G * sum_m dS[m, n] x16[m, :] over the dS matrix the first sweep kept (n_m x n_n)
+static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* x16, const float* scale, float out_mul,
+                        void* out, int out_fp32, cudaStream_t st) {
+    CUtensorMap tmDS, tmX;
+    int rc;
+    if ((rc = make_tmap(&tmDS, w.ds_keep, n_m, n_n, w.ds_ld, true)) != 0) return rc;
+    if ((rc = make_tmap(&tmX, x16, n_m, dim, dim, true)) != 0) return rc;
+    flyp::DstParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_k = n_m; p.n_out = n_n; p.dim = dim;
+    p.out_tiles = ceil_div(n_n, flyp::DST_TILE_ROWS); p.n_dh = ceil_div(dim, flyp::DST_TILE_COLS);
+    p.sched_pairs = w.gemm_pairs; p.transposed = 1;
+    p.scale = scale; p.gmax_bits = w.ctrl.words; p.out_mul = out_mul;
+    p.out = out; p.ld_out = dim; p.out_fp32 = out_fp32;
+    p.part_out = w.gemm_part; p.grid_cnt = w.ctrl.grid_cnt(1);
+    const bool timed = g_ev_sweep[0] != nullptr && g_ev_sweep_idx == 1;
+    if (timed) cudaEventRecord(g_ev_sweep[0], st);
+    flyp::launch_dst_gemm(tmDS, tmX, p, st);
+    if (timed) cudaEventRecord(g_ev_sweep[1], st);
+    CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int flyp_clip_workspace_bytes(int n_rows, int n_cols, int dim, int dtype, size_t* bytes) {
@@ -505,6 +561,11 @@ int flyp_clip_workspace_bytes(int n_rows, int n_cols, int dim, int dtype, size_t
     carve_clip(nullptr, n_rows, n_cols, dim, dtype, w);
     *bytes = w.bytes;
     return 0;
+}
+
+int flyp_clip_keeps_ds(int n_rows, int n_cols, int dim, int dtype) {
+    if (check_common(n_rows, n_cols, dim, dtype) != 0) return 0;
+    return keep_ds_eligible(n_rows, n_cols, dim, dtype) ? 1 : 0;
 }
 
 int flyp_clip_fwd_local(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
@@ -610,6 +671,7 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
         flyp::launch_split_planes_bf16x3(static_cast<const float*>(txt), n_cols, dim, dp, w.stats.planes_b, st);
         CUDA_OK(cudaGetLastError());
     }
+    const bool keep = w.ds_keep != nullptr && d_img && d_txt;      // second gradient from the kept dS (clip_dst_gemm.cu)
     if (d_img) {
         const void* t16 = txt16;
         if (t16 == nullptr) {
@@ -626,9 +688,14 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
         io.out = d_img; io.sweep = 0;
         if (d_scale) { io.dscale_part = w.dscale_part; io.dscale_out = d_scale; }
         io.b_ready = txt_ready; io.b16_ready = txt16_ready;
+        if (keep) { io.ds_keep = w.ds_keep; io.ds_ld = w.ds_ld; }
         if ((rc = run_sweep(io, st)) != 0) return rc;
     }
-    if (d_txt) {
+    if (d_txt && keep) {
+        flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
+        CUDA_OK(cudaGetLastError());
+        if ((rc = run_dst_gemm(w, n_rows, n_cols, dim, w.img16, scale, grad_mul, d_txt, grad_dtype, st)) != 0) return rc;
+    } else if (d_txt) {
         if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(img), n_rows, dim, dp, w.img16, st);
         else flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
         CUDA_OK(cudaGetLastError());
@@ -682,6 +749,8 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
     CUDA_OK(cudaGetLastError());
     const int off = row_offset;
     const int dp = plane_cols(dim);
+    // (carve_clip reserves the dS matrix only for square single-rank problems)
+    const bool keep = w.ds_keep != nullptr && comm == nullptr && d_img && d_txt && img_all != nullptr;
     flyp::PeerPush push;
     memset(&push, 0, sizeof(push));
     if (comm != nullptr && d_scale != nullptr && (rc = flyp::comm_scalar_push_target(comm, seq, &push)) != 0) return rc;
@@ -710,9 +779,19 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
         io.out = d_img; io.sweep = 0;
         if (d_scale) { io.dscale_part = w.dscale_part; io.dscale_out = d_scale; io.ds_push = &push; }
         if (!f32) { io.b_ready = txt_ready; io.b16_ready = txt16_all ? txt16_ready : nullptr; }
+        if (keep) { io.ds_keep = w.ds_keep; io.ds_ld = w.ds_ld; }
         if ((rc = run_sweep(io, st)) != 0) return rc;
     }
-    if (d_txt) {
+    if (d_txt && keep) {
+        // single rank: d_txt = s dS^T I over the dS values the first sweep kept - no second recompute of the logits
+        const void* i16 = img16_all;
+        if (i16 == nullptr) {
+            flyp::launch_to_f16(img_all, dtype, (size_t)n_cols * dim, w.txt16, st);
+            CUDA_OK(cudaGetLastError());
+            i16 = w.txt16;
+        }
+        if ((rc = run_dst_gemm(w, n_rows, n_cols, dim, i16, scale, grad_mul, d_txt, grad_dtype, st)) != 0) return rc;
+    } else if (d_txt) {
         // the transposed problem: text rows of this rank against all images (no B x D reduce-scatter)
         const void* i16 = img16_all;
         if (f32) {                               // (the first sweep is done with the plane buffers: stream order)

@@ -168,7 +168,8 @@ __device__ __noinline__ void sweep_tail_reduce(const BwdParams& p, const int et,
 template <bool ROW_TERM, bool COL_TERM, bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS2, 1)
 bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmBd, const __grid_constant__ BwdParams p) {
+                const __grid_constant__ CUtensorMap tmBd, const __grid_constant__ CUtensorMap tmDS,
+                const __grid_constant__ BwdParams p) {
     using Cfg = PairCfg;
     constexpr int NSLOT = Cfg::NSLOT;
     extern __shared__ uint8_t smem_raw[];
@@ -186,7 +187,8 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
     const uint32_t DSFULL = bar0 + 8u * (2 * NSLOT + 4), DSEMPTY = bar0 + 8u * (2 * NSLOT + 5);
     const uint32_t ACCFULL = bar0 + 8u * (2 * NSLOT + 6), ACCEMPTY = bar0 + 8u * (2 * NSLOT + 7);
     const uint32_t IFULL = bar0 + 8u * (2 * NSLOT + 8), IFREE = bar0 + 8u * (2 * NSLOT + 9);
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 10);
+    const uint32_t DSLOC = bar0 + 8u * (2 * NSLOT + 10);   // keep_ds: this CTA's 256 epilogue threads have written the tile
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();
@@ -202,11 +204,14 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLOT; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(SFULL(s), 1); mbar_init(SEMPTY(s), EPI_ALL); }
-        mbar_init(DSFULL, EPI_ALL); mbar_init(DSEMPTY, 1);
+        // keep_ds: the tile is free again once the dA^T MMAs have read it AND the spill to global memory has
+        mbar_init(DSFULL, EPI_ALL); mbar_init(DSEMPTY, p.keep_ds ? 2 : 1);
+        mbar_init(DSLOC, 256);
         mbar_init(ACCFULL, 1); mbar_init(ACCEMPTY, EPI_ALL);
         mbar_init(IFULL, 1); mbar_init(IFREE, 1);
         fence_mbar_init();
         tma_prefetch_desc(&tmA64); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBd);
+        if (p.keep_ds) tma_prefetch_desc(&tmDS);
     }
     if (warp == 2) { tmem_alloc_cg2(smem_u32(tmem_holder), 512); tmem_relinquish_cg2(); }
     tc_fence_before();
@@ -380,6 +385,31 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 p.prof[5] = w_acc; p.prof[6] = w_ifull; p.prof[7] = gs;
             }
         }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ dS spill (both CTAs, keep_ds only)
+        // The staged fp16 dS tile of every step ([64 rows][256 columns] per CTA, exactly what the dA^T MMAs read) is also
+        // written to global memory: the gradient of the OTHER operand is then a plain product dS^T . A over these values
+        // (clip_dst_gemm.cu) instead of a second sweep that recomputes every logit.
+        if (p.keep_ds && elect_one()) {
+            uint32_t gs = 0;
+            SweepItems iter(p.m_tiles, p.n_dh, p.sched_pairs, NJ, pair);
+            ItemInfo ii;
+            while (iter.next(ii)) {
+                for (int t = ii.t0; t < ii.t1; ++t, ++gs) {
+                    mbar_wait(DSLOC, gs & 1);
+                    if (ii.dh == 0) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4)
+                            tma_store_2d(&tmDS, smem_u32(ds + c4 * 8192), t * Cfg::NSTEP + c4 * 64,
+                                         ii.mb * TILE + (int)cta * 64);
+                        tma_store_commit();
+                        tma_store_wait_read0();
+                    }
+                    mbar_arrive(DSEMPTY);
+                }
+            }
+            tma_store_wait_all0();
+        }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (both CTAs)
         const int q = warp & 3, h = (warp - 4) >> 2;
@@ -430,6 +460,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 store_ds_row(ds + (jq * 2 + h) * 8192 + rloc * 128, rloc, pk);
                 fence_proxy_async_smem();
                 mbar_arrive_cluster(R_DSFULL);
+                if (p.keep_ds) mbar_arrive(DSLOC);
             }
             // -------- row block done: drain dA^T (lanes = feature columns, TMEM columns = the 128 rows of the block)
             ewait(ACCFULL, it & 1, w_accfull);
@@ -489,8 +520,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
     if (warp == 2) tmem_dealloc_cg2(tmem_base, 512);
 }
 
-void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
-                     int num_sms, cudaStream_t st) {
+void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const CUtensorMap* tmDS_opt,
+                     const BwdParams& p, int num_sms, cudaStream_t st) {
+    const CUtensorMap& tmDS = tmDS_opt != nullptr ? *tmDS_opt : tmB;      // (unused unless p.keep_ds)
     (void)num_sms;
     const int grid = p.sched_pairs * 2;
     const size_t smem = bwd_pair_smem_bytes();
@@ -507,7 +539,7 @@ void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUt
     do {                                                                                                       \
         static bool attr_done[64] = {false};                                                                  \
         ensure_smem_attr(bwd_pair_kernel<R, C, W>, smem, attr_done);                                           \
-        cudaLaunchKernelEx(&cfg, bwd_pair_kernel<R, C, W>, tmA64, tmB, tmBd, p);                               \
+        cudaLaunchKernelEx(&cfg, bwd_pair_kernel<R, C, W>, tmA64, tmB, tmBd, tmDS, p);                             \
     } while (0)
     const bool wide = p.kc > 8 || p.n_dh > 1;
     if (wide) {

@@ -1,0 +1,318 @@
+// clip_dst_gemm.cu — gradient products over the KEPT dS matrix (tcgen05 cta_group::2, fp16 x fp16 -> fp32).
+//
+// The backward sweep (clip_bwd_pair.cu, keep_ds) leaves dS = d(loss)/d(logits) in global memory as the staged fp16
+// values its own dS . B product consumed ([n_m rows][n_n columns], scaled by the staging factor G).  The gradient of the
+// OTHER operand is then a plain product over those values,
+//
+//     transposed = 1:  out[n, :] = c * sum_m dS[m, n] X16[m, :]      (d_text  = s dS^T I: contraction over the rows)
+//     transposed = 0:  out[m, :] = c * sum_n dS[m, n] X16[n, :]      (d_image = s dS T:   contraction over the columns)
+//
+// c = scale * out_mul / G, instead of a second sweep that recomputes every logit, its exponentials and its dS: the step
+// executes 8 B^2 D FLOPs, exactly the algorithmic count (forward S, one recompute, dI, dT), not 10 B^2 D.
+//
+// One cluster of two CTAs owns an output tile of 256 rows (128 per CTA = its 128 TMEM lanes) x up to 512 columns
+// (the whole tensor memory: 2 x 256 fp32 columns) and walks over the contraction index in blocks of 128.
+// Per block and CTA the TMA producer loads two [128][64] boxes of dS (its half of the 256 output rows) and, for every
+// 256-column accumulator, two [128][64] boxes of X16 (its half of the columns: the B operand of a pair MMA is split
+// across the two CTAs by halves of N), 16 KiB each, through one ring of 12 slots.  The operands need no transposition:
+//   transposed:      dS boxes are [128 contraction rows][64 output rows]  -> A operand MN-major (two boxes = M 128)
+//   not transposed:  dS boxes are [128 output rows][64 contraction cols]  -> A operand K-major  (two boxes = K 128)
+//   X16 boxes are   [128 contraction rows][64 feature columns]            -> B operand MN-major (two boxes = N 128)
+// Schedule: the (tile, contraction block) units are cut like the sweep's (sched.h: SweepItems): whole tiles in rounds,
+// then a flat tail in P equal ranges whose fp32 partial tiles are summed, in pair order, by the whole grid behind a grid
+// barrier (cooperative launch).
+#include "clip_kernels.cuh"
+#include "sm100.cuh"
+#include "bwd_common.cuh"
+#include "sched.h"
+#include <cstring>
+
+namespace flyp {
+using namespace sm100;
+
+namespace {
+constexpr int GT = 384;                 // threads: warp 0 producer, 1 MMA issuer, 2 TMEM, 4..11 epilogue
+constexpr int G_SLOT = 16384;
+constexpr int G_NSLOT = 12;
+constexpr int G_ROWS = DST_TILE_ROWS;   // output rows per tile (pair)
+constexpr int G_COLS = DST_TILE_COLS;   // output columns per pass
+constexpr int G_KB = 128;               // contraction rows per block
+constexpr int G_SMEM = G_NSLOT * G_SLOT + 1024 /*barriers, scratch*/ + 1024 /*alignment*/;
+
+DEVI uint8_t* g_align1024(uint8_t* p) {
+    return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+DEVI void g_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+DEVI int g_ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// The fp32 partial tiles of the split tail tiles, summed by the whole grid (cf. sweep_tail_reduce in clip_bwd_pair.cu).
+__device__ __noinline__ void gemm_tail_reduce(const DstParams& p, const int et, const int NJ, int* red_i) {
+    __threadfence();
+    g_epi_bar();
+    if (et == 0) {
+        atomicAdd(p.grid_cnt, 1);
+        while (g_ld_acquire(p.grid_cnt) < (int)gridDim.x) __nanosleep(40);
+    }
+    g_epi_bar();
+    __threadfence();
+    const int v_tiles = p.out_tiles * p.n_dh, P = p.sched_pairs;
+    const int first = (v_tiles / P) * P, n_tail = v_tiles - first;
+    constexpr int CPB = (G_ROWS / 128) * (G_COLS / 128);       // [128 x 128] chunks per tile
+    for (int c = blockIdx.x; c < n_tail * CPB; c += gridDim.x) {
+        const int tb = c / CPB, ci = c - tb * CPB;
+        const int r0 = (ci / (G_COLS / 128)) * 128, dl0 = (ci % (G_COLS / 128)) * 128;
+        if (et == 0) {
+            TailParts parts;
+            int np = 0;
+            if (parts.init(v_tiles, NJ, P, tb))
+                for (int sl = parts.next(); sl >= 0; sl = parts.next()) red_i[2 + np++] = sl;
+            red_i[1] = np;
+        }
+        g_epi_bar();
+        const int np = red_i[1];
+        const int vb = first + tb, ob = vb / p.n_dh, dh = vb - ob * p.n_dh;
+        if (np > 0 && dh * G_COLS + dl0 < p.dim) {
+#pragma unroll 1
+            for (int f0 = et; f0 < 128 * 32; f0 += 256 * 8) {
+                float4 acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < np; ++k) {
+                    const float* base = p.part_out + ((size_t)red_i[2 + k] * G_ROWS + r0) * G_COLS + dl0;
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int f = f0 + j * 256, ri = f >> 5;
+                        v[j] = (ob * G_ROWS + r0 + ri < p.n_out)
+                                   ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)ri * G_COLS + (f & 31) * 4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { acc[j].x += v[j].x; acc[j].y += v[j].y; acc[j].z += v[j].z; acc[j].w += v[j].w; }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int f = f0 + j * 256, ri = f >> 5, oi = ob * G_ROWS + r0 + ri;
+                    const int d = dh * G_COLS + dl0 + (f & 31) * 4;
+                    if (oi >= p.n_out) continue;
+                    if (p.out_fp32) {
+                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)oi * p.ld_out + d) = acc[j];
+                    } else {
+                        uint2 u;
+                        u.x = pack_bf16x2(acc[j].x, acc[j].y); u.y = pack_bf16x2(acc[j].z, acc[j].w);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)oi * p.ld_out + d) = u;
+                    }
+                }
+            }
+        }
+        g_epi_bar();
+    }
+}
+
+}  // namespace
+
+int dst_gemm_sched_pairs(int v_tiles, int k_blocks, int num_sms) {
+    int npairs = num_sms / 2;
+    const long long S = (long long)v_tiles * k_blocks;
+    constexpr int MIN_BLOCKS = 8;          // a range shorter than this does not pay for its partial tile
+    long long cap = S / MIN_BLOCKS;
+    if (cap < v_tiles) cap = v_tiles;
+    if (cap < npairs) npairs = (int)cap;
+    return (int)(S < npairs ? S : npairs);
+}
+size_t dst_gemm_part_floats(int pairs) { return (size_t)2 * pairs * G_ROWS * G_COLS; }
+
+template <bool TRANSPOSED>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT, 1)
+dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmX,
+                const __grid_constant__ DstParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* ring = g_align1024(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + G_NSLOT * G_SLOT);
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (G_NSLOT + s); };
+    const uint32_t ACCFULL = bar0 + 8u * (2 * G_NSLOT), ACCEMPTY = bar0 + 8u * (2 * G_NSLOT + 1);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * G_NSLOT + 2);
+    int* red_i = reinterpret_cast<int*>(bars + 2 * G_NSLOT + 4);      // [1] slot count, [2 ..] slot list (<= 2 P entries)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta = cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    const int NJ = (p.n_k + G_KB - 1) / G_KB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G_NSLOT; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(ACCFULL, 1); mbar_init(ACCEMPTY, 512);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmDS); tma_prefetch_desc(&tmX);
+    }
+    if (warp == 2) { tmem_alloc_cg2(smem_u32(tmem_holder), 512); tmem_relinquish_cg2(); }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    // accumulators (256 columns each) of pass dh
+    auto n_acc = [&](int dh) { const int left = p.dim - dh * G_COLS; return left >= G_COLS ? G_COLS / 256 : (left + 255) / 256; };
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
+        if (elect_one()) {
+            int slot = 0; uint32_t ph = 0;
+            auto put = [&](const CUtensorMap* tm, int c0, int c1) {
+                mbar_wait(EMPTY(slot), ph ^ 1);
+                if (cta == 0) mbar_expect_tx(FULL(slot), 2 * G_SLOT);
+                tma_load_2d_cg2(smem_u32(ring + slot * G_SLOT), tm, mapa(FULL(slot), 0), c0, c1);
+                if (++slot == G_NSLOT) { slot = 0; ph ^= 1; }
+            };
+            SweepItems iter(p.out_tiles, p.n_dh, p.sched_pairs, NJ, pair);
+            ItemInfo ii;
+            while (iter.next(ii)) {
+                const int o0 = ii.mb * G_ROWS + (int)cta * 128;      // first output row of this CTA
+                const int na = n_acc(ii.dh);
+                for (int kb = ii.t0; kb < ii.t1; ++kb) {
+                    const int k0 = kb * G_KB;
+                    if (TRANSPOSED) { put(&tmDS, o0, k0); put(&tmDS, o0 + 64, k0); }
+                    else { put(&tmDS, k0, o0); put(&tmDS, k0 + 64, o0); }
+                    for (int a = 0; a < na; ++a)
+                        for (int ds = 0; ds < 2; ++ds)
+                            put(&tmX, ii.dh * G_COLS + a * 256 + (int)cta * 128 + ds * 64, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (cta == 0 && elect_one()) {
+            constexpr uint32_t IDESC = umma_idesc(256, 256, 0, 0, TRANSPOSED ? 1 : 0, 1);   // fp16 x fp16, B MN-major
+            int slot = 0; uint32_t ph = 0; uint32_t it = 0;
+            auto adv = [&]() { if (++slot == G_NSLOT) { slot = 0; ph ^= 1; } };
+            SweepItems iter(p.out_tiles, p.n_dh, p.sched_pairs, NJ, pair);
+            ItemInfo ii;
+            for (; iter.next(ii); ++it) {
+                const int na = n_acc(ii.dh);
+                mbar_wait(ACCEMPTY, (it & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = ii.t0; kb < ii.t1; ++kb) {
+                    mbar_wait(FULL(slot), ph);
+                    const int a_slot = slot;
+                    adv();
+                    mbar_wait(FULL(slot), ph);
+                    adv();
+                    const uint32_t a_addr = smem_u32(ring + a_slot * G_SLOT);
+                    for (int a = 0; a < na; ++a) {
+                        mbar_wait(FULL(slot), ph);
+                        const int b_slot = slot;
+                        adv();
+                        mbar_wait(FULL(slot), ph);
+                        adv();
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(ring + b_slot * G_SLOT);
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            // A, transposed: [16 contraction rows][128 output rows as two 64-wide boxes], MN-major;
+                            //    otherwise:  [128 output rows][16 contraction columns] of box kk / 4, K-major
+                            const uint64_t ad = TRANSPOSED
+                                ? umma_desc_sw128(a_addr + kk * 2048, G_SLOT, 1024)
+                                : umma_desc_sw128(a_addr + (kk >> 2) * G_SLOT + (kk & 3) * 32, 16, 1024);
+                            // B: [16 contraction rows][128 feature columns as two 64-wide boxes], MN-major
+                            const uint64_t bd = umma_desc_sw128(b_addr + kk * 2048, G_SLOT, 1024);
+                            umma_f16_cg2(tmem_base + a * 256, ad, bd, IDESC, !(kb == ii.t0 && kk == 0));
+                        }
+                        umma_commit_cg2(EMPTY(b_slot));
+                        umma_commit_cg2(EMPTY(b_slot + 1));
+                    }
+                    umma_commit_cg2(EMPTY(a_slot));
+                    umma_commit_cg2(EMPTY(a_slot + 1));
+                }
+                umma_commit_cg2(ACCFULL);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (both CTAs)
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int et = threadIdx.x - 128;
+        float G, invG;
+        staging_scale(p.gmax_bits, G, invG);
+        const float omul = *p.scale * p.out_mul * invG;
+        const uint32_t R_ACCEMPTY = mapa(ACCEMPTY, 0);
+        const int rl = (int)cta * 128 + q * 32 + lane;       // row within the tile
+        uint32_t it = 0;
+        SweepItems iter(p.out_tiles, p.n_dh, p.sched_pairs, NJ, pair);
+        ItemInfo ii;
+        for (; iter.next(ii); ++it) {
+            const int na = n_acc(ii.dh);
+            const int orow = ii.mb * G_ROWS + rl;
+            mbar_wait(ACCFULL, it & 1);
+            tc_fence_after();
+            for (int a = 0; a < na; ++a) {
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int dl = a * 256 + h * 128 + cc * 32;      // column within the pass
+                    const int d = ii.dh * G_COLS + dl;
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + dl, r);
+                    tmem_ld_wait();
+                    if (orow >= p.n_out || d >= p.dim) {
+                        // (nothing to write: a padded row or column)
+                    } else if (ii.part >= 0) {
+                        float4* dst = reinterpret_cast<float4*>(p.part_out + ((size_t)ii.part * G_ROWS + rl) * G_COLS + dl);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            dst[k] = make_float4(__uint_as_float(r[4 * k]) * omul, __uint_as_float(r[4 * k + 1]) * omul,
+                                                 __uint_as_float(r[4 * k + 2]) * omul, __uint_as_float(r[4 * k + 3]) * omul);
+                    } else if (p.out_fp32) {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)orow * p.ld_out + d);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            dst[k] = make_float4(__uint_as_float(r[4 * k]) * omul, __uint_as_float(r[4 * k + 1]) * omul,
+                                                 __uint_as_float(r[4 * k + 2]) * omul, __uint_as_float(r[4 * k + 3]) * omul);
+                    } else {
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)orow * p.ld_out + d);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            uint4 u;
+                            u.x = pack_bf16x2(__uint_as_float(r[8 * k]) * omul, __uint_as_float(r[8 * k + 1]) * omul);
+                            u.y = pack_bf16x2(__uint_as_float(r[8 * k + 2]) * omul, __uint_as_float(r[8 * k + 3]) * omul);
+                            u.z = pack_bf16x2(__uint_as_float(r[8 * k + 4]) * omul, __uint_as_float(r[8 * k + 5]) * omul);
+                            u.w = pack_bf16x2(__uint_as_float(r[8 * k + 6]) * omul, __uint_as_float(r[8 * k + 7]) * omul);
+                            dst[k] = u;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(R_ACCEMPTY);
+        }
+        if (p.grid_cnt != nullptr) gemm_tail_reduce(p, et, NJ, red_i);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_cg2(tmem_base, 512);
+}
+
+void launch_dst_gemm(const CUtensorMap& tmDS, const CUtensorMap& tmX, const DstParams& p, cudaStream_t st) {
+    const int grid = p.sched_pairs * 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(GT); cfg.dynamicSmemBytes = G_SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;       // the grid barrier of the tail reduction needs every CTA resident
+    attr[0].val.cooperative = p.grid_cnt != nullptr ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (p.transposed) {
+        static bool done[64] = {false};
+        ensure_smem_attr(dst_gemm_kernel<true>, G_SMEM, done);
+        cudaLaunchKernelEx(&cfg, dst_gemm_kernel<true>, tmDS, tmX, p);
+    } else {
+        static bool done[64] = {false};
+        ensure_smem_attr(dst_gemm_kernel<false>, G_SMEM, done);
+        cudaLaunchKernelEx(&cfg, dst_gemm_kernel<false>, tmDS, tmX, p);
+    }
+}
+
+}  // namespace flyp

@@ -139,6 +139,8 @@ struct BwdParams {
     // pair kernel, end-of-sweep reductions by the whole grid (clip_bwd_pair.cu: sweep_tail_reduce):
     int* grid_cnt;           // arrival counter of the grid barrier, zeroed by the host before the launch; nullptr: no
                              // barrier, the fp32 partials of split blocks and the d(scale) partials are left as they are
+    int keep_ds;             // pair kernel: the staged fp16 dS tiles (scaled by the staging factor) are also written to
+                             // global memory through the tmDS store map, for the product dS^T . A (clip_dst_gemm.cu)
     float* dscale_out;       // the sum of all d(scale) partials (written by CTA 0 after the barrier), published to the
                              // other ranks through ds_push
     PeerPush ds_push;
@@ -162,12 +164,35 @@ void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
                 int num_sms, cudaStream_t st);
 // CTA-pair variant (clip_bwd_pair.cu): requires d_out % 128 == 0, d_out <= 1024; tmA64 has box [64 rows][64 cols];
 // column vectors padded to a multiple of 256; dscale_part has 2 entries per M tile.
-void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
-                     int num_sms, cudaStream_t st);
+// tmDS (p.keep_ds != 0): store map of the kept dS matrix ([n_m][n_n] fp16, box [64 rows][64 cols]).
+void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUtensorMap& tmBd, const CUtensorMap* tmDS,
+                     const BwdParams& p, int num_sms, cudaStream_t st);
 size_t bwd_pair_smem_bytes();
 // number of CTA pairs the schedule of launch_bwd_pair uses (<= num_sms / 2); m_tiles counts VIRTUAL row blocks
 int bwd_pair_sched_pairs(int m_tiles, int n_cols, int num_sms);
 constexpr int PAIR_NSTEP = 256;      // columns per step of the pair kernel
+
+// ---- products over the kept dS matrix (clip_dst_gemm.cu) -----------------------------------------------------------
+constexpr int DST_TILE_ROWS = 256;   // output rows per CTA pair
+constexpr int DST_TILE_COLS = 512;   // output columns per pass (the pair's tensor memory: 2 x 256 fp32 columns per CTA)
+struct DstParams {
+    int n_k;                 // contraction length: rows of dS (transposed) / columns of dS
+    int n_out;               // output rows: columns of dS (transposed) / rows of dS
+    int dim;                 // feature columns of X16 and of the output (a multiple of 8)
+    int out_tiles, n_dh;     // ceil(n_out / 256) tiles x ceil(dim / 512) passes = the virtual tiles of the schedule
+    int sched_pairs;         // CTA pairs (dst_gemm_sched_pairs)
+    int transposed;          // 1: out = c dS^T X16, 0: out = c dS X16
+    const float* scale;      // c = scale * out_mul / G, G the staging factor of dS (gmax_bits, bwd_common.cuh)
+    const uint32_t* gmax_bits;
+    float out_mul;
+    void* out; int ld_out; int out_fp32;
+    float* part_out;         // [2 * sched_pairs][256][512] fp32 partial tiles of the flat tail
+    int* grid_cnt;           // arrival counter of the grid barrier (zeroed before the launch); nullptr: single pair
+};
+int dst_gemm_sched_pairs(int v_tiles, int k_blocks, int num_sms);
+size_t dst_gemm_part_floats(int pairs);
+// tmDS: load map of dS ([rows][cols] fp16, box [128][64]); tmX: load map of X16 ([n_k][dim] fp16, box [128][64])
+void launch_dst_gemm(const CUtensorMap& tmDS, const CUtensorMap& tmX, const DstParams& p, cudaStream_t st);
 
 size_t fwd_smem_bytes(bool stationary);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is needed once per kernel and device, not once per launch

@@ -90,7 +90,8 @@ class _LabeledLoss(torch.autograd.Function):
                     u_r = (sl_r + torch.log(om_r)) / cnt
                     u_c = (sl_c + torch.log(om_c)) / cnt
                     loss = loss + 0.5 * (u_r.mean() + u_c.mean())
-                    extra = (sr_r + torch.exp(-row_nll) / om_r, sr_c + torch.exp(-col_nll) / om_c)      # R_i, R'_j
+                    # R_i, R'_j, and the same sums without the diagonal term (backward: stable diagonal entry)
+                    extra = (sr_r + torch.exp(-row_nll) / om_r, sr_c + torch.exp(-col_nll) / om_c, sr_r, sr_c)
         ctx.save_for_backward(img, txt, s, cls, cnt, row_lse, row_nll, col_lse, col_nll, *extra)
         ctx.variant, ctx.grad_dtype = variant, grad_dtype
         ctx.scale_meta = (torch.is_tensor(scale), scale.shape if torch.is_tensor(scale) else None,
@@ -122,11 +123,13 @@ class _LabeledLoss(torch.autograd.Function):
                 mode = 2
                 bound = 2.0 * w.abs().max() + 2.0 * mk.abs().max()
             else:
-                big_r, big_c = extra
+                big_r, big_c, off_r, off_c = extra
                 wr = (w * (1.0 + big_r / cnt)).contiguous()
                 wc = (w * (1.0 + big_c / cnt)).contiguous()
                 mk = (w / cnt).contiguous()
-                d_diag = wr * p_r + wc * p_c - mk / om_r - mk / om_c
+                # wr p - mk / (1 - p) with R = R_off + p / (1 - p): the 1 / (1 - p) terms cancel analytically
+                # (w p + mk (p R_off - 1 - p)); evaluating them separately loses log10(1 / (1 - p)) digits
+                d_diag = w * (p_r + p_c) + mk * (p_r * off_r + p_c * off_c - 2.0 - p_r - p_c)
                 mode = 3
                 # |dS| <= wr + wc + mk (1 + R_i) + mk (1 + R'_j) (each 1 / (1 - P) of a row is below 1 + its R)
                 bound = (wr.abs() + mk.abs() * (1.0 + big_r)).max() + (wc.abs() + mk.abs() * (1.0 + big_c)).max()

@@ -38,6 +38,11 @@ int flyp_version(void);
  * world_size == 1: n_rows == n_cols, row_offset == 0.
  * ------------------------------------------------------------------------------------------------------------------ */
 int flyp_clip_workspace_bytes(int n_rows, int n_cols, int dim, int dtype, size_t* bytes);
+/* 1 when a backward over this problem that asks for both feature gradients keeps dS (single rank, square, bf16, dim a
+ * multiple of 128, >= 1024 pairs: the first sweep also writes its staged fp16 dS tiles into the workspace - n_rows x
+ * n_cols x 2 bytes of it - and the text gradient is the product dS^T . image over them instead of a second sweep that
+ * recomputes the logits), 0 when it runs two sweeps.  For callers that account FLOPs; FLYP_KEEP_DS=0 switches it off. */
+int flyp_clip_keeps_ds(int n_rows, int n_cols, int dim, int dtype);
 
 /* Forward, local part.  The positive logit of every row is kept out of the tensor-core sums and added back exactly,
  * so losses much smaller than the logits keep full relative accuracy.  Out:

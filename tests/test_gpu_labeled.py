@@ -63,9 +63,12 @@ def test_bf16_shapes(n, d, n_cls, variant):
     In, Tn = I.double().numpy(), T.double().numpy()
     want = orc.labeled_clip_loss(In, Tn, s, y.numpy(), variant)
     wI, wT, wds = orc.labeled_clip_loss_grads(In, Tn, s, y.numpy(), variant)
-    assert abs(loss - want) < (2e-3 + 2.0 ** -8) * abs(want)          # the loss is returned in the feature dtype (bf16)
-    assert rel(dI, 0.7 * wI) < 2e-3 and rel(dT, 0.7 * wT) < 2e-3
-    assert abs(ds - 0.7 * wds) < 2e-3 * abs(wds)
+    # the loss is returned in the feature dtype and autograd stores the gradients of bf16 leaves in bf16: one rounding
+    # (2^-8) on top of the 2e-3 kernel bar, as for the default loss (test_gpu_parity.py)
+    tol = 2e-3 + 2.0 ** -8
+    assert abs(loss - want) < tol * abs(want)
+    assert rel(dI, 0.7 * wI) < tol and rel(dT, 0.7 * wT) < tol
+    assert abs(ds - 0.7 * wds) < tol * abs(wds)
 
 
 @pytest.mark.parametrize("variant", ["soft", "ignore"])
