@@ -76,6 +76,9 @@ SIGNATURES = {
     "flyp_clip_bwd_step": (c_int, [c_void_p, POINTER(Step), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "flyp_clip_bwd_step_phase": (c_int, [c_void_p, POINTER(Step), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "flyp_comm_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
     "flyp_comm_layout_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
     "flyp_comm_create_external": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p), c_void_p, POINTER(c_void_p)]),

@@ -290,6 +290,36 @@ def bwd_local(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, need_i
     return d_img, d_txt, d_s
 
 
+def bwd_step_phase(st: PeerStep, g: torch.Tensor, grad_mul: float, grad_dtype, phase: int, outs=None):
+    """flyp_clip_bwd_step in two phases over the state of the phase-wise forward above (what ``ClipLoss.backward`` runs
+    as ONE call, flyp_b200/step.py): phase 1 enqueues what the rank computes and publishes - the first sweep and, with
+    the kept-dS backward, the product dS^T . image whose partials go straight into the owners' reduce-scatter buffers -
+    phase 2 what waits for the other ranks (sum of the W partials of d_txt, sum of the d(scale) partials).
+    Phase 1 returns ``outs`` = (d_img, d_txt, ds[2] = [total, partial]) to pass to phase 2."""
+    if not st.comm.alive(st.g.seq):
+        raise FlypError("the gathered features of this step were overwritten by a later forward")
+    dev = st.img.device
+    gdt = st.img.dtype if grad_dtype is None else grad_dtype
+    gcode = {torch.bfloat16: _lib.FLYP_BF16, torch.float32: _lib.FLYP_F32}[gdt]
+    if g.dtype not in (torch.float32, torch.bfloat16):
+        g = g.to(torch.float32)
+    g = g.contiguous()
+    g_code = _lib.FLYP_BF16 if g.dtype == torch.bfloat16 else _lib.FLYP_F32
+    with _lib.device_guard(dev):
+        if outs is None:
+            outs = (torch.empty(st.b, st.D, dtype=gdt, device=dev), torch.empty(st.b, st.D, dtype=gdt, device=dev),
+                    torch.empty(2, dtype=torch.float32, device=dev))
+        d_img, d_txt, ds = outs
+        step = _lib.Step()
+        step.gathered, step.stats = st.g, st.st
+        _lib.check(_lib.load().flyp_clip_bwd_step_phase(
+            st.comm._h, ctypes.byref(step), st.img.data_ptr(), st.txt.data_ptr(), st.s.data_ptr(), st.b, st.D,
+            _lib.dtype_code(st.img), st.comm.rank, st.comm.world, st.col_lse.data_ptr(), st.col_nll.data_ptr(),
+            g.data_ptr(), g_code, float(grad_mul), gcode, d_img.data_ptr(), d_txt.data_ptr(), ds.data_ptr() + 4,
+            ds.data_ptr(), st.ws.data_ptr(), st.ws.numel(), int(phase), _lib.stream_ptr(dev)))
+    return outs
+
+
 # ---------------------------------------------------------------------------------------------------- local_loss
 # clip/loss.py:109-111,200-201: with local_loss=True a rank's loss is two one-directional cross-entropies of its OWN rows
 # against the gathered matrices.  The gather is the peer-memory exchange above; the class matrix of each block lives in

@@ -145,7 +145,8 @@ int env_keep_ds() { static const int v = env_int("FLYP_KEEP_DS", 1); return v; }
 int env_keep_ds_max_mb() { static const int v = env_int("FLYP_KEEP_DS_MAX_MB", 24576); return v; }
 inline int keep_ds_ld(int n_cols) { return ceil_div(n_cols, flyp::PAIR_NSTEP) * flyp::PAIR_NSTEP; }
 bool keep_ds_eligible(int n_rows, int n_cols, int dim, int dtype) {
-    if (env_keep_ds() == 0 || n_rows != n_cols || n_rows < 1024) return false;
+    // square: one rank; n_rows < n_cols: the row block of one of n_cols / n_rows ranks (row-sharded loss)
+    if (env_keep_ds() == 0 || n_rows < 1024 || n_cols % n_rows != 0 || n_cols / n_rows > FLYP_COMM_MAX_WORLD) return false;
     if (dtype != FLYP_BF16 || dim % 128 != 0 || dim > 1024) return false;
     if (!use_pair_kernel(dim, dtype, n_rows, n_cols)) return false;
     return (size_t)n_rows * keep_ds_ld(n_cols) * 2 <= (size_t)env_keep_ds_max_mb() << 20;
@@ -532,7 +533,7 @@ static void carve_clip(void* base, int n_rows, int n_cols, int dim, int dtype, C
 
 // out[n, :] = scale * out_mul / G * sum_m dS[m, n] x16[m, :] over the dS matrix the first sweep kept (n_m x n_n)
 static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* x16, const float* scale, float out_mul,
-                        void* out, int out_fp32, cudaStream_t st) {
+                        void* out, int out_fp32, cudaStream_t st, float* const* out_rank = nullptr, int rows_per_rank = 0) {
     CUtensorMap tmDS, tmX;
     int rc;
     if ((rc = make_tmap(&tmDS, w.ds_keep, n_m, n_n, w.ds_ld, true)) != 0) return rc;
@@ -544,6 +545,11 @@ static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* 
     p.sched_pairs = w.gemm_pairs; p.transposed = 1;
     p.scale = scale; p.gmax_bits = w.ctrl.words; p.out_mul = out_mul;
     p.out = out; p.ld_out = dim; p.out_fp32 = out_fp32;
+    if (out_rank != nullptr) {
+        if (n_n % rows_per_rank != 0 || n_n / rows_per_rank > flyp::PEER_MAXW) return fail(FLYP_ERR_ARG, "bad rank split");
+        for (int q = 0; q < n_n / rows_per_rank; ++q) p.out_rank[q] = out_rank[q];
+        p.rows_per_rank = rows_per_rank; p.out_fp32 = 1; p.out = nullptr;
+    }
     p.part_out = w.gemm_part; p.grid_cnt = w.ctrl.grid_cnt(1);
     const bool timed = g_ev_sweep[0] != nullptr && g_ev_sweep_idx == 1;
     if (timed) cudaEventRecord(g_ev_sweep[0], st);
@@ -720,7 +726,7 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
                             int grad_dtype, void* d_img, void* d_txt, float* d_scale, void* workspace,
                             size_t workspace_bytes, const flyp_ready_t* img_ready, const flyp_ready_t* txt_ready,
                             const flyp_ready_t* img16_ready, const flyp_ready_t* txt16_ready, void* stream,
-                            flyp_comm* comm, uint32_t seq, float* d_scale_total) {
+                            flyp_comm* comm, uint32_t seq, float* d_scale_total, int phases = 3) {
     int rc = check_common(n_rows, n_cols, dim, dtype);
     if (rc) return rc;
     if (g_dtype != FLYP_BF16 && g_dtype != FLYP_F32) return fail(FLYP_ERR_ARG, "bad g_dtype %d", g_dtype);
@@ -740,6 +746,20 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
     if (workspace_bytes < w.bytes) return fail(FLYP_ERR_WORKSPACE, "workspace %zu < %zu", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int cp = ceil_div(n_cols, VEC_PAD) * VEC_PAD;
+    // Kept-dS backward (carve_clip reserved the dS matrix): the second gradient is a product over the first sweep's dS.
+    //   single rank (square problem): d_txt = s dS^T I directly;
+    //   row-sharded over a communicator: every rank's partial s dS_r^T I_r of ALL text rows is scattered, by the product
+    //   kernel itself, into the owners' reduce-scatter buffers over NVLink and summed there (keep_rs).
+    const int world = flyp::comm_world(comm);
+    const bool keep = w.ds_keep != nullptr && comm == nullptr && n_rows == n_cols && d_img && d_txt && img_all != nullptr;
+    const bool keep_rs = w.ds_keep != nullptr && comm != nullptr && world > 1 && n_cols == n_rows * world && d_img && d_txt;
+    if ((phases & 1) == 0) {
+        // finish phase only: everything below was enqueued by an earlier call with phase 1
+        if (keep_rs && (rc = flyp::comm_rs_reduce(comm, seq, n_rows, dim, d_txt, grad_dtype, grad_mul, stream)) != 0) return rc;
+        if (comm != nullptr && d_scale != nullptr && d_scale_total != nullptr)
+            return flyp_comm_sum_scalar(comm, seq, d_scale_total, stream);
+        return 0;
+    }
     // global vectors live in the column set (its d / lab arrays hold the row-statistics l2 / f), local ones in the row set
     float *wg = w.cols.w, *l2c = w.cols.l2, *fc = w.cols.f, *l2r = w.cols.d, *fr = reinterpret_cast<float*>(w.cols.lab);
     CUDA_OK(cudaMemsetAsync(w.ctrl.words, 0, CTRL_WORDS * sizeof(uint32_t), st));
@@ -749,8 +769,6 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
     CUDA_OK(cudaGetLastError());
     const int off = row_offset;
     const int dp = plane_cols(dim);
-    // (carve_clip reserves the dS matrix only for square single-rank problems)
-    const bool keep = w.ds_keep != nullptr && comm == nullptr && d_img && d_txt && img_all != nullptr;
     flyp::PeerPush push;
     memset(&push, 0, sizeof(push));
     if (comm != nullptr && d_scale != nullptr && (rc = flyp::comm_scalar_push_target(comm, seq, &push)) != 0) return rc;
@@ -779,10 +797,26 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
         io.out = d_img; io.sweep = 0;
         if (d_scale) { io.dscale_part = w.dscale_part; io.dscale_out = d_scale; io.ds_push = &push; }
         if (!f32) { io.b_ready = txt_ready; io.b16_ready = txt16_all ? txt16_ready : nullptr; }
-        if (keep) { io.ds_keep = w.ds_keep; io.ds_ld = w.ds_ld; }
+        if (keep || keep_rs) { io.ds_keep = w.ds_keep; io.ds_ld = w.ds_ld; }
         if ((rc = run_sweep(io, st)) != 0) return rc;
     }
-    if (d_txt && keep) {
+    if (d_txt && keep_rs) {
+        // this rank's partial of every text row's gradient, written into the owners' buffers by the product kernel
+        float* out_rank[FLYP_COMM_MAX_WORLD];
+        if ((rc = flyp::comm_rs_targets(comm, seq, n_rows, dim, out_rank)) != 0) return rc;
+        const void* i16 = img16_all != nullptr ? static_cast<const uint16_t*>(img16_all) + (size_t)off * dim : nullptr;
+        if (i16 == nullptr) {                         // (own rows: nothing to wait for)
+            flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
+            CUDA_OK(cudaGetLastError());
+            i16 = w.img16;
+        }
+        // (grad_mul is the RECEIVER's factor - gather_with_grad scales the gradients of a rank's own rows - applied by
+        // the sum)
+        if ((rc = run_dst_gemm(w, n_rows, n_cols, dim, i16, scale, 1.0f, nullptr, 1, st, out_rank, n_rows)) != 0) return rc;
+        if ((rc = flyp::comm_rs_signal(comm, seq, stream)) != 0) return rc;
+        if ((phases & 2) != 0 &&
+            (rc = flyp::comm_rs_reduce(comm, seq, n_rows, dim, d_txt, grad_dtype, grad_mul, stream)) != 0) return rc;
+    } else if (d_txt && keep) {
         // single rank: d_txt = s dS^T I over the dS values the first sweep kept - no second recompute of the logits
         const void* i16 = img16_all;
         if (i16 == nullptr) {
@@ -815,7 +849,7 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
         if (!f32) { io.b_ready = img_ready; io.b16_ready = img16_all ? img16_ready : nullptr; }
         if ((rc = run_sweep(io, st)) != 0) return rc;
     }
-    if (comm != nullptr && d_scale != nullptr && d_scale_total != nullptr)
+    if ((phases & 2) != 0 && comm != nullptr && d_scale != nullptr && d_scale_total != nullptr)
         return flyp_comm_sum_scalar(comm, seq, d_scale_total, stream);
     return 0;
 }
@@ -887,7 +921,18 @@ int flyp_clip_bwd_step(flyp_comm* comm, const flyp_step_t* step, const void* img
                        int n_rows, int dim, int dtype, int rank, int world, const float* col_lse, const float* col_nll,
                        const void* g, int g_dtype, float grad_mul, int grad_dtype, void* d_img, void* d_txt,
                        float* d_scale_partial, float* d_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    return flyp_clip_bwd_step_phase(comm, step, img, txt, scale, n_rows, dim, dtype, rank, world, col_lse, col_nll, g,
+                                    g_dtype, grad_mul, grad_dtype, d_img, d_txt, d_scale_partial, d_scale, workspace,
+                                    workspace_bytes, 3, stream);
+}
+
+int flyp_clip_bwd_step_phase(flyp_comm* comm, const flyp_step_t* step, const void* img, const void* txt,
+                             const float* scale, int n_rows, int dim, int dtype, int rank, int world,
+                             const float* col_lse, const float* col_nll, const void* g, int g_dtype, float grad_mul,
+                             int grad_dtype, void* d_img, void* d_txt, float* d_scale_partial, float* d_scale,
+                             void* workspace, size_t workspace_bytes, int phases, void* stream) {
     if (!step) return fail(FLYP_ERR_ARG, "null pointer argument");
+    if (phases < 1 || phases > 3) return fail(FLYP_ERR_ARG, "phases %d (1: compute and publish, 2: finish, 3: both)", phases);
     if (world < 1 || rank < 0 || rank >= world) return fail(FLYP_ERR_ARG, "bad rank %d / world %d", rank, world);
     if (!comm && world != 1) return fail(FLYP_ERR_ARG, "world %d needs a communicator", world);
     const flyp_gathered_t& gg = step->gathered;
@@ -904,7 +949,7 @@ int flyp_clip_bwd_step(flyp_comm* comm, const flyp_step_t* step, const void* img
                             dim, dtype, rank * n_rows, step->stats.row_lse_all, step->stats.row_nll_all, col_lse, col_nll,
                             g, g_dtype, grad_mul, grad_dtype, d_img, d_txt, d_scale_partial, workspace, workspace_bytes,
                             &gg.img_ready, &gg.txt_ready, &gg.img16_ready, &gg.txt16_ready, stream, comm, gg.seq,
-                            d_scale);
+                            d_scale, phases);
 }
 
 // ------------------------------------------------------------------------------------------------ ce head

@@ -49,6 +49,15 @@ DEVI int g_ld_acquire(const int* p) {
     return v;
 }
 
+// start of output row `orow` when the output is fp32 (possibly scattered over the ranks' buffers)
+DEVI float* out_row_f32(const DstParams& p, int orow) {
+    if (p.rows_per_rank > 0) {
+        const int q = orow / p.rows_per_rank;
+        return p.out_rank[q] + (size_t)(orow - q * p.rows_per_rank) * p.ld_out;
+    }
+    return reinterpret_cast<float*>(p.out) + (size_t)orow * p.ld_out;
+}
+
 // The fp32 partial tiles of the split tail tiles, summed by the whole grid (cf. sweep_tail_reduce in clip_bwd_pair.cu).
 __device__ __noinline__ void gemm_tail_reduce(const DstParams& p, const int et, const int NJ, int* red_i) {
     __threadfence();
@@ -100,7 +109,7 @@ __device__ __noinline__ void gemm_tail_reduce(const DstParams& p, const int et, 
                     const int d = dh * G_COLS + dl0 + (f & 31) * 4;
                     if (oi >= p.n_out) continue;
                     if (p.out_fp32) {
-                        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)oi * p.ld_out + d) = acc[j];
+                        *reinterpret_cast<float4*>(out_row_f32(p, oi) + d) = acc[j];
                     } else {
                         uint2 u;
                         u.x = pack_bf16x2(acc[j].x, acc[j].y); u.y = pack_bf16x2(acc[j].z, acc[j].w);
@@ -266,7 +275,7 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                             dst[k] = make_float4(__uint_as_float(r[4 * k]) * omul, __uint_as_float(r[4 * k + 1]) * omul,
                                                  __uint_as_float(r[4 * k + 2]) * omul, __uint_as_float(r[4 * k + 3]) * omul);
                     } else if (p.out_fp32) {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)orow * p.ld_out + d);
+                        float4* dst = reinterpret_cast<float4*>(out_row_f32(p, orow) + d);
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
                             dst[k] = make_float4(__uint_as_float(r[4 * k]) * omul, __uint_as_float(r[4 * k + 1]) * omul,

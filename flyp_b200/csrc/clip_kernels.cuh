@@ -186,6 +186,11 @@ struct DstParams {
     const uint32_t* gmax_bits;
     float out_mul;
     void* out; int ld_out; int out_fp32;
+    // rows_per_rank > 0 (row-sharded loss, fp32 only): output row n belongs to rank q = n / rows_per_rank and is written
+    // to out_rank[q] + (n - q * rows_per_rank) * ld_out - this rank's slot of rank q's reduce-scatter buffer, local or
+    // peer-mapped over NVLink (comm.cu): the product and the scatter half of the reduce-scatter are one kernel
+    float* out_rank[PEER_MAXW];
+    int rows_per_rank;
     float* part_out;         // [2 * sched_pairs][256][512] fp32 partial tiles of the flat tail
     int* grid_cnt;           // arrival counter of the grid barrier (zeroed before the launch); nullptr: single pair
 };

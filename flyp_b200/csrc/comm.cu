@@ -32,6 +32,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 namespace {
@@ -39,7 +40,7 @@ namespace {
 constexpr int MAXW = 16;
 constexpr int MAXG = 8;             // flag words are spaced MAXG words (32 bytes) apart: one word per (flag set, rank)
 enum { ARR_TXT = 0, ARR_TXT16 = 1, ARR_IMG = 2, ARR_IMG16 = 3, N_ARR = 4 };
-enum { FLAG_STAT = N_ARR, FLAG_DS = N_ARR + 1, N_FLAGSETS = N_ARR + 2 };
+enum { FLAG_STAT = N_ARR, FLAG_DS = N_ARR + 1, FLAG_RS = N_ARR + 2, N_FLAGSETS = N_ARR + 3 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -72,6 +73,7 @@ struct flyp_comm {
     uint32_t timeout_ms;        // how long a kernel waits for a peer before it traps (0: for ever)
     // byte offsets inside a segment (identical on every rank)
     size_t off_feat[2][N_ARR], off_colstat[2], off_rowstat[2], off_dscale[2], off_flags, off_seqword[2], off_counter;
+    size_t off_rs[2];           // reduce-scatter buffer of the text gradient: [world (source rank)][rows][dim] fp32
 };
 
 namespace {
@@ -89,6 +91,7 @@ void layout(flyp_comm* c) {
         c->off_colstat[par] = take((size_t)c->world * 3 * cap * sizeof(float));
         c->off_rowstat[par] = take(2 * cap * sizeof(float));
         c->off_dscale[par] = take(MAXW * sizeof(float));
+        c->off_rs[par] = take(cap * c->dim * sizeof(float));
     }
     c->off_flags = take((size_t)N_FLAGSETS * MAXW * MAXG * sizeof(uint32_t));
     c->off_seqword[0] = take(sizeof(uint32_t));
@@ -235,6 +238,41 @@ __global__ void k_sum_scalar(const float* parts, int world, flyp::PeerWait w, fl
     float s = 0.f;
     for (int q = 0; q < world; ++q) s += __ldcg(parts + q);      // fixed rank order: identical bits on every rank
     out[0] = s;
+}
+
+// ---- reduce-scatter of the text gradient (kept-dS backward, api.cu) --------------------------------------------------
+// Scatter half: the product kernel dS^T . I of every rank writes its fp32 partial of rank q's rows straight into slot
+// [own rank] of rank q's buffer (remote stores over NVLink, clip_dst_gemm.cu).  k_rs_signal, enqueued behind that kernel,
+// releases the sequence number into every rank's flag word; k_rs_reduce waits for the W flags and sums the W slots in
+// rank order (identical bits whatever the arrival order).
+__global__ void k_rs_signal(SegPtrs uni, int world, int rank, size_t off_flags, uint32_t seq) {
+    if ((int)threadIdx.x < world) {
+        __threadfence_system();
+        flyp::st_release_sys_u32(reinterpret_cast<uint32_t*>(uni.seg[threadIdx.x] + off_flags) + (FLAG_RS * MAXW + rank) * MAXG, seq);
+    }
+}
+
+__global__ void k_rs_reduce(const float* __restrict__ slots, int world, size_t slot_floats, flyp::PeerWait w, void* out,
+                            int out_fp32, float mul) {
+    if (threadIdx.x == 0) flyp::peer_wait_all(w);
+    __syncthreads();
+    const size_t n4 = slot_floats / 4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < world; ++q) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(slots + (size_t)q * slot_floats) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        acc.x *= mul; acc.y *= mul; acc.z *= mul; acc.w *= mul;
+        if (out_fp32) {
+            reinterpret_cast<float4*>(out)[i] = acc;
+        } else {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&lo); u.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(out)[i] = u;
+        }
+    }
 }
 
 int check_comm(const flyp_comm* c, bool need_connected) {
@@ -537,6 +575,47 @@ int comm_scalar_push_target(flyp_comm* c, uint32_t seq, PeerPush* out) {
     out->n_flag = c->world;
     for (int q = 0; q < c->world; ++q) out->flag[q] = flag_ptr(c, q, FLAG_DS, c->rank);
     out->seq = seq;
+    return 0;
+}
+
+// Reduce-scatter buffer of step `seq`: out_rank[q] = this rank's slot ([n_rows][dim] fp32) in rank q's segment.
+int comm_rs_targets(flyp_comm* c, uint32_t seq, int n_rows, int dim, float** out_rank) {
+    int rc = check_comm(c, true);
+    if (rc) return rc;
+    if (n_rows <= 0 || n_rows > c->max_rows || dim != c->dim) {
+        flyp::set_error(FLYP_ERR_ARG, "reduce-scatter block [%d, %d] does not fit the communicator", n_rows, dim);
+        return FLYP_ERR_ARG;
+    }
+    const size_t off = c->off_rs[seq & 1u] + (size_t)c->rank * n_rows * dim * sizeof(float);
+    for (int q = 0; q < c->world; ++q) out_rank[q] = reinterpret_cast<float*>(c->seg[q] + off);
+    return 0;
+}
+
+int comm_world(const flyp_comm* c) { return c != nullptr ? c->world : 1; }
+
+int comm_rs_signal(flyp_comm* c, uint32_t seq, void* stream) {
+    int rc = check_comm(c, true);
+    if (rc) return rc;
+    SegPtrs uni;
+    for (int q = 0; q < MAXW; ++q) uni.seg[q] = q < c->world ? c->seg[q] : nullptr;
+    k_rs_signal<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(uni, c->world, c->rank, c->off_flags, seq);
+    COMM_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int comm_rs_reduce(flyp_comm* c, uint32_t seq, int n_rows, int dim, void* out, int out_fp32, float mul, void* stream) {
+    int rc = check_comm(c, true);
+    if (rc) return rc;
+    flyp::PeerWait w;
+    w.flags = flag_ptr(c, c->rank, FLAG_RS, 0); w.seq = seq; w.n_flags = c->world; w.rows_per_flag = 1; w.err = c->err_dev;
+    w.sub = 1; w.stride = MAXG; w.timeout_ms = c->timeout_ms;
+    const size_t slot = (size_t)n_rows * dim;
+    int blocks = (int)((slot / 4 + 255) / 256);
+    if (blocks > 592) blocks = 592;                 // 4 per SM: an HBM-bound sum of W x n_rows x dim floats
+    if (blocks < 1) blocks = 1;
+    k_rs_reduce<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float*>(c->seg[c->rank] + c->off_rs[seq & 1u]), c->world, slot, w, out, out_fp32, mul);
+    COMM_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

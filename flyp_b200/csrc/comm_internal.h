@@ -23,6 +23,14 @@ int comm_gather(flyp_comm* c, const void* img, const void* txt, int n_rows, int 
 // Destinations of this rank's d(logit_scale) partial of step `seq` (published by the last CTA of the first sweep).
 int comm_scalar_push_target(flyp_comm* c, uint32_t seq, PeerPush* out);
 
+// Reduce-scatter of the text gradient (kept-dS backward): where this rank's fp32 partials of rank q's rows go
+// (out_rank[world], local or peer-mapped), the release of the step's flag behind the kernel that wrote them, and the
+// sum of the W slots of the own buffer, times mul, into out[n_rows, dim] (fp32 or bf16) once every rank's flag has arrived.
+int comm_rs_targets(flyp_comm* c, uint32_t seq, int n_rows, int dim, float** out_rank);
+int comm_rs_signal(flyp_comm* c, uint32_t seq, void* stream);
+int comm_rs_reduce(flyp_comm* c, uint32_t seq, int n_rows, int dim, void* out, int out_fp32, float mul, void* stream);
+int comm_world(const flyp_comm* c);
+
 void set_error(int code, const char* fmt, ...);   // api.cu: thread-local message returned by flyp_last_error()
 
 }  // namespace flyp

@@ -254,6 +254,17 @@ int flyp_clip_bwd_step(flyp_comm* comm, const flyp_step_t* step, const void* img
                        const void* g, int g_dtype, float grad_mul, int grad_dtype, void* d_img, void* d_txt,
                        float* d_scale_partial, float* d_scale, void* workspace, size_t workspace_bytes, void* stream);
 
+/* flyp_clip_bwd_step in two phases, for callers that step several ranks from ONE thread (a kernel must never wait for
+ * a kernel that has not been enqueued): phases = 1 enqueues everything a rank computes and publishes (the sweeps; with
+ * the kept-dS backward the product dS^T . image whose fp32 partials go straight into the owners' reduce-scatter buffers
+ * over NVLink, and the release of the step's flags), phases = 2 what waits for the other ranks (the sum of the W
+ * partials of the text gradient into d_txt, the sum of the d(logit_scale) partials), 3 = both = flyp_clip_bwd_step. */
+int flyp_clip_bwd_step_phase(flyp_comm* comm, const flyp_step_t* step, const void* img, const void* txt,
+                             const float* scale, int n_rows, int dim, int dtype, int rank, int world,
+                             const float* col_lse, const float* col_nll, const void* g, int g_dtype, float grad_mul,
+                             int grad_dtype, void* d_img, void* d_txt, float* d_scale_partial, float* d_scale,
+                             void* workspace, size_t workspace_bytes, int phases, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Row-wise L2 normalisation x / ||x||_2 (no epsilon), clip/model.py:375-376, src/models/ce_ablation.py:115-118.
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -127,3 +127,60 @@ def test_soak_changing_inputs_two_gpus():
     line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["check"]["passed"] and line["check"]["soak"]["passed"], line["check"]
     assert line["check"]["soak"]["steps"] == 2000 and line["check"]["soak"]["mismatching_gathered_elements"] == 0
+
+
+def _kept_worker(rank, world, port, b, dim, gwg, steps, ret):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from flyp_b200 import ClipLoss, _lib
+    from oracle import torch_port
+    assert _lib.load().flyp_clip_keeps_ds(b, b * world, dim, _lib.FLYP_BF16) == 1
+    fn = ClipLoss(gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world, grad_dtype=torch.float32)
+    out = {}
+    for step in range(steps):                     # several steps: both parities of the reduce-scatter buffers
+        I, T = torch_port.synthetic_pairs(b * world, dim, seed=40 + step, dtype=torch.bfloat16)
+        Il = I[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+        Tl = T[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+        sc = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
+        g = (torch.rand(b * world, generator=torch.Generator().manual_seed(50 + step)) / (b * world)).to(dev)
+        loss = fn(Il, Tl, sc)
+        (loss.float() * g).sum().backward()
+        torch.cuda.synchronize()
+        out[step] = dict(loss=loss.detach().float().cpu().numpy(), dI=Il.grad.float().cpu().numpy(),
+                         dT=Tl.grad.float().cpu().numpy(), ds=sc.grad.float().cpu().numpy())
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,b,dim", [(2, 1024, 256), (4, 1024, 128), (8, 1024, 128)])
+@pytest.mark.parametrize("gwg", [False, True])
+def test_multi_gpu_kept_ds_reduce_scatter(world, b, dim, gwg):
+    """The kept-dS backward over real GPUs: the product kernel of every rank writes its fp32 partials of the text
+    gradient into the owners' buffers over NVLink, each rank sums its W slots (csrc/clip_dst_gemm.cu, csrc/comm.cu)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from oracle import clip_oracle as orc
+    from oracle import torch_port
+    steps = 3
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    _PORT[0] += 1
+    mp.spawn(_kept_worker, args=(world, _PORT[0], b, dim, gwg, steps, ret), nprocs=world, join=True)
+    tol = 2.0 ** -8 + 2e-3                        # (autograd stores the gradients of bf16 leaves in bf16)
+    for step in range(steps):
+        I, T = torch_port.synthetic_pairs(b * world, dim, seed=40 + step, dtype=torch.bfloat16)
+        In, Tn = I.double().numpy(), T.double().numpy()
+        g = (torch.rand(b * world, generator=torch.Generator().manual_seed(50 + step)) / (b * world)).double().numpy()
+        Ib, Tb = [In[r * b:(r + 1) * b] for r in range(world)], [Tn[r * b:(r + 1) * b] for r in range(world)]
+        for r in range(world):
+            got = ret[r][step]
+            want = orc.clip_loss_distributed(Ib, Tb, 1 / 0.07, r, False)
+            wI, wT, ws = orc.clip_loss_distributed_grads(Ib, Tb, 1 / 0.07, r, False, gwg, g)
+            assert rel(got["loss"], want) < tol
+            assert rel(got["dI"], wI) < tol and rel(got["dT"], wT) < tol, (step, r, rel(got["dI"], wI), rel(got["dT"], wT))
+            assert abs(got["ds"] - ws) < tol * abs(ws)

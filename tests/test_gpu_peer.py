@@ -309,3 +309,58 @@ def test_stale_step_is_refused():
         torch.cuda.synchronize()
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("world,b,dim", [(2, 1024, 512), (4, 1024, 256), (2, 1100, 384), (8, 4096, 512), (2, 2048, 1024)])
+def test_kept_ds_reduce_scatter_emulated(world, b, dim):
+    """The multi-GPU kept-dS backward (csrc/clip_dst_gemm.cu + the reduce-scatter buffers of csrc/comm.cu) with W emulated
+    ranks on ONE GPU, phase by phase: every rank's first sweep keeps its dS, its product dS_r^T . I_r writes the fp32
+    partials of ALL text rows into the owners' buffers, then every rank sums its W slots.  Sampled rows of d image /
+    d text of every rank and the all-reduced d(scale) against the float64 reference, over two steps (buffer parity),
+    with the gather_with_grad factor on the odd ranks (it scales a rank's OWN rows: SURVEY 8c)."""
+    from flyp_b200 import _lib, comm as peer
+    from flyp_b200.comm import PeerComm
+    from oracle import torch_port
+    from tools import sampled_check as sck
+    dev = torch.device("cuda:0")
+    B = world * b
+    assert _lib.load().flyp_clip_keeps_ds(b, B, dim, _lib.FLYP_BF16) == 1
+    s = 1.0 / 0.07
+    sc = torch.tensor([s], device=dev)
+    comms = [PeerComm(r, world, b, dim, dev) for r in range(world)]
+    PeerComm.connect_local(comms)
+    try:
+        for step in range(2):
+            I, T = torch_port.synthetic_pairs(B, dim, seed=20 + step, dtype=torch.bfloat16)
+            Id, Td = I.to(dev), T.to(dev)
+            g = (torch.rand(B, generator=torch.Generator().manual_seed(13 + step)) / B).to(dev)
+            steps = [peer.fwd_gather(comms[r], Id[r * b:(r + 1) * b], Td[r * b:(r + 1) * b], sc) for r in range(world)]
+            for st in steps:
+                peer.fwd_local(st)
+            for st in steps:
+                peer.fwd_finish(st)
+            mul = [float(world) if r % 2 else 1.0 for r in range(world)]
+            outs = [peer.bwd_step_phase(st, g, mul[r], torch.float32, 1) for r, st in enumerate(steps)]
+            for r, st in enumerate(steps):
+                peer.bwd_step_phase(st, g, mul[r], torch.float32, 2, outs[r])
+            torch.cuda.synchronize()
+            for c in comms:
+                c.check_error()
+            lse64 = sck.full_lse(Id, Td, s)
+            gen = np.random.default_rng(5 + step)
+            tot = 0.0
+            for r in range(world):
+                d_img, d_txt, ds = outs[r]
+                loc = torch.tensor(gen.choice(b, 32, replace=False), device=dev)
+                idx = loc + r * b
+                _, want_dI, want_dT = sck.sampled_reference(Id, Td, s, g, idx, lse=lse64)
+                for got, want, what in ((d_img[loc], mul[r] * want_dI, "d image"), (d_txt[loc], mul[r] * want_dT, "d text")):
+                    glob, per_row = sck.row_errors(got, want)
+                    assert glob < 2e-3 and per_row < 6e-3, (step, r, what, glob, per_row)
+                tot += (d_txt.double() * Td[r * b:(r + 1) * b].double()).sum().item() / (mul[r] * s)
+            # d(scale) = sum over all rows of <dT_j, T_j> / s; identical bits on every rank (fixed summation order)
+            assert len({o[2][0].item() for o in outs}) == 1
+            assert abs(outs[0][2][0].item() - tot) < 1e-3 * abs(tot)
+    finally:
+        for c in comms:
+            c.close()
