@@ -11,9 +11,10 @@ A step = one forward (per-item loss vector) + one backward of loss.mean() throug
 `roofline`   the dominant kernel (the tcgen05 backward sweep `bwd_pair_kernel`), timed ALONE with CUDA events that the
              library records around its launch inside real module steps (flyp_debug_kernel_events); credited with its
              ALGORITHMIC FLOPs and compared with the BURST bf16 peak of MEASURED_PEAKS.json (kernel timed in isolation).
-             One GPU: the kept-dS backward runs ONE sweep (4 b B D: the recompute + dS . T, all algorithmic) and the
-             d-text product over the kept dS (`dst_gemm_kernel`, 2 b B D, reported beside it).  Several GPUs: two
-             sweeps, 3 b B D credited per launch (half of the one credited recompute + one output product).
+             The kept-dS backward runs ONE sweep (4 b B D: the recompute + dS . T, all algorithmic) and the d-text
+             product over the kept dS (`dst_gemm_kernel`, 2 b B D, reported beside it; on several GPUs its epilogue is
+             the scatter half of the reduce-scatter of the text gradient).  Shapes that do not keep dS run two sweeps,
+             3 b B D credited per launch (half of the one credited recompute + one output product).
 `step_frac`  8 B^2 D / ms_per_step / n_gpus / burst peak: the whole step against the tensor-core roofline.
 `check`      sampled rows of d image AND d text (32 per rank) and the loss against a float64 reference on the GPU
              (tools/sampled_check.py), at every world size; for n_gpus > 1 also a soak over changing inputs.
@@ -415,12 +416,14 @@ def run_ours(args):
 
     pk = peaks()
     from flyp_b200 import _lib as _flyp_lib
-    kept = world == 1 and bool(_flyp_lib.load().flyp_clip_keeps_ds(b, B, D, _flyp_lib.FLYP_BF16 if fdt == torch.bfloat16
-                                                                     else _flyp_lib.FLYP_F32))
+    kept = bool(_flyp_lib.load().flyp_clip_keeps_ds(b, B, D, _flyp_lib.FLYP_BF16 if fdt == torch.bfloat16
+                                                    else _flyp_lib.FLYP_F32))
     f_exec = 4.0 * b * B * D                     # executed by a sweep launch (S recompute + one output GEMM)
     if kept:
         # kept-dS backward: ONE sweep (S recompute + dS . T, and the dS tiles written out) and the product dS^T . I:
-        # every executed FLOP is algorithmic (8 B^2 D per step: forward S, one recompute, dI, dT)
+        # every executed FLOP is algorithmic (8 B^2 D per step: forward S, one recompute, dI, dT).  Several GPUs: the
+        # product covers the rank's rows of dS against ALL text rows and its epilogue scatters the fp32 partials into the
+        # owners' buffers over NVLink (the scatter half of a reduce-scatter), a small kernel sums the W slots
         f_sweep = f_exec
         sweep_ms = sweep0_ms
         kname = ("bwd_pair_kernel (the backward sweep: S recompute + dS . T product, dS tiles kept in HBM for the "
@@ -460,7 +463,8 @@ def run_ours(args):
         # own kernels per step: 1 GPU 5 forward (preparation, tcgen05 sweep, finalize, 2 gated robust-path stubs) + 4
         # backward (2 vector kernels, 2 tcgen05 sweeps); peer path 7 forward (pack, sweep, finalize, 2 gated stubs,
         # statistics push, finish) + 5 backward (2 vector kernels, 2 sweeps, d(scale) sum)
-        "gpu_launches": (9 if world == 1 else 12) * args.steps,
+        # kept-dS backward on several GPUs: 2 vector kernels, sweep, product, flag release, slot sum, d(scale) sum = 7
+        "gpu_launches": (9 if world == 1 else (14 if kept else 12)) * args.steps,
         "roofline": {"bound": "tensor", "kernel": kname,
                      "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"],
                      "peak_kind": "burst bf16 (kernel timed alone), " + pk["source"],

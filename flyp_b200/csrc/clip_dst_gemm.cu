@@ -37,7 +37,9 @@ constexpr int G_NSLOT = 12;
 constexpr int G_ROWS = DST_TILE_ROWS;   // output rows per tile (pair)
 constexpr int G_COLS = DST_TILE_COLS;   // output columns per pass
 constexpr int G_KB = 128;               // contraction rows per block
-constexpr int G_SMEM = G_NSLOT * G_SLOT + 1024 /*barriers, scratch*/ + 1024 /*alignment*/;
+constexpr int G_STAGE = 8 * 32 * 32 * 4;   // epilogue: one [32][32] fp32 transposition buffer per warp
+constexpr int G_SMEM = G_NSLOT * G_SLOT + G_STAGE + 1024 /*barriers, scratch*/ + 1024 /*alignment*/;
+static_assert(G_SMEM <= 232448, "shared memory budget of one CTA");
 
 DEVI uint8_t* g_align1024(uint8_t* p) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
@@ -141,7 +143,8 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                 const __grid_constant__ DstParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* ring = g_align1024(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + G_NSLOT * G_SLOT);
+    float* stage = reinterpret_cast<float*>(ring + G_NSLOT * G_SLOT);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + G_NSLOT * G_SLOT + G_STAGE);
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (G_NSLOT + s); };
@@ -249,49 +252,49 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
         staging_scale(p.gmax_bits, G, invG);
         const float omul = *p.scale * p.out_mul * invG;
         const uint32_t R_ACCEMPTY = mapa(ACCEMPTY, 0);
-        const int rl = (int)cta * 128 + q * 32 + lane;       // row within the tile
+        float* const stg = stage + (warp - 4) * 1024;        // this warp's [32][32] fp32 transposition buffer
         uint32_t it = 0;
         SweepItems iter(p.out_tiles, p.n_dh, p.sched_pairs, NJ, pair);
         ItemInfo ii;
         for (; iter.next(ii); ++it) {
             const int na = n_acc(ii.dh);
-            const int orow = ii.mb * G_ROWS + rl;
             mbar_wait(ACCFULL, it & 1);
             tc_fence_after();
             for (int a = 0; a < na; ++a) {
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
-                    const int dl = a * 256 + h * 128 + cc * 32;      // column within the pass
-                    const int d = ii.dh * G_COLS + dl;
+                    const int dl = a * 256 + h * 128 + cc * 32;      // first of this warp's 32 columns within the pass
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + dl, r);
                     tmem_ld_wait();
-                    if (orow >= p.n_out || d >= p.dim) {
-                        // (nothing to write: a padded row or column)
-                    } else if (ii.part >= 0) {
-                        float4* dst = reinterpret_cast<float4*>(p.part_out + ((size_t)ii.part * G_ROWS + rl) * G_COLS + dl);
+                    // [32 rows (lanes)][32 columns] -> shared memory (XOR-swizzled: conflict-free both ways) -> each
+                    // store instruction of the warp writes four full 128-byte row segments instead of 32 scattered
+                    // 16-byte pieces (what a lane = row mapping gives): it matters for the partials that go to another
+                    // GPU's memory over NVLink, where small scattered writes run at a fraction of the link rate
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            dst[k] = make_float4(__uint_as_float(r[4 * k]) * omul, __uint_as_float(r[4 * k + 1]) * omul,
-                                                 __uint_as_float(r[4 * k + 2]) * omul, __uint_as_float(r[4 * k + 3]) * omul);
-                    } else if (p.out_fp32) {
-                        float4* dst = reinterpret_cast<float4*>(out_row_f32(p, orow) + d);
+                    for (int k = 0; k < 32; ++k) stg[lane * 32 + (k ^ lane)] = __uint_as_float(r[k]) * omul;
+                    __syncwarp();
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            dst[k] = make_float4(__uint_as_float(r[4 * k]) * omul, __uint_as_float(r[4 * k + 1]) * omul,
-                                                 __uint_as_float(r[4 * k + 2]) * omul, __uint_as_float(r[4 * k + 3]) * omul);
-                    } else {
-                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)orow * p.ld_out + d);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            uint4 u;
-                            u.x = pack_bf16x2(__uint_as_float(r[8 * k]) * omul, __uint_as_float(r[8 * k + 1]) * omul);
-                            u.y = pack_bf16x2(__uint_as_float(r[8 * k + 2]) * omul, __uint_as_float(r[8 * k + 3]) * omul);
-                            u.z = pack_bf16x2(__uint_as_float(r[8 * k + 4]) * omul, __uint_as_float(r[8 * k + 5]) * omul);
-                            u.w = pack_bf16x2(__uint_as_float(r[8 * k + 6]) * omul, __uint_as_float(r[8 * k + 7]) * omul);
-                            dst[k] = u;
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = i * 4 + (lane >> 3), c0 = (lane & 7) * 4;
+                        float4 v;
+                        v.x = stg[rr * 32 + ((c0 + 0) ^ rr)]; v.y = stg[rr * 32 + ((c0 + 1) ^ rr)];
+                        v.z = stg[rr * 32 + ((c0 + 2) ^ rr)]; v.w = stg[rr * 32 + ((c0 + 3) ^ rr)];
+                        const int rt = (int)cta * 128 + q * 32 + rr;         // row within the tile
+                        const int orow = ii.mb * G_ROWS + rt;
+                        const int d = ii.dh * G_COLS + dl + c0;
+                        if (orow >= p.n_out || d >= p.dim) continue;
+                        if (ii.part >= 0) {
+                            *reinterpret_cast<float4*>(p.part_out + ((size_t)ii.part * G_ROWS + rt) * G_COLS + dl + c0) = v;
+                        } else if (p.out_fp32) {
+                            *reinterpret_cast<float4*>(out_row_f32(p, orow) + d) = v;
+                        } else {
+                            uint2 u;
+                            u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)orow * p.ld_out + d) = u;
                         }
                     }
+                    __syncwarp();
                 }
             }
             tc_fence_before();

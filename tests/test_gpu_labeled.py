@@ -82,7 +82,8 @@ def test_distinct_labels_give_the_default_loss(variant):
     ref = ClipLoss(grad_dtype=torch.float32)(Ic, Tc, sc).float().mean()
     ref.backward()
     assert abs(loss - float(ref)) < 2.0 ** -7 * abs(float(ref))
-    assert rel(dI, Ic.grad.double().cpu().numpy()) < 1e-3 and rel(dT, Tc.grad.double().cpu().numpy()) < 1e-3
+    # (both sides were stored in bf16 by autograd: they may differ by one bf16 step)
+    assert rel(dI, Ic.grad.double().cpu().numpy()) < 2.0 ** -7 and rel(dT, Tc.grad.double().cpu().numpy()) < 2.0 ** -7
 
 
 def test_world_size_above_one_raises():
