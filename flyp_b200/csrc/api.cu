@@ -523,8 +523,7 @@ static void carve_clip(void* base, int n_rows, int n_cols, int dim, int dtype, C
     w.ds_keep = nullptr; w.gemm_part = nullptr; w.ds_ld = 0; w.gemm_pairs = 0;
     if (keep_ds_eligible(n_rows, n_cols, dim, dtype)) {
         w.ds_ld = keep_ds_ld(n_cols);
-        w.gemm_pairs = flyp::dst_gemm_sched_pairs(ceil_div(n_cols, flyp::DST_TILE_ROWS) * ceil_div(dim, flyp::DST_TILE_COLS),
-                                                  ceil_div(n_rows, 128), num_sms());
+        w.gemm_pairs = num_sms() / 2;                                 // (upper bound: the schedule is chosen per launch)
         w.gemm_part = c.take<float>(flyp::dst_gemm_part_floats(w.gemm_pairs));
         w.ds_keep = c.take<uint16_t>((size_t)n_rows * w.ds_ld);
     }
@@ -541,8 +540,15 @@ static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* 
     flyp::DstParams p;
     memset(&p, 0, sizeof(p));
     p.n_k = n_m; p.n_out = n_n; p.dim = dim;
-    p.out_tiles = ceil_div(n_n, flyp::DST_TILE_ROWS); p.n_dh = ceil_div(dim, flyp::DST_TILE_COLS);
-    p.sched_pairs = w.gemm_pairs; p.transposed = 1;
+    // partials that go to other GPUs: 256-column tiles in two accumulator stages, so that the NVLink-bound drain of a
+    // tile overlaps the MMAs of the next (dS is then read ceil(dim / 256) times - from this rank's HBM, cheap beside it)
+    p.tile_cols = out_rank != nullptr ? 256 : flyp::DST_TILE_COLS;
+    if (env_int("FLYP_GEMM_TILE_COLS", 0) == 256 || env_int("FLYP_GEMM_TILE_COLS", 0) == 512)      // A/B switch
+        p.tile_cols = env_int("FLYP_GEMM_TILE_COLS", 0);
+    p.out_tiles = ceil_div(n_n, flyp::DST_TILE_ROWS); p.n_dh = ceil_div(dim, p.tile_cols);
+    p.sched_pairs = flyp::dst_gemm_sched_pairs(p.out_tiles * p.n_dh, ceil_div(n_m, 128), num_sms());
+    if (p.sched_pairs > w.gemm_pairs) return fail(FLYP_ERR_WORKSPACE, "partial-tile scratch of the dS product");
+    p.transposed = 1;
     p.scale = scale; p.gmax_bits = w.ctrl.words; p.out_mul = out_mul;
     p.out = out; p.ld_out = dim; p.out_fp32 = out_fp32;
     if (out_rank != nullptr) {
@@ -550,7 +556,9 @@ static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* 
         for (int q = 0; q < n_n / rows_per_rank; ++q) p.out_rank[q] = out_rank[q];
         p.rows_per_rank = rows_per_rank; p.out_fp32 = 1; p.out = nullptr;
     }
-    p.part_out = w.gemm_part; p.grid_cnt = w.ctrl.grid_cnt(1);
+    // (no flat tail when the pairs divide the tiles: no partial tiles, no grid barrier, an ordinary launch)
+    p.part_out = w.gemm_part;
+    p.grid_cnt = (p.out_tiles * p.n_dh) % p.sched_pairs == 0 ? nullptr : w.ctrl.grid_cnt(1);
     const bool timed = g_ev_sweep[0] != nullptr && g_ev_sweep_idx == 1;
     if (timed) cudaEventRecord(g_ev_sweep[0], st);
     flyp::launch_dst_gemm(tmDS, tmX, p, st);
@@ -752,7 +760,9 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
     //   kernel itself, into the owners' reduce-scatter buffers over NVLink and summed there (keep_rs).
     const int world = flyp::comm_world(comm);
     const bool keep = w.ds_keep != nullptr && comm == nullptr && n_rows == n_cols && d_img && d_txt && img_all != nullptr;
-    const bool keep_rs = w.ds_keep != nullptr && comm != nullptr && world > 1 && n_cols == n_rows * world && d_img && d_txt;
+    static const int rs_on = env_int("FLYP_KEEP_DS_RS", 1);       // A/B switch: 0 = two sweeps on several GPUs
+    const bool keep_rs = rs_on != 0 && w.ds_keep != nullptr && comm != nullptr && world > 1 && n_cols == n_rows * world &&
+                         d_img && d_txt;
     if ((phases & 1) == 0) {
         // finish phase only: everything below was enqueued by an earlier call with phase 1
         if (keep_rs && (rc = flyp::comm_rs_reduce(comm, seq, n_rows, dim, d_txt, grad_dtype, grad_mul, stream)) != 0) return rc;

@@ -72,10 +72,11 @@ __device__ __noinline__ void gemm_tail_reduce(const DstParams& p, const int et, 
     __threadfence();
     const int v_tiles = p.out_tiles * p.n_dh, P = p.sched_pairs;
     const int first = (v_tiles / P) * P, n_tail = v_tiles - first;
-    constexpr int CPB = (G_ROWS / 128) * (G_COLS / 128);       // [128 x 128] chunks per tile
+    const int COLS = p.tile_cols;
+    const int CPB = (G_ROWS / 128) * (COLS / 128);              // [128 x 128] chunks per tile
     for (int c = blockIdx.x; c < n_tail * CPB; c += gridDim.x) {
         const int tb = c / CPB, ci = c - tb * CPB;
-        const int r0 = (ci / (G_COLS / 128)) * 128, dl0 = (ci % (G_COLS / 128)) * 128;
+        const int r0 = (ci / (COLS / 128)) * 128, dl0 = (ci % (COLS / 128)) * 128;
         if (et == 0) {
             TailParts parts;
             int np = 0;
@@ -86,20 +87,20 @@ __device__ __noinline__ void gemm_tail_reduce(const DstParams& p, const int et, 
         g_epi_bar();
         const int np = red_i[1];
         const int vb = first + tb, ob = vb / p.n_dh, dh = vb - ob * p.n_dh;
-        if (np > 0 && dh * G_COLS + dl0 < p.dim) {
+        if (np > 0 && dh * COLS + dl0 < p.dim) {
 #pragma unroll 1
             for (int f0 = et; f0 < 128 * 32; f0 += 256 * 8) {
                 float4 acc[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int k = 0; k < np; ++k) {
-                    const float* base = p.part_out + ((size_t)red_i[2 + k] * G_ROWS + r0) * G_COLS + dl0;
+                    const float* base = p.part_out + ((size_t)red_i[2 + k] * G_ROWS + r0) * COLS + dl0;
                     float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int f = f0 + j * 256, ri = f >> 5;
                         v[j] = (ob * G_ROWS + r0 + ri < p.n_out)
-                                   ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)ri * G_COLS + (f & 31) * 4))
+                                   ? __ldcg(reinterpret_cast<const float4*>(base + (size_t)ri * COLS + (f & 31) * 4))
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
@@ -108,7 +109,7 @@ __device__ __noinline__ void gemm_tail_reduce(const DstParams& p, const int et, 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int f = f0 + j * 256, ri = f >> 5, oi = ob * G_ROWS + r0 + ri;
-                    const int d = dh * G_COLS + dl0 + (f & 31) * 4;
+                    const int d = dh * COLS + dl0 + (f & 31) * 4;
                     if (oi >= p.n_out) continue;
                     if (p.out_fp32) {
                         *reinterpret_cast<float4*>(out_row_f32(p, oi) + d) = acc[j];
@@ -129,6 +130,16 @@ __device__ __noinline__ void gemm_tail_reduce(const DstParams& p, const int et, 
 int dst_gemm_sched_pairs(int v_tiles, int k_blocks, int num_sms) {
     int npairs = num_sms / 2;
     const long long S = (long long)v_tiles * k_blocks;
+    // Whole tiles only (ceil(v_tiles / pairs) rounds on a number of pairs that divides v_tiles) when that costs no more
+    // than the flat schedule's equal shares PLUS its tail: partial tiles written to scratch, a grid barrier, the sum -
+    // about TAIL_BLOCKS contraction blocks' worth of time, during which no MMA runs (and, when the output goes to
+    // other GPUs, all of the split tiles' NVLink traffic comes at the very end).
+    constexpr int TAIL_BLOCKS = 48;
+    {
+        const int rounds = (v_tiles + npairs - 1) / npairs;
+        const int pw = (v_tiles + rounds - 1) / rounds;
+        if (v_tiles % pw == 0 && (long long)rounds * k_blocks <= S / npairs + TAIL_BLOCKS) return pw;
+    }
     constexpr int MIN_BLOCKS = 8;          // a range shorter than this does not pay for its partial tile
     long long cap = S / MIN_BLOCKS;
     if (cap < v_tiles) cap = v_tiles;
@@ -148,9 +159,13 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (G_NSLOT + s); };
-    const uint32_t ACCFULL = bar0 + 8u * (2 * G_NSLOT), ACCEMPTY = bar0 + 8u * (2 * G_NSLOT + 1);
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * G_NSLOT + 2);
-    int* red_i = reinterpret_cast<int*>(bars + 2 * G_NSLOT + 4);      // [1] slot count, [2 ..] slot list (<= 2 P entries)
+    auto ACCFULL = [&](int s) { return bar0 + 8u * (2 * G_NSLOT + s); };
+    auto ACCEMPTY = [&](int s) { return bar0 + 8u * (2 * G_NSLOT + 2 + s); };
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * G_NSLOT + 4);
+    int* red_i = reinterpret_cast<int*>(bars + 2 * G_NSLOT + 6);      // [1] slot count, [2 ..] slot list (<= 2 P entries)
+    // tile width: 512 columns = the whole tensor memory, one accumulator stage; or 256 columns in TWO stages, so that the
+    // drain of a tile - slow when it goes to another GPU over NVLink - overlaps the MMAs of the next one
+    const int COLS = p.tile_cols, STAGES = G_COLS / COLS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();
@@ -159,7 +174,7 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < G_NSLOT; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-        mbar_init(ACCFULL, 1); mbar_init(ACCEMPTY, 512);
+        for (int s = 0; s < 2; ++s) { mbar_init(ACCFULL(s), 1); mbar_init(ACCEMPTY(s), 512); }
         fence_mbar_init();
         tma_prefetch_desc(&tmDS); tma_prefetch_desc(&tmX);
     }
@@ -170,7 +185,7 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
     const uint32_t tmem_base = *tmem_holder;
 
     // accumulators (256 columns each) of pass dh
-    auto n_acc = [&](int dh) { const int left = p.dim - dh * G_COLS; return left >= G_COLS ? G_COLS / 256 : (left + 255) / 256; };
+    auto n_acc = [&](int dh) { const int left = p.dim - dh * COLS; return left >= COLS ? COLS / 256 : (left + 255) / 256; };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
@@ -193,7 +208,7 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                     else { put(&tmDS, k0, o0); put(&tmDS, k0 + 64, o0); }
                     for (int a = 0; a < na; ++a)
                         for (int ds = 0; ds < 2; ++ds)
-                            put(&tmX, ii.dh * G_COLS + a * 256 + (int)cta * 128 + ds * 64, k0);
+                            put(&tmX, ii.dh * COLS + a * 256 + (int)cta * 128 + ds * 64, k0);
                 }
             }
         }
@@ -207,8 +222,11 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
             ItemInfo ii;
             for (; iter.next(ii); ++it) {
                 const int na = n_acc(ii.dh);
-                mbar_wait(ACCEMPTY, (it & 1) ^ 1);
+                const int as = (int)(it % (uint32_t)STAGES);
+                const uint32_t use = it / (uint32_t)STAGES;
+                mbar_wait(ACCEMPTY(as), (use & 1) ^ 1);
                 tc_fence_after();
+                const uint32_t tm_acc = tmem_base + as * COLS;
                 for (int kb = ii.t0; kb < ii.t1; ++kb) {
                     mbar_wait(FULL(slot), ph);
                     const int a_slot = slot;
@@ -233,7 +251,7 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                                 : umma_desc_sw128(a_addr + (kk >> 2) * G_SLOT + (kk & 3) * 32, 16, 1024);
                             // B: [16 contraction rows][128 feature columns as two 64-wide boxes], MN-major
                             const uint64_t bd = umma_desc_sw128(b_addr + kk * 2048, G_SLOT, 1024);
-                            umma_f16_cg2(tmem_base + a * 256, ad, bd, IDESC, !(kb == ii.t0 && kk == 0));
+                            umma_f16_cg2(tm_acc + a * 256, ad, bd, IDESC, !(kb == ii.t0 && kk == 0));
                         }
                         umma_commit_cg2(EMPTY(b_slot));
                         umma_commit_cg2(EMPTY(b_slot + 1));
@@ -241,7 +259,7 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                     umma_commit_cg2(EMPTY(a_slot));
                     umma_commit_cg2(EMPTY(a_slot + 1));
                 }
-                umma_commit_cg2(ACCFULL);
+                umma_commit_cg2(ACCFULL(as));
             }
         }
     } else if (warp >= 4) {
@@ -251,21 +269,23 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
         float G, invG;
         staging_scale(p.gmax_bits, G, invG);
         const float omul = *p.scale * p.out_mul * invG;
-        const uint32_t R_ACCEMPTY = mapa(ACCEMPTY, 0);
+        const uint32_t R_ACCEMPTY0 = mapa(ACCEMPTY(0), 0), R_ACCEMPTY1 = mapa(ACCEMPTY(1), 0);
         float* const stg = stage + (warp - 4) * 1024;        // this warp's [32][32] fp32 transposition buffer
         uint32_t it = 0;
         SweepItems iter(p.out_tiles, p.n_dh, p.sched_pairs, NJ, pair);
         ItemInfo ii;
         for (; iter.next(ii); ++it) {
             const int na = n_acc(ii.dh);
-            mbar_wait(ACCFULL, it & 1);
+            const int as = (int)(it % (uint32_t)STAGES);
+            const uint32_t use = it / (uint32_t)STAGES;
+            mbar_wait(ACCFULL(as), use & 1);
             tc_fence_after();
             for (int a = 0; a < na; ++a) {
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
                     const int dl = a * 256 + h * 128 + cc * 32;      // first of this warp's 32 columns within the pass
                     uint32_t r[32];
-                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + dl, r);
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * COLS + dl, r);
                     tmem_ld_wait();
                     // [32 rows (lanes)][32 columns] -> shared memory (XOR-swizzled: conflict-free both ways) -> each
                     // store instruction of the warp writes four full 128-byte row segments instead of 32 scattered
@@ -282,10 +302,10 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                         v.z = stg[rr * 32 + ((c0 + 2) ^ rr)]; v.w = stg[rr * 32 + ((c0 + 3) ^ rr)];
                         const int rt = (int)cta * 128 + q * 32 + rr;         // row within the tile
                         const int orow = ii.mb * G_ROWS + rt;
-                        const int d = ii.dh * G_COLS + dl + c0;
+                        const int d = ii.dh * COLS + dl + c0;
                         if (orow >= p.n_out || d >= p.dim) continue;
                         if (ii.part >= 0) {
-                            *reinterpret_cast<float4*>(p.part_out + ((size_t)ii.part * G_ROWS + rt) * G_COLS + dl + c0) = v;
+                            *reinterpret_cast<float4*>(p.part_out + ((size_t)ii.part * G_ROWS + rt) * COLS + dl + c0) = v;
                         } else if (p.out_fp32) {
                             *reinterpret_cast<float4*>(out_row_f32(p, orow) + d) = v;
                         } else {
@@ -298,7 +318,7 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                 }
             }
             tc_fence_before();
-            mbar_arrive_cluster(R_ACCEMPTY);
+            mbar_arrive_cluster(as ? R_ACCEMPTY1 : R_ACCEMPTY0);
         }
         if (p.grid_cnt != nullptr) gemm_tail_reduce(p, et, NJ, red_i);
     }

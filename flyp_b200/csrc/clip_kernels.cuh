@@ -179,7 +179,10 @@ struct DstParams {
     int n_k;                 // contraction length: rows of dS (transposed) / columns of dS
     int n_out;               // output rows: columns of dS (transposed) / rows of dS
     int dim;                 // feature columns of X16 and of the output (a multiple of 8)
-    int out_tiles, n_dh;     // ceil(n_out / 256) tiles x ceil(dim / 512) passes = the virtual tiles of the schedule
+    int tile_cols;           // output columns per tile and pass: 512 (one accumulator stage = the whole tensor memory) or
+                             // 256 (two stages: the drain of a tile overlaps the MMAs of the next - used when the
+                             // epilogue writes to other GPUs over NVLink)
+    int out_tiles, n_dh;     // ceil(n_out / 256) tiles x ceil(dim / tile_cols) passes = the virtual tiles of the schedule
     int sched_pairs;         // CTA pairs (dst_gemm_sched_pairs)
     int transposed;          // 1: out = c dS^T X16, 0: out = c dS X16
     const float* scale;      // c = scale * out_mul / G, G the staging factor of dS (gmax_bits, bwd_common.cuh)
