@@ -418,6 +418,8 @@ def run_ours(args):
     from flyp_b200 import _lib as _flyp_lib
     kept = bool(_flyp_lib.load().flyp_clip_keeps_ds(b, B, D, _flyp_lib.FLYP_BF16 if fdt == torch.bfloat16
                                                     else _flyp_lib.FLYP_F32))
+    if world > 1 and os.environ.get("FLYP_KEEP_DS_RS", "1") == "0":      # (the library's A/B switch)
+        kept = False
     f_exec = 4.0 * b * B * D                     # executed by a sweep launch (S recompute + one output GEMM)
     if kept:
         # kept-dS backward: ONE sweep (S recompute + dS . T, and the dS tiles written out) and the product dS^T . I:

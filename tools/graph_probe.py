@@ -62,4 +62,29 @@ for B in Bs:
             except Exception as exc:  # noqa: BLE001
                 out[name + "_graph_us"] = f"capture failed: {type(exc).__name__}: {str(exc)[:80]}"
             del graph
+        # torch.cuda.make_graphed_callables: what a training loop can use as it is (forward and backward captured as two
+        # graphs behind an autograd function, static input / output buffers managed by torch)
+        try:
+            Id = I.to(dev).requires_grad_(True); Td = T.to(dev).requires_grad_(True)
+            sc = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
+            mod = flyp_b200.ClipLoss(cache_labels=True)
+            gfn = torch.cuda.make_graphed_callables(mod, (Id, Td, sc))
+            want = mod(Id, Td, sc).float().mean().item()
+
+            def gstep():
+                Id.grad = Td.grad = sc.grad = None
+                gfn(Id, Td, sc).mean().backward()
+
+            for _ in range(5):
+                gstep()
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(100):
+                gstep()
+            e1.record(); torch.cuda.synchronize()
+            out["flyp_b200_graphed_callable_us"] = round(e0.elapsed_time(e1) * 10, 1)
+            out["graphed_callable_loss_matches"] = abs(gfn(Id, Td, sc).float().mean().item() - want) < 1e-2 * abs(want)
+        except Exception as exc:  # noqa: BLE001
+            out["flyp_b200_graphed_callable_us"] = f"failed: {type(exc).__name__}: {str(exc)[:120]}"
         print(json.dumps(out), flush=True)
