@@ -369,13 +369,22 @@ def run_ours(args):
             lib.flyp_debug_kernel_events(None, None, None, None, 0)
         return sum(fwd) / len(fwd), sum(swp) / len(swp)
 
+    # backward plan of this shape (include/flyp_clip.h: flyp_clip_backward_plan): 0 two sweeps, 1 sweep + product,
+    # 2 (one GPU) dS kernel + two products
+    code = _lib.FLYP_BF16 if fdt == torch.bfloat16 else _lib.FLYP_F32
+    plan = int(lib.flyp_clip_backward_plan(b, B, D, code))
+    if world > 1:
+        plan = min(plan, 1)
+        if os.environ.get("FLYP_KEEP_DS_RS", "1") == "0":                # (the library's A/B switch)
+            plan = 0
     n_k = max(3, min(args.steps, 10))
-    fwd_ms, sweep0_ms = kernel_ms(0, n_k)
-    _, sweep1_ms = kernel_ms(1, n_k)
-    kt = torch.tensor([fwd_ms, sweep0_ms, sweep1_ms], device=dev, dtype=torch.float64)
+    fwd_ms, sweep0_ms = kernel_ms(0, n_k)                # event pair 0: first sweep / dS kernel
+    _, sweep1_ms = kernel_ms(1, n_k)                     # 1: second sweep / product dS^T . image
+    gemm_di_ms = kernel_ms(2, n_k)[1] if plan == 2 else 0.0              # 2: product dS . text (unfused backward only)
+    kt = torch.tensor([fwd_ms, sweep0_ms, sweep1_ms, gemm_di_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(kt, op=dist.ReduceOp.MAX)
-    fwd_ms, sweep0_ms, sweep1_ms = kt.tolist()
+    fwd_ms, sweep0_ms, sweep1_ms, gemm_di_ms = kt.tolist()
 
     # ---- correctness of the measured configuration, outside the timed region (every rank holds the synthetic batch) ----
     loss_vec = step_resident().detach()
@@ -415,13 +424,19 @@ def run_ours(args):
     del Ia, Ta
 
     pk = peaks()
-    from flyp_b200 import _lib as _flyp_lib
-    kept = bool(_flyp_lib.load().flyp_clip_keeps_ds(b, B, D, _flyp_lib.FLYP_BF16 if fdt == torch.bfloat16
-                                                    else _flyp_lib.FLYP_F32))
-    if world > 1 and os.environ.get("FLYP_KEEP_DS_RS", "1") == "0":      # (the library's A/B switch)
-        kept = False
+    kept = plan >= 1
     f_exec = 4.0 * b * B * D                     # executed by a sweep launch (S recompute + one output GEMM)
-    if kept:
+    if plan == 2:
+        # unfused backward: dS kernel (S recompute + dS, 2 b B D) and two products (2 b B D each), all algorithmic; the
+        # roofline entry is the SLOWEST of the three tensor-core kernels
+        cands = [("ds_kernel_mc (dS kernel of the unfused backward: S recompute on the forward's pipeline, dS written to "
+                  "HBM as fp16)", sweep0_ms),
+                 ("dst_gemm_kernel<transposed> (d text = dS^T . image over the kept dS)", sweep1_ms),
+                 ("dst_gemm_kernel (d image = dS . text over the kept dS)", gemm_di_ms)]
+        kname, sweep_ms = max(cands, key=lambda c: c[1])
+        kname += ", per launch; the slowest of the three backward kernels"
+        f_sweep = f_exec = 2.0 * b * B * D
+    elif kept:
         # kept-dS backward: ONE sweep (S recompute + dS . T, and the dS tiles written out) and the product dS^T . I:
         # every executed FLOP is algorithmic (8 B^2 D per step: forward S, one recompute, dI, dT).  Several GPUs: the
         # product covers the rank's rows of dS against ALL text rows and its epilogue scatters the fp32 partials into the
@@ -442,6 +457,8 @@ def run_ours(args):
         with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
             prof = json.load(f)
         key = ("bwd_pair_kernel_keep" if kept else "bwd_pair_kernel") if world == 1 else f"bwd_pair_kernel_w{world}"
+        if plan == 2:
+            key = "ds_kernel_mc" if kname.startswith("ds_kernel") else "dst_gemm_kernel"
         if (B, D) == (32768, 512) and fdt == torch.bfloat16 and key in prof:
             traffic = prof[key]["traffic_bytes_per_launch"]
     except Exception:
@@ -466,23 +483,32 @@ def run_ours(args):
         # backward (2 vector kernels, 2 tcgen05 sweeps); peer path 7 forward (pack, sweep, finalize, 2 gated stubs,
         # statistics push, finish) + 5 backward (2 vector kernels, 2 sweeps, d(scale) sum)
         # kept-dS backward on several GPUs: 2 vector kernels, sweep, product, flag release, slot sum, d(scale) sum = 7
-        "gpu_launches": (9 if world == 1 else (14 if kept else 12)) * args.steps,
+        # unfused backward on one GPU: 2 vector kernels, dS kernel, d(scale) sum, 2 products = 6 (11 with the forward's 5)
+        "gpu_launches": ((11 if plan == 2 else 9) if world == 1 else (14 if kept else 12)) * args.steps,
         "roofline": {"bound": "tensor", "kernel": kname,
                      "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"],
                      "peak_kind": "burst bf16 (kernel timed alone), " + pk["source"],
                      "frac_of_sustained": ach / pk["sustained"],
                      "ms_per_launch": sweep_ms, "ms_d_image_launch": sweep0_ms, "ms_d_text_launch": sweep1_ms,
+                     "backward_plan": plan,
                      "d_text_kernel": ("dst_gemm_kernel (dS^T . I over the kept dS, 2 b B D FLOPs)" if kept
                                        else "bwd_pair_kernel (second sweep)"),
                      "d_text_tflops": (2.0 if kept else 3.0) * b * B * D / (sweep1_ms * 1e-3) / 1e12,
+                     **({"ds_kernel_ms": sweep0_ms, "ds_kernel_tflops": 2.0 * b * B * D / (sweep0_ms * 1e-3) / 1e12,
+                         "d_image_product_ms": gemm_di_ms,
+                         "d_image_product_tflops": 2.0 * b * B * D / (gemm_di_ms * 1e-3) / 1e12} if plan == 2 else {}),
                      "algorithmic_flops_per_launch": f_sweep, "executed_flops_per_launch": f_exec,
                      "executed_tflops": f_exec / (sweep_ms * 1e-3) / 1e12,
                      "how": "cudaEventRecord by the library right before / after the kernel launch, inside real module steps",
                      "traffic": traffic,
                      "traffic_unit": "bytes per launch (dram read + write, profiles/ncu_summary.json)"},
         "step_breakdown": {"fwd_kernel_ms": fwd_ms, "fwd_kernel_tflops": 2.0 * b * B * D / (fwd_ms * 1e-3) / 1e12,
-                           "bwd_sweep_ms": [sweep0_ms, sweep1_ms], "kernels_ms": fwd_ms + sweep0_ms + sweep1_ms,
-                           "other_ms": ms_res - (fwd_ms + sweep0_ms + sweep1_ms),
+                           "bwd_sweep_ms": [sweep0_ms, sweep1_ms] + ([gemm_di_ms] if plan == 2 else []),
+                           "bwd_kernels": (["ds_kernel_mc", "dst_gemm_kernel (d text)", "dst_gemm_kernel (d image)"]
+                                           if plan == 2 else ["bwd_pair_kernel", "dst_gemm_kernel (d text)"] if plan == 1
+                                           else ["bwd_pair_kernel (d image)", "bwd_pair_kernel (d text)"]),
+                           "kernels_ms": fwd_ms + sweep0_ms + sweep1_ms + gemm_di_ms,
+                           "other_ms": ms_res - (fwd_ms + sweep0_ms + sweep1_ms + gemm_di_ms),
                            "step_tflops_8B2D_per_gpu": step_tflops, "step_frac_of_burst": step_tflops / pk["burst"],
                            "step_frac_of_sustained": step_tflops / pk["sustained"],
                            "executed_flops_per_step": (8.0 if kept else 10.0) * b * B * D,

@@ -51,6 +51,7 @@ SIGNATURES = {
     "flyp_version": (c_int, []),
     "flyp_clip_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "flyp_clip_keeps_ds": (c_int, [c_int, c_int, c_int, c_int]),
+    "flyp_clip_backward_plan": (c_int, [c_int, c_int, c_int, c_int]),
     "flyp_clip_fwd_local": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "flyp_clip_fwd_finish": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

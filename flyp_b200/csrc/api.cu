@@ -130,7 +130,8 @@ size_t sweep_dscale_slots(int n_m, int n_n, int dim, int dtype) {
     const size_t single = (size_t)m_tiles * ceil_div(dim, 256);      // bwd_kernel: one per (row block, 256 output columns)
     if (!use_pair_kernel(dim, dtype, n_m, n_n)) return single;
     // (the label-aware sweeps always run the single-CTA kernel: room for either)
-    const size_t pair = (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles * pair_n_dh(dim), n_n, num_sms());
+    size_t pair = (size_t)2 * flyp::bwd_pair_sched_pairs(m_tiles * pair_n_dh(dim), n_n, num_sms());
+    if (pair < (size_t)num_sms()) pair = (size_t)num_sms();      // (the dS kernel: one per CTA)
     return pair > single ? pair : single;
 }
 size_t sweep_part_floats(int n_m, int n_n, int dim, int dtype) {
@@ -531,35 +532,94 @@ static void carve_clip(void* base, int n_rows, int n_cols, int dim, int dtype, C
 }
 
 // out[n, :] = scale * out_mul / G * sum_m dS[m, n] x16[m, :] over the dS matrix the first sweep kept (n_m x n_n)
+// Unfused backward (single rank, bf16, D <= 512, dS kept; OFF by default, FLYP_UNFUSED=1 switches it on): the dS kernel -
+// the forward's tensor-core pipeline with an epilogue that writes dS and the d(scale) partials - then the two plain
+// products dS . T and dS^T . I.  The idea: the fused sweep does its S product with 64 rows per SM (the accumulators of
+// 128 rows x D take an SM's whole tensor memory) and runs at 71 % of burst where plain products run at 80 - 85 %.
+// Measured (B = 32768, D = 512): the two products take 0.82 ms each as expected, but the dS kernel takes 1.41 ms against
+// 0.76 ms for the forward - its epilogue (exponential, weights, fp16 packing, transposition, 32 KiB of stores per tile)
+// has to keep up with a full-rate 128 x 128 S tile every ~2000 clocks, twice the element rate the fused sweep's epilogue
+// sustains; the step is 3.93 ms against 3.49 ms fused.  Kept, tested, as the measured alternative.
+int env_unfused() { static const int v = env_int("FLYP_UNFUSED", 0); return v; }
+static bool unfused_eligible(const ClipWs& w, int n_rows, int n_cols, int dim) {
+    return env_unfused() != 0 && w.ds_keep != nullptr && n_rows == n_cols && dim <= 512 && w.stats.use_mc;
+}
+// io: the fields of the d-image sweep (A = image rows, B = text rows, the row / column vectors)
+static int run_ds_kernel(const SweepIO& io, const ClipWs& w, int* n_parts, cudaStream_t st) {
+    CUtensorMap tmA64, tmB;
+    int rc;
+    if ((rc = make_tmap(&tmA64, io.A, io.n_m, io.dim, io.dim, false, 64)) != 0) return rc;
+    if ((rc = make_tmap(&tmB, io.B, io.n_n, io.dim, io.dim)) != 0) return rc;
+    flyp::FwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_m = io.n_m; p.n_n = io.n_n; p.kc = ceil_div(io.dim, flyp::KCHUNK); p.kplan = flyp::kplan_bf16();
+    p.m_tiles = ceil_div(io.n_m, flyp::TILE); p.n_tiles = ceil_div(io.n_n, flyp::TILE);
+    p.scale = io.scale; p.wait_b = to_wait(io.b_ready);
+    flyp::BwdParams b;
+    memset(&b, 0, sizeof(b));
+    b.n_m = io.n_m; b.n_n = io.n_n; b.scale = io.scale;
+    b.wr = io.wr; b.lr = io.lr; b.wc = io.wc; b.lc = io.lc; b.labr = io.labr; b.dr = io.dr; b.labc = io.labc; b.dc = io.dc;
+    b.fa = io.fa; b.fb = io.fb; b.fast_info = io.fast_info; b.gmax_bits = io.ctrl->words;
+    b.dscale_part = io.dscale_part; b.ds_out = w.ds_keep; b.ds_ld = w.ds_ld;
+    const bool timed = g_ev_sweep[0] != nullptr && g_ev_sweep_idx == 0;
+    if (timed) cudaEventRecord(g_ev_sweep[0], st);
+    const int n = flyp::launch_ds_mc(tmA64, tmB, p, b, num_sms(), st);
+    if (timed) cudaEventRecord(g_ev_sweep[1], st);
+    CUDA_OK(cudaGetLastError());
+    if ((size_t)n > io.n_dscale) return fail(FLYP_ERR_WORKSPACE, "d(scale) partial slots");
+    *n_parts = n;
+    return 0;
+}
+
 static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* x16, const float* scale, float out_mul,
-                        void* out, int out_fp32, cudaStream_t st, float* const* out_rank = nullptr, int rows_per_rank = 0) {
+                        void* out, int out_fp32, cudaStream_t st, float* const* out_rank, int rows_per_rank, int transposed,
+                        int counter);
+// dS kernel, d(scale), d_img = s dS T, d_txt = s dS^T I.  io: the d-image sweep's fields; i16: fp16 copy of the image rows
+static int run_unfused_backward(const SweepIO& io, const ClipWs& w, const void* i16, void* d_img, void* d_txt,
+                                float* d_scale, cudaStream_t st) {
+    int rc, n_parts = 0;
+    if ((rc = run_ds_kernel(io, w, &n_parts, st)) != 0) return rc;
+    if (d_scale != nullptr) {
+        flyp::launch_sum_parts(io.dscale_part, n_parts, d_scale, nullptr, st);
+        CUDA_OK(cudaGetLastError());
+    }
+    if ((rc = run_dst_gemm(w, io.n_m, io.n_n, io.dim, io.B_f16, io.scale, io.out_mul, d_img, io.out_fp32, st, nullptr, 0,
+                           /*transposed=*/0, /*counter=*/0)) != 0) return rc;
+    return run_dst_gemm(w, io.n_m, io.n_n, io.dim, i16, io.scale, io.out_mul, d_txt, io.out_fp32, st, nullptr, 0, 1, 1);
+}
+
+// transposed = 0: out[m, :] = scale * out_mul / G * sum_n dS[m, n] x16[n, :] (x16 has n_n rows)
+static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* x16, const float* scale, float out_mul,
+                        void* out, int out_fp32, cudaStream_t st, float* const* out_rank, int rows_per_rank,
+                        int transposed, int counter) {
     CUtensorMap tmDS, tmX;
     int rc;
+    const int n_k = transposed ? n_m : n_n, n_o = transposed ? n_n : n_m;
     if ((rc = make_tmap(&tmDS, w.ds_keep, n_m, n_n, w.ds_ld, true)) != 0) return rc;
-    if ((rc = make_tmap(&tmX, x16, n_m, dim, dim, true)) != 0) return rc;
+    if ((rc = make_tmap(&tmX, x16, n_k, dim, dim, true)) != 0) return rc;
     flyp::DstParams p;
     memset(&p, 0, sizeof(p));
-    p.n_k = n_m; p.n_out = n_n; p.dim = dim;
+    p.n_k = n_k; p.n_out = n_o; p.dim = dim;
     // partials that go to other GPUs: 256-column tiles in two accumulator stages, so that the NVLink-bound drain of a
     // tile overlaps the MMAs of the next (dS is then read ceil(dim / 256) times - from this rank's HBM, cheap beside it)
     p.tile_cols = out_rank != nullptr ? 256 : flyp::DST_TILE_COLS;
     if (env_int("FLYP_GEMM_TILE_COLS", 0) == 256 || env_int("FLYP_GEMM_TILE_COLS", 0) == 512)      // A/B switch
         p.tile_cols = env_int("FLYP_GEMM_TILE_COLS", 0);
-    p.out_tiles = ceil_div(n_n, flyp::DST_TILE_ROWS); p.n_dh = ceil_div(dim, p.tile_cols);
-    p.sched_pairs = flyp::dst_gemm_sched_pairs(p.out_tiles * p.n_dh, ceil_div(n_m, 128), num_sms());
+    p.out_tiles = ceil_div(n_o, flyp::DST_TILE_ROWS); p.n_dh = ceil_div(dim, p.tile_cols);
+    p.sched_pairs = flyp::dst_gemm_sched_pairs(p.out_tiles * p.n_dh, ceil_div(n_k, 128), num_sms());
     if (p.sched_pairs > w.gemm_pairs) return fail(FLYP_ERR_WORKSPACE, "partial-tile scratch of the dS product");
-    p.transposed = 1;
+    p.transposed = transposed;
     p.scale = scale; p.gmax_bits = w.ctrl.words; p.out_mul = out_mul;
     p.out = out; p.ld_out = dim; p.out_fp32 = out_fp32;
     if (out_rank != nullptr) {
-        if (n_n % rows_per_rank != 0 || n_n / rows_per_rank > flyp::PEER_MAXW) return fail(FLYP_ERR_ARG, "bad rank split");
-        for (int q = 0; q < n_n / rows_per_rank; ++q) p.out_rank[q] = out_rank[q];
+        if (n_o % rows_per_rank != 0 || n_o / rows_per_rank > flyp::PEER_MAXW) return fail(FLYP_ERR_ARG, "bad rank split");
+        for (int q = 0; q < n_o / rows_per_rank; ++q) p.out_rank[q] = out_rank[q];
         p.rows_per_rank = rows_per_rank; p.out_fp32 = 1; p.out = nullptr;
     }
     // (no flat tail when the pairs divide the tiles: no partial tiles, no grid barrier, an ordinary launch)
     p.part_out = w.gemm_part;
-    p.grid_cnt = (p.out_tiles * p.n_dh) % p.sched_pairs == 0 ? nullptr : w.ctrl.grid_cnt(1);
-    const bool timed = g_ev_sweep[0] != nullptr && g_ev_sweep_idx == 1;
+    p.grid_cnt = (p.out_tiles * p.n_dh) % p.sched_pairs == 0 ? nullptr : w.ctrl.grid_cnt(counter);
+    const bool timed = g_ev_sweep[0] != nullptr && g_ev_sweep_idx == (transposed ? 1 : 2);
     if (timed) cudaEventRecord(g_ev_sweep[0], st);
     flyp::launch_dst_gemm(tmDS, tmX, p, st);
     if (timed) cudaEventRecord(g_ev_sweep[1], st);
@@ -580,6 +640,15 @@ int flyp_clip_workspace_bytes(int n_rows, int n_cols, int dim, int dtype, size_t
 int flyp_clip_keeps_ds(int n_rows, int n_cols, int dim, int dtype) {
     if (check_common(n_rows, n_cols, dim, dtype) != 0) return 0;
     return keep_ds_eligible(n_rows, n_cols, dim, dtype) ? 1 : 0;
+}
+
+int flyp_clip_backward_plan(int n_rows, int n_cols, int dim, int dtype) {
+    if (check_common(n_rows, n_cols, dim, dtype) != 0) return 0;
+    if (!keep_ds_eligible(n_rows, n_cols, dim, dtype)) return 0;
+    ClipWs w;
+    carve_clip(nullptr, n_rows, n_cols, dim, dtype, w);
+    w.ds_keep = reinterpret_cast<uint16_t*>(1);                    // (size query: only "is it there" matters)
+    return unfused_eligible(w, n_rows, n_cols, dim) ? 2 : 1;
 }
 
 int flyp_clip_fwd_local(const void* img, const void* txt, const float* scale, int n_rows, int n_cols, int dim,
@@ -703,12 +772,17 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
         if (d_scale) { io.dscale_part = w.dscale_part; io.dscale_out = d_scale; }
         io.b_ready = txt_ready; io.b16_ready = txt16_ready;
         if (keep) { io.ds_keep = w.ds_keep; io.ds_ld = w.ds_ld; }
+        if (keep && unfused_eligible(w, n_rows, n_cols, dim) && txt_ready == nullptr) {
+            flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
+            CUDA_OK(cudaGetLastError());
+            return run_unfused_backward(io, w, w.img16, d_img, d_txt, d_scale, st);
+        }
         if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     if (d_txt && keep) {
         flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
         CUDA_OK(cudaGetLastError());
-        if ((rc = run_dst_gemm(w, n_rows, n_cols, dim, w.img16, scale, grad_mul, d_txt, grad_dtype, st)) != 0) return rc;
+        if ((rc = run_dst_gemm(w, n_rows, n_cols, dim, w.img16, scale, grad_mul, d_txt, grad_dtype, st, nullptr, 0, 1, 1)) != 0) return rc;
     } else if (d_txt) {
         if (f32) flyp::launch_split_planes_f16x2(static_cast<const float*>(img), n_rows, dim, dp, w.img16, st);
         else flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
@@ -808,6 +882,15 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
         if (d_scale) { io.dscale_part = w.dscale_part; io.dscale_out = d_scale; io.ds_push = &push; }
         if (!f32) { io.b_ready = txt_ready; io.b16_ready = txt16_all ? txt16_ready : nullptr; }
         if (keep || keep_rs) { io.ds_keep = w.ds_keep; io.ds_ld = w.ds_ld; }
+        if (keep && unfused_eligible(w, n_rows, n_cols, dim)) {
+            const void* i16 = img16_all;
+            if (i16 == nullptr) {
+                flyp::launch_to_f16(img_all, dtype, (size_t)n_cols * dim, w.img16, st);
+                CUDA_OK(cudaGetLastError());
+                i16 = w.img16;
+            }
+            return run_unfused_backward(io, w, i16, d_img, d_txt, d_scale, st);
+        }
         if ((rc = run_sweep(io, st)) != 0) return rc;
     }
     if (d_txt && keep_rs) {
@@ -822,7 +905,7 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
         }
         // (grad_mul is the RECEIVER's factor - gather_with_grad scales the gradients of a rank's own rows - applied by
         // the sum)
-        if ((rc = run_dst_gemm(w, n_rows, n_cols, dim, i16, scale, 1.0f, nullptr, 1, st, out_rank, n_rows)) != 0) return rc;
+        if ((rc = run_dst_gemm(w, n_rows, n_cols, dim, i16, scale, 1.0f, nullptr, 1, st, out_rank, n_rows, 1, 1)) != 0) return rc;
         if ((rc = flyp::comm_rs_signal(comm, seq, stream)) != 0) return rc;
         if ((phases & 2) != 0 &&
             (rc = flyp::comm_rs_reduce(comm, seq, n_rows, dim, d_txt, grad_dtype, grad_mul, stream)) != 0) return rc;
@@ -834,7 +917,7 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
             CUDA_OK(cudaGetLastError());
             i16 = w.txt16;
         }
-        if ((rc = run_dst_gemm(w, n_rows, n_cols, dim, i16, scale, grad_mul, d_txt, grad_dtype, st)) != 0) return rc;
+        if ((rc = run_dst_gemm(w, n_rows, n_cols, dim, i16, scale, grad_mul, d_txt, grad_dtype, st, nullptr, 0, 1, 1)) != 0) return rc;
     } else if (d_txt) {
         // the transposed problem: text rows of this rank against all images (no B x D reduce-scatter)
         const void* i16 = img16_all;

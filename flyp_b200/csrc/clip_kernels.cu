@@ -48,10 +48,20 @@ size_t fwd_smem_bytes(bool stationary) {
 //
 // MC: clusters of two CTAs sweep two adjacent column blocks over the SAME stream of A tiles; each CTA fetches half of
 // every A chunk and multicasts it to both (halves the L2 -> SM traffic, the measured limiter of the 1-CTA kernel).
-template <bool STAT, bool ROBUST, bool MC>
+// DS (with STAT, MC, not ROBUST): instead of the statistics the epilogue turns every S tile into dS = d(loss)/d(logits)
+// (bwd_common.cuh: ds_tile, the same code as the backward sweep's) and writes it, as fp16 scaled by the staging factor,
+// to the dS matrix bp.ds_out ([n_m][bp.ds_ld]) - the first of the three kernels of the unfused backward (api.cu): this one
+// at the forward's tensor-core efficiency (M = 128 rows per SM, stationary B), then two plain products over dS
+// (clip_dst_gemm.cu).  d(scale) = sum dS . <a, b> comes out of the same epilogue loop (one partial per CTA).
+constexpr int DS_TRANS_BYTES = 8 * 2048;      // DS: one [16 rows][128 bytes] transposition buffer per epilogue warp
+
+template <bool STAT, bool ROBUST, bool MC, bool DS = false>
 __device__ __forceinline__ void
-fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, const int worker, const int nworkers) {
+fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, const int worker, const int nworkers,
+         const BwdParams* bp = nullptr) {
     using Cfg = FwdCfg<STAT>;
+    static_assert(!DS || (STAT && MC && !ROBUST), "the dS mode is built on the multicast stationary forward");
+    constexpr int RED_BYTES = DS ? DS_TRANS_BYTES : Cfg::RED_BYTES;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int ACC_STAGES = Cfg::ACC_STAGES;
 
@@ -60,7 +70,7 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
     uint8_t* stat_b = smem;
     uint8_t* ring = smem + Cfg::STAT_BYTES;
     float* red = reinterpret_cast<float*>(ring + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red) + Cfg::RED_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red) + RED_BYTES);
     // barrier map: [0,S) full  [S,2S) empty  2S bfull  2S+1 bfree  [2S+2, +ACC) tfull  [.., +ACC) tempty
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -156,6 +166,83 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
                     if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
                 }
                 if (STAT) umma_commit(BFREE);
+            }
+        }
+    } else if (warp >= 4 && DS) {
+        // ------------------------------------------------------------------ epilogue, dS mode
+        if constexpr (DS) {
+            const BwdParams& b = *bp;
+            const int q = warp & 3, h = (warp - 4) >> 2;
+            const float s = *p.scale;
+            const float c1 = s * LOG2E;
+            float G, invG;
+            staging_scale(b.gmax_bits, G, invG);
+            const bool fast = b.fast_info != nullptr && b.fast_info[1] != 0.f;
+            const float c0 = fast ? b.fast_info[0] : 0.f;
+            const bool want_ds = b.dscale_part != nullptr;
+            float dsum = 0.f;
+            uint4* const tb = reinterpret_cast<uint4*>(red) + (warp - 4) * 128;      // [16 rows][8 x 16 bytes]
+            int as = 0; uint32_t aphase = 0;
+            FwdItems items(p.m_tiles, n_units, p.n_local, p.nb_rot, nworkers, worker);
+            FwdItem fi;
+            while (items.next(fi)) {
+                const int nb = 2 * fi.u + cta;
+                const bool nb_live = nb < p.n_tiles;
+                const int col0 = nb * TILE + h * 64;
+                for (int mt = fi.mt0; mt < fi.mt1; ++mt) {
+                    mbar_wait(TFULL(as), aphase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * TILE + h * 64;
+                    uint32_t r0[32], r1[32];
+                    tmem_ld_32x32b_x32(taddr, r0);
+                    tmem_ld_32x32b_x32(taddr + 32, r1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(TEMPTY(as));
+                    if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
+                    if (!nb_live) continue;                       // (warp-uniform)
+                    const int row = mt * TILE + q * 32 + lane;
+                    const RowCtx rc = load_row_ctx<true>(b, row, fast, G);
+                    float v[64];
+                    ds_tile<true, true>(r0, r1, b, rc, col0, c1, fast, c0, G, v, want_ds, dsum);
+                    uint32_t pk[32];
+                    pack_ds(v, pk);
+                    // lane = row holds 128 contiguous bytes of its dS row: through a small transposition buffer every
+                    // store instruction writes four full 128-byte row segments (two passes of 16 rows)
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        if ((lane >> 4) == half) {
+                            const int r = lane & 15;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                tb[r * 8 + (j ^ (r & 7))] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int idx = i * 32 + lane, r = idx >> 3, j = idx & 7;
+                            const uint4 val = tb[r * 8 + (j ^ (r & 7))];
+                            const int grow = mt * TILE + q * 32 + half * 16 + r;
+                            if (grow < p.n_m)
+                                *reinterpret_cast<uint4*>(b.ds_out + (size_t)grow * b.ds_ld + col0 + j * 8) = val;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            if (want_ds) {
+                // one d(scale) partial per CTA (fixed order: warps, then the host-side sum over CTAs)
+                float* redf = reinterpret_cast<float*>(red);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
+                epi_bar_sync();                                   // (the transposition buffers are done with)
+                if (lane == 0) redf[warp - 4] = dsum;
+                epi_bar_sync();
+                if (threadIdx.x == 128) {
+                    float tot = 0.f;
+                    for (int k = 0; k < 8; ++k) tot += redf[k];
+                    b.dscale_part[worker * 2 + cta] = tot * invG;
+                }
             }
         }
     } else if (warp >= 4) {
@@ -354,6 +441,13 @@ fwd_kernel_mc(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__
     fwd_body<true, false, true>(tmA64, tmB, p, (int)(blockIdx.x >> 1), (int)(gridDim.x >> 1));
 }
 
+// The dS kernel of the unfused backward: same schedule, producer and MMA issuer as fwd_kernel_mc.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+ds_kernel_mc(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmB, const FwdParams p,
+             const __grid_constant__ BwdParams bp) {
+    fwd_body<true, false, true, true>(tmA64, tmB, p, (int)(blockIdx.x >> 1), (int)(gridDim.x >> 1), &bp);
+}
+
 int fwd_workers(int m_tiles, int n_tiles, bool mc, int num_sms) {
     return mc ? fwd_sched_workers(m_tiles, (n_tiles + 1) / 2, num_sms / 2) : fwd_sched_workers(m_tiles, n_tiles, num_sms);
 }
@@ -364,6 +458,16 @@ void launch_fwd_mc(const CUtensorMap& tmA64, const CUtensorMap& tmB, const FwdPa
     static bool attr_done[64] = {false};
     ensure_smem_attr(fwd_kernel_mc, smem, attr_done);
     fwd_kernel_mc<<<workers * 2, NTHREADS, smem, st>>>(tmA64, tmB, p);
+}
+
+int launch_ds_mc(const CUtensorMap& tmA64, const CUtensorMap& tmB, const FwdParams& p, const BwdParams& bp, int num_sms,
+                 cudaStream_t st) {
+    const int workers = fwd_workers(p.m_tiles, p.n_tiles, true, num_sms);
+    const size_t smem = fwd_smem_bytes(true) - FwdCfg<true>::RED_BYTES + DS_TRANS_BYTES;
+    static bool attr_done[64] = {false};
+    ensure_smem_attr(ds_kernel_mc, smem, attr_done);
+    ds_kernel_mc<<<workers * 2, NTHREADS, smem, st>>>(tmA64, tmB, p, bp);
+    return workers * 2;          // CTAs = d(scale) partials written
 }
 
 static bool fwd_stationary(const FwdParams& p) { return p.kplan.n_terms == 1 && p.kc <= FwdCfg<true>::KC_MAX; }

@@ -139,6 +139,8 @@ struct BwdParams {
     // pair kernel, end-of-sweep reductions by the whole grid (clip_bwd_pair.cu: sweep_tail_reduce):
     int* grid_cnt;           // arrival counter of the grid barrier, zeroed by the host before the launch; nullptr: no
                              // barrier, the fp32 partials of split blocks and the d(scale) partials are left as they are
+    uint16_t* ds_out;        // dS kernel (clip_kernels.cu: ds_kernel_mc): the dS matrix [n_m][ds_ld] fp16 it writes
+    int ds_ld;
     int keep_ds;             // pair kernel: the staged fp16 dS tiles (scaled by the staging factor) are also written to
                              // global memory through the tmDS store map, for the product dS^T . A (clip_dst_gemm.cu)
     float* dscale_out;       // the sum of all d(scale) partials (written by CTA 0 after the barrier), published to the
@@ -159,6 +161,12 @@ void launch_fwd_robust2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Fw
 // Multicast variant of the fast forward (bf16, D <= 512, no debug logits): tmA64 has [64 rows][64 cols] boxes; the
 // schedule runs over (n_tiles + 1) / 2 column-block pairs on fwd_workers(.., true, ..) clusters.
 void launch_fwd_mc(const CUtensorMap& tmA64, const CUtensorMap& tmB, const FwdParams& p, int num_sms, cudaStream_t st);
+// dS kernel of the unfused backward (bf16, D <= 512): the forward's schedule / producer / MMA issuer with an epilogue
+// that writes dS (bp.ds_out, fp16 scaled by the staging factor) and one d(scale) partial per CTA (bp.dscale_part).
+// Returns the number of CTAs (= partials).  Forward declaration of BwdParams: defined below.
+struct BwdParams;
+int launch_ds_mc(const CUtensorMap& tmA64, const CUtensorMap& tmB, const FwdParams& p, const BwdParams& bp, int num_sms,
+                 cudaStream_t st);
 // tmBd: tensor map used for the N-side operand rows as the B operand of the dA MMA (box [64 d][128 n]).
 void launch_bwd(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBd, const BwdParams& p,
                 int num_sms, cudaStream_t st);

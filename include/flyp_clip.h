@@ -43,6 +43,13 @@ int flyp_clip_workspace_bytes(int n_rows, int n_cols, int dim, int dtype, size_t
  * n_cols x 2 bytes of it - and the text gradient is the product dS^T . image over them instead of a second sweep that
  * recomputes the logits), 0 when it runs two sweeps.  For callers that account FLOPs; FLYP_KEEP_DS=0 switches it off. */
 int flyp_clip_keeps_ds(int n_rows, int n_cols, int dim, int dtype);
+/* Which kernels a backward over this problem runs when both feature gradients are wanted - for callers that account
+ * FLOPs and time kernels: 0 = two sweeps (S recomputed twice: 10 n_rows n_cols dim executed per fwd+bwd), 1 = one sweep
+ * that keeps dS + the product dS^T . image (8, = algorithmic), 2 (single rank, bf16, dim <= 512) = the unfused backward:
+ * a dS kernel with the forward's tensor-core pipeline + the two products dS . text and dS^T . image (8).  On several
+ * ranks plan 2 is not used (1 or 0).  Plan 2 is off unless FLYP_UNFUSED=1 (measured slower: its dS kernel is bound by
+ * its epilogue); FLYP_KEEP_DS=0 forces plan 0 (A/B measurements). */
+int flyp_clip_backward_plan(int n_rows, int n_cols, int dim, int dtype);
 
 /* Forward, local part.  The positive logit of every row is kept out of the tensor-core sums and added back exactly,
  * so losses much smaller than the logits keep full relative accuracy.  Out:

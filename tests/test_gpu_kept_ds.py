@@ -57,11 +57,34 @@ np.save(sys.argv[1], dT.detach().float().cpu().numpy())
 
 def test_kept_ds_agrees_with_the_two_sweep_path(tmp_path):
     outs = []
-    for keep in ("1", "0"):
-        f = str(tmp_path / f"dt_{keep}.npy")
-        env = dict(os.environ, FLYP_KEEP_DS=keep)
+    # default (sweep + product), two sweeps, and the unfused plan (dS kernel + two products; off by default)
+    for tag, extra in (("keep", {}), ("sweeps", {"FLYP_KEEP_DS": "0"}), ("unfused", {"FLYP_UNFUSED": "1"})):
+        f = str(tmp_path / f"dt_{tag}.npy")
+        env = dict(os.environ, **extra)
         subprocess.run([sys.executable, "-c", _CHILD.format(root=ROOT), f], check=True, env=env, timeout=600)
         outs.append(np.load(f))
-    # the same fp16-staged dS values enter both products: the results differ by accumulation order only
-    assert rel(outs[0], outs[1]) < 2e-4
+    # the same fp16-staged dS values enter all products: the results differ by accumulation order only
+    assert rel(outs[0], outs[1]) < 2e-4 and rel(outs[0], outs[2]) < 2e-4
     assert not np.array_equal(outs[0], np.zeros_like(outs[0]))
+
+
+_CHILD_FULL = """
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from flyp_b200 import _lib
+from test_gpu_parity import make_inputs, check_against_oracle
+assert _lib.load().flyp_clip_backward_plan(1536, 1536, 512, _lib.FLYP_BF16) == 2
+for n, d, s in ((1536, 512, 1 / 0.07), (1100, 384, 100.0), (4096, 256, 1 / 0.07)):
+    I, T, g = make_inputs(n, d, seed=n, mix=0.5 if s < 50 else 0.15)
+    check_against_oracle(I, T, s, g)
+print("ok")
+"""
+
+
+def test_unfused_plan_matches_oracle():
+    """FLYP_UNFUSED=1: the dS kernel (the forward's pipeline with the dS epilogue) + two products, against the oracle through
+    the C-ABI wrappers, the whole-step entry points and the module (loss, d image, d text, d scale, per row)."""
+    env = dict(os.environ, FLYP_UNFUSED="1")
+    res = subprocess.run([sys.executable, "-c", _CHILD_FULL.format(root=ROOT)], env=env, timeout=600, capture_output=True,
+                         text=True)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
