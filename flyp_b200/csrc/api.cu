@@ -358,7 +358,7 @@ void carve_vecs(Carver& c, int n_pad, VecSet& v) {
 
 // Control words of one backward call, cleared by ONE memset at its start:
 //   [0..3]  {bits(max|g|), key(max lse2), ~key(min lse2), -} accumulated by the prep kernels
-//   [4 + s] arrival counter of the end-of-sweep grid barrier of sweep s (0, 1)
+//   [4 + s] arrival counter of the end-of-kernel grid barrier of sweep / product s (0, 1, 2)
 constexpr int CTRL_WORDS = 8;
 struct BwdCtrl {
     uint32_t* words;
@@ -395,6 +395,8 @@ struct SweepIO {
     const float *mk_r, *mk_c;
     int mask_mode;
     uint16_t* ds_keep; int ds_ld;        // pair sweep: also write the staged dS tiles here ([n_m][ds_ld] fp16); may be null
+    int first_pass_only;                 // wide problems (dim > 512) that keep dS: only the first pair_d_half(dim) output
+                                         // columns; the others come from a product over the kept dS (no second S recompute)
 };
 
 int run_sweep(const SweepIO& io, cudaStream_t st) {
@@ -438,7 +440,7 @@ int run_sweep(const SweepIO& io, cudaStream_t st) {
         CUtensorMap tmA64;
         if ((rc = make_tmap(&tmA64, io.A, n_m, dim, dim, false, 64)) != 0) return rc;
         if (io.part_scratch == nullptr) return fail(FLYP_ERR_ARG, "the pair sweep needs its partial-sum scratch");
-        p.n_dh = pair_n_dh(dim); p.d_half = pair_d_half(dim);
+        p.n_dh = io.first_pass_only ? 1 : pair_n_dh(dim); p.d_half = pair_d_half(dim);
         p.sched_pairs = flyp::bwd_pair_sched_pairs(p.m_tiles * p.n_dh, n_n, num_sms());
         p.part_out = io.part_scratch;
         p.grid_cnt = (env_dbg() & 2) ? nullptr : io.ctrl->grid_cnt(io.sweep);   // (debug bit 1: partials left unreduced)
@@ -573,7 +575,7 @@ static int run_ds_kernel(const SweepIO& io, const ClipWs& w, int* n_parts, cudaS
 
 static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* x16, const float* scale, float out_mul,
                         void* out, int out_fp32, cudaStream_t st, float* const* out_rank, int rows_per_rank, int transposed,
-                        int counter);
+                        int counter, int col_begin = 0);
 // dS kernel, d(scale), d_img = s dS T, d_txt = s dS^T I.  io: the d-image sweep's fields; i16: fp16 copy of the image rows
 static int run_unfused_backward(const SweepIO& io, const ClipWs& w, const void* i16, void* d_img, void* d_txt,
                                 float* d_scale, cudaStream_t st) {
@@ -588,10 +590,21 @@ static int run_unfused_backward(const SweepIO& io, const ClipWs& w, const void* 
     return run_dst_gemm(w, io.n_m, io.n_n, io.dim, i16, io.scale, io.out_mul, d_txt, io.out_fp32, st, nullptr, 0, 1, 1);
 }
 
+// Wide problems (dim > 512) that keep dS: the sweep covered the output columns [0, pair_d_half(dim)); the others are the
+// product dS . x16[:, d_half:] - S is recomputed ONCE per sweep, not once per 512 output columns (FLYP_WIDE_PRODUCT=0: A/B)
+static bool wide_product(int dim) {
+    static const int on = env_int("FLYP_WIDE_PRODUCT", 1);
+    return on != 0 && pair_n_dh(dim) > 1;
+}
+static int run_wide_rest(const SweepIO& io, const ClipWs& w, cudaStream_t st) {
+    return run_dst_gemm(w, io.n_m, io.n_n, io.dim, io.B_f16, io.scale, io.out_mul, io.out, io.out_fp32, st, nullptr, 0,
+                        /*transposed=*/0, /*counter=*/2, /*col_begin=*/pair_d_half(io.dim));
+}
+
 // transposed = 0: out[m, :] = scale * out_mul / G * sum_n dS[m, n] x16[n, :] (x16 has n_n rows)
 static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* x16, const float* scale, float out_mul,
                         void* out, int out_fp32, cudaStream_t st, float* const* out_rank, int rows_per_rank,
-                        int transposed, int counter) {
+                        int transposed, int counter, int col_begin) {
     CUtensorMap tmDS, tmX;
     int rc;
     const int n_k = transposed ? n_m : n_n, n_o = transposed ? n_n : n_m;
@@ -599,13 +612,13 @@ static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* 
     if ((rc = make_tmap(&tmX, x16, n_k, dim, dim, true)) != 0) return rc;
     flyp::DstParams p;
     memset(&p, 0, sizeof(p));
-    p.n_k = n_k; p.n_out = n_o; p.dim = dim;
+    p.n_k = n_k; p.n_out = n_o; p.dim = dim; p.col_begin = col_begin;
     // partials that go to other GPUs: 256-column tiles in two accumulator stages, so that the NVLink-bound drain of a
     // tile overlaps the MMAs of the next (dS is then read ceil(dim / 256) times - from this rank's HBM, cheap beside it)
     p.tile_cols = out_rank != nullptr ? 256 : flyp::DST_TILE_COLS;
     if (env_int("FLYP_GEMM_TILE_COLS", 0) == 256 || env_int("FLYP_GEMM_TILE_COLS", 0) == 512)      // A/B switch
         p.tile_cols = env_int("FLYP_GEMM_TILE_COLS", 0);
-    p.out_tiles = ceil_div(n_o, flyp::DST_TILE_ROWS); p.n_dh = ceil_div(dim, p.tile_cols);
+    p.out_tiles = ceil_div(n_o, flyp::DST_TILE_ROWS); p.n_dh = ceil_div(dim - col_begin, p.tile_cols);
     p.sched_pairs = flyp::dst_gemm_sched_pairs(p.out_tiles * p.n_dh, ceil_div(n_k, 128), num_sms());
     if (p.sched_pairs > w.gemm_pairs) return fail(FLYP_ERR_WORKSPACE, "partial-tile scratch of the dS product");
     p.transposed = transposed;
@@ -619,7 +632,7 @@ static int run_dst_gemm(const ClipWs& w, int n_m, int n_n, int dim, const void* 
     // (no flat tail when the pairs divide the tiles: no partial tiles, no grid barrier, an ordinary launch)
     p.part_out = w.gemm_part;
     p.grid_cnt = (p.out_tiles * p.n_dh) % p.sched_pairs == 0 ? nullptr : w.ctrl.grid_cnt(counter);
-    const bool timed = g_ev_sweep[0] != nullptr && g_ev_sweep_idx == (transposed ? 1 : 2);
+    const bool timed = g_ev_sweep[0] != nullptr && g_ev_sweep_idx == (transposed ? 1 : 2) && col_begin == 0;
     if (timed) cudaEventRecord(g_ev_sweep[0], st);
     flyp::launch_dst_gemm(tmDS, tmX, p, st);
     if (timed) cudaEventRecord(g_ev_sweep[1], st);
@@ -777,7 +790,9 @@ int flyp_clip_bwd_local_ex(const void* img, const void* txt, const float* scale,
             CUDA_OK(cudaGetLastError());
             return run_unfused_backward(io, w, w.img16, d_img, d_txt, d_scale, st);
         }
+        if (keep && wide_product(dim)) io.first_pass_only = 1;
         if ((rc = run_sweep(io, st)) != 0) return rc;
+        if (io.first_pass_only && (rc = run_wide_rest(io, w, st)) != 0) return rc;
     }
     if (d_txt && keep) {
         flyp::launch_to_f16(img, dtype, (size_t)n_rows * dim, w.img16, st);
@@ -891,7 +906,9 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
             }
             return run_unfused_backward(io, w, i16, d_img, d_txt, d_scale, st);
         }
+        if ((keep || keep_rs) && wide_product(dim)) io.first_pass_only = 1;
         if ((rc = run_sweep(io, st)) != 0) return rc;
+        if (io.first_pass_only && (rc = run_wide_rest(io, w, st)) != 0) return rc;
     }
     if (d_txt && keep_rs) {
         // this rank's partial of every text row's gradient, written into the owners' buffers by the product kernel

@@ -87,7 +87,7 @@ __device__ __noinline__ void gemm_tail_reduce(const DstParams& p, const int et, 
         g_epi_bar();
         const int np = red_i[1];
         const int vb = first + tb, ob = vb / p.n_dh, dh = vb - ob * p.n_dh;
-        if (np > 0 && dh * COLS + dl0 < p.dim) {
+        if (np > 0 && p.col_begin + dh * COLS + dl0 < p.dim) {
 #pragma unroll 1
             for (int f0 = et; f0 < 128 * 32; f0 += 256 * 8) {
                 float4 acc[8];
@@ -109,7 +109,7 @@ __device__ __noinline__ void gemm_tail_reduce(const DstParams& p, const int et, 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int f = f0 + j * 256, ri = f >> 5, oi = ob * G_ROWS + r0 + ri;
-                    const int d = dh * COLS + dl0 + (f & 31) * 4;
+                    const int d = p.col_begin + dh * COLS + dl0 + (f & 31) * 4;
                     if (oi >= p.n_out) continue;
                     if (p.out_fp32) {
                         *reinterpret_cast<float4*>(out_row_f32(p, oi) + d) = acc[j];
@@ -185,7 +185,7 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
     const uint32_t tmem_base = *tmem_holder;
 
     // accumulators (256 columns each) of pass dh
-    auto n_acc = [&](int dh) { const int left = p.dim - dh * COLS; return left >= COLS ? COLS / 256 : (left + 255) / 256; };
+    auto n_acc = [&](int dh) { const int left = p.dim - p.col_begin - dh * COLS; return left >= COLS ? COLS / 256 : (left + 255) / 256; };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
@@ -208,7 +208,7 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                     else { put(&tmDS, k0, o0); put(&tmDS, k0 + 64, o0); }
                     for (int a = 0; a < na; ++a)
                         for (int ds = 0; ds < 2; ++ds)
-                            put(&tmX, ii.dh * COLS + a * 256 + (int)cta * 128 + ds * 64, k0);
+                            put(&tmX, p.col_begin + ii.dh * COLS + a * 256 + (int)cta * 128 + ds * 64, k0);
                 }
             }
         }
@@ -302,7 +302,7 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                         v.z = stg[rr * 32 + ((c0 + 2) ^ rr)]; v.w = stg[rr * 32 + ((c0 + 3) ^ rr)];
                         const int rt = (int)cta * 128 + q * 32 + rr;         // row within the tile
                         const int orow = ii.mb * G_ROWS + rt;
-                        const int d = ii.dh * COLS + dl + c0;
+                        const int d = p.col_begin + ii.dh * COLS + dl + c0;
                         if (orow >= p.n_out || d >= p.dim) continue;
                         if (ii.part >= 0) {
                             *reinterpret_cast<float4*>(p.part_out + ((size_t)ii.part * G_ROWS + rt) * COLS + dl + c0) = v;

@@ -187,6 +187,9 @@ struct DstParams {
     int n_k;                 // contraction length: rows of dS (transposed) / columns of dS
     int n_out;               // output rows: columns of dS (transposed) / rows of dS
     int dim;                 // feature columns of X16 and of the output (a multiple of 8)
+    int col_begin;           // first output column (a multiple of 64): the product covers columns [col_begin, dim) - the
+                             // sweep of a wide problem (dim > 512) computes the first columns of its gradient itself and
+                             // leaves the others to this product instead of recomputing S for a second pass
     int tile_cols;           // output columns per tile and pass: 512 (one accumulator stage = the whole tensor memory) or
                              // 256 (two stages: the drain of a tile overlaps the MMAs of the next - used when the
                              // epilogue writes to other GPUs over NVLink)

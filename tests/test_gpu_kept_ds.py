@@ -88,3 +88,36 @@ def test_unfused_plan_matches_oracle():
     res = subprocess.run([sys.executable, "-c", _CHILD_FULL.format(root=ROOT)], env=env, timeout=600, capture_output=True,
                          text=True)
     assert res.returncode == 0 and "ok" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
+
+
+def test_kept_ds_with_unnormalised_inputs_two_exponential_form():
+    """Row norms vary by 30x and logit_scale = 100: the forward takes its robust path and the logsumexps spread so far
+    that the backward cannot use the one-exponential form - the kept dS then holds the two-exponential values, and the
+    product over it must still match the oracle."""
+    n, d, s = 1280, 512, 100.0
+    gen = torch.Generator().manual_seed(9)
+    I = (torch.randn(n, d, generator=gen) * torch.logspace(-1.5, 0.0, n)[:, None] * 0.2).bfloat16()
+    T = (torch.randn(n, d, generator=gen) * 0.2).bfloat16()
+    g = torch.rand(n, generator=gen) / n
+    loss, dI, dT, ds = run_abi_fp32(I, T, s, g)
+    In, Tn = I.double().numpy(), T.double().numpy()
+    assert rel(to_np(loss), orc.clip_loss(In, Tn, s)) < 1e-5
+    wI, wT, wds = orc.clip_loss_grads(In, Tn, s, g.double().numpy())
+    assert rel(to_np(dI), wI) < TOL and rel(to_np(dT), wT) < TOL
+    assert abs(float(ds) - wds) < TOL * abs(wds)
+
+
+def test_kept_ds_only_one_gradient_wanted_runs_a_plain_sweep():
+    n, d, s = 2048, 512, 1 / 0.07
+    I, T, g = make_inputs(n, d, seed=21)
+    Ic, Tc, gd = I.to(DEV), T.to(DEV), g.to(DEV)
+    sc = torch.tensor([float(s)], device=DEV)
+    row_lse, row_nll, col_stat, status = ops.clip_fwd_local(Ic, Tc, sc)
+    col_lse, col_nll, loss = ops.clip_fwd_finish(col_stat, 1, row_nll, n)
+    wI, wT, wds = orc.clip_loss_grads(I.double().numpy(), T.double().numpy(), s, g.double().numpy())
+    dI, none, ds = ops.clip_bwd_local(Ic, Tc, sc, 0, row_lse, row_nll, col_lse, col_nll, gd, gd, grad_dtype=torch.float32,
+                                      need_txt=False)
+    assert none is None and rel(to_np(dI), wI) < TOL and abs(float(ds) - wds) < TOL * abs(wds)
+    none, dT, _ = ops.clip_bwd_local(Ic, Tc, sc, 0, row_lse, row_nll, col_lse, col_nll, gd, gd, grad_dtype=torch.float32,
+                                     need_img=False, need_scale=False)
+    assert none is None and rel(to_np(dT), wT) < TOL
