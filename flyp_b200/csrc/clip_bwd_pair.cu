@@ -39,9 +39,14 @@ constexpr float LOG2E2 = 1.4426950408889634f;
 
 struct PairCfg {
     static constexpr int SLOT = 16384;
-    static constexpr int NSLOT = 8;
+    // Ring slots x dS tiles: 8 x 1 or 6 x 2 fit (the code below handles both).  Measured at B = 32768, D = 512: two tiles
+    // (the epilogue writes tile t + 1 while the MMAs and the spill still read tile t) do not pay for the two ring slots
+    // they cost - 1.61 / 1.96 ms per sweep without / with the dS spill against 1.52 / 1.80 ms.
+    static constexpr int NSLOT = 8;                    // (even: the dA^T operand boxes are consumed as (even, odd) pairs)
     static constexpr int IST_BYTES = 65536;            // 8 chunks [64 rows][64] bf16
-    static constexpr int DS_BYTES = 32768;             // 4 chunks [64 rows][64] fp16
+    static constexpr int DS_TILE = 32768;              // one dS tile: 4 chunks [64 rows][64] fp16
+    static constexpr int DS_TILES = 1;
+    static constexpr int DS_BYTES = DS_TILES * DS_TILE;
     static constexpr int RED_BYTES = 512;              // 8 d(scale) partials, a flag, the slot list of a split block
     static constexpr int SMEM_BYTES = IST_BYTES + NSLOT * SLOT + DS_BYTES + RED_BYTES + 256 + 1024;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget of one CTA");
@@ -165,7 +170,9 @@ __device__ __noinline__ void sweep_tail_reduce(const BwdParams& p, const int et,
 
 // WIDE: feature dim > 512 (streamed A chunks, two passes over the output columns); the narrow instantiation compiles
 // that logic away.
-template <bool ROW_TERM, bool COL_TERM, bool WIDE>
+// PROF: per-role wait-cycle counters (tools/pair_prof.py); a template parameter so that the MMA issuer's hot loop carries
+// no profiling branches otherwise.
+template <bool ROW_TERM, bool COL_TERM, bool WIDE, bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS2, 1)
 bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmBd, const __grid_constant__ CUtensorMap tmDS,
@@ -184,11 +191,12 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
     auto EMPTY = [&](int s) { return bar0 + 8u * (NSLOT + s); };
     auto SFULL = [&](int s) { return bar0 + 8u * (2 * NSLOT + s); };
     auto SEMPTY = [&](int s) { return bar0 + 8u * (2 * NSLOT + 2 + s); };
-    const uint32_t DSFULL = bar0 + 8u * (2 * NSLOT + 4), DSEMPTY = bar0 + 8u * (2 * NSLOT + 5);
-    const uint32_t ACCFULL = bar0 + 8u * (2 * NSLOT + 6), ACCEMPTY = bar0 + 8u * (2 * NSLOT + 7);
-    const uint32_t IFULL = bar0 + 8u * (2 * NSLOT + 8), IFREE = bar0 + 8u * (2 * NSLOT + 9);
-    const uint32_t DSLOC = bar0 + 8u * (2 * NSLOT + 10);   // keep_ds: this CTA's 256 epilogue threads have written the tile
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 11);
+    auto DSFULL = [&](int b) { return bar0 + 8u * (2 * NSLOT + 4 + b); };
+    auto DSEMPTY = [&](int b) { return bar0 + 8u * (2 * NSLOT + 6 + b); };
+    auto DSLOC = [&](int b) { return bar0 + 8u * (2 * NSLOT + 8 + b); };   // keep_ds: this CTA's 256 epilogue threads wrote tile b
+    const uint32_t ACCFULL = bar0 + 8u * (2 * NSLOT + 10), ACCEMPTY = bar0 + 8u * (2 * NSLOT + 11);
+    const uint32_t IFULL = bar0 + 8u * (2 * NSLOT + 12), IFREE = bar0 + 8u * (2 * NSLOT + 13);
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta = cluster_ctarank();
@@ -204,9 +212,10 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLOT; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(SFULL(s), 1); mbar_init(SEMPTY(s), EPI_ALL); }
-        // keep_ds: the tile is free again once the dA^T MMAs have read it AND the spill to global memory has
-        mbar_init(DSFULL, EPI_ALL); mbar_init(DSEMPTY, p.keep_ds ? 2 : 1);
-        mbar_init(DSLOC, 256);
+        for (int b = 0; b < 2; ++b) {
+            // keep_ds: a tile is free again once the dA^T MMAs have read it AND its spill to global memory has
+            mbar_init(DSFULL(b), EPI_ALL); mbar_init(DSEMPTY(b), p.keep_ds ? 2 : 1); mbar_init(DSLOC(b), 256);
+        }
         mbar_init(ACCFULL, 1); mbar_init(ACCEMPTY, EPI_ALL);
         mbar_init(IFULL, 1); mbar_init(IFREE, 1);
         fence_mbar_init();
@@ -294,15 +303,48 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             constexpr uint32_t IDESC_S = umma_idesc(128, 256, 1, 1, 0, 0);     // bf16 x bf16, both K-major
             constexpr uint32_t IDESC_D = umma_idesc(256, 128, 0, 0, 1, 0);     // fp16 x fp16, A MN-major, B K-major
             int slot = 0; uint32_t ph = 0; uint32_t gs = 0, gd = 0, it = 0;
-            const bool prof = p.prof != nullptr && pair == 0;
+            const bool prof = PROF && p.prof != nullptr && pair == 0;
             long long w_sempty = 0, w_full_s = 0, w_dsfull = 0, w_full_t = 0, w_acc = 0, w_ifull = 0;
-            const long long t_begin = clock64();
+            const long long t_begin = PROF ? clock64() : 0;
             auto twait = [&](uint32_t bar, uint32_t parity, long long& acc) {
-                if (prof) { const long long t0 = clock64(); mbar_wait(bar, parity); acc += clock64() - t0; }
-                else mbar_wait(bar, parity);
+                if constexpr (PROF) {
+                    if (prof) { const long long t0 = clock64(); mbar_wait(bar, parity); acc += clock64() - t0; return; }
+                }
+                mbar_wait(bar, parity);
             };
             auto adv = [&]() { if (++slot == NSLOT) { slot = 0; ph ^= 1; } };
+            // descriptor halves (sm100.cuh): per MMA only an integer add on the low word
+            constexpr uint32_t HI = umma_desc_hi(1024);
+            const uint32_t ist_lo = umma_desc_lo(smem_u32(ist), 16);            // stationary A chunks, K-major
+            const uint32_t ring_lo = umma_desc_lo(smem_u32(ring), 16);          // streamed B chunks, K-major
+            const uint32_t ring_lo_mn = umma_desc_lo(smem_u32(ring), Cfg::SLOT); // feature boxes, MN-major (LBO = next box)
+            const uint32_t ds_lo = umma_desc_lo(smem_u32(ds), 16);              // dS tile, K-major
+            // narrow features: the poll of the NEXT slot's barrier is issued before the MMAs of the current one, so that
+            // its latency (and the branch on it) overlaps their issue instead of preceding the next chunk
+            auto mma_s_narrow = [&]() {
+                const int sb = gs & 1;
+                twait(SEMPTY(sb), ((gs >> 1) & 1) ^ 1, w_sempty);
+                const uint32_t d_tmem = TM_S + sb * 128;
+                uint32_t ok = mbar_try_wait(FULL(slot), ph);
+#pragma unroll 1
+                for (int c = 0; c < KC; ++c) {
+                    if (!ok) twait(FULL(slot), ph, w_full_s);
+                    tc_fence_after();
+                    const int cur = slot;
+                    adv();
+                    if (c + 1 < KC) ok = mbar_try_wait(FULL(slot), ph);
+                    const uint32_t a_lo = ist_lo + c * (8192 >> 4), b_lo = ring_lo + cur * (Cfg::SLOT >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16_cg2(d_tmem, umma_desc_join(a_lo + k * 2, HI), umma_desc_join(b_lo + k * 2, HI), IDESC_S,
+                                     (c | k) != 0);
+                    umma_commit_cg2(EMPTY(cur));
+                }
+                umma_commit_cg2(SFULL(sb));
+                ++gs;
+            };
             auto mma_s = [&]() {
+                if constexpr (!WIDE) { mma_s_narrow(); return; }
                 const int sb = gs & 1;
                 twait(SEMPTY(sb), ((gs >> 1) & 1) ^ 1, w_sempty);
                 tc_fence_after();
@@ -341,30 +383,33 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
             };
             auto mma_d = [&](bool first) {
                 if (first) twait(ACCEMPTY, (it & 1) ^ 1, w_acc);
-                twait(DSFULL, gd & 1, w_dsfull);
-                tc_fence_after();
-                const uint32_t ds_addr = smem_u32(ds);
-                for (int dblk = 0; dblk < ND; ++dblk) {
-                    for (int jh = 0; jh < 2; ++jh) {
-                        twait(FULL(slot), ph, w_full_t);    // the two feature boxes (64 + 64 columns) of this K half
-                        twait(FULL(slot + 1), ph, w_full_t);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(ring + slot * Cfg::SLOT);
+                const int db = gd % Cfg::DS_TILES;
+                twait(DSFULL(db), (gd / Cfg::DS_TILES) & 1, w_dsfull);
+                // (the polls of the next group's two slots are issued before the MMAs of the current group)
+                uint32_t ok0 = mbar_try_wait(FULL(slot), ph), ok1 = mbar_try_wait(FULL(slot + 1), ph);
+#pragma unroll 1
+                for (int g = 0; g < 2 * ND; ++g) {                  // g = dblk * 2 + jh
+                    const int dblk = g >> 1, jh = g & 1;
+                    if (!ok0) twait(FULL(slot), ph, w_full_t);      // the two feature boxes (64 + 64 columns) of this K half
+                    if (!ok1) twait(FULL(slot + 1), ph, w_full_t);
+                    tc_fence_after();
+                    const int cur = slot;
+                    adv(); adv();
+                    if (g + 1 < 2 * ND) { ok0 = mbar_try_wait(FULL(slot), ph); ok1 = mbar_try_wait(FULL(slot + 1), ph); }
+                    // A: [K = 16 n-rows][M = 128 feature columns as two 64-wide boxes], MN-major
+                    const uint32_t a_lo = ring_lo_mn + cur * (Cfg::SLOT >> 4);
+                    // B: dS [N = 64 rows per CTA][K], K-major, four 64-wide chunks of 8 KiB
+                    const uint32_t b_lo = ds_lo + db * (Cfg::DS_TILE >> 4) + jh * (2 * 8192 >> 4);
+                    const uint32_t d_tmem = TM_ACC + dblk * 128;
 #pragma unroll
-                        for (int k8 = 0; k8 < 8; ++k8) {
-                            const int kk = jh * 8 + k8;
-                            // A: [K = 16 n-rows][M = 128 feature columns as two 64-wide boxes], MN-major
-                            const uint64_t ad = umma_desc_sw128(a_addr + k8 * 2048, Cfg::SLOT, 1024);
-                            // B: dS [N = 64 rows per CTA][K], K-major, four 64-wide chunks of 8 KiB
-                            const uint64_t bd = umma_desc_sw128(ds_addr + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024);
-                            umma_f16_cg2(TM_ACC + dblk * 128, ad, bd, IDESC_D, !(first && kk == 0));
-                        }
-                        umma_commit_cg2(EMPTY(slot));
-                        umma_commit_cg2(EMPTY(slot + 1));
-                        adv(); adv();
-                    }
+                    for (int k8 = 0; k8 < 8; ++k8)
+                        umma_f16_cg2(d_tmem, umma_desc_join(a_lo + k8 * (2048 >> 4), HI),
+                                     umma_desc_join(b_lo + (k8 >> 2) * (8192 >> 4) + (k8 & 3) * 2, HI), IDESC_D,
+                                     !(first && jh == 0 && k8 == 0));
+                    umma_commit_cg2(EMPTY(cur));
+                    umma_commit_cg2(EMPTY(cur + 1));
                 }
-                umma_commit_cg2(DSEMPTY);
+                umma_commit_cg2(DSEMPTY(db));
                 ++gd;
             };
             SweepItems iter(p.m_tiles, p.n_dh, p.sched_pairs, NJ, pair);
@@ -379,7 +424,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 umma_commit_cg2(ACCFULL);
                 umma_commit_cg2(IFREE);
             }
-            if (prof) {
+            if (PROF && prof) {
                 p.prof[0] = (unsigned long long)(clock64() - t_begin);
                 p.prof[1] = w_sempty; p.prof[2] = w_full_s; p.prof[3] = w_dsfull; p.prof[4] = w_full_t;
                 p.prof[5] = w_acc; p.prof[6] = w_ifull; p.prof[7] = gs;
@@ -389,23 +434,30 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
         // ------------------------------------------------------------------ dS spill (both CTAs, keep_ds only)
         // The staged fp16 dS tile of every step ([64 rows][256 columns] per CTA, exactly what the dA^T MMAs read) is also
         // written to global memory: the gradient of the OTHER operand is then a plain product dS^T . A over these values
-        // (clip_dst_gemm.cu) instead of a second sweep that recomputes every logit.
+        // (clip_dst_gemm.cu) instead of a second sweep that recomputes every logit.  Four cp.async.bulk.tensor stores per
+        // step (the TMA undoes the swizzle), with an L2 evict-first policy: 2 GiB of dS stream through the L2 per sweep and
+        // must not displace the 64 MiB of operands every pair re-reads (L2 hit rate of the operand loads 95 % without the
+        // spill, 77 % with a plain store).  (Measured alternatives: 32-byte stores from the epilogue's registers 1.92 ms
+        // per sweep, a copy warp with ordinary loads / stores 2.00 ms, this store without the policy 1.80 ms; no spill
+        // 1.53 ms.)
         if (p.keep_ds && elect_one()) {
             uint32_t gs = 0;
+            const uint64_t pol_first = l2_policy_evict_first();
             SweepItems iter(p.m_tiles, p.n_dh, p.sched_pairs, NJ, pair);
             ItemInfo ii;
             while (iter.next(ii)) {
                 for (int t = ii.t0; t < ii.t1; ++t, ++gs) {
-                    mbar_wait(DSLOC, gs & 1);
-                    if (ii.dh == 0) {
+                    const int db = gs % Cfg::DS_TILES;
+                    mbar_wait(DSLOC(db), (gs / Cfg::DS_TILES) & 1);
+                    if (ii.dh == 0 && !(p.dbg & 32)) {         // (FLYP_DBG bit 5: measurement - the spill is skipped)
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4)
-                            tma_store_2d(&tmDS, smem_u32(ds + c4 * 8192), t * Cfg::NSTEP + c4 * 64,
-                                         ii.mb * TILE + (int)cta * 64);
+                            tma_store_2d_hint(&tmDS, smem_u32(ds + db * Cfg::DS_TILE + c4 * 8192), t * Cfg::NSTEP + c4 * 64,
+                                              ii.mb * TILE + (int)cta * 64, pol_first);
                         tma_store_commit();
                         tma_store_wait_read0();
                     }
-                    mbar_arrive(DSEMPTY);
+                    mbar_arrive(DSEMPTY(db));
                 }
             }
             tma_store_wait_all0();
@@ -421,7 +473,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
         const bool fast = p.fast_info != nullptr && p.fast_info[1] != 0.f;
         const float c0 = fast ? p.fast_info[0] : 0.f;
         const uint32_t R_SEMPTY0 = mapa(SEMPTY(0), 0), R_SEMPTY1 = mapa(SEMPTY(1), 0);
-        const uint32_t R_DSFULL = mapa(DSFULL, 0), R_ACCEMPTY = mapa(ACCEMPTY, 0);
+        const uint32_t R_DSFULL0 = mapa(DSFULL(0), 0), R_DSFULL1 = mapa(DSFULL(1), 0), R_ACCEMPTY = mapa(ACCEMPTY, 0);
         const int rloc = (q & 1) * 32 + lane;       // row within this CTA's 64-row slice
         const int jq = q >> 1;                      // which 128-column half of the step this lane quarter holds
         uint32_t gs = 0, it = 0;
@@ -456,11 +508,12 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 ds_tile<ROW_TERM, COL_TERM>(r0, r1, p, rc, n0, c1, fast, c0, G, v, want_ds && ii.dh == 0, dsum);
                 uint32_t pk[32];
                 pack_ds(v, pk);
-                ewait(DSEMPTY, (gs & 1) ^ 1, w_dsempty);
-                store_ds_row(ds + (jq * 2 + h) * 8192 + rloc * 128, rloc, pk);
+                const int db = gs % Cfg::DS_TILES;          // dS tile of this step
+                ewait(DSEMPTY(db), ((gs / Cfg::DS_TILES) & 1) ^ 1, w_dsempty);
+                store_ds_row(ds + db * Cfg::DS_TILE + (jq * 2 + h) * 8192 + rloc * 128, rloc, pk);
                 fence_proxy_async_smem();
-                mbar_arrive_cluster(R_DSFULL);
-                if (p.keep_ds) mbar_arrive(DSLOC);
+                mbar_arrive_cluster(db ? R_DSFULL1 : R_DSFULL0);
+                if (p.keep_ds) mbar_arrive(DSLOC(db));
             }
             // -------- row block done: drain dA^T (lanes = feature columns, TMEM columns = the 128 rows of the block)
             ewait(ACCFULL, it & 1, w_accfull);
@@ -535,11 +588,15 @@ void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUt
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = p.grid_cnt != nullptr ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-#define FLYP_LAUNCH_BWD2(R, C, W)                                                                              \
+#define FLYP_LAUNCH_BWD2_P(R, C, W, P)                                                                         \
     do {                                                                                                       \
         static bool attr_done[64] = {false};                                                                  \
-        ensure_smem_attr(bwd_pair_kernel<R, C, W>, smem, attr_done);                                           \
-        cudaLaunchKernelEx(&cfg, bwd_pair_kernel<R, C, W>, tmA64, tmB, tmBd, tmDS, p);                             \
+        ensure_smem_attr(bwd_pair_kernel<R, C, W, P>, smem, attr_done);                                        \
+        cudaLaunchKernelEx(&cfg, bwd_pair_kernel<R, C, W, P>, tmA64, tmB, tmBd, tmDS, p);                      \
+    } while (0)
+#define FLYP_LAUNCH_BWD2(R, C, W)                                                                              \
+    do {                                                                                                       \
+        if (p.prof != nullptr) FLYP_LAUNCH_BWD2_P(R, C, W, true); else FLYP_LAUNCH_BWD2_P(R, C, W, false);     \
     } while (0)
     const bool wide = p.kc > 8 || p.n_dh > 1;
     if (wide) {
@@ -552,6 +609,7 @@ void launch_bwd_pair(const CUtensorMap& tmA64, const CUtensorMap& tmB, const CUt
         else FLYP_LAUNCH_BWD2(false, true, false);
     }
 #undef FLYP_LAUNCH_BWD2
+#undef FLYP_LAUNCH_BWD2_P
 }
 
 }  // namespace flyp

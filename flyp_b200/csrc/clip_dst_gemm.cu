@@ -218,6 +218,8 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
             constexpr uint32_t IDESC = umma_idesc(256, 256, 0, 0, TRANSPOSED ? 1 : 0, 1);   // fp16 x fp16, B MN-major
             int slot = 0; uint32_t ph = 0; uint32_t it = 0;
             auto adv = [&]() { if (++slot == G_NSLOT) { slot = 0; ph ^= 1; } };
+            constexpr uint32_t HI = umma_desc_hi(1024);
+            const uint32_t ring_lo_mn = umma_desc_lo(smem_u32(ring), G_SLOT), ring_lo_k = umma_desc_lo(smem_u32(ring), 16);
             SweepItems iter(p.out_tiles, p.n_dh, p.sched_pairs, NJ, pair);
             ItemInfo ii;
             for (; iter.next(ii); ++it) {
@@ -233,7 +235,8 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                     adv();
                     mbar_wait(FULL(slot), ph);
                     adv();
-                    const uint32_t a_addr = smem_u32(ring + a_slot * G_SLOT);
+                    // (descriptors: base word + an integer add per MMA, sm100.cuh)
+                    const uint32_t a_lo = (TRANSPOSED ? ring_lo_mn : ring_lo_k) + a_slot * (G_SLOT >> 4);
                     for (int a = 0; a < na; ++a) {
                         mbar_wait(FULL(slot), ph);
                         const int b_slot = slot;
@@ -241,16 +244,15 @@ dst_gemm_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant_
                         mbar_wait(FULL(slot), ph);
                         adv();
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(ring + b_slot * G_SLOT);
+                        const uint32_t b_lo = ring_lo_mn + b_slot * (G_SLOT >> 4);
 #pragma unroll
                         for (int kk = 0; kk < 8; ++kk) {
                             // A, transposed: [16 contraction rows][128 output rows as two 64-wide boxes], MN-major;
                             //    otherwise:  [128 output rows][16 contraction columns] of box kk / 4, K-major
-                            const uint64_t ad = TRANSPOSED
-                                ? umma_desc_sw128(a_addr + kk * 2048, G_SLOT, 1024)
-                                : umma_desc_sw128(a_addr + (kk >> 2) * G_SLOT + (kk & 3) * 32, 16, 1024);
+                            const uint64_t ad = umma_desc_join(
+                                TRANSPOSED ? a_lo + kk * (2048 >> 4) : a_lo + (kk >> 2) * (G_SLOT >> 4) + (kk & 3) * 2, HI);
                             // B: [16 contraction rows][128 feature columns as two 64-wide boxes], MN-major
-                            const uint64_t bd = umma_desc_sw128(b_addr + kk * 2048, G_SLOT, 1024);
+                            const uint64_t bd = umma_desc_join(b_lo + kk * (2048 >> 4), HI);
                             umma_f16_cg2(tm_acc + a * 256, ad, bd, IDESC, !(kb == ii.t0 && kk == 0));
                         }
                         umma_commit_cg2(EMPTY(b_slot));

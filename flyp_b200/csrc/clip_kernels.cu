@@ -141,26 +141,34 @@ fwd_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const FwdParams& p, con
             int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0; uint32_t it = 0;
             FwdItems items(p.m_tiles, n_units, p.n_local, p.nb_rot, nworkers, worker);
             FwdItem fi;
+            // The issuing thread's own instruction stream bounds a kernel whose MMAs are 64 clocks long: descriptors are a
+            // base word plus an integer add per MMA (sm100.cuh), and the poll of the NEXT stage's barrier is issued before
+            // the MMAs of the current one so that its latency overlaps their issue.
+            constexpr uint32_t HI = umma_desc_hi(1024);
+            const uint32_t ring_lo = umma_desc_lo(smem_u32(ring), 16), stat_lo = umma_desc_lo(smem_u32(stat_b), 16);
+            const int kc_total = p.kc * p.kplan.n_terms;
             for (; items.next(fi); ++it) {
                 const int mt0 = fi.mt0, mt1 = fi.mt1;
                 if (STAT) { mbar_wait(BFULL, it & 1); tc_fence_after(); }
+                uint32_t ok = mbar_try_wait(FULL(stage), phase);
                 for (int mt = mt0; mt < mt1; ++mt) {
                     mbar_wait(TEMPTY(as), aphase ^ 1);
-                    tc_fence_after();
                     const uint32_t d_tmem = tmem_base + as * TILE;
-                    const int kc_total = p.kc * p.kplan.n_terms;
+#pragma unroll 1
                     for (int c = 0; c < kc_total; ++c) {
-                        mbar_wait(FULL(stage), phase);
+                        if (!ok) mbar_wait(FULL(stage), phase);
                         tc_fence_after();
-                        const uint32_t a_addr = smem_u32(ring + stage * Cfg::STAGE_BYTES);
-                        const uint32_t b_addr = STAT ? smem_u32(stat_b + c * CHUNK_BYTES) : a_addr + CHUNK_BYTES;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                                      umma_desc_sw128(b_addr + k * 32, 16, 1024), IDESC, (c | k) != 0);
-                        }
-                        if (MC) umma_commit_mc(EMPTY(stage), (uint16_t)3); else umma_commit(EMPTY(stage));
+                        const int cur = stage;
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        // (the next chunk of this item; the last poll of an item is redone by the next item)
+                        ok = (c + 1 < kc_total || mt + 1 < mt1) ? mbar_try_wait(FULL(stage), phase) : 0u;
+                        const uint32_t a_lo = ring_lo + cur * (Cfg::STAGE_BYTES >> 4);
+                        const uint32_t b_lo = STAT ? stat_lo + c * (CHUNK_BYTES >> 4) : a_lo + (CHUNK_BYTES >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_tmem, umma_desc_join(a_lo + k * 2, HI), umma_desc_join(b_lo + k * 2, HI), IDESC,
+                                      (c | k) != 0);
+                        if (MC) umma_commit_mc(EMPTY(cur), (uint16_t)3); else umma_commit(EMPTY(cur));
                     }
                     umma_commit(TFULL(as));
                     if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }

@@ -142,7 +142,7 @@ struct BwdParams {
     uint16_t* ds_out;        // dS kernel (clip_kernels.cu: ds_kernel_mc): the dS matrix [n_m][ds_ld] fp16 it writes
     int ds_ld;
     int keep_ds;             // pair kernel: the staged fp16 dS tiles (scaled by the staging factor) are also written to
-                             // global memory through the tmDS store map, for the product dS^T . A (clip_dst_gemm.cu)
+                             // global memory through the tmDS store map, for the products over dS (clip_dst_gemm.cu)
     float* dscale_out;       // the sum of all d(scale) partials (written by CTA 0 after the barrier), published to the
                              // other ranks through ds_push
     PeerPush ds_push;

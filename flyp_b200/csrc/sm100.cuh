@@ -73,6 +73,23 @@ DEVI void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
                  : "memory");
 }
+// L2 cache policies for bulk copies (createpolicy): evict_first for streams that are written / read once, evict_last for
+// working sets that must stay
+DEVI uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+DEVI uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+DEVI void tma_store_2d_hint(const CUtensorMap* m, uint32_t src, int c0, int c1, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "l"(policy)
+                 : "memory");
+}
 DEVI void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores of this thread have finished READING shared memory (the source may be overwritten)
 DEVI void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -130,6 +147,18 @@ DEVI uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_b
     return d;
 }
 
+// The same descriptor in two 32-bit halves.  Only the start-address field changes from one MMA to the next, and it sits
+// in the low bits of the low word: an MMA issuer keeps `lo` of an operand's base and ADDS (byte offset >> 4) per
+// instruction (one integer add instead of shift / mask / or chains - the issuing thread's own instruction stream is
+// what bounds kernels whose MMAs are only 64 clocks long).  Valid while base + offset stays below 256 KiB.
+DEVI uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+DEVI uint64_t umma_desc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 //   [4,6) c_format (1 = F32)  [7,10) a_format (1 = BF16)  [10,13) b_format (1 = BF16)
 //   [15] a_major (0 = K, 1 = MN)  [16] b_major  [17,23) N >> 3  [24,29) M >> 4
@@ -164,6 +193,12 @@ DEVI uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 
+// one 32-byte global store (sm_100: STG.256) of eight 32-bit words; p must be 32-byte aligned
+DEVI void st_global_256(void* p, const uint32_t* w) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
 DEVI uint32_t pack_f16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
