@@ -622,22 +622,27 @@ bwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             constexpr uint32_t IDESC_D = umma_idesc_bf16(TILE, Cfg::DPART, 0, 1) & ~((7u << 7) | (7u << 10));
             int stage = 0; uint32_t phase = 0; uint32_t gs = 0, gd = 0, gtb = 0, it = 0;
             const int kc_total = p.kc * p.kplan.n_terms;
+            // (lean issue path as in the forward: descriptor base words + integer adds, next stage polled ahead)
+            constexpr uint32_t HI = umma_desc_hi(1024);
+            const uint32_t ring_lo = umma_desc_lo(smem_u32(ring), 16);
             auto mma_s = [&]() {
                 const int sb = gs & 1;
                 mbar_wait(SEMPTY(sb), ((gs >> 1) & 1) ^ 1);
-                tc_fence_after();
                 const uint32_t d_tmem = TM_S + sb * TILE;
+                uint32_t ok = mbar_try_wait(FULL(stage), phase);
+#pragma unroll 1
                 for (int c = 0; c < kc_total; ++c) {
-                    mbar_wait(FULL(stage), phase);
+                    if (!ok) mbar_wait(FULL(stage), phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(ring + stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + CHUNK_BYTES;
+                    const int cur = stage;
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    if (c + 1 < kc_total) ok = mbar_try_wait(FULL(stage), phase);
+                    const uint32_t a_lo = ring_lo + cur * (Cfg::STAGE_BYTES >> 4), b_lo = a_lo + (CHUNK_BYTES >> 4);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                                  umma_desc_sw128(b_addr + k * 32, 16, 1024), IDESC_S, (c | k) != 0);
-                    umma_commit(EMPTY(stage));
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                        umma_bf16(d_tmem, umma_desc_join(a_lo + k * 2, HI), umma_desc_join(b_lo + k * 2, HI), IDESC_S,
+                                  (c | k) != 0);
+                    umma_commit(EMPTY(cur));
                 }
                 umma_commit(SFULL(sb));
                 ++gs;
