@@ -350,31 +350,36 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant
                 tc_fence_after();
                 const uint32_t d_tmem = TM_S + sb * 128;
                 int a_slot = 0;
+                uint32_t ok = mbar_try_wait(FULL(slot), ph);       // (polls issued one slot ahead, as in mma_s_narrow)
+#pragma unroll 1
                 for (int c = 0; c < KC; ++c) {
-                    uint32_t a_addr;
-                    if (!WIDE || c < KCS) {
-                        a_addr = smem_u32(ist + c * 8192);
+                    uint32_t a_lo;
+                    if (c < KCS) {
+                        a_lo = ist_lo + c * (8192 >> 4);
                     } else {
                         if ((c & 1) == 0) {                    // the slot holding the streamed A chunks c and c + 1
-                            twait(FULL(slot), ph, w_full_s);
+                            if (!ok) twait(FULL(slot), ph, w_full_s);
                             a_slot = slot;
                             adv();
+                            ok = mbar_try_wait(FULL(slot), ph);
                         }
-                        a_addr = smem_u32(ring + a_slot * Cfg::SLOT + (c & 1) * 8192);
+                        a_lo = ring_lo + a_slot * (Cfg::SLOT >> 4) + (c & 1) * (8192 >> 4);
                     }
-                    twait(FULL(slot), ph, w_full_s);
+                    if (!ok) twait(FULL(slot), ph, w_full_s);
                     tc_fence_after();
-                    const uint32_t b_addr = smem_u32(ring + slot * Cfg::SLOT);
+                    const int cur = slot;
+                    adv();
+                    ok = mbar_try_wait(FULL(slot), ph);
+                    const uint32_t b_lo = ring_lo + cur * (Cfg::SLOT >> 4);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_f16_cg2(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024),
-                                     umma_desc_sw128(b_addr + k * 32, 16, 1024), IDESC_S, (c | k) != 0);
-                    umma_commit_cg2(EMPTY(slot));
-                    if (WIDE && c >= KCS && (c & 1) == 1) umma_commit_cg2(EMPTY(a_slot));
-                    adv();
+                        umma_f16_cg2(d_tmem, umma_desc_join(a_lo + k * 2, HI), umma_desc_join(b_lo + k * 2, HI), IDESC_S,
+                                     (c | k) != 0);
+                    umma_commit_cg2(EMPTY(cur));
+                    if (c >= KCS && (c & 1) == 1) umma_commit_cg2(EMPTY(a_slot));
                 }
                 if (pad_slot) {
-                    twait(FULL(slot), ph, w_full_s);
+                    if (!ok) twait(FULL(slot), ph, w_full_s);
                     umma_commit_cg2(EMPTY(slot));
                     adv();
                 }

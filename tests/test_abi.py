@@ -65,3 +65,30 @@ def test_sources_are_sm100a_only():
         open(os.path.join(ROOT, "flyp_b200", "csrc", "sm100.cuh")).read()
     for needle in ("tcgen05.mma", "tcgen05.ld", "cp.async.bulk.tensor", "tcgen05.alloc"):
         assert needle in src
+
+
+def test_backward_plan_and_workspace_of_the_kept_ds_backward():
+    """flyp_clip_backward_plan / flyp_clip_keeps_ds (host logic, no GPU work): which shapes keep dS, and that their
+    workspace holds the n_rows x n_cols fp16 matrix."""
+    import ctypes
+    from flyp_b200 import _lib
+    lib = _lib.load()
+    bf16, f32 = _lib.FLYP_BF16, _lib.FLYP_F32
+
+    def ws(n, m, d, dt):
+        sz = ctypes.c_size_t()
+        assert lib.flyp_clip_workspace_bytes(n, m, d, dt, ctypes.byref(sz)) == 0
+        return sz.value
+
+    # one rank, bf16, D a multiple of 128, >= 1024 pairs: one sweep + the product over the kept dS
+    assert lib.flyp_clip_keeps_ds(32768, 32768, 512, bf16) == 1 and lib.flyp_clip_backward_plan(32768, 32768, 512, bf16) == 1
+    assert lib.flyp_clip_keeps_ds(2048, 2048, 1024, bf16) == 1
+    # a rank's row block of a row-sharded problem (8 ranks x 4096 rows)
+    assert lib.flyp_clip_keeps_ds(4096, 32768, 512, bf16) == 1
+    # not kept: small batches, fp32 features, D not a multiple of 128, rows that do not divide the columns
+    for n, m, d, dt in ((512, 512, 512, bf16), (4096, 4096, 512, f32), (2048, 2048, 520, bf16), (3000, 7000, 512, bf16)):
+        assert lib.flyp_clip_keeps_ds(n, m, d, dt) == 0 and lib.flyp_clip_backward_plan(n, m, d, dt) == 0
+    # the workspace of a kept shape holds the fp16 dS matrix (2 bytes per logit) on top of the O(n D) scratch
+    assert ws(8192, 8192, 512, bf16) >= 8192 * 8192 * 2
+    assert ws(8192, 8192, 520, bf16) < 8192 * 8192 * 2
+    assert ws(4096, 32768, 512, bf16) >= 4096 * 32768 * 2
