@@ -127,25 +127,7 @@ __device__ __noinline__ void gemm_tail_reduce(const DstParams& p, const int et, 
 
 }  // namespace
 
-int dst_gemm_sched_pairs(int v_tiles, int k_blocks, int num_sms) {
-    int npairs = num_sms / 2;
-    const long long S = (long long)v_tiles * k_blocks;
-    // Whole tiles only (ceil(v_tiles / pairs) rounds on a number of pairs that divides v_tiles) when that costs no more
-    // than the flat schedule's equal shares PLUS its tail: partial tiles written to scratch, a grid barrier, the sum -
-    // about TAIL_BLOCKS contraction blocks' worth of time, during which no MMA runs (and, when the output goes to
-    // other GPUs, all of the split tiles' NVLink traffic comes at the very end).
-    constexpr int TAIL_BLOCKS = 48;
-    {
-        const int rounds = (v_tiles + npairs - 1) / npairs;
-        const int pw = (v_tiles + rounds - 1) / rounds;
-        if (v_tiles % pw == 0 && (long long)rounds * k_blocks <= S / npairs + TAIL_BLOCKS) return pw;
-    }
-    constexpr int MIN_BLOCKS = 8;          // a range shorter than this does not pay for its partial tile
-    long long cap = S / MIN_BLOCKS;
-    if (cap < v_tiles) cap = v_tiles;
-    if (cap < npairs) npairs = (int)cap;
-    return (int)(S < npairs ? S : npairs);
-}
+int dst_gemm_sched_pairs(int v_tiles, int k_blocks, int num_sms) { return dst_sched_pairs(v_tiles, k_blocks, num_sms / 2); }
 size_t dst_gemm_part_floats(int pairs) { return (size_t)2 * pairs * G_ROWS * G_COLS; }
 
 template <bool TRANSPOSED>

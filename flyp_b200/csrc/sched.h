@@ -81,6 +81,27 @@ struct TailParts {
     }
 };
 
+// CTA pairs of the products over the kept dS (clip_dst_gemm.cu): v_tiles output tiles of k_blocks contraction blocks
+// each, walked with SweepItems / TailParts like the sweep.  Whole tiles only (ceil(v_tiles / pairs) rounds on a number
+// of pairs that divides v_tiles) when that costs no more than the flat schedule's equal shares PLUS its tail - partial
+// tiles written to scratch, a grid barrier, the sum: about TAIL_BLOCKS contraction blocks' worth of time during which no
+// MMA runs (and, when the output goes to other GPUs, all of the split tiles' NVLink traffic comes at the very end).
+// Otherwise every pair takes part, but no range is shorter than MIN_BLOCKS blocks.
+FLYP_HD int dst_sched_pairs(int v_tiles, int k_blocks, int max_pairs) {
+    constexpr int TAIL_BLOCKS = 48, MIN_BLOCKS = 8;
+    int npairs = max_pairs;
+    const long long S = (long long)v_tiles * k_blocks;
+    {
+        const int rounds = (v_tiles + npairs - 1) / npairs;
+        const int pw = (v_tiles + rounds - 1) / rounds;
+        if (v_tiles % pw == 0 && (long long)rounds * k_blocks <= S / npairs + TAIL_BLOCKS) return pw;
+    }
+    long long cap = S / MIN_BLOCKS;
+    if (cap < v_tiles) cap = v_tiles;
+    if (cap < npairs) npairs = (int)cap;
+    return (int)(S < npairs ? S : npairs);
+}
+
 // ---------------------------------------------------------------------------------------------------- forward
 // Flat schedule of the forward statistics sweep.  A unit = (column unit u, row tile mt): u is one 128-column block of
 // the N side (the multicast kernel: a pair of adjacent blocks, swept by the two CTAs of a cluster), mt one 128-row tile

@@ -13,10 +13,14 @@
 
 using namespace flyp;
 
+static int check_p(int m_tiles, int n_dh, int NJ, int P);
 static int check(int m_tiles, int n_dh, int NJ, int npairs) {
     const int v_tiles = m_tiles * n_dh;
     const long long S_total = (long long)v_tiles * NJ;
-    const int P = (int)(S_total < npairs ? S_total : npairs);           // bwd_pair_sched_pairs
+    return check_p(m_tiles, n_dh, NJ, (int)(S_total < npairs ? S_total : npairs));      // bwd_pair_sched_pairs
+}
+static int check_p(int m_tiles, int n_dh, int NJ, int P) {
+    const int v_tiles = m_tiles * n_dh;
     std::vector<int> cover((size_t)v_tiles * NJ, 0);
     std::map<int, std::vector<int>> slots_of_block;                     // virtual block -> partial slots, in pair order
     std::set<int> used_slots, whole_blocks;
@@ -109,6 +113,18 @@ int main() {
                         ++n;
                     }
             }
+    // products over the kept dS (clip_dst_gemm.cu): the pair count comes from dst_sched_pairs (whole-tile rounds or a flat
+    // tail); out_tiles x n_dh virtual tiles of k_blocks contraction blocks
+    for (int max_pairs : {1, 2, 37, 66, 74})
+        for (int n_dh = 1; n_dh <= 4; ++n_dh)
+            for (int out_tiles = 1; out_tiles <= 520; out_tiles += (out_tiles < 140 ? 1 : 31))
+                for (int kb : {1, 2, 7, 8, 9, 32, 64, 128, 256, 512}) {
+                    const int P = dst_sched_pairs(out_tiles * n_dh, kb, max_pairs);
+                    if (P < 1 || P > max_pairs) { printf("FAIL dst pairs %d\n", P); return 1; }
+                    const int rc = check_p(out_tiles, n_dh, kb, P);
+                    if (rc) { printf("FAIL dst rc=%d out_tiles=%d n_dh=%d kb=%d P=%d\n", rc, out_tiles, n_dh, kb, P); return 1; }
+                    ++n;
+                }
     const int npairs_list[] = {1, 2, 3, 7, 64, 66, 70, 74};
     for (int npairs : npairs_list)
         for (int n_dh = 1; n_dh <= 2; ++n_dh)
