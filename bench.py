@@ -375,7 +375,9 @@ def run_ours(args):
     plan = int(lib.flyp_clip_backward_plan(b, B, D, code))
     if world > 1:
         plan = min(plan, 1)
-        if os.environ.get("FLYP_KEEP_DS_RS", "1") == "0":                # (the library's A/B switch)
+        # (the library's A/B switch; and the communicator's threshold: the product + NVLink reduce-scatter of the text
+        # gradient from 6144 rows per rank on, the transposed sweep below)
+        if os.environ.get("FLYP_KEEP_DS_RS", "1") == "0" or b < int(os.environ.get("FLYP_RS_MIN_ROWS", "6144")):
             plan = 0
     n_k = max(3, min(args.steps, 10))
     fwd_ms, sweep0_ms = kernel_ms(0, n_k)                # event pair 0: first sweep / dS kernel

@@ -83,6 +83,7 @@ SIGNATURES = {
     "flyp_comm_create": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
     "flyp_comm_layout_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
     "flyp_comm_create_external": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_void_p), c_void_p, POINTER(c_void_p)]),
+    "flyp_comm_set_rs_min_rows": (c_int, [c_void_p, c_int]),
     "flyp_comm_has_multicast": (c_int, [c_void_p]),
     "flyp_comm_segment_bytes": (c_int, [c_void_p, POINTER(c_size_t)]),
     "flyp_comm_ipc_handle": (c_int, [c_void_p, c_void_p]),

@@ -167,6 +167,11 @@ class PeerComm:
     def reset_error(self) -> None:
         _lib.load().flyp_comm_reset_error(self._h)
 
+    def set_rs_min_rows(self, rows: int) -> None:
+        """Rows per rank from which the text gradient goes through the kept-dS product + NVLink reduce-scatter (default
+        6144; 0 = whenever the shape keeps dS).  Must be the same on every rank."""
+        _lib.check(_lib.load().flyp_comm_set_rs_min_rows(self._h, int(rows)))
+
     def set_timeout_ms(self, ms: int) -> None:
         _lib.check(_lib.load().flyp_comm_set_timeout_ms(self._h, int(ms)))
 

@@ -851,7 +851,7 @@ static int bwd_sharded_impl(const void* img, const void* txt, const void* img_al
     const bool keep = w.ds_keep != nullptr && comm == nullptr && n_rows == n_cols && d_img && d_txt && img_all != nullptr;
     static const int rs_on = env_int("FLYP_KEEP_DS_RS", 1);       // A/B switch: 0 = two sweeps on several GPUs
     const bool keep_rs = rs_on != 0 && w.ds_keep != nullptr && comm != nullptr && world > 1 && n_cols == n_rows * world &&
-                         d_img && d_txt;
+                         d_img && d_txt && n_rows >= flyp::comm_rs_min_rows(comm);
     if ((phases & 1) == 0) {
         // finish phase only: everything below was enqueued by an earlier call with phase 1
         if (keep_rs && (rc = flyp::comm_rs_reduce(comm, seq, n_rows, dim, d_txt, grad_dtype, grad_mul, stream)) != 0) return rc;

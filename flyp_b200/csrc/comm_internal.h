@@ -30,6 +30,7 @@ int comm_rs_targets(flyp_comm* c, uint32_t seq, int n_rows, int dim, float** out
 int comm_rs_signal(flyp_comm* c, uint32_t seq, void* stream);
 int comm_rs_reduce(flyp_comm* c, uint32_t seq, int n_rows, int dim, void* out, int out_fp32, float mul, void* stream);
 int comm_world(const flyp_comm* c);
+int comm_rs_min_rows(const flyp_comm* c);   // rows per rank from which the kept-dS product + reduce-scatter is used
 
 void set_error(int code, const char* fmt, ...);   // api.cu: thread-local message returned by flyp_last_error()
 

@@ -172,6 +172,11 @@ int flyp_comm_reset_error(flyp_comm* comm);
 /* How long a kernel waits for a peer's rows before it traps (default 600000 = 10 min, or FLYP_PEER_TIMEOUT_MS at
  * creation; 0 = for ever). */
 int flyp_comm_set_timeout_ms(flyp_comm* comm, uint32_t timeout_ms);
+/* Rows per rank from which a backward over this communicator computes the text gradient as the product over the kept dS
+ * with its NVLink reduce-scatter instead of the transposed sweep (default 6144, or FLYP_RS_MIN_ROWS at creation; 0 =
+ * whenever the shape keeps dS, see flyp_clip_keeps_ds): the scatter moves (W - 1) / W x B x D x 4 bytes per rank however
+ * small the rank's share, the sweep it replaces shrinks with it.  Must be the same on every rank. */
+int flyp_comm_set_rs_min_rows(flyp_comm* comm, int rows);
 int flyp_comm_destroy(flyp_comm* comm);
 
 /* clip/loss.py:59-67 without torch.cat: a pack kernel on `stream` copies the local rows (and their fp16 copies) into

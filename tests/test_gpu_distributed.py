@@ -132,6 +132,7 @@ def test_soak_changing_inputs_two_gpus():
 def _kept_worker(rank, world, port, b, dim, gwg, steps, ret):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["FLYP_RS_MIN_ROWS"] = "0"          # (the default keeps the transposed sweep below 6144 rows per rank)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
