@@ -125,6 +125,12 @@ int main() {
                     if (rc) { printf("FAIL dst rc=%d out_tiles=%d n_dh=%d kb=%d P=%d\n", rc, out_tiles, n_dh, kb, P); return 1; }
                     ++n;
                 }
+    // the cases the design notes quote: 8 ranks x 4096 rows, 256-column tiles -> four whole-tile rounds on 64 pairs;
+    // one GPU at B = 32768 -> the flat schedule on all 74 pairs; a 2-GPU B = 8192 problem -> one whole-tile round
+    if (dst_sched_pairs(256, 32, 74) != 64 || dst_sched_pairs(128, 256, 74) != 74 || dst_sched_pairs(64, 32, 74) != 64) {
+        printf("FAIL dst_sched_pairs reference cases\n");
+        return 1;
+    }
     const int npairs_list[] = {1, 2, 3, 7, 64, 66, 70, 74};
     for (int npairs : npairs_list)
         for (int n_dh = 1; n_dh <= 2; ++n_dh)

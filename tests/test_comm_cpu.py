@@ -41,6 +41,7 @@ def test_null_communicator_is_an_argument_error():
     st = _lib.Stats()
     assert lib.flyp_comm_push_stats(None, 1, None, None, None, 128, 256, ctypes.byref(st), None) == -1
     assert lib.flyp_comm_push_scalar(None, 1, None, None) == -1
+    assert lib.flyp_comm_set_rs_min_rows(None, 0) == -1
     assert lib.flyp_comm_sum_scalar(None, 1, None, None) == -1
     assert lib.flyp_comm_error(None) == 0
     assert lib.flyp_comm_has_multicast(None) == 0
